@@ -1,0 +1,156 @@
+/*
+ * score_b200.h - C ABI of the B200-native SCoRe training / scoring hot path.
+ *
+ * This is the drop-in boundary for ONE path of qinjr/SCoRe: the model object that
+ * code/score/train_score.py drives (construct :171, model.train :227, model.eval :153,
+ * model.save :252, model.restore :80) and whose TensorFlow graph is built by
+ * code/score/score.py (class SCORE :188-224 and the ablations :227-369).  Everything behind
+ * these entry points is hand-written CUDA for sm_100a; there is no CPU fallback: every call
+ * fails with SCORE_ERR_CUDA when no device / kernel image is available.
+ *
+ * Conventions
+ *  - plain C types only; a handle owns every parameter, optimizer slot and workspace on ONE
+ *    device (the reference keeps them in the tf.Session; one live model per process there);
+ *  - int return: 0 = ok, otherwise a SCORE_ERR_* code; score_last_error() gives the text;
+ *  - id tensors are int32, row-major, in the loader's layout (graph_loader.py:383):
+ *      user_1hop [B,T,K,item_fnum]  user_2hop [B,T,K,user_fnum]
+ *      item_1hop [B,T,K,user_fnum]  item_2hop [B,T,K,item_fnum]
+ *      target_user [B,user_fnum]    target_item [B,item_fnum]   label [B]   length [B]
+ *    every id indexes the single shared table (0 = dummy node, zero vector, no gradient);
+ *  - calls on one handle are not re-entrant (train_score.py is single-threaded).
+ */
+#ifndef SCORE_B200_H
+#define SCORE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ScoreModel* ScoreHandle;
+
+enum {
+    SCORE_OK = 0,
+    SCORE_ERR_ARG = 1,      /* bad argument / shape (reference: TF raises from sess.run)          */
+    SCORE_ERR_CUDA = 2,     /* CUDA runtime error, no device, or no sm_100a kernel image           */
+    SCORE_ERR_ID_RANGE = 3, /* an id outside [0, feature_size) (reference: embedding_lookup raises) */
+    SCORE_ERR_IO = 4,       /* save / restore file error                                           */
+    SCORE_ERR_NAME = 5      /* unknown tensor name                                                 */
+};
+
+/* model_type: which class of score.py the handle mirrors (train_score.py:170-182). */
+enum { SCORE_MODEL_SCORE = 0, SCORE_MODEL_RIA = 1, SCORE_MODEL_RCA = 2,
+       SCORE_MODEL_SCORE_USER = 3, SCORE_MODEL_SCORE_ITEM = 4 };
+
+/* Embedding optimizer mode.  The reference's emb_mtx gradient is dense (score.py:45-47 route the
+ * lookup through a dense multiply), so tf.train.AdamOptimizer moves EVERY row EVERY step.
+ *  DENSE  : literal - sparse row update for touched rows + a full-table zero-gradient sweep.
+ *  LAZY   : exact same results as DENSE; a row's skipped zero-gradient steps are replayed
+ *           (same fp32 op sequence) the next time the row is gathered, read back or saved.
+ *  SPARSE : touched rows only (not step-for-step identical to the reference; perf mode).     */
+enum { SCORE_ADAM_DENSE = 0, SCORE_ADAM_LAZY = 1, SCORE_ADAM_SPARSE = 2 };
+
+/* Mirrors SCOREBASE.__init__(feature_size, eb_dim, hidden_size, max_time_len,
+ * obj_per_time_slice, user_fnum, item_fnum)  (score.py:12-13), plus build options. */
+typedef struct ScoreConfig {
+    int64_t feature_size;       /* V: rows of emb_mtx                                  */
+    int32_t eb_dim;             /* d (multiple of 4)                                   */
+    int32_t hidden_size;        /* H                                                   */
+    int32_t max_time_len;       /* T                                                   */
+    int32_t obj_per_time_slice; /* K (<= 32)                                           */
+    int32_t user_fnum;
+    int32_t item_fnum;
+    int32_t model_type;         /* SCORE_MODEL_*                                       */
+    int32_t adam_mode;          /* SCORE_ADAM_*                                        */
+    int32_t max_batch;          /* workspace capacity hint (grows on demand)           */
+    uint64_t seed;              /* weight-init and dropout RNG seed                    */
+    int32_t init_weights;       /* 1: draw TF-default initial weights on the device    */
+    int32_t use_graph;          /* 1: replay the step as a CUDA graph (per batch size) */
+} ScoreConfig;
+
+/* Host id arrays of one batch, in batch_data order (score.py:103-110). */
+typedef struct ScoreBatch {
+    const int32_t* user_1hop;
+    const int32_t* user_2hop;
+    const int32_t* item_1hop;
+    const int32_t* item_2hop;
+    const int32_t* target_user;
+    const int32_t* target_item;
+    const int32_t* label;
+    const int32_t* length;
+    int32_t batch_size;         /* B (dynamic: the last batch is short, graph_loader.py:321-324) */
+    int32_t on_device;          /* 0: host pointers (copied H2D inside the call); 1: device pointers */
+} ScoreBatch;
+
+/* replaces SCORE(...) construction + sess.run(global_variables_initializer) (train_score.py:171,188) */
+int score_create(const ScoreConfig* cfg, int device, ScoreHandle* out);
+int score_destroy(ScoreHandle h);
+const char* score_last_error(ScoreHandle h); /* h may be NULL: error of the last failed create */
+
+/* replaces SCOREBASE.train (score.py:101-116): one forward + backward + Adam update.
+ * *loss_out is the pre-update loss incl. the L2 term (what sess.run([loss, train_step]) returns).
+ * keep_prob is 0.8 in the reference (score.py:113). */
+int score_train_step(ScoreHandle h, const ScoreBatch* batch, float lr, float reg_lambda,
+                     float keep_prob, float* loss_out);
+/* asynchronous variant: enqueue only; score_wait() returns the loss of the last enqueued step. */
+int score_train_step_async(ScoreHandle h, const ScoreBatch* batch, float lr, float reg_lambda,
+                           float keep_prob);
+int score_wait(ScoreHandle h, float* loss_out);
+
+/* replaces SCOREBASE.eval (score.py:118-133): keep_prob = 1; preds_out[B] = y_pred,
+ * *loss_out = log-loss + L2 term. */
+int score_eval(ScoreHandle h, const ScoreBatch* batch, float reg_lambda, float* preds_out,
+               float* loss_out);
+
+/* Parity / inspection: forward + backward WITHOUT the optimizer update.  Afterwards every
+ * intermediate and gradient can be read with score_get_buffer().  Dense gradients are under
+ * "grad/<tf var name>"; the embedding gradient row set under "emb_grad/rows" (int32, ascending)
+ * and "emb_grad/values" ([U,d]). */
+int score_forward_backward(ScoreHandle h, const ScoreBatch* batch, float reg_lambda,
+                           float keep_prob, float* loss_out);
+/* size query: data == NULL -> *count = number of elements.  dtype: 0 = float32, 1 = int32. */
+int score_get_buffer(ScoreHandle h, const char* name, void* data, size_t capacity_bytes,
+                     size_t* count, int* dtype);
+
+/* Parameters and Adam slots by TF variable name ("emb_mtx", "dense/kernel", ...,
+ * "<var>/Adam", "<var>/Adam_1", "beta1_power", "beta2_power").
+ * Replaces reading / assigning tf variables; used for checkpoint interop and parity. */
+int score_tensor_count(ScoreHandle h);
+int score_tensor_info(ScoreHandle h, int index, char* name, size_t name_cap, int64_t* rows, int64_t* cols);
+int score_get_tensor(ScoreHandle h, const char* name, float* data, size_t count);
+int score_set_tensor(ScoreHandle h, const char* name, const float* data, size_t count);
+/* row-range access to emb_mtx and its slots for tables too large for one host buffer */
+int score_get_rows(ScoreHandle h, const char* name, int64_t row0, int64_t nrows, float* data);
+int score_set_rows(ScoreHandle h, const char* name, int64_t row0, int64_t nrows, const float* data);
+
+/* replaces SCOREBASE.save / restore (score.py:135-142): all variables incl. Adam slots. */
+int score_save(ScoreHandle h, const char* path);
+int score_restore(ScoreHandle h, const char* path);
+
+/* replaces the arithmetic of eval() + get_ranking_quality (train_score.py:122-163) for N
+ * predictions in groups of `group` (100): out9 = logloss, auc, ndcg@5, ndcg@10, hr@1, hr@5,
+ * hr@10, mrr, <unused 0>.  Host pointers. */
+int score_eval_metrics(ScoreHandle h, const float* preds, const int32_t* target_iids,
+                       const int32_t* labels, int64_t n, int32_t group, double* out9);
+
+/* The CUDA stream every call of this handle is ordered on (a cudaStream_t). */
+int score_stream(ScoreHandle h, void** cuda_stream);
+
+/* Measurement hooks (bench.py).
+ * score_launch_count: kernels launched by this library since the handle was created.
+ * score_enable_probes / score_probe_times: CUDA-event timing of named kernels inside the timed
+ *   train steps, on the stream they are launched on.  out[2*p] = accumulated ms, out[2*p+1] = number
+ *   of samples, p = 0 coatt_fwd (gather), 1 coatt_bwd, 2 emb_update (scatter+Adam), 3 sort, 4 whole step.
+ * score_last_step_stats: out3 = { positions N, live positions (non-zero key), unique rows U } of the
+ *   last train step - the factors of the algorithmic byte counts in DESIGN.md. */
+int64_t score_launch_count(ScoreHandle h);
+int score_enable_probes(ScoreHandle h, int on);
+int score_probe_times(ScoreHandle h, double* out, int n);
+int score_last_step_stats(ScoreHandle h, int64_t* out3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCORE_B200_H */

@@ -1,0 +1,71 @@
+// Shared device helpers for the SCoRe hot-path kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define FULL_MASK 0xffffffffu
+
+namespace score {
+
+// Step-scoped scalars the kernels read from device memory, so a captured CUDA graph can be
+// replayed with new hyper-parameters by overwriting this one struct.
+struct Hyper {
+    float lr;
+    float reg_lambda;
+    float keep_prob;      // 1.0 disables dropout
+    float alpha;          // TF Adam: lr * sqrt(1 - beta2^t) / (1 - beta1^t)
+    float inv_batch;      // 1 / global batch (loss mean)
+    uint32_t seed_lo, seed_hi;
+    int32_t step;         // 1-based optimizer step this launch performs
+    int32_t batch;        // B of this launch
+    int32_t train;        // 1: training step (dropout active when keep_prob < 1)
+    int32_t pad0, pad1;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
+
+// 16-byte async global->shared copy, L2 only (embedding rows are random: no L1 reuse).
+// src_bytes == 0 zero-fills the destination (dummy node id 0 -> zero vector).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Philox4x32-10 counter RNG (dropout masks, weight init): stateless, keyed by (seed, counter).
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+// uniform [0,1) for element `idx` of stream (`stream_id`, `step`)
+__device__ __forceinline__ float philox_uniform(uint32_t seed_lo, uint32_t seed_hi, uint32_t stream_id,
+                                                uint32_t step, uint64_t idx) {
+    uint4 c = make_uint4((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), stream_id, step);
+    uint4 r = philox4x32(c, make_uint2(seed_lo, seed_hi));
+    uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
+    return (float)(w >> 8) * (1.0f / 16777216.0f);
+}
+
+}  // namespace score

@@ -1,0 +1,214 @@
+// Launcher declarations shared by the kernel translation units and model.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace score {
+
+// Every launcher bumps this (bench.py reports it as gpu_launches).
+extern int64_t g_launch_count;
+
+// ---------------------------------------------------------------- dense layers (gemm.cu)
+enum GemmEpi {
+    EPI_STORE = 0,        // C = acc
+    EPI_BIAS = 1,         // C = acc + bias[n]
+    EPI_BIAS_RELU = 2,    // C = relu(acc + bias[n])
+    EPI_BIAS_RELU_DROP = 3,  // tf.nn.dropout(relu(acc + bias)) : x / keep_prob * mask   (score.py:70-73)
+    EPI_MASK = 4,         // C = aux[m,n] > 0 ? acc (/ keep_prob if mask_dropout) : 0     (relu/dropout backward)
+    EPI_ACCUM = 5,        // C += acc
+    EPI_SPLIT = 6         // split-K partials: C + z * c_split_stride (deterministic two-stage reduce)
+};
+
+struct GemmArgs {
+    const float* A; int64_t a_rs, a_cs;   // A(m,k) = A[m*a_rs + k*a_cs]
+    const float* B; int64_t b_rs, b_cs;   // B(k,n) = B[k*b_rs + n*b_cs]
+    float* C; int64_t c_rs;               // C(m,n) = C[m*c_rs + n]
+    int M, N, K;
+    int epi;
+    const float* bias;
+    const float* aux; int64_t aux_rs;
+    int mask_dropout;
+    int splits; int64_t c_split_stride;
+    float* colsum; int64_t colsum_split_stride;   // EPI_SPLIT: also sum_k B(k,n) -> bias gradient
+    const Hyper* hp; uint32_t rng_stream;
+};
+void launch_gemm(cudaStream_t st, const GemmArgs& a);
+
+// ---------------------------------------------------------------- embedding front end (embed.cu)
+struct Dims {
+    int64_t V;
+    int B, T, K, d, H, fu, fi;
+    int Du, Di, Ds, Dk, Dfc;      // user/item node width, GRU input width, key width, fc input width
+    int ldx;                       // Ds + H: leading dim of the [x || h] buffers
+    int64_t off_u1, off_u2, off_i1, off_i2, off_tu, off_ti, N;  // position offsets in the flat id list
+    int model_type;
+};
+
+void launch_build_keys(cudaStream_t st, const Dims& dm, const int32_t* ids, const int32_t* length,
+                       int32_t* keys, int32_t* err_flag);
+
+struct TargetArgs {
+    const float* emb; const int32_t* keys;
+    const float* w_item; const float* b_item;   // co-attention #1 kernel [3*Di] (rows: target|seq1|seq2), bias
+    const float* w_user; const float* b_user;   // co-attention #2 kernel [3*Du]
+    float* q0;      // [B, Ds]  = [target_user || target_item]      (score.py:210)
+    float* fc_in; int fc_off;   // fc_in[b, fc_off:] = [target_item || target_user] (score.py:217)
+    float* c_item; float* c_user;   // [B] target part of the relatedness pre-activation (+bias)
+};
+void launch_target_fwd(cudaStream_t st, const Dims& dm, const TargetArgs& a);
+
+struct CoattArgs {
+    const float* emb; const int32_t* keys; const int32_t* length;
+    const float* w_item; const float* w_user;
+    const float* c_item; const float* c_user;
+    float* xhg_u; float* xhc_u; float* xhg_i; float* xhc_i;   // [M, ldx], x part written here
+    float* key; int ldkey; int key_off;                       // atten_info -> key[:, key_off : key_off+4K]
+    float* save_r; float* save_w;                             // [M, 2K]
+};
+void launch_coatt_fwd(cudaStream_t st, const Dims& dm, const CoattArgs& a);
+
+struct CoattBwdArgs {
+    const float* emb; const int32_t* keys; const int32_t* length;
+    const float* w_item; const float* w_user;
+    const float* save_r; const float* save_w;
+    const float* dxu; const float* dxi;        // [M, Ds]
+    const float* dkey; int ldkey; int key_off; // d atten_info
+    float* grad_rows;                          // [N, d] per-position embedding gradient rows
+    float* sdz;                                // [M, 2]  sum_i d z_i per slice and co-attention
+    float* partials; int n_partials;           // [n_partials, 2*Di + 2*Du] per-CTA dW1|dW2 (item), dW1|dW2 (user)
+};
+int coatt_bwd_num_ctas();
+void launch_coatt_bwd(cudaStream_t st, const Dims& dm, const CoattBwdArgs& a);
+
+struct TargetBwdArgs {
+    const int32_t* length;
+    const float* w_item; const float* w_user;
+    const float* q0; const float* dq0;         // [B, Ds]
+    const float* dfc_in; int fc_off; int ldfc; // d fc_in[b, fc_off:]
+    const float* sdz;
+    float* grad_rows;
+    float* partials; int n_partials;           // [n_partials, Di + 1 + Du + 1]: dWt_item | db_item | dWt_user | db_user
+};
+int target_bwd_num_ctas();
+void launch_target_bwd(cudaStream_t st, const Dims& dm, const TargetBwdArgs& a);
+
+// reduce the co-attention partials of both kernels into the flat dense gradient buffer (split 0)
+void launch_coatt_grad_reduce(cudaStream_t st, const Dims& dm, const float* coatt_partials, int n_coatt,
+                              const float* target_partials, int n_target,
+                              float* g_w_item, float* g_b_item, float* g_w_user, float* g_b_user);
+
+// ---------------------------------------------------------------- sequence encoder + head (seq.cu)
+struct GruArgs {
+    const int32_t* length;
+    const float* px[2];            // [M, 3H] input projections (no bias)
+    const float* wg[2]; const float* bg[2];   // gates kernel [ldx, 2H] (rows Ds.. are the state part), bias [2H]
+    const float* wc[2]; const float* bc[2];   // candidate kernel [ldx, H], bias [H]
+    float* xhg[2]; float* xhc[2];  // [M, ldx]: state part (cols Ds..) written: h_prev and r*h_prev
+    float* r[2]; float* u[2]; float* c[2];    // [M, H] saved gate values
+    float* out; int ldout;         // key: side s writes out[m, s*H : (s+1)*H]  (0 for t >= length)
+    float* last;  int ldlast;      // optional final state -> last[b, s*H:...] (RIA), may be null
+};
+void launch_gru_fwd(cudaStream_t st, const Dims& dm, const GruArgs& a);
+
+struct GruBwdArgs {
+    const int32_t* length;
+    const float* wg[2]; const float* wc[2];
+    const float* xhg[2];
+    const float* r[2]; const float* u[2]; const float* c[2];
+    const float* dout; int lddout;   // d key[:, s*H:(s+1)*H]
+    const float* dlast; int lddlast; // optional gradient of the final state (RIA), may be null
+    float* dpx[2];                   // [M, 3H]
+};
+void launch_gru_bwd(cudaStream_t st, const Dims& dm, const GruBwdArgs& a);
+
+// attention input [q, key, q-key, q*key] (score.py:174) and its backward
+void launch_att_inp_fwd(cudaStream_t st, const Dims& dm, const float* q, const float* key, float* a1);
+void launch_att_inp_bwd(cudaStream_t st, const Dims& dm, const float* q, const float* key, const float* da1,
+                        float* dkey, float* dq /* [B,Dk] */, int accumulate_cols /* first cols of dkey hold pooling grads */);
+
+struct AttPoolArgs {
+    const int32_t* length;
+    const float* f2;              // [M, 40]
+    const float* w3; const float* b3;
+    const float* key; int ldkey;  // rep_t = key[:, 0:2H]
+    float* score;                 // [B, T]
+    float* fc_in; int ldfc;       // user_final -> [0:H], item_final -> [H:2H] (model-type dependent)
+};
+void launch_att_pool_fwd(cudaStream_t st, const Dims& dm, const AttPoolArgs& a);
+
+struct AttPoolBwdArgs {
+    const int32_t* length;
+    const float* score; const float* key; int ldkey;
+    const float* dfc_in; int ldfc;
+    float* ds;                    // [M] gradient of the pre-softmax scores
+    float* dkey;                  // [M, ldkey]: cols 0:2H <- pooling gradient (overwritten)
+};
+void launch_att_pool_bwd(cudaStream_t st, const Dims& dm, const AttPoolBwdArgs& a);
+
+// batch-norm in inference mode (score.py:69): z = x * gamma/sqrt(var+eps) + (beta - mean*inv)
+void launch_bn_fwd(cudaStream_t st, int B, int F, const float* x, const float* gamma, const float* beta,
+                   const float* mean, const float* var, float* z);
+void launch_bn_bwd(cudaStream_t st, int B, int F, const float* x, const float* dz, const float* gamma,
+                   const float* mean, const float* var, float* dx, float* dgamma, float* dbeta);
+
+// logit = g2 . w3 + b3; y = sigmoid; per-sample log-loss (eps 1e-7) and d loss / d logit
+void launch_head(cudaStream_t st, int B, int F, const float* g2, const float* w3, const float* b3,
+                 const int32_t* label, const Hyper* hp, float* y, float* loss_b, float* dlogit);
+// loss = sum_b loss_b * inv_batch + reg_lambda * l2sum    (fixed-order reduction)
+void launch_loss_final(cudaStream_t st, int B, const float* loss_b, const float* l2sum, const Hyper* hp, float* loss);
+
+// ---------------------------------------------------------------- optimizer + scatter (scatter.cu)
+// sum of v*v/2 over L2-regularised dense parameters (flags bit0)
+void launch_l2_sum(cudaStream_t st, const float* params, const uint8_t* flags, int n, float* out);
+// G[i] = sum_s partial[s][i]
+void launch_reduce_partials(cudaStream_t st, const float* partials, int splits, int n, float* g);
+void launch_add_l2(cudaStream_t st, float* g, const float* p, const uint8_t* flags, int n, const Hyper* hp);
+// dense Adam on the flat parameter buffer: g = G + reg*p (flags bit0), skip non-trainables (flags bit1 clear)
+void launch_dense_adam(cudaStream_t st, float* p, float* m, float* v, const float* g, const uint8_t* flags,
+                       int n, const Hyper* hp, float* alpha_hist /* LAZY: alpha_hist[step] = alpha, may be null */);
+
+struct SortBufs {
+    int32_t* keys[2]; int32_t* vals[2];   // ping-pong
+    uint32_t* hist;                        // [256 * nblocks]
+    int n_cap;
+};
+size_t sort_hist_elems(int64_t n);
+// stable LSD radix sort of (key, position) pairs; keys_in is left untouched, values start as 0..n-1;
+// returns the index (0/1) of the ping-pong buffer that holds the result
+int launch_sort_pairs(cudaStream_t st, SortBufs& sb, const int32_t* keys_in, int64_t n, int key_bits);
+
+struct EmbUpdateArgs {
+    const int32_t* skeys; const int32_t* spos; int64_t n;
+    const float* grad_rows; int d;
+    float* emb; float* m; float* v; int32_t* last_step;
+    const Hyper* hp;
+    int mode;                      // 0: apply Adam, 1: export (seg sums to out_rows at head index, no update)
+    float* out_rows; int32_t* out_heads;
+};
+void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a);
+// DENSE mode: zero-gradient Adam step for every row whose last_step != hp->step
+void launch_emb_dense_sweep(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d,
+                            const Hyper* hp);
+// LAZY mode: replay skipped zero-gradient steps of the rows about to be gathered (keys in position order;
+// duplicates are resolved by an atomic claim on last_step, the replay result does not depend on the winner)
+void launch_emb_catchup_rows(cudaStream_t st, const int32_t* keys, int64_t n, float* emb, float* m, float* v,
+                             int32_t* last_step, int d, const float* alpha_hist, const Hyper* hp);
+// LAZY mode: bring the whole table up to `upto_step` (before read-back / save / eval of everything)
+void launch_emb_catchup_all(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d,
+                            const float* alpha_hist, int upto_step);
+
+// device-side TF-default initialisers
+void launch_init_trunc_normal(cudaStream_t st, float* p, int64_t n, uint64_t seed, uint32_t stream_id);
+void launch_init_uniform(cudaStream_t st, float* p, int64_t n, float limit, uint64_t seed, uint32_t stream_id);
+void launch_fill(cudaStream_t st, float* p, int64_t n, float v);
+void launch_fill_i32(cudaStream_t st, int32_t* p, int64_t n, int32_t v);
+
+// ---------------------------------------------------------------- eval metrics (metrics.cu)
+// sums[0] = sum of log-loss terms; sums[2..7] = sums of ndcg5 ndcg10 hr1 hr5 hr10 mrr over groups;
+// sums[8] = sum over positives of mid-ranks, sums[9] = number of positives.  terms: >= max(2n, 6n/group) doubles.
+cudaError_t compute_eval_metrics(cudaStream_t st, const float* preds, const int32_t* iids, const int32_t* labels,
+                                 int64_t n, int group, SortBufs& sb, int32_t* keys, int32_t* pos_rank, double* terms,
+                                 double* sums);
+
+}  // namespace score

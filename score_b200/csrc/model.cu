@@ -1,0 +1,1146 @@
+// Model handle, workspace and step orchestration behind the C ABI (include/score_b200.h).
+//
+// One handle = one model on one device: the single shared embedding table with its Adam slots,
+// one flat buffer of every dense variable (TF names and creation order of score.py), the
+// per-batch workspace, two streams (main + scatter/sort branch) and, optionally, one captured
+// CUDA graph per batch size.  The step is the data-parallel hot path of
+// code/score/score.py:101-133 (train / eval) with the graph of score.py:188-224 underneath.
+#include "../../include/score_b200.h"
+#include "kernels.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace score;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int kSplits = 16;   // fixed number of batch-row chunks for weight gradients (deterministic two-stage sum)
+
+struct Tensor {
+    std::string name;
+    int64_t rows, cols;
+    int64_t off;       // float offset in the flat dense buffer (unused for emb_mtx)
+    bool is_emb;
+    uint8_t flags;     // bit0: L2-regularised (score.py:92-94), bit1: trainable
+};
+
+struct Buf {
+    void* ptr; size_t count; int dtype;   // 0 float32, 1 int32
+};
+
+enum Probe { PR_COATT_FWD = 0, PR_COATT_BWD, PR_EMB_UPDATE, PR_SORT, PR_STEP, PR_COUNT };
+
+}  // namespace
+
+struct ScoreModel {
+    ScoreConfig cfg;
+    int device = 0;
+    std::string err;
+    Dims dm;                        // dm.B / offsets are per call
+    cudaStream_t st = nullptr, st2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+
+    // parameters
+    std::vector<Tensor> tensors;
+    std::map<std::string, int> tindex;
+    int64_t n_dense = 0;
+    float *emb = nullptr, *emb_m = nullptr, *emb_v = nullptr;
+    int32_t* last_step = nullptr;   // per-row step at which the row is current (DENSE / LAZY)
+    float *P = nullptr, *G = nullptr, *M1 = nullptr, *V1 = nullptr, *PG = nullptr;
+    uint8_t* flags = nullptr;
+    float* alpha_hist = nullptr; int64_t alpha_cap = 0;
+    std::vector<float> alpha_host;
+
+    // optimizer scalars (fp32 like the TF slot variables)
+    int32_t step = 0;
+    float beta1_power = 0.9f, beta2_power = 0.999f;
+
+    // workspace
+    int cap_B = 0;
+    std::vector<void*> allocs;       // per-capacity allocations (freed on regrow)
+    std::map<std::string, Buf> bufs;
+    int32_t *ids = nullptr, *label = nullptr, *length = nullptr, *keys = nullptr;
+    float *q0, *c_item, *c_user, *xhg[2], *xhc[2], *key, *save_r, *save_w, *px[2], *gr[2], *gu[2], *gc[2];
+    float *q, *a1, *f1, *f2, *score, *fc_in, *z0, *g1, *g2, *y, *loss_b, *dlogit;
+    float *dg2, *dg1, *dz0, *dfc_in, *ds, *df2, *df1, *da1, *dkey, *dq, *dq0, *dpx[2], *dx[2], *sdz, *grad_rows;
+    float *coatt_part, *target_part;
+    int n_coatt_part = 0, n_target_part = 0;
+    SortBufs sb{};
+    int sort_out = 0;
+    float *seg_rows = nullptr; int32_t* seg_heads = nullptr; int64_t seg_cap = 0;
+    int64_t last_N = 0;
+    float *l2sum = nullptr, *loss_dev = nullptr;
+    int32_t* err_flag = nullptr;
+    Hyper* hyper_dev = nullptr;
+    // pinned host staging
+    Hyper* hyper_host = nullptr;
+    float* loss_host = nullptr;
+    int32_t* err_host = nullptr;
+
+    // external emb-grad source (multi-GPU replicated table)
+    const int32_t* ext_keys = nullptr; const float* ext_rows = nullptr; int64_t ext_n = 0;
+
+    // graphs
+    std::map<int, cudaGraphExec_t> graphs_train;
+    std::map<int, int> warm_train;
+    bool capturing = false;
+
+    // timing probes
+    bool probes_on = false;
+    cudaEvent_t pr_beg[PR_COUNT], pr_end[PR_COUNT];
+    double pr_ms[PR_COUNT]; int64_t pr_n[PR_COUNT];
+    bool pending_step = false;
+    int last_mode = -1;
+
+    int64_t launches0 = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char b_[512];                                                                          \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            h->err = b_;                                                                           \
+            return SCORE_ERR_CUDA;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+int fail(ScoreModel* h, int code, const std::string& msg) {
+    h->err = msg;
+    return code;
+}
+
+const Tensor* find_tensor(ScoreModel* h, const std::string& name) {
+    auto it = h->tindex.find(name);
+    return it == h->tindex.end() ? nullptr : &h->tensors[it->second];
+}
+float* pp(ScoreModel* h, const char* name) { return h->P + find_tensor(h, name)->off; }
+int64_t po(ScoreModel* h, const char* name) { return find_tensor(h, name)->off; }
+
+// TF variable names by role (oracle/score_ref.py:role_names states the numbering rule)
+struct Names {
+    std::string co_item, co_user, att_q, att1, att2, att3;
+};
+Names role_names(int model_type) {
+    Names n;
+    int k = 0;
+    auto next = [&]() { std::string s = k == 0 ? "dense" : "dense_" + std::to_string(k); ++k; return s; };
+    if (model_type != SCORE_MODEL_RCA) { n.co_item = next(); n.co_user = next(); }
+    if (model_type != SCORE_MODEL_RIA) { n.att_q = next(); n.att1 = next(); n.att2 = next(); n.att3 = next(); }
+    return n;
+}
+
+void build_registry(ScoreModel* h) {
+    const ScoreConfig& c = h->cfg;
+    const int d = c.eb_dim, H = c.hidden_size, K = c.obj_per_time_slice;
+    const int Du = c.user_fnum * d, Di = c.item_fnum * d, Ds = Du + Di;
+    const int mt = c.model_type;
+    const int Dk = (mt == SCORE_MODEL_RCA) ? 2 * H : 2 * H + 4 * K;
+    const int nstate = (mt == SCORE_MODEL_SCORE_USER || mt == SCORE_MODEL_SCORE_ITEM) ? 1 : 2;
+    const int Dfc = nstate * H + Du + Di;
+    Dims& dm = h->dm;
+    dm.V = c.feature_size; dm.T = c.max_time_len; dm.K = K; dm.d = d; dm.H = H;
+    dm.fu = c.user_fnum; dm.fi = c.item_fnum; dm.Du = Du; dm.Di = Di; dm.Ds = Ds; dm.Dk = Dk; dm.Dfc = Dfc;
+    dm.ldx = Ds + H; dm.model_type = mt; dm.B = 0;
+
+    int64_t off = 0;
+    auto add = [&](const std::string& name, int64_t r, int64_t cdim, uint8_t flags, bool emb = false) {
+        Tensor t{name, r, cdim, emb ? -1 : off, emb, flags};
+        if (!emb) off += (r * cdim + 3) / 4 * 4;
+        h->tindex[name] = (int)h->tensors.size();
+        h->tensors.push_back(t);
+    };
+    auto kb = [&](const std::string& prefix, int64_t r, int64_t cdim) {
+        add(prefix + "/kernel", r, cdim, 3);
+        add(prefix + "/bias", 1, cdim, 2);
+    };
+    Names nm = role_names(mt);
+    add("emb_mtx", c.feature_size, d, 2, true);
+    if (mt != SCORE_MODEL_RCA) { kb(nm.co_item, 3 * Di, 1); kb(nm.co_user, 3 * Du, 1); }
+    for (const char* side : {"gru_user_side", "gru_item_side"}) {
+        kb(std::string(side) + "/gru_cell/gates", Ds + H, 2 * H);
+        kb(std::string(side) + "/gru_cell/candidate", Ds + H, H);
+    }
+    if (mt != SCORE_MODEL_RIA) { kb(nm.att_q, Ds, Dk); kb(nm.att1, 4 * Dk, 80); kb(nm.att2, 80, 40); kb(nm.att3, 40, 1); }
+    add("bn1/gamma", 1, Dfc, 3);
+    add("bn1/beta", 1, Dfc, 3);
+    add("bn1/moving_mean", 1, Dfc, 0);
+    add("bn1/moving_variance", 1, Dfc, 0);
+    kb("fc1", Dfc, 200); kb("fc2", 200, 80); kb("fc3", 80, 1);
+    h->n_dense = off;
+}
+
+int alloc_params(ScoreModel* h) {
+    const int64_t V = h->cfg.feature_size, d = h->cfg.eb_dim;
+    CK(cudaMalloc(&h->emb, sizeof(float) * V * d));
+    CK(cudaMalloc(&h->emb_m, sizeof(float) * V * d));
+    CK(cudaMalloc(&h->emb_v, sizeof(float) * V * d));
+    CK(cudaMemsetAsync(h->emb_m, 0, sizeof(float) * V * d, h->st));
+    CK(cudaMemsetAsync(h->emb_v, 0, sizeof(float) * V * d, h->st));
+    CK(cudaMemsetAsync(h->emb, 0, sizeof(float) * V * d, h->st));
+    if (h->cfg.adam_mode != SCORE_ADAM_SPARSE) {
+        CK(cudaMalloc(&h->last_step, sizeof(int32_t) * V));
+        CK(cudaMemsetAsync(h->last_step, 0, sizeof(int32_t) * V, h->st));
+    }
+    const int64_t n = h->n_dense;
+    CK(cudaMalloc(&h->P, sizeof(float) * n));
+    CK(cudaMalloc(&h->G, sizeof(float) * n));
+    CK(cudaMalloc(&h->M1, sizeof(float) * n));
+    CK(cudaMalloc(&h->V1, sizeof(float) * n));
+    CK(cudaMalloc(&h->PG, sizeof(float) * n * kSplits));
+    CK(cudaMalloc(&h->flags, n));
+    CK(cudaMemsetAsync(h->P, 0, sizeof(float) * n, h->st));
+    CK(cudaMemsetAsync(h->G, 0, sizeof(float) * n, h->st));
+    CK(cudaMemsetAsync(h->M1, 0, sizeof(float) * n, h->st));
+    CK(cudaMemsetAsync(h->V1, 0, sizeof(float) * n, h->st));
+    std::vector<uint8_t> fl(n, 0);
+    for (const Tensor& t : h->tensors)
+        if (!t.is_emb)
+            for (int64_t i = 0; i < t.rows * t.cols; ++i) fl[t.off + i] = t.flags;
+    CK(cudaMemcpy(h->flags, fl.data(), n, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->l2sum, sizeof(float)));
+    CK(cudaMalloc(&h->loss_dev, sizeof(float)));
+    CK(cudaMalloc(&h->err_flag, sizeof(int32_t)));
+    CK(cudaMemsetAsync(h->err_flag, 0, sizeof(int32_t), h->st));
+    CK(cudaMalloc(&h->hyper_dev, sizeof(Hyper)));
+    CK(cudaMallocHost(&h->hyper_host, sizeof(Hyper)));
+    CK(cudaMallocHost(&h->loss_host, sizeof(float)));
+    CK(cudaMallocHost(&h->err_host, sizeof(int32_t)));
+    if (h->cfg.adam_mode == SCORE_ADAM_LAZY) {
+        h->alpha_cap = 1 << 20;
+        CK(cudaMalloc(&h->alpha_hist, sizeof(float) * h->alpha_cap));
+        CK(cudaMemsetAsync(h->alpha_hist, 0, sizeof(float) * h->alpha_cap, h->st));
+    }
+    return SCORE_OK;
+}
+
+// TF-default initial values (score.py:44 truncated_normal; tf.layers.dense glorot_uniform / zeros;
+// GRUCell gate bias 1.0; batch_normalization gamma 1, beta 0, moving_mean 0, moving_variance 1)
+int init_weights(ScoreModel* h) {
+    const uint64_t seed = h->cfg.seed;
+    launch_init_trunc_normal(h->st, h->emb, h->cfg.feature_size * h->cfg.eb_dim, seed, 1000u);
+    uint32_t sid = 1;
+    for (const Tensor& t : h->tensors) {
+        if (t.is_emb) continue;
+        float* p = h->P + t.off;
+        const int64_t n = t.rows * t.cols;
+        const std::string& nm = t.name;
+        auto ends = [&](const char* s) { size_t l = strlen(s); return nm.size() >= l && nm.compare(nm.size() - l, l, s) == 0; };
+        if (ends("/kernel")) {
+            float lim = sqrtf(6.0f / (float)(t.rows + t.cols));
+            launch_init_uniform(h->st, p, n, lim, seed, sid++);
+        } else if (ends("gates/bias") || nm == "bn1/gamma" || nm == "bn1/moving_variance") {
+            launch_fill(h->st, p, n, 1.0f);
+        } else {
+            launch_fill(h->st, p, n, 0.0f);
+        }
+    }
+    CK(cudaStreamSynchronize(h->st));
+    return SCORE_OK;
+}
+
+void free_workspace(ScoreModel* h) {
+    for (void* p : h->allocs) cudaFree(p);
+    h->allocs.clear();
+    h->bufs.clear();
+    for (auto& kv : h->graphs_train) cudaGraphExecDestroy(kv.second);
+    h->graphs_train.clear();
+    h->warm_train.clear();
+    h->cap_B = 0;
+}
+
+template <typename T>
+int ws_alloc(ScoreModel* h, T** out, size_t count, const char* name, int dtype = 0) {
+    void* p = nullptr;
+    size_t bytes = (count ? count : 1) * sizeof(T);
+    CK(cudaMalloc(&p, bytes));
+    CK(cudaMemsetAsync(p, 0, bytes, h->st));
+    h->allocs.push_back(p);
+    *out = (T*)p;
+    if (name) h->bufs[name] = Buf{p, count, dtype};
+    return SCORE_OK;
+}
+
+#define WS(ptr, count, name)                                   \
+    do {                                                       \
+        int rc_ = ws_alloc(h, &(ptr), (size_t)(count), name);  \
+        if (rc_) return rc_;                                   \
+    } while (0)
+#define WSI(ptr, count, name)                                     \
+    do {                                                          \
+        int rc_ = ws_alloc(h, &(ptr), (size_t)(count), name, 1);  \
+        if (rc_) return rc_;                                      \
+    } while (0)
+
+int64_t ids_per_sample(const Dims& dm) {
+    return (int64_t)dm.T * dm.K * 2 * (dm.fu + dm.fi) + dm.fu + dm.fi;
+}
+
+int ensure_workspace(ScoreModel* h, int B) {
+    if (B <= h->cap_B) return SCORE_OK;
+    CK(cudaStreamSynchronize(h->st));
+    free_workspace(h);
+    int cap = B;
+    const Dims& dm = h->dm;
+    const int64_t M = (int64_t)cap * dm.T, N = (int64_t)cap * ids_per_sample(dm);
+    const int H = dm.H, K = dm.K, Ds = dm.Ds, Dk = dm.Dk, Dfc = dm.Dfc, ldx = dm.ldx;
+    WSI(h->ids, N, "ids"); WSI(h->label, cap, "label"); WSI(h->length, cap, "length"); WSI(h->keys, N, "keys");
+    WS(h->q0, (int64_t)cap * Ds, "q0"); WS(h->c_item, cap, "c_item"); WS(h->c_user, cap, "c_user");
+    WS(h->xhg[0], M * ldx, "xhg_user"); WS(h->xhg[1], M * ldx, "xhg_item");
+    WS(h->xhc[0], M * ldx, "xhc_user"); WS(h->xhc[1], M * ldx, "xhc_item");
+    WS(h->key, M * Dk, "key"); WS(h->save_r, M * 2 * K, "coatt_r"); WS(h->save_w, M * 2 * K, "coatt_w");
+    for (int s = 0; s < 2; ++s) {
+        const char* sn = s == 0 ? "user" : "item";
+        std::string a = std::string("px_") + sn, b = std::string("gru_r_") + sn, c = std::string("gru_u_") + sn,
+                    e = std::string("gru_c_") + sn, f = std::string("dpx_") + sn, g = std::string("dx_") + sn;
+        WS(h->px[s], M * 3 * H, a.c_str()); WS(h->gr[s], M * H, b.c_str()); WS(h->gu[s], M * H, c.c_str());
+        WS(h->gc[s], M * H, e.c_str()); WS(h->dpx[s], M * 3 * H, f.c_str()); WS(h->dx[s], M * Ds, g.c_str());
+    }
+    WS(h->q, (int64_t)cap * Dk, "q"); WS(h->a1, M * 4 * Dk, "att_inp"); WS(h->f1, M * 80, "att_fc1");
+    WS(h->f2, M * 40, "att_fc2"); WS(h->score, M, "score"); WS(h->fc_in, (int64_t)cap * Dfc, "fc_in");
+    WS(h->z0, (int64_t)cap * Dfc, "bn1"); WS(h->g1, (int64_t)cap * 200, "fc1"); WS(h->g2, (int64_t)cap * 80, "fc2");
+    WS(h->y, cap, "y_pred"); WS(h->loss_b, cap, "loss_b"); WS(h->dlogit, cap, "dlogit");
+    WS(h->dg2, (int64_t)cap * 80, "d_fc2"); WS(h->dg1, (int64_t)cap * 200, "d_fc1"); WS(h->dz0, (int64_t)cap * Dfc, "d_bn1");
+    WS(h->dfc_in, (int64_t)cap * Dfc, "d_fc_in"); WS(h->ds, M, "d_score"); WS(h->df2, M * 40, "d_att_fc2");
+    WS(h->df1, M * 80, "d_att_fc1"); WS(h->da1, M * 4 * Dk, "d_att_inp"); WS(h->dkey, M * Dk, "d_key");
+    WS(h->dq, (int64_t)cap * Dk, "d_q"); WS(h->dq0, (int64_t)cap * Ds, "d_q0"); WS(h->sdz, M * 2, "sdz");
+    WS(h->grad_rows, N * dm.d, "grad_rows");
+    h->n_coatt_part = coatt_bwd_num_ctas();
+    h->n_target_part = target_bwd_num_ctas();
+    WS(h->coatt_part, (int64_t)h->n_coatt_part * (2 * dm.Di + 2 * dm.Du), nullptr);
+    WS(h->target_part, (int64_t)h->n_target_part * (dm.Di + dm.Du + 2), nullptr);
+    WSI(h->sb.keys[0], N, nullptr); WSI(h->sb.keys[1], N, nullptr);
+    WSI(h->sb.vals[0], N, nullptr); WSI(h->sb.vals[1], N, nullptr);
+    {
+        uint32_t* hist = nullptr;
+        int rc = ws_alloc(h, &hist, sort_hist_elems(N), nullptr);
+        if (rc) return rc;
+        h->sb.hist = hist;
+    }
+    h->seg_rows = nullptr; h->seg_heads = nullptr; h->seg_cap = 0;
+    h->cap_B = cap;
+    CK(cudaStreamSynchronize(h->st));
+    return SCORE_OK;
+}
+
+void set_batch_dims(ScoreModel* h, int B) {
+    Dims& dm = h->dm;
+    dm.B = B;
+    const int64_t M = (int64_t)B * dm.T;
+    dm.off_u1 = 0;
+    dm.off_u2 = dm.off_u1 + M * dm.K * dm.fi;
+    dm.off_i1 = dm.off_u2 + M * dm.K * dm.fu;
+    dm.off_i2 = dm.off_i1 + M * dm.K * dm.fu;
+    dm.off_tu = dm.off_i2 + M * dm.K * dm.fi;
+    dm.off_ti = dm.off_tu + (int64_t)B * dm.fu;
+    dm.N = dm.off_ti + (int64_t)B * dm.fi;
+}
+
+int upload_batch(ScoreModel* h, const ScoreBatch* b) {
+    const Dims& dm = h->dm;
+    const int B = b->batch_size;
+    const int64_t M = (int64_t)B * dm.T;
+    const cudaMemcpyKind kind = b->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const size_t s_i = sizeof(int32_t);
+    CK(cudaMemcpyAsync(h->ids + dm.off_u1, b->user_1hop, s_i * M * dm.K * dm.fi, kind, h->st));
+    CK(cudaMemcpyAsync(h->ids + dm.off_u2, b->user_2hop, s_i * M * dm.K * dm.fu, kind, h->st));
+    CK(cudaMemcpyAsync(h->ids + dm.off_i1, b->item_1hop, s_i * M * dm.K * dm.fu, kind, h->st));
+    CK(cudaMemcpyAsync(h->ids + dm.off_i2, b->item_2hop, s_i * M * dm.K * dm.fi, kind, h->st));
+    CK(cudaMemcpyAsync(h->ids + dm.off_tu, b->target_user, s_i * B * dm.fu, kind, h->st));
+    CK(cudaMemcpyAsync(h->ids + dm.off_ti, b->target_item, s_i * B * dm.fi, kind, h->st));
+    CK(cudaMemcpyAsync(h->label, b->label, s_i * B, kind, h->st));
+    CK(cudaMemcpyAsync(h->length, b->length, s_i * B, kind, h->st));
+    return SCORE_OK;
+}
+
+// ------------------------------------------------------------------------------------------ GEMM helpers
+void gemm_fwd(ScoreModel* h, const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+              int M, int N, int K, int epi, uint32_t rng_stream = 0) {
+    GemmArgs g{};
+    g.A = A; g.a_rs = lda; g.a_cs = 1;
+    g.B = W; g.b_rs = ldw; g.b_cs = 1;
+    g.C = C; g.c_rs = ldc; g.M = M; g.N = N; g.K = K; g.epi = epi; g.bias = bias;
+    g.splits = 1; g.hp = h->hyper_dev; g.rng_stream = rng_stream;
+    launch_gemm(h->st, g);
+}
+// dA[M, Kl] = dC[M, Nl] W[Kl, Nl]^T, optionally masked by the saved activation
+void gemm_bwd_data(ScoreModel* h, const float* dC, int lddc, const float* W, int ldw, float* dA, int ldda, int M,
+                   int Kl, int Nl, int epi, const float* aux = nullptr, int aux_rs = 0, int mask_dropout = 0) {
+    GemmArgs g{};
+    g.A = dC; g.a_rs = lddc; g.a_cs = 1;
+    g.B = W; g.b_rs = 1; g.b_cs = ldw;
+    g.C = dA; g.c_rs = ldda; g.M = M; g.N = Kl; g.K = Nl; g.epi = epi;
+    g.aux = aux; g.aux_rs = aux_rs; g.mask_dropout = mask_dropout;
+    g.splits = 1; g.hp = h->hyper_dev;
+    launch_gemm(h->st, g);
+}
+// dW[Kl, Nl] (+ db[Nl]) = A[M, Kl]^T dC[M, Nl], into the kSplits partial planes of PG
+void gemm_bwd_weight(ScoreModel* h, const float* A, int lda, const float* dC, int lddc, int64_t w_off, int64_t b_off,
+                     int M, int Kl, int Nl) {
+    GemmArgs g{};
+    g.A = A; g.a_rs = 1; g.a_cs = lda;
+    g.B = dC; g.b_rs = lddc; g.b_cs = 1;
+    g.C = h->PG + w_off; g.c_rs = Nl; g.M = Kl; g.N = Nl; g.K = M; g.epi = EPI_SPLIT;
+    g.splits = kSplits; g.c_split_stride = h->n_dense;
+    g.colsum = (b_off >= 0) ? h->PG + b_off : nullptr; g.colsum_split_stride = h->n_dense;
+    g.hp = h->hyper_dev;
+    launch_gemm(h->st, g);
+}
+
+void probe_begin(ScoreModel* h, int p, cudaStream_t s) {
+    if (h->probes_on) cudaEventRecordWithFlags(h->pr_beg[p], s, h->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
+void probe_end(ScoreModel* h, int p, cudaStream_t s) {
+    if (h->probes_on) cudaEventRecordWithFlags(h->pr_end[p], s, h->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
+
+enum StepMode { MODE_TRAIN = 0, MODE_EVAL = 1, MODE_FWDBWD = 2, MODE_BEGIN = 3 };
+
+// forward graph of class SCORE (score.py:188-224); everything enqueued on h->st
+void enqueue_forward(ScoreModel* h) {
+    const Dims& dm = h->dm;
+    const int B = dm.B, T = dm.T, H = dm.H, Ds = dm.Ds, Dk = dm.Dk, Dfc = dm.Dfc, ldx = dm.ldx;
+    const int M = B * T;
+    Names nm = role_names(dm.model_type);
+    auto W = [&](const std::string& n) { return pp(h, (n + "/kernel").c_str()); };
+    auto Bi = [&](const std::string& n) { return pp(h, (n + "/bias").c_str()); };
+
+    launch_l2_sum(h->st, h->P, h->flags, (int)h->n_dense, h->l2sum);
+
+    TargetArgs ta{};
+    ta.emb = h->emb; ta.keys = h->keys;
+    ta.w_item = W(nm.co_item); ta.b_item = Bi(nm.co_item); ta.w_user = W(nm.co_user); ta.b_user = Bi(nm.co_user);
+    ta.q0 = h->q0; ta.fc_in = h->fc_in; ta.fc_off = Dfc - Ds; ta.c_item = h->c_item; ta.c_user = h->c_user;
+    launch_target_fwd(h->st, dm, ta);
+
+    CoattArgs ca{};
+    ca.emb = h->emb; ca.keys = h->keys; ca.length = h->length;
+    ca.w_item = W(nm.co_item); ca.w_user = W(nm.co_user); ca.c_item = h->c_item; ca.c_user = h->c_user;
+    ca.xhg_u = h->xhg[0]; ca.xhc_u = h->xhc[0]; ca.xhg_i = h->xhg[1]; ca.xhc_i = h->xhc[1];
+    ca.key = h->key; ca.ldkey = Dk; ca.key_off = 2 * H; ca.save_r = h->save_r; ca.save_w = h->save_w;
+    probe_begin(h, PR_COATT_FWD, h->st);
+    launch_coatt_fwd(h->st, dm, ca);
+    probe_end(h, PR_COATT_FWD, h->st);
+
+    const char* sides[2] = {"gru_user_side", "gru_item_side"};
+    GruArgs ga{};
+    ga.length = h->length;
+    for (int s = 0; s < 2; ++s) {
+        std::string g = std::string(sides[s]) + "/gru_cell/gates", c = std::string(sides[s]) + "/gru_cell/candidate";
+        // input part of both matmuls for all (b,t) rows at once: px = x [Wg_x | Wc_x]
+        gemm_fwd(h, h->xhg[s], ldx, W(g), 2 * H, nullptr, h->px[s], 3 * H, M, 2 * H, Ds, EPI_STORE);
+        gemm_fwd(h, h->xhg[s], ldx, W(c), H, nullptr, h->px[s] + 2 * H, 3 * H, M, H, Ds, EPI_STORE);
+        ga.px[s] = h->px[s]; ga.wg[s] = W(g); ga.bg[s] = Bi(g); ga.wc[s] = W(c); ga.bc[s] = Bi(c);
+        ga.xhg[s] = h->xhg[s]; ga.xhc[s] = h->xhc[s]; ga.r[s] = h->gr[s]; ga.u[s] = h->gu[s]; ga.c[s] = h->gc[s];
+    }
+    ga.out = h->key; ga.ldout = Dk; ga.last = nullptr; ga.ldlast = 0;
+    launch_gru_fwd(h->st, dm, ga);
+
+    // attention over the T slices (score.py:169-186)
+    gemm_fwd(h, h->q0, Ds, W(nm.att_q), Dk, Bi(nm.att_q), h->q, Dk, B, Dk, Ds, EPI_BIAS);
+    launch_att_inp_fwd(h->st, dm, h->q, h->key, h->a1);
+    gemm_fwd(h, h->a1, 4 * Dk, W(nm.att1), 80, Bi(nm.att1), h->f1, 80, M, 80, 4 * Dk, EPI_BIAS_RELU);
+    gemm_fwd(h, h->f1, 80, W(nm.att2), 40, Bi(nm.att2), h->f2, 40, M, 40, 80, EPI_BIAS_RELU);
+    AttPoolArgs pa{};
+    pa.length = h->length; pa.f2 = h->f2; pa.w3 = W(nm.att3); pa.b3 = Bi(nm.att3);
+    pa.key = h->key; pa.ldkey = Dk; pa.score = h->score; pa.fc_in = h->fc_in; pa.ldfc = Dfc;
+    launch_att_pool_fwd(h->st, dm, pa);
+
+    // build_fc_net + log-loss (score.py:68-81)
+    launch_bn_fwd(h->st, B, Dfc, h->fc_in, pp(h, "bn1/gamma"), pp(h, "bn1/beta"), pp(h, "bn1/moving_mean"),
+                  pp(h, "bn1/moving_variance"), h->z0);
+    gemm_fwd(h, h->z0, Dfc, pp(h, "fc1/kernel"), 200, pp(h, "fc1/bias"), h->g1, 200, B, 200, Dfc, EPI_BIAS_RELU_DROP, 1);
+    gemm_fwd(h, h->g1, 200, pp(h, "fc2/kernel"), 80, pp(h, "fc2/bias"), h->g2, 80, B, 80, 200, EPI_BIAS_RELU_DROP, 2);
+    launch_head(h->st, B, 80, h->g2, pp(h, "fc3/kernel"), pp(h, "fc3/bias"), h->label, h->hyper_dev, h->y, h->loss_b,
+                h->dlogit);
+    launch_loss_final(h->st, B, h->loss_b, h->l2sum, h->hyper_dev, h->loss_dev);
+}
+
+void enqueue_backward(ScoreModel* h) {
+    const Dims& dm = h->dm;
+    const int B = dm.B, T = dm.T, H = dm.H, Ds = dm.Ds, Dk = dm.Dk, Dfc = dm.Dfc, ldx = dm.ldx;
+    const int M = B * T;
+    Names nm = role_names(dm.model_type);
+    auto W = [&](const std::string& n) { return pp(h, (n + "/kernel").c_str()); };
+    auto Wo = [&](const std::string& n) { return po(h, (n + "/kernel").c_str()); };
+    auto Bo = [&](const std::string& n) { return po(h, (n + "/bias").c_str()); };
+
+    cudaMemsetAsync(h->PG, 0, sizeof(float) * h->n_dense * kSplits, h->st);
+
+    // prediction MLP
+    gemm_bwd_weight(h, h->g2, 80, h->dlogit, 1, Wo("fc3"), Bo("fc3"), B, 80, 1);
+    gemm_bwd_data(h, h->dlogit, 1, W("fc3"), 1, h->dg2, 80, B, 80, 1, EPI_MASK, h->g2, 80, 1);
+    gemm_bwd_weight(h, h->g1, 200, h->dg2, 80, Wo("fc2"), Bo("fc2"), B, 200, 80);
+    gemm_bwd_data(h, h->dg2, 80, W("fc2"), 80, h->dg1, 200, B, 200, 80, EPI_MASK, h->g1, 200, 1);
+    gemm_bwd_weight(h, h->z0, Dfc, h->dg1, 200, Wo("fc1"), Bo("fc1"), B, Dfc, 200);
+    gemm_bwd_data(h, h->dg1, 200, W("fc1"), 200, h->dz0, Dfc, B, Dfc, 200, EPI_STORE);
+    launch_bn_bwd(h->st, B, Dfc, h->fc_in, h->dz0, pp(h, "bn1/gamma"), pp(h, "bn1/moving_mean"),
+                  pp(h, "bn1/moving_variance"), h->dfc_in, h->PG + po(h, "bn1/gamma"), h->PG + po(h, "bn1/beta"));
+
+    // attention
+    AttPoolBwdArgs pb{};
+    pb.length = h->length; pb.score = h->score; pb.key = h->key; pb.ldkey = Dk; pb.dfc_in = h->dfc_in; pb.ldfc = Dfc;
+    pb.ds = h->ds; pb.dkey = h->dkey;
+    launch_att_pool_bwd(h->st, dm, pb);
+    gemm_bwd_weight(h, h->f2, 40, h->ds, 1, Wo(nm.att3), Bo(nm.att3), M, 40, 1);
+    gemm_bwd_data(h, h->ds, 1, W(nm.att3), 1, h->df2, 40, M, 40, 1, EPI_MASK, h->f2, 40, 0);
+    gemm_bwd_weight(h, h->f1, 80, h->df2, 40, Wo(nm.att2), Bo(nm.att2), M, 80, 40);
+    gemm_bwd_data(h, h->df2, 40, W(nm.att2), 40, h->df1, 80, M, 80, 40, EPI_MASK, h->f1, 80, 0);
+    gemm_bwd_weight(h, h->a1, 4 * Dk, h->df1, 80, Wo(nm.att1), Bo(nm.att1), M, 4 * Dk, 80);
+    gemm_bwd_data(h, h->df1, 80, W(nm.att1), 80, h->da1, 4 * Dk, M, 4 * Dk, 80, EPI_STORE);
+    launch_att_inp_bwd(h->st, dm, h->q, h->key, h->da1, h->dkey, h->dq, 2 * H);
+    gemm_bwd_weight(h, h->q0, Ds, h->dq, Dk, Wo(nm.att_q), Bo(nm.att_q), B, Ds, Dk);
+    gemm_bwd_data(h, h->dq, Dk, W(nm.att_q), Dk, h->dq0, Ds, B, Ds, Dk, EPI_STORE);
+
+    // GRUs
+    const char* sides[2] = {"gru_user_side", "gru_item_side"};
+    GruBwdArgs gb{};
+    gb.length = h->length; gb.dout = h->dkey; gb.lddout = Dk; gb.dlast = nullptr; gb.lddlast = 0;
+    for (int s = 0; s < 2; ++s) {
+        std::string g = std::string(sides[s]) + "/gru_cell/gates", c = std::string(sides[s]) + "/gru_cell/candidate";
+        gb.wg[s] = W(g); gb.wc[s] = W(c); gb.xhg[s] = h->xhg[s];
+        gb.r[s] = h->gr[s]; gb.u[s] = h->gu[s]; gb.c[s] = h->gc[s]; gb.dpx[s] = h->dpx[s];
+    }
+    launch_gru_bwd(h->st, dm, gb);
+    for (int s = 0; s < 2; ++s) {
+        std::string g = std::string(sides[s]) + "/gru_cell/gates", c = std::string(sides[s]) + "/gru_cell/candidate";
+        gemm_bwd_weight(h, h->xhg[s], ldx, h->dpx[s], 3 * H, Wo(g), Bo(g), M, ldx, 2 * H);
+        gemm_bwd_weight(h, h->xhc[s], ldx, h->dpx[s] + 2 * H, 3 * H, Wo(c), Bo(c), M, ldx, H);
+        gemm_bwd_data(h, h->dpx[s], 3 * H, W(g), 2 * H, h->dx[s], Ds, M, Ds, 2 * H, EPI_STORE);
+        gemm_bwd_data(h, h->dpx[s] + 2 * H, 3 * H, W(c), H, h->dx[s], Ds, M, Ds, H, EPI_ACCUM);
+    }
+
+    // co-attention + gather backward: per-position embedding gradient rows
+    CoattBwdArgs cb{};
+    cb.emb = h->emb; cb.keys = h->keys; cb.length = h->length;
+    cb.w_item = W(nm.co_item); cb.w_user = W(nm.co_user); cb.save_r = h->save_r; cb.save_w = h->save_w;
+    cb.dxu = h->dx[0]; cb.dxi = h->dx[1]; cb.dkey = h->dkey; cb.ldkey = Dk; cb.key_off = 2 * H;
+    cb.grad_rows = h->grad_rows; cb.sdz = h->sdz; cb.partials = h->coatt_part; cb.n_partials = h->n_coatt_part;
+    probe_begin(h, PR_COATT_BWD, h->st);
+    launch_coatt_bwd(h->st, dm, cb);
+    probe_end(h, PR_COATT_BWD, h->st);
+    TargetBwdArgs tb{};
+    tb.length = h->length; tb.w_item = W(nm.co_item); tb.w_user = W(nm.co_user); tb.q0 = h->q0; tb.dq0 = h->dq0;
+    tb.dfc_in = h->dfc_in; tb.fc_off = Dfc - Ds; tb.ldfc = Dfc; tb.sdz = h->sdz; tb.grad_rows = h->grad_rows;
+    tb.partials = h->target_part; tb.n_partials = h->n_target_part;
+    launch_target_bwd(h->st, dm, tb);
+    launch_coatt_grad_reduce(h->st, dm, h->coatt_part, h->n_coatt_part, h->target_part, h->n_target_part,
+                             h->PG + Wo(nm.co_item), h->PG + Bo(nm.co_item), h->PG + Wo(nm.co_user),
+                             h->PG + Bo(nm.co_user));
+    launch_reduce_partials(h->st, h->PG, kSplits, (int)h->n_dense, h->G);
+}
+
+int key_bits(int64_t V) {
+    int bits = 1;
+    while (((int64_t)1 << bits) < V) ++bits;
+    return bits;
+}
+
+int ensure_seg(ScoreModel* h, int64_t N) {
+    if (N <= h->seg_cap) return SCORE_OK;
+    if (h->seg_rows) { cudaFree(h->seg_rows); cudaFree(h->seg_heads); }
+    CK(cudaMalloc(&h->seg_rows, sizeof(float) * N * h->dm.d));
+    CK(cudaMalloc(&h->seg_heads, sizeof(int32_t) * N));
+    h->seg_cap = N;
+    return SCORE_OK;
+}
+
+// Everything of one step that runs on the device, in stream order (capturable).
+void enqueue_step(ScoreModel* h, int mode) {
+    const Dims& dm = h->dm;
+    const bool train = (mode == MODE_TRAIN);
+    const bool need_bwd = (mode != MODE_EVAL);
+    probe_begin(h, PR_STEP, h->st);
+    launch_build_keys(h->st, dm, h->ids, h->length, h->keys, h->err_flag);
+    if (h->cfg.adam_mode == SCORE_ADAM_LAZY)
+        launch_emb_catchup_rows(h->st, h->keys, dm.N, h->emb, h->emb_m, h->emb_v, h->last_step, dm.d, h->alpha_hist,
+                                h->hyper_dev);
+    if (need_bwd) {   // the sort depends on ids only: run it on the side stream under forward/backward
+        cudaEventRecord(h->ev_fork, h->st);
+        cudaStreamWaitEvent(h->st2, h->ev_fork, 0);
+        probe_begin(h, PR_SORT, h->st2);
+        h->sort_out = launch_sort_pairs(h->st2, h->sb, h->keys, dm.N, key_bits(dm.V));
+        probe_end(h, PR_SORT, h->st2);
+        cudaEventRecord(h->ev_join, h->st2);
+    }
+    enqueue_forward(h);
+    if (need_bwd) {
+        enqueue_backward(h);
+        cudaStreamWaitEvent(h->st, h->ev_join, 0);
+    }
+    if (mode == MODE_FWDBWD) {
+        launch_add_l2(h->st, h->G, h->P, h->flags, (int)h->n_dense, h->hyper_dev);
+        cudaMemsetAsync(h->seg_heads, 0, sizeof(int32_t) * dm.N, h->st);
+        EmbUpdateArgs ea{};
+        ea.skeys = h->sb.keys[h->sort_out]; ea.spos = h->sb.vals[h->sort_out]; ea.n = dm.N;
+        ea.grad_rows = h->grad_rows; ea.d = dm.d; ea.hp = h->hyper_dev; ea.mode = 1;
+        ea.out_rows = h->seg_rows; ea.out_heads = h->seg_heads;
+        launch_emb_update(h->st, ea);
+    }
+    if (train) {
+        launch_dense_adam(h->st, h->P, h->M1, h->V1, h->G, h->flags, (int)h->n_dense, h->hyper_dev, h->alpha_hist);
+        EmbUpdateArgs ea{};
+        ea.skeys = h->sb.keys[h->sort_out]; ea.spos = h->sb.vals[h->sort_out]; ea.n = dm.N;
+        ea.grad_rows = h->grad_rows; ea.d = dm.d;
+        ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.last_step = h->last_step;
+        ea.hp = h->hyper_dev; ea.mode = 0;
+        probe_begin(h, PR_EMB_UPDATE, h->st);
+        launch_emb_update(h->st, ea);
+        probe_end(h, PR_EMB_UPDATE, h->st);
+        if (h->cfg.adam_mode == SCORE_ADAM_DENSE)
+            launch_emb_dense_sweep(h->st, h->emb, h->emb_m, h->emb_v, h->last_step, dm.V, dm.d, h->hyper_dev);
+    }
+    probe_end(h, PR_STEP, h->st);
+}
+
+int check_batch(ScoreModel* h, const ScoreBatch* b) {
+    if (!b) return fail(h, SCORE_ERR_ARG, "batch is NULL");
+    if (b->batch_size <= 0) return fail(h, SCORE_ERR_ARG, "batch_size must be positive");
+    if (!b->user_1hop || !b->user_2hop || !b->item_1hop || !b->item_2hop || !b->target_user || !b->target_item ||
+        !b->label || !b->length)
+        return fail(h, SCORE_ERR_ARG, "batch has a NULL id array");
+    if ((int64_t)b->batch_size * ids_per_sample(h->dm) >= ((int64_t)1 << 31))
+        return fail(h, SCORE_ERR_ARG, "batch too large: position index must fit int32");
+    return SCORE_OK;
+}
+
+void fill_hyper(ScoreModel* h, int B, float lr, float reg_lambda, float keep_prob, int train, int global_batch) {
+    Hyper& hp = *h->hyper_host;
+    hp.lr = lr; hp.reg_lambda = reg_lambda; hp.keep_prob = keep_prob;
+    const float one = 1.0f;
+    hp.alpha = lr * sqrtf(one - h->beta2_power) / (one - h->beta1_power);
+    hp.inv_batch = 1.0f / (float)(global_batch > 0 ? global_batch : B);
+    hp.seed_lo = (uint32_t)h->cfg.seed; hp.seed_hi = (uint32_t)(h->cfg.seed >> 32);
+    hp.step = h->step + 1; hp.batch = B; hp.train = train; hp.pad0 = hp.pad1 = 0;
+}
+
+int flush_lazy(ScoreModel* h) {
+    if (h->cfg.adam_mode == SCORE_ADAM_LAZY && h->step > 0) {
+        launch_emb_catchup_all(h->st, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.V, h->dm.d, h->alpha_hist, h->step);
+        CK(cudaStreamSynchronize(h->st));
+    }
+    return SCORE_OK;
+}
+
+int finish_sync(ScoreModel* h, float* loss_out) {
+    CK(cudaMemcpyAsync(h->loss_host, h->loss_dev, sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(h->err_host, h->err_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaGetLastError());
+    if (h->probes_on && h->last_mode == MODE_TRAIN) {
+        for (int p = 0; p < PR_COUNT; ++p) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, h->pr_beg[p], h->pr_end[p]) == cudaSuccess) { h->pr_ms[p] += ms; h->pr_n[p]++; }
+            else cudaGetLastError();
+        }
+    }
+    if (loss_out) *loss_out = *h->loss_host;
+    if (*h->err_host) {
+        cudaMemsetAsync(h->err_flag, 0, sizeof(int32_t), h->st);
+        return fail(h, SCORE_ERR_ID_RANGE, "an id in the batch is outside [0, feature_size)");
+    }
+    return SCORE_OK;
+}
+
+int run_step(ScoreModel* h, const ScoreBatch* b, int mode, float lr, float reg_lambda, float keep_prob,
+             int global_batch, bool sync, float* loss_out) {
+    int rc = check_batch(h, b);
+    if (rc) return rc;
+    if (h->dm.model_type != SCORE_MODEL_SCORE) return fail(h, SCORE_ERR_ARG, "model_type not implemented yet");
+    CK(cudaSetDevice(h->device));
+    const int B = b->batch_size;
+    rc = ensure_workspace(h, B > h->cfg.max_batch ? B : h->cfg.max_batch);
+    if (rc) return rc;
+    set_batch_dims(h, B);
+    if (mode == MODE_FWDBWD) { rc = ensure_seg(h, h->dm.N); if (rc) return rc; }
+    const bool train = (mode == MODE_TRAIN);
+    if (train && h->cfg.adam_mode == SCORE_ADAM_LAZY && h->step + 2 >= h->alpha_cap)
+        return fail(h, SCORE_ERR_ARG, "lazy Adam step history exhausted");
+    fill_hyper(h, B, lr, reg_lambda, (mode == MODE_EVAL) ? 1.0f : keep_prob, mode != MODE_EVAL, global_batch);
+    rc = upload_batch(h, b);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->hyper_dev, h->hyper_host, sizeof(Hyper), cudaMemcpyHostToDevice, h->st));
+    h->last_N = h->dm.N;
+    h->last_mode = mode;
+
+    bool launched = false;
+    if (train && h->cfg.use_graph) {
+        auto it = h->graphs_train.find(B);
+        if (it != h->graphs_train.end()) {
+            CK(cudaGraphLaunch(it->second, h->st));
+            launched = true;
+        } else if (h->warm_train[B] >= 1) {
+            // second time this batch size is seen: capture (the first run set all func attributes)
+            cudaGraph_t graph = nullptr;
+            h->capturing = true;
+            CK(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+            enqueue_step(h, mode);
+            cudaError_t ce = cudaStreamEndCapture(h->st, &graph);
+            h->capturing = false;
+            if (ce != cudaSuccess) { h->err = std::string("graph capture failed: ") + cudaGetErrorString(ce); return SCORE_ERR_CUDA; }
+            cudaGraphExec_t exec = nullptr;
+            CK(cudaGraphInstantiate(&exec, graph, 0));
+            cudaGraphDestroy(graph);
+            h->graphs_train[B] = exec;
+            CK(cudaGraphLaunch(exec, h->st));
+            launched = true;
+        }
+        h->warm_train[B]++;
+    }
+    if (!launched) enqueue_step(h, mode);
+    if (train) {
+        h->step += 1;
+        h->beta1_power = h->beta1_power * 0.9f;
+        h->beta2_power = h->beta2_power * 0.999f;
+    }
+    h->pending_step = true;
+    if (sync) {
+        h->pending_step = false;
+        return finish_sync(h, loss_out);
+    }
+    return SCORE_OK;
+}
+
+}  // namespace
+
+// ============================================================================================ C ABI
+extern "C" {
+
+const char* score_last_error(ScoreHandle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int score_create(const ScoreConfig* cfg, int device, ScoreHandle* out) {
+    if (!cfg || !out) { g_create_error = "cfg/out is NULL"; return SCORE_ERR_ARG; }
+    *out = nullptr;
+    auto bad = [&](const char* m) { g_create_error = m; return SCORE_ERR_ARG; };
+    if (cfg->feature_size < 2 || cfg->feature_size >= ((int64_t)1 << 31)) return bad("feature_size must be in [2, 2^31)");
+    const int d = cfg->eb_dim;
+    if (d < 4 || d > 128 || (d & (d - 1))) return bad("eb_dim must be a power of two in [4, 128]");
+    if (cfg->obj_per_time_slice < 1 || cfg->obj_per_time_slice > 32) return bad("obj_per_time_slice must be in [1, 32]");
+    if (cfg->hidden_size < 1 || cfg->hidden_size > 128) return bad("hidden_size must be in [1, 128]");
+    if (cfg->max_time_len < 1 || cfg->user_fnum < 1 || cfg->item_fnum < 1) return bad("max_time_len / fnum must be positive");
+    if (cfg->model_type < 0 || cfg->model_type > 4) return bad("unknown model_type");
+    if (cfg->adam_mode < 0 || cfg->adam_mode > 2) return bad("unknown adam_mode");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
+        return SCORE_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) return bad("device index out of range");
+    ScoreModel* h = new ScoreModel();
+    h->cfg = *cfg;
+    h->device = device;
+    auto die = [&](int rc) { g_create_error = h->err; score_destroy(h); return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return die(SCORE_ERR_CUDA); }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { h->err = "cudaGetDeviceProperties failed"; return die(SCORE_ERR_CUDA); }
+    if (prop.major != 10) {
+        h->err = "this build contains sm_100a kernels only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+        return die(SCORE_ERR_CUDA);
+    }
+    if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        h->err = "stream/event creation failed";
+        return die(SCORE_ERR_CUDA);
+    }
+    for (int p = 0; p < PR_COUNT; ++p) {
+        cudaEventCreate(&h->pr_beg[p]); cudaEventCreate(&h->pr_end[p]);
+        h->pr_ms[p] = 0; h->pr_n[p] = 0;
+    }
+    build_registry(h);
+    int rc = alloc_params(h);
+    if (rc) return die(rc);
+    if (cfg->init_weights) { rc = init_weights(h); if (rc) return die(rc); }
+    if (cudaStreamSynchronize(h->st) != cudaSuccess) { h->err = "initialisation failed"; return die(SCORE_ERR_CUDA); }
+    h->launches0 = g_launch_count;
+    *out = h;
+    return SCORE_OK;
+}
+
+int score_destroy(ScoreHandle h) {
+    if (!h) return SCORE_OK;
+    cudaSetDevice(h->device);
+    if (h->st) cudaStreamSynchronize(h->st);
+    free_workspace(h);
+    for (void* p : {(void*)h->emb, (void*)h->emb_m, (void*)h->emb_v, (void*)h->last_step, (void*)h->P, (void*)h->G,
+                    (void*)h->M1, (void*)h->V1, (void*)h->PG, (void*)h->flags, (void*)h->alpha_hist, (void*)h->l2sum,
+                    (void*)h->loss_dev, (void*)h->err_flag, (void*)h->hyper_dev, (void*)h->seg_rows, (void*)h->seg_heads})
+        if (p) cudaFree(p);
+    if (h->hyper_host) cudaFreeHost(h->hyper_host);
+    if (h->loss_host) cudaFreeHost(h->loss_host);
+    if (h->err_host) cudaFreeHost(h->err_host);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->st) {
+        for (int p = 0; p < PR_COUNT; ++p) { cudaEventDestroy(h->pr_beg[p]); cudaEventDestroy(h->pr_end[p]); }
+        cudaStreamDestroy(h->st);
+    }
+    if (h->st2) cudaStreamDestroy(h->st2);
+    delete h;
+    return SCORE_OK;
+}
+
+int score_train_step(ScoreHandle h, const ScoreBatch* batch, float lr, float reg_lambda, float keep_prob,
+                     float* loss_out) {
+    if (!h) return SCORE_ERR_ARG;
+    return run_step(h, batch, MODE_TRAIN, lr, reg_lambda, keep_prob, 0, true, loss_out);
+}
+
+int score_train_step_async(ScoreHandle h, const ScoreBatch* batch, float lr, float reg_lambda, float keep_prob) {
+    if (!h) return SCORE_ERR_ARG;
+    return run_step(h, batch, MODE_TRAIN, lr, reg_lambda, keep_prob, 0, false, nullptr);
+}
+
+int score_wait(ScoreHandle h, float* loss_out) {
+    if (!h) return SCORE_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    h->pending_step = false;
+    return finish_sync(h, loss_out);
+}
+
+int score_eval(ScoreHandle h, const ScoreBatch* batch, float reg_lambda, float* preds_out, float* loss_out) {
+    if (!h) return SCORE_ERR_ARG;
+    int rc = run_step(h, batch, MODE_EVAL, 0.f, reg_lambda, 1.0f, 0, false, nullptr);
+    if (rc) return rc;
+    if (preds_out) CK(cudaMemcpyAsync(preds_out, h->y, sizeof(float) * batch->batch_size, cudaMemcpyDeviceToHost, h->st));
+    return finish_sync(h, loss_out);
+}
+
+int score_forward_backward(ScoreHandle h, const ScoreBatch* batch, float reg_lambda, float keep_prob, float* loss_out) {
+    if (!h) return SCORE_ERR_ARG;
+    return run_step(h, batch, MODE_FWDBWD, 0.f, reg_lambda, keep_prob, 0, true, loss_out);
+}
+
+int score_get_buffer(ScoreHandle h, const char* name, void* data, size_t capacity_bytes, size_t* count, int* dtype) {
+    if (!h || !name) return SCORE_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    std::string n(name);
+    const void* src = nullptr; size_t cnt = 0; int dt = 0;
+    const Dims& dm = h->dm;
+    if (n.rfind("grad/", 0) == 0) {
+        const Tensor* t = find_tensor(h, n.substr(5));
+        if (!t || t->is_emb) return fail(h, SCORE_ERR_NAME, "unknown gradient: " + n);
+        src = h->G + t->off; cnt = (size_t)(t->rows * t->cols);
+    } else if (n == "emb_grad/heads") {
+        src = h->seg_heads; cnt = (size_t)h->last_N; dt = 1;
+    } else if (n == "emb_grad/seg_rows") {
+        src = h->seg_rows; cnt = (size_t)h->last_N * dm.d;
+    } else if (n == "sorted_keys") {
+        src = h->sb.keys[h->sort_out]; cnt = (size_t)h->last_N; dt = 1;
+    } else if (n == "sorted_pos") {
+        src = h->sb.vals[h->sort_out]; cnt = (size_t)h->last_N; dt = 1;
+    } else {
+        auto it = h->bufs.find(n);
+        if (it == h->bufs.end()) return fail(h, SCORE_ERR_NAME, "unknown buffer: " + n);
+        src = it->second.ptr; dt = it->second.dtype;
+        // report the live extent for the current batch, not the capacity
+        cnt = it->second.count / (size_t)h->cap_B * (size_t)dm.B;
+    }
+    if (count) *count = cnt;
+    if (dtype) *dtype = dt;
+    if (!data) return SCORE_OK;
+    if (!src) return fail(h, SCORE_ERR_ARG, "buffer not populated: " + n);
+    if (capacity_bytes < cnt * 4) return fail(h, SCORE_ERR_ARG, "capacity too small for " + n);
+    CK(cudaMemcpyAsync(data, src, cnt * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return SCORE_OK;
+}
+
+int score_tensor_count(ScoreHandle h) { return h ? (int)h->tensors.size() : 0; }
+
+int score_tensor_info(ScoreHandle h, int index, char* name, size_t name_cap, int64_t* rows, int64_t* cols) {
+    if (!h || index < 0 || index >= (int)h->tensors.size()) return SCORE_ERR_ARG;
+    const Tensor& t = h->tensors[index];
+    if (name && name_cap) { strncpy(name, t.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    if (rows) *rows = t.rows;
+    if (cols) *cols = t.cols;
+    return SCORE_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// resolve "<var>", "<var>/Adam", "<var>/Adam_1" to a device pointer + element count
+int resolve(ScoreModel* h, const std::string& name, float** ptr, size_t* count, bool* is_emb) {
+    std::string base = name;
+    int slot = 0;
+    auto ends = [&](const std::string& s, const char* suf) {
+        size_t l = strlen(suf);
+        return s.size() > l && s.compare(s.size() - l, l, suf) == 0;
+    };
+    if (ends(name, "/Adam_1")) { base = name.substr(0, name.size() - 7); slot = 2; }
+    else if (ends(name, "/Adam")) { base = name.substr(0, name.size() - 5); slot = 1; }
+    const Tensor* t = find_tensor(h, base);
+    if (!t) return fail(h, SCORE_ERR_NAME, "unknown tensor: " + name);
+    if (slot && !(t->flags & 2)) return fail(h, SCORE_ERR_NAME, "no Adam slot for non-trainable " + base);
+    *count = (size_t)(t->rows * t->cols);
+    *is_emb = t->is_emb;
+    if (t->is_emb) *ptr = slot == 0 ? h->emb : slot == 1 ? h->emb_m : h->emb_v;
+    else *ptr = (slot == 0 ? h->P : slot == 1 ? h->M1 : h->V1) + t->off;
+    return SCORE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int score_get_tensor(ScoreHandle h, const char* name, float* data, size_t count) {
+    if (!h || !name || !data) return SCORE_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    std::string n(name);
+    if (n == "beta1_power" || n == "beta2_power") {
+        if (count < 1) return fail(h, SCORE_ERR_ARG, "count too small");
+        data[0] = n == "beta1_power" ? h->beta1_power : h->beta2_power;
+        return SCORE_OK;
+    }
+    float* p; size_t cnt; bool is_emb;
+    int rc = resolve(h, n, &p, &cnt, &is_emb);
+    if (rc) return rc;
+    if (count != cnt) return fail(h, SCORE_ERR_ARG, "element count mismatch for " + n);
+    if (is_emb) { rc = flush_lazy(h); if (rc) return rc; }
+    CK(cudaMemcpyAsync(data, p, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return SCORE_OK;
+}
+
+int score_set_tensor(ScoreHandle h, const char* name, const float* data, size_t count) {
+    if (!h || !name || !data) return SCORE_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    std::string n(name);
+    if (n == "beta1_power" || n == "beta2_power") {
+        if (count < 1) return fail(h, SCORE_ERR_ARG, "count too small");
+        (n == "beta1_power" ? h->beta1_power : h->beta2_power) = data[0];
+        if (n == "beta1_power") {   // recover the step counter from the slot variable (0.9^(step+1))
+            double s = log((double)data[0]) / log(0.9) - 1.0;
+            h->step = (int32_t)llround(s < 0 ? 0 : s);
+        }
+        return SCORE_OK;
+    }
+    float* p; size_t cnt; bool is_emb;
+    int rc = resolve(h, n, &p, &cnt, &is_emb);
+    if (rc) return rc;
+    if (count != cnt) return fail(h, SCORE_ERR_ARG, "element count mismatch for " + n);
+    if (is_emb) { rc = flush_lazy(h); if (rc) return rc; }
+    CK(cudaMemcpyAsync(p, data, cnt * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return SCORE_OK;
+}
+
+int score_get_rows(ScoreHandle h, const char* name, int64_t row0, int64_t nrows, float* data) {
+    if (!h || !name || !data) return SCORE_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    float* p; size_t cnt; bool is_emb;
+    int rc = resolve(h, name, &p, &cnt, &is_emb);
+    if (rc) return rc;
+    if (!is_emb) return fail(h, SCORE_ERR_ARG, "row access is for emb_mtx and its slots");
+    if (row0 < 0 || nrows < 0 || row0 + nrows > h->dm.V) return fail(h, SCORE_ERR_ARG, "row range out of bounds");
+    rc = flush_lazy(h);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(data, p + row0 * h->dm.d, sizeof(float) * nrows * h->dm.d, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return SCORE_OK;
+}
+
+int score_set_rows(ScoreHandle h, const char* name, int64_t row0, int64_t nrows, const float* data) {
+    if (!h || !name || !data) return SCORE_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    float* p; size_t cnt; bool is_emb;
+    int rc = resolve(h, name, &p, &cnt, &is_emb);
+    if (rc) return rc;
+    if (!is_emb) return fail(h, SCORE_ERR_ARG, "row access is for emb_mtx and its slots");
+    if (row0 < 0 || nrows < 0 || row0 + nrows > h->dm.V) return fail(h, SCORE_ERR_ARG, "row range out of bounds");
+    rc = flush_lazy(h);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(p + row0 * h->dm.d, data, sizeof(float) * nrows * h->dm.d, cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return SCORE_OK;
+}
+
+// Checkpoint: "SCB2CKPT" | version | n tensors | per tensor {name, rows, cols, var, [Adam, Adam_1]} | beta powers.
+// Keys are the TF variable names so a tf.train.Saver user can convert (score.py:135-142 saves all global variables).
+int score_save(ScoreHandle h, const char* path) {
+    if (!h || !path) return SCORE_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = flush_lazy(h);
+    if (rc) return rc;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(h, SCORE_ERR_IO, std::string("cannot open for writing: ") + path);
+    const char magic[8] = {'S', 'C', 'B', '2', 'C', 'K', 'P', 'T'};
+    uint32_t ver = 1, nt = (uint32_t)h->tensors.size();
+    bool ok = fwrite(magic, 1, 8, f) == 8 && fwrite(&ver, 4, 1, f) == 1 && fwrite(&nt, 4, 1, f) == 1;
+    const size_t chunk = (size_t)1 << 24;   // floats per staging chunk
+    std::vector<float> host(chunk);
+    for (const Tensor& t : h->tensors) {
+        uint32_t nl = (uint32_t)t.name.size();
+        uint32_t nslots = (t.flags & 2) ? 3 : 1;
+        ok = ok && fwrite(&nl, 4, 1, f) == 1 && fwrite(t.name.data(), 1, nl, f) == nl && fwrite(&t.rows, 8, 1, f) == 1 &&
+             fwrite(&t.cols, 8, 1, f) == 1 && fwrite(&nslots, 4, 1, f) == 1;
+        const size_t cnt = (size_t)(t.rows * t.cols);
+        for (uint32_t s = 0; s < nslots && ok; ++s) {
+            const float* src = t.is_emb ? (s == 0 ? h->emb : s == 1 ? h->emb_m : h->emb_v)
+                                        : (s == 0 ? h->P : s == 1 ? h->M1 : h->V1) + t.off;
+            for (size_t o = 0; o < cnt && ok; o += chunk) {
+                size_t n = cnt - o < chunk ? cnt - o : chunk;
+                if (cudaMemcpy(host.data(), src + o, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
+                    fclose(f);
+                    return fail(h, SCORE_ERR_CUDA, "device read failed during save");
+                }
+                ok = fwrite(host.data(), sizeof(float), n, f) == n;
+            }
+        }
+    }
+    ok = ok && fwrite(&h->beta1_power, 4, 1, f) == 1 && fwrite(&h->beta2_power, 4, 1, f) == 1 &&
+         fwrite(&h->step, 4, 1, f) == 1;
+    ok = (fclose(f) == 0) && ok;
+    return ok ? SCORE_OK : fail(h, SCORE_ERR_IO, std::string("short write: ") + path);
+}
+
+int score_restore(ScoreHandle h, const char* path) {
+    if (!h || !path) return SCORE_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(h, SCORE_ERR_IO, std::string("cannot open checkpoint: ") + path);
+    char magic[8]; uint32_t ver = 0, nt = 0;
+    bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "SCB2CKPT", 8) == 0 && fread(&ver, 4, 1, f) == 1 &&
+              fread(&nt, 4, 1, f) == 1 && ver == 1;
+    if (!ok || nt != h->tensors.size()) { fclose(f); return fail(h, SCORE_ERR_IO, "not a matching score_b200 checkpoint"); }
+    const size_t chunk = (size_t)1 << 24;
+    std::vector<float> host(chunk);
+    for (uint32_t i = 0; i < nt; ++i) {
+        uint32_t nl = 0, nslots = 0; int64_t rows = 0, cols = 0;
+        if (fread(&nl, 4, 1, f) != 1 || nl > 4096) { fclose(f); return fail(h, SCORE_ERR_IO, "corrupt checkpoint"); }
+        std::string name(nl, '\0');
+        if (fread(&name[0], 1, nl, f) != nl || fread(&rows, 8, 1, f) != 1 || fread(&cols, 8, 1, f) != 1 ||
+            fread(&nslots, 4, 1, f) != 1) { fclose(f); return fail(h, SCORE_ERR_IO, "corrupt checkpoint"); }
+        const Tensor* t = find_tensor(h, name);
+        if (!t || t->rows != rows || t->cols != cols) { fclose(f); return fail(h, SCORE_ERR_IO, "checkpoint tensor mismatch: " + name); }
+        const size_t cnt = (size_t)(rows * cols);
+        for (uint32_t s = 0; s < nslots; ++s) {
+            float* dst = t->is_emb ? (s == 0 ? h->emb : s == 1 ? h->emb_m : h->emb_v)
+                                   : (s == 0 ? h->P : s == 1 ? h->M1 : h->V1) + t->off;
+            for (size_t o = 0; o < cnt; o += chunk) {
+                size_t n = cnt - o < chunk ? cnt - o : chunk;
+                if (fread(host.data(), sizeof(float), n, f) != n) { fclose(f); return fail(h, SCORE_ERR_IO, "truncated checkpoint"); }
+                if (cudaMemcpy(dst + o, host.data(), n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+                    fclose(f);
+                    return fail(h, SCORE_ERR_CUDA, "device write failed during restore");
+                }
+            }
+        }
+    }
+    ok = fread(&h->beta1_power, 4, 1, f) == 1 && fread(&h->beta2_power, 4, 1, f) == 1 && fread(&h->step, 4, 1, f) == 1;
+    fclose(f);
+    if (!ok) return fail(h, SCORE_ERR_IO, "truncated checkpoint");
+    if (h->last_step) {   // every row of a restored table is current at the restored step
+        launch_fill_i32(h->st, h->last_step, h->dm.V, h->step);
+        CK(cudaStreamSynchronize(h->st));
+    }
+    return SCORE_OK;
+}
+
+int score_eval_metrics(ScoreHandle h, const float* preds, const int32_t* target_iids, const int32_t* labels,
+                       int64_t n, int32_t group, double* out9) {
+    if (!h || !preds || !target_iids || !labels || !out9) return SCORE_ERR_ARG;
+    if (n <= 0 || group <= 0 || n % group != 0) return fail(h, SCORE_ERR_ARG, "n must be a positive multiple of group");
+    if (n >= ((int64_t)1 << 31)) return fail(h, SCORE_ERR_ARG, "n too large");
+    CK(cudaSetDevice(h->device));
+    float* d_preds = nullptr; int32_t *d_iids = nullptr, *d_labels = nullptr, *d_keys = nullptr, *d_rank = nullptr;
+    double *d_terms = nullptr, *d_sums = nullptr;
+    SortBufs sb{};
+    uint32_t* hist = nullptr;
+    std::vector<void*> owned;
+    auto cleanup = [&]() { for (void* p : owned) cudaFree(p); };
+    auto A = [&](void** p, size_t bytes) { cudaError_t e = cudaMalloc(p, bytes); if (e == cudaSuccess) owned.push_back(*p); return e; };
+    const int64_t n_groups = n / group;
+    const size_t nterms = (size_t)(2 * n > 6 * n_groups ? 2 * n : 6 * n_groups);
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = A((void**)&d_preds, sizeof(float) * n);
+    if (e == cudaSuccess) e = A((void**)&d_iids, sizeof(int32_t) * n);
+    if (e == cudaSuccess) e = A((void**)&d_labels, sizeof(int32_t) * n);
+    if (e == cudaSuccess) e = A((void**)&d_keys, sizeof(int32_t) * n);
+    if (e == cudaSuccess) e = A((void**)&d_rank, sizeof(int32_t) * n_groups);
+    if (e == cudaSuccess) e = A((void**)&d_terms, sizeof(double) * nterms);
+    if (e == cudaSuccess) e = A((void**)&d_sums, sizeof(double) * 16);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = A((void**)&sb.keys[i], sizeof(int32_t) * n);
+        if (e == cudaSuccess) e = A((void**)&sb.vals[i], sizeof(int32_t) * n);
+    }
+    if (e == cudaSuccess) e = A((void**)&hist, sizeof(uint32_t) * sort_hist_elems(n));
+    sb.hist = hist;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_preds, preds, sizeof(float) * n, cudaMemcpyHostToDevice, h->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_iids, target_iids, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_labels, labels, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_sums, 0, sizeof(double) * 16, h->st);
+    if (e == cudaSuccess) e = compute_eval_metrics(h->st, d_preds, d_iids, d_labels, n, group, sb, d_keys, d_rank, d_terms, d_sums);
+    double sums[16] = {0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sums, d_sums, sizeof(sums), cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    cleanup();
+    if (e != cudaSuccess) return fail(h, SCORE_ERR_CUDA, std::string("eval metrics failed: ") + cudaGetErrorString(e));
+    const double npos = sums[9], nneg = (double)n - npos;
+    out9[0] = sums[0] / (double)n;
+    out9[1] = (npos > 0 && nneg > 0) ? (sums[8] - npos * (npos + 1.0) * 0.5) / (npos * nneg) : NAN;
+    for (int k = 0; k < 6; ++k) out9[2 + k] = sums[2 + k] / (double)n_groups;
+    out9[8] = 0.0;
+    return SCORE_OK;
+}
+
+int score_stream(ScoreHandle h, void** cuda_stream) {
+    if (!h || !cuda_stream) return SCORE_ERR_ARG;
+    *cuda_stream = (void*)h->st;
+    return SCORE_OK;
+}
+
+int64_t score_launch_count(ScoreHandle h) { return h ? g_launch_count - h->launches0 : 0; }
+
+int score_enable_probes(ScoreHandle h, int on) {
+    if (!h) return SCORE_ERR_ARG;
+    h->probes_on = on != 0;
+    for (int p = 0; p < PR_COUNT; ++p) { h->pr_ms[p] = 0; h->pr_n[p] = 0; }
+    // graphs captured without probe nodes must be rebuilt
+    for (auto& kv : h->graphs_train) cudaGraphExecDestroy(kv.second);
+    h->graphs_train.clear();
+    return SCORE_OK;
+}
+
+// out[2*p] = accumulated ms, out[2*p+1] = samples, for p in coatt_fwd, coatt_bwd, emb_update, sort, step
+int score_probe_times(ScoreHandle h, double* out, int n) {
+    if (!h || !out) return SCORE_ERR_ARG;
+    for (int p = 0; p < PR_COUNT && 2 * p + 1 < n; ++p) { out[2 * p] = h->pr_ms[p]; out[2 * p + 1] = (double)h->pr_n[p]; }
+    return PR_COUNT;
+}
+
+// bytes-level facts of the last step for roofline arithmetic: out = {N positions, live (non-zero key) positions, unique rows}
+int score_last_step_stats(ScoreHandle h, int64_t* out3) {
+    if (!h || !out3) return SCORE_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    const int64_t N = h->last_N;
+    std::vector<int32_t> sk((size_t)N);
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaMemcpy(sk.data(), h->sb.keys[h->sort_out], sizeof(int32_t) * N, cudaMemcpyDeviceToHost));
+    int64_t live = 0, uniq = 0;
+    for (int64_t i = 0; i < N; ++i) {
+        if (sk[i] == 0) continue;
+        ++live;
+        if (i == 0 || sk[i - 1] != sk[i]) ++uniq;
+    }
+    out3[0] = N; out3[1] = live; out3[2] = uniq;
+    return SCORE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,392 @@
+// Optimizer side of the SCoRe path: deterministic embedding-gradient scatter + Adam.
+//
+// The reference gets its embedding gradient by autodiff through six embedding_lookups on a
+// dense [V,d] tensor (score.py:45-66) and applies tf.train.AdamOptimizer to it (score.py:98).
+// Here the per-position gradient rows produced by the backward kernels are combined WITHOUT
+// float atomics:  stable LSD radix sort of (row id, position)  ->  one thread group per unique
+// row walks its run in position order (fixed summation order)  ->  fused TF-formulation Adam
+// on that row's (var, m, v) with 128-bit accesses.
+//
+// Adam arithmetic uses explicit round-to-nearest intrinsics in the op order of TF's ApplyAdam
+// kernel so that no FMA contraction changes a bit:
+//     alpha = lr * sqrt(1 - beta2^t) / (1 - beta1^t)          (host, fp32)
+//     m += (g - m) * (1 - beta1);  v += (g*g - v) * (1 - beta2);  var -= (m * alpha) / (sqrt(v) + eps)
+#include "kernels.h"
+
+namespace score {
+
+__device__ __forceinline__ void adam_elem(float& var, float& m, float& v, float g, float alpha) {
+    const float omb1 = 1.0f - 0.9f, omb2 = 1.0f - 0.999f, eps = 1e-8f;
+    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), omb1));
+    v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), omb2));
+    var = __fsub_rn(var, __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), eps)));
+}
+__device__ __forceinline__ void adam4(float4& var, float4& m, float4& v, const float4& g, float alpha) {
+    adam_elem(var.x, m.x, v.x, g.x, alpha);
+    adam_elem(var.y, m.y, v.y, g.y, alpha);
+    adam_elem(var.z, m.z, v.z, g.z, alpha);
+    adam_elem(var.w, m.w, v.w, g.w, alpha);
+}
+__device__ __forceinline__ bool all_zero(const float4& a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f && a.w == 0.f; }
+
+// ------------------------------------------------------------------------------------------ dense parameters
+// 0.5 * sum v^2 over L2-regularised parameters; single block, fixed-shape tree (deterministic)
+__global__ void l2_sum_kernel(const float* __restrict__ p, const uint8_t* __restrict__ flags, int n, float* out) {
+    __shared__ float red[1024];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += 1024)
+        if (flags[i] & 1) s += p[i] * p[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0] * 0.5f;
+}
+void launch_l2_sum(cudaStream_t st, const float* params, const uint8_t* flags, int n, float* out) {
+    l2_sum_kernel<<<1, 1024, 0, st>>>(params, flags, n, out);
+    ++g_launch_count;
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int splits, int n, float* __restrict__ g) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partials[(int64_t)k * n + i];
+    g[i] = s;
+}
+void launch_reduce_partials(cudaStream_t st, const float* partials, int splits, int n, float* g) {
+    reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(partials, splits, n, g);
+    ++g_launch_count;
+}
+
+// inspection only (score_forward_backward): G += reg_lambda * p for L2-regularised parameters, so the exported
+// gradient is the gradient of the full loss as tf.gradients would report it
+__global__ void add_l2_kernel(float* __restrict__ g, const float* __restrict__ p, const uint8_t* __restrict__ flags, int n,
+                              const Hyper* hp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (flags[i] & 1)) g[i] = __fadd_rn(g[i], __fmul_rn(hp->reg_lambda, p[i]));
+}
+void launch_add_l2(cudaStream_t st, float* g, const float* p, const uint8_t* flags, int n, const Hyper* hp) {
+    add_l2_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, p, flags, n, hp);
+    ++g_launch_count;
+}
+
+__global__ void dense_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                  const float* __restrict__ g, const uint8_t* __restrict__ flags, int n,
+                                  const Hyper* hp, float* alpha_hist) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && alpha_hist) alpha_hist[hp->step] = hp->alpha;
+    if (i >= n) return;
+    uint8_t f = flags[i];
+    if (!(f & 2)) return;   // non-trainable (bn moving statistics)
+    float var = p[i], mm = m[i], vv = v[i];
+    float gi = g[i];
+    if (f & 1) gi = __fadd_rn(gi, __fmul_rn(hp->reg_lambda, var));   // d/dv of reg_lambda * l2_loss(v)
+    adam_elem(var, mm, vv, gi, hp->alpha);
+    p[i] = var; m[i] = mm; v[i] = vv;
+}
+void launch_dense_adam(cudaStream_t st, float* p, float* m, float* v, const float* g, const uint8_t* flags,
+                       int n, const Hyper* hp, float* alpha_hist) {
+    dense_adam_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, m, v, g, flags, n, hp, alpha_hist);
+    ++g_launch_count;
+}
+
+// ------------------------------------------------------------------------------------------ radix sort
+// Stable LSD radix sort of (key, value) pairs, 8-bit digits, three kernels per pass:
+// per-tile digit histogram -> exclusive scan over (digit-major, tile-minor) -> ranked scatter.
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 8;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+
+size_t sort_hist_elems(int64_t n) { return (size_t)256 * ((n + SORT_TILE - 1) / SORT_TILE) + 1; }
+
+__global__ void sort_hist_kernel(const int32_t* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ hist,
+                                 int nblocks) {
+    __shared__ uint32_t cnt[256];
+    cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; ++r) {
+        int64_t i = base + r * SORT_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&cnt[((uint32_t)keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
+}
+
+// in-place exclusive scan of `total` counters by one block of 1024 threads
+__global__ void sort_scan_kernel(uint32_t* __restrict__ hist, int total) {
+    __shared__ uint32_t sums[1024];
+    const int chunk = (total + 1023) / 1024;
+    const int lo = threadIdx.x * chunk, hi = min(total, lo + chunk);
+    uint32_t s = 0;
+    for (int i = lo; i < hi; ++i) s += hist[i];
+    sums[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {   // Hillis-Steele inclusive scan
+        uint32_t add = (threadIdx.x >= o) ? sums[threadIdx.x - o] : 0u;
+        __syncthreads();
+        sums[threadIdx.x] += add;
+        __syncthreads();
+    }
+    uint32_t run = (threadIdx.x == 0) ? 0u : sums[threadIdx.x - 1];
+    for (int i = lo; i < hi; ++i) { uint32_t c = hist[i]; hist[i] = run; run += c; }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
+                    int32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out, int64_t n, int shift,
+                    const uint32_t* __restrict__ hist, int nblocks) {
+    constexpr int WARPS = SORT_THREADS / 32;
+    __shared__ uint32_t whist[WARPS][256];
+    __shared__ uint32_t gbase[256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < WARPS * 256; i += SORT_THREADS) (&whist[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t wbase = (int64_t)blockIdx.x * SORT_TILE + warp * (32 * SORT_ITEMS);
+    int32_t k[SORT_ITEMS];
+    uint32_t lrank[SORT_ITEMS];
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; ++r) {
+        int64_t i = wbase + r * 32 + lane;
+        bool ok = i < n;
+        k[r] = ok ? keys_in[i] : 0;
+        uint32_t digit = ok ? (((uint32_t)k[r] >> shift) & 255u) : (256u + lane);   // invalid lanes match only themselves
+        uint32_t peers = __match_any_sync(FULL_MASK, digit);
+        uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (ok && lane == leader) { old = whist[warp][digit]; whist[warp][digit] = old + __popc(peers); }
+        old = __shfl_sync(FULL_MASK, old, leader);
+        lrank[r] = old + rank;
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // exclusive prefix over warps for each digit; global base of (digit, this tile)
+        const int dgt = threadIdx.x;
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) { uint32_t c = whist[w][dgt]; whist[w][dgt] = run; run += c; }
+        gbase[dgt] = hist[(int64_t)dgt * nblocks + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; ++r) {
+        int64_t i = wbase + r * 32 + lane;
+        if (i < n) {
+            uint32_t digit = ((uint32_t)k[r] >> shift) & 255u;
+            uint32_t pos = gbase[digit] + whist[warp][digit] + lrank[r];
+            keys_out[pos] = k[r];
+            vals_out[pos] = vals_in ? vals_in[i] : (int32_t)i;
+        }
+    }
+}
+
+int launch_sort_pairs(cudaStream_t st, SortBufs& sb, const int32_t* keys_in, int64_t n, int key_bits) {
+    int passes = (key_bits + 7) / 8;
+    if (passes < 1) passes = 1;
+    const int nblocks = (int)((n + SORT_TILE - 1) / SORT_TILE);
+    const int32_t* kin = keys_in;
+    const int32_t* vin = nullptr;
+    int out = 0;
+    for (int p = 0; p < passes; ++p) {
+        out = p & 1;
+        sort_hist_kernel<<<nblocks, SORT_THREADS, 0, st>>>(kin, n, 8 * p, sb.hist, nblocks);
+        sort_scan_kernel<<<1, 1024, 0, st>>>(sb.hist, 256 * nblocks);
+        sort_scatter_kernel<<<nblocks, SORT_THREADS, 0, st>>>(kin, vin, sb.keys[out], sb.vals[out], n, 8 * p, sb.hist,
+                                                             nblocks);
+        g_launch_count += 3;
+        kin = sb.keys[out];
+        vin = sb.vals[out];
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------ segment reduce + row Adam
+// One group of d/4 lanes per sorted index; the group at the head of a run of equal keys sums the
+// run's gradient rows in sorted (= ascending position) order and updates the row.
+__global__ void emb_update_kernel(EmbUpdateArgs a) {
+    const int lpr = a.d >> 2;
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / lpr;
+    const int sub = threadIdx.x % lpr;
+    if (gid >= a.n) return;
+    const int32_t key = a.skeys[gid];
+    if (key == 0) return;
+    if (gid > 0 && a.skeys[gid - 1] == key) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t j = gid; j < a.n && a.skeys[j] == key; ++j) {
+        const float4 g = *reinterpret_cast<const float4*>(a.grad_rows + (int64_t)a.spos[j] * a.d + sub * 4);
+        acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+    }
+    if (a.mode == 1) {
+        *reinterpret_cast<float4*>(a.out_rows + gid * a.d + sub * 4) = acc;
+        if (sub == 0) a.out_heads[gid] = key;
+        return;
+    }
+    const int64_t off = (int64_t)key * a.d + sub * 4;
+    float4 var = *reinterpret_cast<float4*>(a.emb + off);
+    float4 m = *reinterpret_cast<float4*>(a.m + off);
+    float4 v = *reinterpret_cast<float4*>(a.v + off);
+    adam4(var, m, v, acc, a.hp->alpha);
+    *reinterpret_cast<float4*>(a.emb + off) = var;
+    *reinterpret_cast<float4*>(a.m + off) = m;
+    *reinterpret_cast<float4*>(a.v + off) = v;
+    if (sub == 0 && a.last_step) a.last_step[key] = a.hp->step;
+}
+void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a) {
+    const int lpr = a.d >> 2;
+    int64_t threads = a.n * lpr;
+    emb_update_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a);
+    ++g_launch_count;
+}
+
+// DENSE mode: the zero-gradient Adam step of every row the batch did not touch (row 0 included:
+// its gradient is always zero, so its slots stay zero and it never moves).
+__global__ void emb_dense_sweep_kernel(float* __restrict__ emb, float* __restrict__ m, float* __restrict__ v,
+                                       const int32_t* __restrict__ last_step, int64_t V, int d, const Hyper* hp) {
+    const int lpr = d >> 2;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= V * lpr) return;
+    const int64_t row = idx / lpr;
+    if (last_step[row] == hp->step) return;
+    float4 mm = reinterpret_cast<float4*>(m)[idx];
+    float4 vv = reinterpret_cast<float4*>(v)[idx];
+    if (all_zero(mm) && all_zero(vv)) return;   // never touched: the update is exactly a no-op
+    float4 var = reinterpret_cast<float4*>(emb)[idx];
+    adam4(var, mm, vv, make_float4(0.f, 0.f, 0.f, 0.f), hp->alpha);
+    reinterpret_cast<float4*>(emb)[idx] = var;
+    reinterpret_cast<float4*>(m)[idx] = mm;
+    reinterpret_cast<float4*>(v)[idx] = vv;
+}
+void launch_emb_dense_sweep(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d,
+                            const Hyper* hp) {
+    int64_t n = V * (d >> 2);
+    emb_dense_sweep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(emb, m, v, last_step, V, d, hp);
+    ++g_launch_count;
+}
+
+// LAZY mode: replay the zero-gradient steps (from, upto] of one row chunk, same op sequence as the sweep.
+__device__ __forceinline__ void replay4(float4& var, float4& m, float4& v, int from, int upto,
+                                        const float* __restrict__ alpha_hist) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = from + 1; s <= upto; ++s) adam4(var, m, v, z, alpha_hist[s]);
+}
+// one group per gathered position; the group that wins the atomic claim of the row replays it
+__global__ void emb_catchup_rows_kernel(const int32_t* __restrict__ keys, int64_t n, float* __restrict__ emb,
+                                        float* __restrict__ m, float* __restrict__ v, int32_t* __restrict__ last_step,
+                                        int d, const float* __restrict__ alpha_hist, const Hyper* hp) {
+    const int lpr = d >> 2;
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / lpr;
+    const int sub = threadIdx.x % lpr;
+    const int upto = hp->step - 1;
+    int32_t key = (gid < n) ? keys[gid] : 0;
+    int old = upto;
+    if (key != 0 && sub == 0) old = atomicExch(&last_step[key], upto);
+    old = __shfl_sync(FULL_MASK, old, 0, lpr);
+    if (key == 0 || old >= upto) return;
+    const int64_t off = (int64_t)key * d + sub * 4;
+    float4 mm = *reinterpret_cast<float4*>(m + off);
+    float4 vv = *reinterpret_cast<float4*>(v + off);
+    if (all_zero(mm) && all_zero(vv)) return;
+    float4 var = *reinterpret_cast<float4*>(emb + off);
+    replay4(var, mm, vv, old, upto, alpha_hist);
+    *reinterpret_cast<float4*>(emb + off) = var;
+    *reinterpret_cast<float4*>(m + off) = mm;
+    *reinterpret_cast<float4*>(v + off) = vv;
+}
+void launch_emb_catchup_rows(cudaStream_t st, const int32_t* keys, int64_t n, float* emb, float* m, float* v,
+                             int32_t* last_step, int d, const float* alpha_hist, const Hyper* hp) {
+    const int lpr = d >> 2;
+    int64_t threads = n * lpr;
+    emb_catchup_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(keys, n, emb, m, v, last_step, d,
+                                                                               alpha_hist, hp);
+    ++g_launch_count;
+}
+__global__ void emb_catchup_all_kernel(float* __restrict__ emb, float* __restrict__ m, float* __restrict__ v,
+                                       int32_t* __restrict__ last_step, int64_t V, int d,
+                                       const float* __restrict__ alpha_hist, int upto) {
+    const int lpr = d >> 2;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = idx / lpr;
+    const bool ok = idx < V * lpr;
+    int old = ok ? last_step[row] : upto;
+    // every lane of a row must read last_step before lane 0 overwrites it
+    __syncwarp();
+    if (!ok || old >= upto) return;
+    float4 mm = reinterpret_cast<float4*>(m)[idx];
+    float4 vv = reinterpret_cast<float4*>(v)[idx];
+    if (!(all_zero(mm) && all_zero(vv))) {
+        float4 var = reinterpret_cast<float4*>(emb)[idx];
+        replay4(var, mm, vv, old, upto, alpha_hist);
+        reinterpret_cast<float4*>(emb)[idx] = var;
+        reinterpret_cast<float4*>(m)[idx] = mm;
+        reinterpret_cast<float4*>(v)[idx] = vv;
+    }
+}
+__global__ void set_last_step_kernel(int32_t* last_step, int64_t V, int upto) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < V && last_step[i] < upto) last_step[i] = upto;
+}
+void launch_emb_catchup_all(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d,
+                            const float* alpha_hist, int upto) {
+    int64_t n = V * (d >> 2);
+    emb_catchup_all_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(emb, m, v, last_step, V, d, alpha_hist, upto);
+    set_last_step_kernel<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(last_step, V, upto);
+    g_launch_count += 2;
+}
+
+// ------------------------------------------------------------------------------------------ initialisers
+__global__ void init_trunc_normal_kernel(float* __restrict__ p, int64_t n, uint32_t lo, uint32_t hi, uint32_t stream_id) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float z = 0.f;
+    for (uint32_t attempt = 0; attempt < 64; ++attempt) {   // tf.truncated_normal: re-draw beyond 2 sigma
+        float u1 = philox_uniform(lo, hi, stream_id, 2 * attempt, (uint64_t)i);
+        float u2 = philox_uniform(lo, hi, stream_id, 2 * attempt + 1, (uint64_t)i);
+        u1 = fmaxf(u1, 5.9604645e-8f);
+        z = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+        if (fabsf(z) <= 2.0f) break;
+        z = 0.f;
+    }
+    p[i] = z;
+}
+void launch_init_trunc_normal(cudaStream_t st, float* p, int64_t n, uint64_t seed, uint32_t stream_id) {
+    init_trunc_normal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, (uint32_t)seed, (uint32_t)(seed >> 32),
+                                                                          stream_id);
+    ++g_launch_count;
+}
+__global__ void init_uniform_kernel(float* __restrict__ p, int64_t n, float limit, uint32_t lo, uint32_t hi,
+                                    uint32_t stream_id) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float u = philox_uniform(lo, hi, stream_id, 0, (uint64_t)i);
+    p[i] = (2.0f * u - 1.0f) * limit;
+}
+void launch_init_uniform(cudaStream_t st, float* p, int64_t n, float limit, uint64_t seed, uint32_t stream_id) {
+    init_uniform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, limit, (uint32_t)seed, (uint32_t)(seed >> 32),
+                                                                     stream_id);
+    ++g_launch_count;
+}
+__global__ void fill_kernel(float* p, int64_t n, float v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+void launch_fill(cudaStream_t st, float* p, int64_t n, float v) {
+    if (n <= 0) return;
+    fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
+    ++g_launch_count;
+}
+__global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+void launch_fill_i32(cudaStream_t st, int32_t* p, int64_t n, int32_t v) {
+    if (n <= 0) return;
+    fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
+    ++g_launch_count;
+}
+
+}  // namespace score

@@ -1,0 +1,410 @@
+// Dual-side sequence encoder, attention over time slices, prediction head and loss.
+//
+//   GRU     tf.nn.dynamic_rnn(GRUCell(H), sequence_length=length)          score.py:205-208
+//           TF gate order (r,u), r*h applied BEFORE the candidate matmul, outputs zero and state
+//           copied through for t >= length.  The input part of both matmuls is hoisted out of the
+//           time loop into one SGEMM over all B*T rows (px); this kernel runs the recurrence with
+//           the state-side weights resident in shared memory.
+//   attention()  [q, key, q-key, q*key] -> 80 -> 40 -> 1 -> mask -> softmax over T  score.py:169-186
+//   pooling + build_fc_net + log-loss                                       score.py:214-217, 68-81
+#include "kernels.h"
+
+namespace score {
+
+// ------------------------------------------------------------------------------------------ GRU forward
+// block = (2H threads) x (RB rows); grid = (ceil(B/RB), 2 sides)
+__global__ void gru_fwd_kernel(Dims dm, GruArgs a, int RB) {
+    extern __shared__ float sm[];
+    const int H = dm.H, H2 = 2 * dm.H, T = dm.T;
+    const int side = blockIdx.y;
+    const int j = threadIdx.x, r = threadIdx.y;
+    const int nthreads = blockDim.x * blockDim.y, tid = r * blockDim.x + j;
+    const int sg = H2 + 1, sc = H + 1;           // padded row strides (bank-conflict free both ways)
+    float* Wg = sm;                              // [H][2H+1] state rows of the gates kernel
+    float* Wc = Wg + H * sg;                     // [H][H+1]
+    float* hs = Wc + H * sc;                     // [RB][H]   current state
+    float* rh = hs + RB * H;                     // [RB][H]   r * h
+    float* us = rh + RB * H;                     // [RB][H]   update gate
+    const float* wg = a.wg[side] + (int64_t)dm.Ds * H2;
+    const float* wc = a.wc[side] + (int64_t)dm.Ds * H;
+    for (int i = tid; i < H * H2; i += nthreads) Wg[(i / H2) * sg + (i % H2)] = wg[i];
+    for (int i = tid; i < H * H; i += nthreads) Wc[(i / H) * sc + (i % H)] = wc[i];
+    for (int i = tid; i < RB * H; i += nthreads) hs[i] = 0.f;
+    __syncthreads();
+    const int b = blockIdx.x * RB + r;
+    const bool row_ok = b < dm.B;
+    const int len = row_ok ? a.length[b] : 0;
+    const float bgj = a.bg[side][j];
+    const float bcj = (j < H) ? a.bc[side][j] : 0.f;
+    const float* px = a.px[side];
+    for (int t = 0; t < T; ++t) {
+        const int64_t m = (int64_t)b * T + t;
+        float val = 0.f;
+        if (row_ok) {
+            float acc = px[m * 3 * H + j] + bgj;
+            const float* h = hs + r * H;
+            for (int k = 0; k < H; ++k) acc = fmaf(h[k], Wg[k * sg + j], acc);
+            val = sigmoidf_acc(acc);
+            if (j < H) { rh[r * H + j] = val * h[j]; a.r[side][m * H + j] = val; }
+            else { us[r * H + j - H] = val; a.u[side][m * H + j - H] = val; }
+        }
+        __syncthreads();
+        float hn = 0.f;
+        if (row_ok && j < H) {
+            float acc = px[m * 3 * H + H2 + j] + bcj;
+            const float* q = rh + r * H;
+            for (int k = 0; k < H; ++k) acc = fmaf(q[k], Wc[k * sc + j], acc);
+            float c = tanhf(acc);
+            float u = us[r * H + j];
+            float hold = hs[r * H + j];
+            hn = u * hold + (1.f - u) * c;
+            const bool alive = t < len;
+            a.c[side][m * H + j] = c;
+            a.xhg[side][m * dm.ldx + dm.Ds + j] = hold;            // h_{t-1}   (state input of the gates matmul)
+            a.xhc[side][m * dm.ldx + dm.Ds + j] = rh[r * H + j];   // r*h_{t-1} (state input of the candidate matmul)
+            a.out[m * a.ldout + side * H + j] = alive ? hn : 0.f;
+            hn = alive ? hn : hold;
+        }
+        __syncthreads();
+        if (row_ok && j < H) hs[r * H + j] = hn;
+        __syncthreads();
+    }
+    if (a.last && row_ok && j < H) a.last[(int64_t)b * a.ldlast + side * H + j] = hs[r * H + j];
+}
+
+static void gru_geometry(const Dims& dm, int* RB, size_t* smem, bool bwd) {
+    int h2 = 2 * dm.H;
+    int rb = 256 / h2;
+    if (rb < 1) rb = 1;
+    *RB = rb;
+    size_t fl = (size_t)dm.H * (h2 + 1) + (size_t)dm.H * (dm.H + 1) + (size_t)rb * dm.H * (bwd ? 5 : 3);
+    *smem = fl * sizeof(float);
+}
+
+void launch_gru_fwd(cudaStream_t st, const Dims& dm, const GruArgs& a) {
+    int RB; size_t smem;
+    gru_geometry(dm, &RB, &smem, false);
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+        cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = smem;
+    }
+    dim3 block(2 * dm.H, RB), grid((dm.B + RB - 1) / RB, 2);
+    gru_fwd_kernel<<<grid, block, smem, st>>>(dm, a, RB);
+    ++g_launch_count;
+}
+
+// ------------------------------------------------------------------------------------------ GRU backward (BPTT)
+//   h' = u h + (1-u) c ;  c = tanh(px_c + (r h) Wc_h + bc) ;  [r,u] = sigmoid(px_g + h Wg_h + bg)
+__global__ void gru_bwd_kernel(Dims dm, GruBwdArgs a, int RB) {
+    extern __shared__ float sm[];
+    const int H = dm.H, H2 = 2 * dm.H, T = dm.T;
+    const int side = blockIdx.y;
+    const int j = threadIdx.x, r = threadIdx.y;
+    const int nthreads = blockDim.x * blockDim.y, tid = r * blockDim.x + j;
+    const int sg = H2 + 1, sc = H + 1;
+    float* Wg = sm;                              // [H][2H+1]
+    float* Wc = Wg + H * sg;                     // [H][H+1]
+    float* dh = Wc + H * sc;                     // [RB][H]  carried d state
+    float* dcp = dh + RB * H;                    // [RB][H]  d candidate pre-activation
+    float* dg = dcp + RB * H;                    // [RB][2H] d gate pre-activations (r | u)
+    float* dhd = dg + RB * H2;                   // [RB][H]  direct part of d h_{t-1}
+    const float* wg = a.wg[side] + (int64_t)dm.Ds * H2;
+    const float* wc = a.wc[side] + (int64_t)dm.Ds * H;
+    for (int i = tid; i < H * H2; i += nthreads) Wg[(i / H2) * sg + (i % H2)] = wg[i];
+    for (int i = tid; i < H * H; i += nthreads) Wc[(i / H) * sc + (i % H)] = wc[i];
+    const int b = blockIdx.x * RB + r;
+    const bool row_ok = b < dm.B;
+    const int len = row_ok ? a.length[b] : 0;
+    if (j < H) dh[r * H + j] = (a.dlast && row_ok) ? a.dlast[(int64_t)b * a.lddlast + side * H + j] : 0.f;
+    __syncthreads();
+    float* dpx = a.dpx[side];
+    for (int t = T - 1; t >= 0; --t) {
+        const int64_t m = (int64_t)b * T + t;
+        const bool alive = row_ok && (t < len);
+        float hp = 0.f, rr = 0.f;
+        // phase A: through h' = u h + (1-u) c
+        if (j < H) {
+            float dcpv = 0.f, dguv = 0.f, direct = dh[r * H + j];
+            if (alive) {
+                float dhn = dh[r * H + j] + (a.dout ? a.dout[m * a.lddout + side * H + j] : 0.f);
+                float u = a.u[side][m * H + j], c = a.c[side][m * H + j];
+                hp = a.xhg[side][m * dm.ldx + dm.Ds + j];
+                rr = a.r[side][m * H + j];
+                float du = dhn * (hp - c);
+                float dc = dhn * (1.f - u);
+                direct = dhn * u;
+                dcpv = dc * (1.f - c * c);
+                dguv = du * u * (1.f - u);
+            }
+            dcp[r * H + j] = dcpv;
+            dg[r * H2 + H + j] = dguv;
+            dhd[r * H + j] = direct;
+            if (row_ok) { dpx[m * 3 * H + H2 + j] = dcpv; dpx[m * 3 * H + H + j] = dguv; }
+        }
+        __syncthreads();
+        // phase B: through the candidate matmul, d(r h) = dcp Wc_h^T
+        if (j < H) {
+            float dgrv = 0.f;
+            if (alive) {
+                float drh = 0.f;
+                const float* q = dcp + r * H;
+                for (int k = 0; k < H; ++k) drh = fmaf(q[k], Wc[j * sc + k], drh);
+                float dr = drh * hp;
+                dhd[r * H + j] += drh * rr;
+                dgrv = dr * rr * (1.f - rr);
+            }
+            dg[r * H2 + j] = dgrv;
+            if (row_ok) dpx[m * 3 * H + j] = dgrv;
+        }
+        __syncthreads();
+        // phase C: through the gates matmul, d h += dg Wg_h^T
+        if (j < H) {
+            float v = dhd[r * H + j];
+            if (alive) {
+                const float* q = dg + r * H2;
+                for (int k = 0; k < H2; ++k) v = fmaf(q[k], Wg[j * sg + k], v);
+            }
+            dh[r * H + j] = v;
+        }
+        __syncthreads();
+    }
+}
+
+void launch_gru_bwd(cudaStream_t st, const Dims& dm, const GruBwdArgs& a) {
+    int RB; size_t smem;
+    gru_geometry(dm, &RB, &smem, true);
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+        cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = smem;
+    }
+    dim3 block(2 * dm.H, RB), grid((dm.B + RB - 1) / RB, 2);
+    gru_bwd_kernel<<<grid, block, smem, st>>>(dm, a, RB);
+    ++g_launch_count;
+}
+
+// ------------------------------------------------------------------------------------------ attention input
+// a1[m] = [q_b | key_m | q_b - key_m | q_b * key_m]
+__global__ void att_inp_fwd_kernel(int64_t M, int T, int Dk, const float* __restrict__ q,
+                                   const float* __restrict__ key, float* __restrict__ a1) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * Dk) return;
+    int64_t m = idx / Dk; int c = (int)(idx - m * Dk);
+    int64_t b = m / T;
+    float qv = q[b * Dk + c], kv = key[m * Dk + c];
+    float* o = a1 + m * 4 * Dk;
+    o[c] = qv; o[Dk + c] = kv; o[2 * Dk + c] = qv - kv; o[3 * Dk + c] = qv * kv;
+}
+void launch_att_inp_fwd(cudaStream_t st, const Dims& dm, const float* q, const float* key, float* a1) {
+    int64_t n = (int64_t)dm.B * dm.T * dm.Dk;
+    att_inp_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int64_t)dm.B * dm.T, dm.T, dm.Dk, q, key, a1);
+    ++g_launch_count;
+}
+
+// da1 = [dA | dB | dC | dD]:  dq_b = sum_t (dA + dC + dD*key),  dkey = dB - dC + dD*q (+ pooling grad in cols < acc_cols)
+// one thread per (b, c): loops over t in fixed order
+__global__ void att_inp_bwd_kernel(int B, int T, int Dk, const float* __restrict__ q, const float* __restrict__ key,
+                                   const float* __restrict__ da1, float* __restrict__ dkey, float* __restrict__ dq,
+                                   int acc_cols) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * Dk) return;
+    int b = idx / Dk, c = idx - b * Dk;
+    float qv = q[idx];
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) {
+        int64_t m = (int64_t)b * T + t;
+        const float* g = da1 + m * 4 * Dk;
+        float kv = key[m * Dk + c];
+        float dA = g[c], dBv = g[Dk + c], dC = g[2 * Dk + c], dD = g[3 * Dk + c];
+        s += dA + dC + dD * kv;
+        float dk = dBv - dC + dD * qv;
+        if (c < acc_cols) dk += dkey[m * Dk + c];
+        dkey[m * Dk + c] = dk;
+    }
+    dq[idx] = s;
+}
+void launch_att_inp_bwd(cudaStream_t st, const Dims& dm, const float* q, const float* key, const float* da1,
+                        float* dkey, float* dq, int accumulate_cols) {
+    int n = dm.B * dm.Dk;
+    att_inp_bwd_kernel<<<(n + 127) / 128, 128, 0, st>>>(dm.B, dm.T, dm.Dk, q, key, da1, dkey, dq, accumulate_cols);
+    ++g_launch_count;
+}
+
+// ------------------------------------------------------------------------------------------ attention pooling
+// one warp per sample: s_t = f2[m] . w3 + b3 ; masked softmax over T ; final = sum_t rep_t * score_t
+__global__ void att_pool_fwd_kernel(Dims dm, AttPoolArgs a) {
+    extern __shared__ float sm[];
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* sc = sm + warp * dm.T;
+    const int b = blockIdx.x * warps + warp;
+    if (b >= dm.B) return;
+    const int T = dm.T, H = dm.H;
+    const int len = a.length[b];
+    const float pad = -4294967296.0f;   // float32(-2**32 + 1)  score.py:180
+    for (int t = 0; t < T; ++t) {
+        const float* f = a.f2 + ((int64_t)b * T + t) * 40;
+        float p = 0.f;
+        for (int c = lane; c < 40; c += 32) p += f[c] * a.w3[c];
+        p = warp_sum(p) + a.b3[0];
+        if (lane == 0) sc[t] = (t < len) ? p : pad;
+    }
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int t = lane; t < T; t += 32) mx = fmaxf(mx, sc[t]);
+    mx = warp_max(mx);
+    float den = 0.f;
+    for (int t = lane; t < T; t += 32) den += expf(sc[t] - mx);
+    den = warp_sum(den);
+    __syncwarp();
+    for (int t = lane; t < T; t += 32) {
+        float w = expf(sc[t] - mx) / den;
+        sc[t] = w;
+        a.score[(int64_t)b * T + t] = w;
+    }
+    __syncwarp();
+    // pooled states; destination layout depends on the model type (score.py:217, 325, 362)
+    const int mt = dm.model_type;
+    for (int c = lane; c < 2 * H; c += 32) {
+        float s = 0.f;
+        for (int t = 0; t < T; ++t) s += a.key[((int64_t)b * T + t) * a.ldkey + c] * sc[t];
+        int dst = c;
+        if (mt == 3) { if (c >= H) continue; }            // SCORE_USER keeps only the user state
+        else if (mt == 4) { if (c < H) continue; dst = c - H; }   // SCORE_ITEM keeps only the item state
+        a.fc_in[(int64_t)b * a.ldfc + dst] = s;
+    }
+}
+void launch_att_pool_fwd(cudaStream_t st, const Dims& dm, const AttPoolArgs& a) {
+    const int warps = 4;
+    att_pool_fwd_kernel<<<(dm.B + warps - 1) / warps, warps * 32, warps * dm.T * sizeof(float), st>>>(dm, a);
+    ++g_launch_count;
+}
+
+// backward: dscore_t = d_final . rep_t ; ds_t = score_t (dscore_t - sum score dscore) for live t ;
+// dkey[:, 0:2H] = score_t * d_final
+__global__ void att_pool_bwd_kernel(Dims dm, AttPoolBwdArgs a) {
+    extern __shared__ float sm[];
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* dsc = sm + warp * dm.T;
+    const int b = blockIdx.x * warps + warp;
+    if (b >= dm.B) return;
+    const int T = dm.T, H = dm.H, mt = dm.model_type;
+    const int len = a.length[b];
+    const float* dfc = a.dfc_in + (int64_t)b * a.ldfc;
+    for (int t = 0; t < T; ++t) {
+        const int64_t m = (int64_t)b * T + t;
+        const float sct = a.score[m];
+        float p = 0.f;
+        for (int c = lane; c < 2 * H; c += 32) {
+            float d;
+            if (mt == 3) d = (c < H) ? dfc[c] : 0.f;
+            else if (mt == 4) d = (c >= H) ? dfc[c - H] : 0.f;
+            else d = dfc[c];
+            p += d * a.key[m * a.ldkey + c];
+            a.dkey[m * a.ldkey + c] = d * sct;
+        }
+        p = warp_sum(p);
+        if (lane == 0) dsc[t] = p;
+    }
+    __syncwarp();
+    float dot = 0.f;
+    for (int t = lane; t < T; t += 32) dot += a.score[(int64_t)b * T + t] * dsc[t];
+    dot = warp_sum(dot);
+    for (int t = lane; t < T; t += 32) {
+        float s = a.score[(int64_t)b * T + t];
+        a.ds[(int64_t)b * T + t] = (t < len) ? s * (dsc[t] - dot) : 0.f;   // tf.where blocks the gradient of padded slots
+    }
+}
+void launch_att_pool_bwd(cudaStream_t st, const Dims& dm, const AttPoolBwdArgs& a) {
+    const int warps = 4;
+    att_pool_bwd_kernel<<<(dm.B + warps - 1) / warps, warps * 32, warps * dm.T * sizeof(float), st>>>(dm, a);
+    ++g_launch_count;
+}
+
+// ------------------------------------------------------------------------------------------ batch norm (inference mode)
+__global__ void bn_fwd_kernel(int B, int F, const float* __restrict__ x, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, const float* __restrict__ mean,
+                              const float* __restrict__ var, float* __restrict__ z) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * F) return;
+    int c = idx % F;
+    float inv = gamma[c] / sqrtf(var[c] + 1e-3f);
+    z[idx] = x[idx] * inv + (beta[c] - mean[c] * inv);
+}
+void launch_bn_fwd(cudaStream_t st, int B, int F, const float* x, const float* gamma, const float* beta,
+                   const float* mean, const float* var, float* z) {
+    int n = B * F;
+    bn_fwd_kernel<<<(n + 255) / 256, 256, 0, st>>>(B, F, x, gamma, beta, mean, var, z);
+    ++g_launch_count;
+}
+// dx = dz * inv ; dgamma_c = sum_b dz (x - mean)/sqrt(var+eps) ; dbeta_c = sum_b dz   (one thread per column, fixed order)
+__global__ void bn_bwd_kernel(int B, int F, const float* __restrict__ x, const float* __restrict__ dz,
+                              const float* __restrict__ gamma, const float* __restrict__ mean,
+                              const float* __restrict__ var, float* __restrict__ dx, float* __restrict__ dgamma,
+                              float* __restrict__ dbeta) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= F) return;
+    float rstd = 1.0f / sqrtf(var[c] + 1e-3f);
+    float inv = gamma[c] * rstd, mu = mean[c];
+    float sg = 0.f, sb = 0.f;
+    for (int b = 0; b < B; ++b) {
+        float d = dz[(int64_t)b * F + c];
+        sg += d * ((x[(int64_t)b * F + c] - mu) * rstd);
+        sb += d;
+        dx[(int64_t)b * F + c] = d * inv;
+    }
+    dgamma[c] = sg; dbeta[c] = sb;
+}
+void launch_bn_bwd(cudaStream_t st, int B, int F, const float* x, const float* dz, const float* gamma,
+                   const float* mean, const float* var, float* dx, float* dgamma, float* dbeta) {
+    bn_bwd_kernel<<<(F + 63) / 64, 64, 0, st>>>(B, F, x, dz, gamma, mean, var, dx, dgamma, dbeta);
+    ++g_launch_count;
+}
+
+// ------------------------------------------------------------------------------------------ head + loss
+// one warp per sample
+__global__ void head_kernel(int B, int F, const float* __restrict__ g2, const float* __restrict__ w3,
+                            const float* __restrict__ b3, const int32_t* __restrict__ label, const Hyper* hp,
+                            float* __restrict__ y, float* __restrict__ loss_b, float* __restrict__ dlogit) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    float p = 0.f;
+    for (int c = lane; c < F; c += 32) p += g2[(int64_t)warp * F + c] * w3[c];
+    p = warp_sum(p) + b3[0];
+    if (lane == 0) {
+        float pr = sigmoidf_acc(p);
+        float yl = (float)label[warp];
+        const float eps = 1e-7f;
+        y[warp] = pr;
+        loss_b[warp] = -yl * logf(pr + eps) - (1.f - yl) * logf(1.f - pr + eps);
+        float dp = (-yl / (pr + eps) + (1.f - yl) / (1.f - pr + eps)) * hp->inv_batch;
+        dlogit[warp] = dp * pr * (1.f - pr);
+    }
+}
+void launch_head(cudaStream_t st, int B, int F, const float* g2, const float* w3, const float* b3,
+                 const int32_t* label, const Hyper* hp, float* y, float* loss_b, float* dlogit) {
+    int threads = 128;
+    head_kernel<<<(B * 32 + threads - 1) / threads, threads, 0, st>>>(B, F, g2, w3, b3, label, hp, y, loss_b, dlogit);
+    ++g_launch_count;
+}
+
+// loss = (sum_b loss_b) * inv_batch + reg_lambda * l2sum ; single block, fixed-shape tree
+__global__ void loss_final_kernel(int B, const float* __restrict__ loss_b, const float* __restrict__ l2sum,
+                                  const Hyper* hp, float* __restrict__ loss) {
+    __shared__ float red[256];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < B; i += 256) s += loss_b[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = red[0] * hp->inv_batch + hp->reg_lambda * l2sum[0];
+}
+void launch_loss_final(cudaStream_t st, int B, const float* loss_b, const float* l2sum, const Hyper* hp, float* loss) {
+    loss_final_kernel<<<1, 256, 0, st>>>(B, loss_b, l2sum, hp, loss);
+    ++g_launch_count;
+}
+
+}  // namespace score

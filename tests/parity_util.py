@@ -1,0 +1,146 @@
+"""Shared helpers of the GPU parity tests: run the CUDA path and the CPU oracle on identical inputs
+and weights and report the error of every intermediate, gradient and updated variable."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import score_ref as ref  # noqa: E402  (tests are allowed to use the oracle as the checker)
+from score_b200 import model as sb  # noqa: E402
+from score_b200.synth import SHAPES, Shape, make_batch  # noqa: E402
+
+REL_TOL = 1e-5   # BASELINE.json: forward logits and embedding/dense gradients within 1e-5 relative in fp32
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|_inf, tiny): relative to the tensor's scale (entries near zero carry the
+    absolute rounding error of the largest terms that cancelled)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    if a.size == 0:
+        return 0.0
+    scale = max(float(np.abs(b).max()), 1e-30)
+    return float(np.abs(a - b).max() / scale)
+
+
+def make_models(shape: Shape, seed=7, adam_mode="dense", model_type="SCORE", use_graph=False, dtype=torch.float32):
+    cfg = ref.ScoreConfig(*shape.ctor_args(), model_type=model_type)
+    params = ref.init_params(cfg, seed, torch.float32)
+    cls = getattr(sb, model_type)
+    m = cls(*shape.ctor_args(), adam_mode=adam_mode, init_weights=False, use_graph=use_graph, seed=seed)
+    m.load_params(params)
+    if dtype != torch.float32:
+        params = type(params)((k, v.to(dtype)) for k, v in params.items())
+    return cfg, params, m
+
+
+def forward_backward_report(shape: Shape, batch, seed=7, reg_lambda=1e-4, keep_prob=1.0, model_type="SCORE",
+                            dtype=torch.float32):
+    """Returns {name: relative error} for every compared tensor plus exact-match flags."""
+    cfg, params, m = make_models(shape, seed, model_type=model_type, dtype=dtype)
+    loss_c = m.forward_backward(batch, reg_lambda, keep_prob)
+    B = batch[0].shape[0]
+    T, K, H = cfg.max_time_len, cfg.obj_per_time_slice, cfg.hidden_size
+    Ds, Dk = cfg.d_side, cfg.d_key
+    masks = None
+    if keep_prob < 1.0:   # inject the masks the CUDA path drew (a zero output is either dropped or relu-dead)
+        g1 = m.get_buffer("fc1").reshape(B, 200)
+        g2 = m.get_buffer("fc2").reshape(B, 80)
+        masks = (torch.from_numpy((g1 != 0).astype(np.float32)), torch.from_numpy((g2 != 0).astype(np.float32)))
+    tb = ref.to_batch(batch)
+    loss_o, y_o, g_o, inter = ref.loss_and_grads(params, tb, cfg, reg_lambda, keep_prob, masks)
+    rep = {}
+    live = (np.arange(T)[None, :] < np.asarray(batch[7])[:, None])   # [B,T]
+    ldx = Ds + H
+
+    def live_rows(x, width):
+        return x.reshape(B, T, width)[live]
+
+    rep["loss"] = rel_err(loss_c, float(loss_o))
+    rep["y_pred"] = rel_err(m.get_buffer("y_pred"), y_o.numpy())
+    xu = m.get_buffer("xhg_user").reshape(B * T, ldx)[:, :Ds]
+    xi = m.get_buffer("xhg_item").reshape(B * T, ldx)[:, :Ds]
+    rep["user_side"] = rel_err(live_rows(xu, Ds), inter["user_side"].numpy()[live])
+    rep["item_side"] = rel_err(live_rows(xi, Ds), inter["item_side"].numpy()[live])
+    key = m.get_buffer("key").reshape(B * T, Dk)
+    rep["user_rep_t"] = rel_err(key[:, :H].reshape(B, T, H), inter["user_rep_t"].numpy())
+    rep["item_rep_t"] = rel_err(key[:, H:2 * H].reshape(B, T, H), inter["item_rep_t"].numpy())
+    if inter.get("atten_info") is not None and model_type != "RIA":
+        rep["atten_info"] = rel_err(live_rows(key[:, 2 * H:], 4 * K), inter["atten_info"].numpy()[live])
+    if inter.get("score") is not None:
+        rep["att_score"] = rel_err(m.get_buffer("score").reshape(B, T), inter["score"].numpy().reshape(B, T))
+    rep["fc_in"] = rel_err(m.get_buffer("fc_in").reshape(B, -1), inter["fc_in"].numpy())
+    for name, _ in m.tensor_names():
+        if name == "emb_mtx" or name in ref.NON_TRAINABLE:
+            continue
+        rep["grad/" + name] = rel_err(m.get_buffer("grad/" + name), g_o[name].numpy().reshape(-1))
+    rows_c, vals_c = m.embedding_row_grads()
+    rows_o, vals_o = ref.embedding_row_grads(g_o["emb_mtx"])
+    rep["emb_rows_exact"] = bool(np.array_equal(rows_c, rows_o.numpy()))
+    if rep["emb_rows_exact"]:
+        rep["emb_row_grads"] = rel_err(vals_c, vals_o.numpy())
+    else:
+        common = np.intersect1d(rows_c, rows_o.numpy())
+        rep["emb_rows_missing"] = int(len(rows_o) - len(common))
+        rep["emb_rows_extra"] = int(len(rows_c) - len(common))
+    # gathered ids / neighbor masks: the sanitized key list must equal ids masked by slice liveness
+    keys = m.get_buffer("keys")
+    rep["keys_exact"] = bool(np.array_equal(keys, expected_keys(batch, cfg)))
+    m.close()
+    return rep
+
+
+def expected_keys(batch, cfg):
+    """ids in flat position order [u1|u2|i1|i2|tu|ti], zeroed where t >= length (masked slices)."""
+    T = cfg.max_time_len
+    live = (np.arange(T)[None, :] < np.asarray(batch[7])[:, None])
+    parts = []
+    for x in batch[:4]:
+        a = np.asarray(x).astype(np.int32).copy()
+        a[~live] = 0
+        parts.append(a.reshape(-1))
+    parts.append(np.asarray(batch[4]).astype(np.int32).reshape(-1))
+    parts.append(np.asarray(batch[5]).astype(np.int32).reshape(-1))
+    return np.concatenate(parts)
+
+
+def train_steps_report(shape: Shape, batches, seed=7, lr=5e-4, reg_lambda=1e-4, adam_mode="dense",
+                       use_graph=False, model_type="SCORE"):
+    """Run len(batches) training steps (keep_prob=1) on both paths; compare losses and every variable."""
+    cfg, params, m = make_models(shape, seed, adam_mode=adam_mode, use_graph=use_graph, model_type=model_type)
+    orc = ref.ScoreOracle(*shape.ctor_args(), model_type=model_type, seed=seed)
+    rep = {}
+    for i, b in enumerate(batches):
+        lc = m.train(None, b, lr, reg_lambda, keep_prob=1.0)
+        lo = orc.train(None, b, lr, reg_lambda, keep_prob=1.0)
+        rep["loss_step%d" % i] = rel_err(lc, lo)
+    for name, _ in m.tensor_names():
+        rep["var/" + name] = rel_err(m.get_tensor(name), orc.params[name].numpy())
+        if name not in ref.NON_TRAINABLE:
+            rep["m/" + name] = rel_err(m.get_tensor(name + "/Adam"), orc.opt.m[name].numpy())
+            rep["v/" + name] = rel_err(m.get_tensor(name + "/Adam_1"), orc.opt.v[name].numpy())
+    m.close()
+    return rep
+
+
+def print_report(title, rep, tol=REL_TOL):
+    print("== %s" % title)
+    worst = 0.0
+    for k, v in rep.items():
+        if isinstance(v, bool):
+            print("   %-48s %s" % (k, "exact" if v else "MISMATCH"))
+        elif isinstance(v, int):
+            print("   %-48s %d" % (k, v))
+        else:
+            flag = "" if v <= tol else "   <-- above %.0e" % tol
+            worst = max(worst, v)
+            print("   %-48s %.3e%s" % (k, v, flag))
+    print("   worst relative error: %.3e" % worst)
+    return worst
