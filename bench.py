@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py - SCoRe training throughput (samples/s) on synthetic data of the reference's shapes.
+
+One "step" = one pass of the hot path (forward + backward + Adam, code/score/score.py:101-116) over one
+synthetic batch.  Workload at N=1: Taobao shape (BASELINE.json configs[2]: V=5 042 754 rows, d=16, T=8,
+K=10, batch 1024), the config the >=100x target is quoted on.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload taobao]
+
+Prints ONE JSON line (rank 0).  `value` = whole-job samples/s with the id tensors already resident in
+HBM; `e2e` = the same metric through the reference-facing call model.train(sess, batch, lr, reg) with
+pinned HOST buffers (H2D of the ids and D2H of the loss inside the timed region).  `roofline` is the
+embedding gather kernel (coatt_fwd) timed with CUDA events on its own stream inside the timed steps;
+`roofline_scatter` the sort-free part of the scatter (segment-reduce + row Adam).  `cpu_baseline` is the
+literal CPU restatement of score.py (oracle/, "port": TF 1.x cannot be installed offline) timed on the
+box's host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LR, REG = 5e-4, 1e-4          # train_score.py:371-372 (first grid point)
+POOL = 16                      # distinct batches rotated through the timed region
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(shape, batch_size, budget_s=20.0, max_steps=8):
+    """Literal CPU restatement of score.py timed on the host cores (bounded sample of the workload)."""
+    import torch
+    from oracle import score_ref as ref
+    from score_b200.synth import make_batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    o = ref.ScoreOracle(*shape.ctor_args(), seed=1111)
+    b = make_batch(shape, batch=batch_size, seed=1)
+    o.train(None, b, LR, REG)                      # warm-up (allocations, thread pools)
+    times = []
+    t_all = time.perf_counter()
+    for i in range(max_steps):
+        b = make_batch(shape, batch=batch_size, seed=2 + i)
+        t0 = time.perf_counter()
+        o.train(None, b, LR, REG)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all > budget_s:
+            break
+    med = float(np.median(times))
+    return {"value": batch_size / med, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "%d train steps of batch %d (median step %.3f s); literal restatement of score.py in "
+                      "PyTorch-CPU fp32 (materialised KxK co-attention, dense-table Adam); TF 1.x could not be "
+                      "installed offline" % (len(times), batch_size, med)}, med
+
+
+def run_reference(args, shape, rank, world):
+    if rank != 0:
+        return
+    cb, med = cpu_baseline(shape, shape.batch, budget_s=max(10.0, 3.0 * (args.steps + args.warmup)),
+                           max_steps=max(1, args.steps))
+    line = {"impl": "reference", "metric": "train_samples_per_sec", "value": cb["value"], "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(shape, args, shape.batch),
+            "cpu_baseline": dict(cb),
+            "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(shape, args, global_batch):
+    return {"workload": "SCoRe %s-shape synthetic (V=%d rows, d=%d, T=%d, K=%d, uf/if=%d/%d, H=%d)" % (
+                shape.name, shape.feature_size, shape.eb_dim, shape.max_time_len, shape.obj_per_time_slice,
+                shape.user_fnum, shape.item_fnum, shape.hidden_size),
+            "global_batch": global_batch, "per_gpu_batch": shape.batch, "length": shape.length,
+            "ids": "uniform" if not args.zipf else "zipf %.2f" % args.zipf,
+            "adam": args.adam_mode, "cuda_graph": not args.no_graph,
+            "parallelism": "single GPU" if args.gpus == 1 else "dp%d (dense all-reduce + embedding-gradient all-gather)" % args.gpus,
+            "l2_policy": "inputs larger than L2: %.2f GB of embedding state (var+m+v), uniform-random rows, %d rotating "
+                         "batches; no explicit flush" % (3 * shape.feature_size * shape.eb_dim * 4 / 1e9, POOL)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="taobao")
+    ap.add_argument("--adam-mode", default="lazy", choices=["dense", "lazy", "sparse"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--zipf", type=float, default=0.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    from score_b200.synth import SHAPES, make_batch
+    shape = SHAPES[args.workload]
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+
+    if args.impl == "reference":
+        run_reference(args, shape, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from score_b200 import model as sb
+    from score_b200 import parallel
+
+    B = shape.batch
+    m = sb.SCORE(*shape.ctor_args(), device=local, adam_mode=args.adam_mode, use_graph=not args.no_graph,
+                 seed=1111, max_batch=B)
+    trainer = parallel.DataParallelTrainer(m, world, rank) if world > 1 else None
+    stream = torch.cuda.ExternalStream(m.stream(), device=torch.device("cuda", local))
+
+    host_pool = [make_batch(shape, batch=B, seed=1000 * (rank + 1) + i, zipf=args.zipf) for i in range(POOL)]
+    dev_pool = [tuple(torch.from_numpy(x).cuda() for x in b) for b in host_pool]
+    pin_pool = [tuple(torch.from_numpy(x).pin_memory() for x in b) for b in host_pool]
+    torch.cuda.synchronize()
+
+    def step_dev(i):
+        b = dev_pool[i % POOL]
+        if trainer:
+            trainer.train_async(b, LR, REG)
+        else:
+            m.train_async(b, LR, REG)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput
+    for i in range(args.warmup):
+        step_dev(i)
+    m.wait()
+    m.enable_probes(True)
+    for i in range(3):          # graphs are re-captured with the probe events
+        step_dev(i)
+        m.wait()
+    m.enable_probes(True)       # same state: resets the accumulators only, graphs are kept
+    launches0 = m.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for i in range(args.steps):
+            step_dev(i)
+        ev1.record(stream)
+    loss = m.wait()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    launches = m.launch_count() - launches0
+    probes = m.probe_times()
+    stats = m.last_step_stats()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+
+    # ---------------- end to end through the reference-facing API, host buffers
+    m.enable_probes(False)
+    e2e_steps = args.e2e_steps or max(20, args.steps // 4)
+
+    def step_host(i):
+        b = pin_pool[i % POOL]
+        return trainer.train(None, b, LR, REG) if trainer else m.train(None, b, LR, REG)
+
+    for i in range(3):
+        step_host(i)
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        ev2.record(stream)
+        for i in range(e2e_steps):
+            loss_e2e = step_host(i)
+        ev3.record(stream)
+    torch.cuda.synchronize()
+    e2e_ms = max(ev2.elapsed_time(ev3), (time.perf_counter() - t0) * 1e3)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = B * world / (e2e_ms / e2e_steps * 1e-3)
+    h2d = int(sum(x.numel() * 4 for x in pin_pool[0]))
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        d = shape.eb_dim
+        live, uniq = stats["live"], stats["unique_rows"]
+        gather_bytes = live * (4 + 4 * d)
+        scatter_bytes = live * (4 + 4 * d) + uniq * 6 * 4 * d
+
+        def per_launch(name):
+            tot, n = probes[name]
+            return tot / n if n else None
+
+        t_g, t_s = per_launch("coatt_fwd"), per_launch("emb_update")
+        roof = {"bound": "hbm", "kernel": "coatt_fwd_kernel (fused embedding gather + co-attention + pooling)",
+                "achieved": gather_bytes / (t_g * 1e-3) / 1e9 if t_g else None, "peak": peak, "unit": "GB/s",
+                "frac": gather_bytes / (t_g * 1e-3) / 1e9 / peak if t_g else None, "traffic": None,
+                "peak_source": peak_src, "bytes_per_launch": gather_bytes, "ms_per_launch": t_g,
+                "bytes_rule": "live non-zero ids x (4 + 4d)"}
+        roof_s = {"bound": "hbm", "kernel": "emb_update_kernel (segment-reduce + fused row Adam)",
+                  "achieved": scatter_bytes / (t_s * 1e-3) / 1e9 if t_s else None, "peak": peak, "unit": "GB/s",
+                  "frac": scatter_bytes / (t_s * 1e-3) / 1e9 / peak if t_s else None, "traffic": None,
+                  "bytes_per_launch": scatter_bytes, "ms_per_launch": t_s, "unique_rows": uniq,
+                  "bytes_rule": "live ids x (4 + 4d) + unique rows x 6 x 4d"}
+        line = {"metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(shape, args, B * world),
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                        "steps": e2e_steps, "api": "SCORE.train(sess, batch_data, lr, reg_lambda) -> float, pinned host ids"},
+                "gpu_launches": int(launches),
+                "roofline": roof, "roofline_scatter": roof_s,
+                "kernel_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in probes.items()},
+                "final_loss": loss}
+        if not args.no_cpu_baseline and world == 1:
+            cb, _ = cpu_baseline(shape, B)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    m.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

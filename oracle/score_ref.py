@@ -384,20 +384,25 @@ class AdamState:
 
 
 def adam_apply(params, grads, st: AdamState, lr: float):
-    """Dense ApplyAdam on every trainable variable (TF kernel op order), in place."""
-    dt = st.beta1_power.dtype
-    one = torch.tensor(1.0, dtype=dt)
-    alpha = torch.tensor(lr, dtype=dt) * torch.sqrt(one - st.beta2_power) / (one - st.beta1_power)
-    omb1 = one - torch.tensor(ADAM_B1, dtype=dt)
-    omb2 = one - torch.tensor(ADAM_B2, dtype=dt)
-    eps = torch.tensor(ADAM_EPS, dtype=dt)
+    """Dense ApplyAdam on every trainable variable, in place, in the op order of TF's kernel:
+        alpha = lr * sqrt(1 - beta2_power) / (1 - beta1_power)
+        m += (g - m) * (1 - beta1);  v += (g*g - v) * (1 - beta2);  var -= (m * alpha) / (sqrt(v) + eps)
+    Evaluated with NumPy element-wise ops in the variables' dtype: every step is one correctly rounded
+    IEEE operation (Eigen's SSE/AVX sqrt and div are too), which torch's CPU sqrt (a vendor vector-math
+    routine) does not guarantee to the last bit."""
+    np_dt = np.float32 if st.beta1_power.dtype == torch.float32 else np.float64
+    f = np_dt
+    b1p, b2p = f(st.beta1_power.item()), f(st.beta2_power.item())
+    alpha = f(f(f(lr) * np.sqrt(f(1) - b2p, dtype=np_dt)) / f(f(1) - b1p))
+    omb1, omb2, eps = f(f(1) - f(ADAM_B1)), f(f(1) - f(ADAM_B2)), f(ADAM_EPS)
     for n, g in grads.items():
-        m, v, var = st.m[n], st.v[n], params[n]
-        m += (g - m) * omb1
-        v += (g * g - v) * omb2
-        var -= (m * alpha) / (torch.sqrt(v) + eps)
-    st.beta1_power = st.beta1_power * torch.tensor(ADAM_B1, dtype=dt)
-    st.beta2_power = st.beta2_power * torch.tensor(ADAM_B2, dtype=dt)
+        gn = g.detach().numpy().astype(np_dt, copy=False)
+        m, v, var = st.m[n].numpy(), st.v[n].numpy(), params[n].numpy()   # views: updated in place
+        m += (gn - m) * omb1
+        v += (gn * gn - v) * omb2
+        var -= (m * alpha) / (np.sqrt(v) + eps)
+    st.beta1_power = torch.tensor(f(b1p * f(ADAM_B1)), dtype=st.beta1_power.dtype)
+    st.beta2_power = torch.tensor(f(b2p * f(ADAM_B2)), dtype=st.beta2_power.dtype)
 
 
 class ScoreOracle:

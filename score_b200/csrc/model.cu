@@ -91,6 +91,7 @@ struct ScoreModel {
     // graphs
     std::map<int, cudaGraphExec_t> graphs_train;
     std::map<int, int> warm_train;
+    std::map<int, int64_t> graph_kernels;   // kernels inside the captured graph of each batch size
     bool capturing = false;
 
     // timing probes
@@ -257,6 +258,7 @@ void free_workspace(ScoreModel* h) {
     for (auto& kv : h->graphs_train) cudaGraphExecDestroy(kv.second);
     h->graphs_train.clear();
     h->warm_train.clear();
+    h->graph_kernels.clear();
     h->cap_B = 0;
 }
 
@@ -679,13 +681,16 @@ int run_step(ScoreModel* h, const ScoreBatch* b, int mode, float lr, float reg_l
         auto it = h->graphs_train.find(B);
         if (it != h->graphs_train.end()) {
             CK(cudaGraphLaunch(it->second, h->st));
+            g_launch_count += h->graph_kernels[B];
             launched = true;
         } else if (h->warm_train[B] >= 1) {
             // second time this batch size is seen: capture (the first run set all func attributes)
             cudaGraph_t graph = nullptr;
             h->capturing = true;
+            const int64_t before = g_launch_count;
             CK(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
             enqueue_step(h, mode);
+            h->graph_kernels[B] = g_launch_count - before;
             cudaError_t ce = cudaStreamEndCapture(h->st, &graph);
             h->capturing = false;
             if (ce != cudaSuccess) { h->err = std::string("graph capture failed: ") + cudaGetErrorString(ce); return SCORE_ERR_CUDA; }
@@ -1110,11 +1115,14 @@ int64_t score_launch_count(ScoreHandle h) { return h ? g_launch_count - h->launc
 
 int score_enable_probes(ScoreHandle h, int on) {
     if (!h) return SCORE_ERR_ARG;
-    h->probes_on = on != 0;
+    const bool want = on != 0;
     for (int p = 0; p < PR_COUNT; ++p) { h->pr_ms[p] = 0; h->pr_n[p] = 0; }
-    // graphs captured without probe nodes must be rebuilt
+    if (want == h->probes_on) return SCORE_OK;   // same state: only reset the accumulators
+    h->probes_on = want;
+    // graphs captured with / without the probe event nodes must be rebuilt
     for (auto& kv : h->graphs_train) cudaGraphExecDestroy(kv.second);
     h->graphs_train.clear();
+    h->graph_kernels.clear();
     return SCORE_OK;
 }
 
