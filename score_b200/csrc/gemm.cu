@@ -1,4 +1,4 @@
-// Dense layers of the SCoRe path: one fp32 SGEMM with fused epilogues.
+// Dense layers of the SCoRe path: one fp32 SGEMM family with fused epilogues.
 //
 // Every tf.layers.dense on the path (score.py:69-74,156,172-177), the GRU input projection
 // (score.py:205-208) and all their backward contractions are tall-skinny fp32 products
@@ -7,9 +7,12 @@
 // the whole dense block is ~1-15 MFLOP/sample.
 //
 // Operands are addressed by (row stride, col stride) so the same kernel serves
-//   forward          C = act(A W + b)
-//   backward data    dA = (dC W^T) (*) relu/dropout mask
-//   backward weight  dW = A^T dC, split over the batch rows into fixed partials (+ bias colsum)
+//   forward          C = act(A W + b)                         A k-contiguous, W n-contiguous
+//   backward data    dA = (dC W^T) (*) relu/dropout mask      dC k-contiguous, W^T k-contiguous
+//   backward weight  dW = A^T dC, split over the batch rows   A^T m-contiguous, dC n-contiguous
+// Tiles are staged with a 3-stage cp.async pipeline (16-byte copies when the contiguous dimension
+// is 16-byte aligned, 4-byte copies otherwise); each operand is kept in shared memory in the
+// orientation of its contiguous global dimension so the copies never transpose.
 // Split partials are reduced in a fixed order by reduce_partials -> deterministic gradients.
 #include "kernels.h"
 
@@ -17,21 +20,69 @@ namespace score {
 
 int64_t g_launch_count = 0;
 
-template <int BM, int BN, int BK, int TM, int TN>
-__global__ void __launch_bounds__((BM / TM) * (BN / TN))
-gemm_kernel(GemmArgs p) {
-    constexpr int NT = (BM / TM) * (BN / TN);
-    constexpr int LA = BM * BK / NT;   // A elements per thread per tile
-    constexpr int LB = BN * BK / NT;
-    static_assert(BM * BK % NT == 0 && BN * BK % NT == 0, "tile/thread mismatch");
-    __shared__ __align__(16) float As[BK][BM + 4];
-    __shared__ __align__(16) float Bs[BK][BN + 4];
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4, STAGES = 3;
+constexpr int NT = (BM / TM) * (BN / TN);   // 256 threads
+constexpr int LDK = BK + 4;                 // row stride of a [rows][k] tile (k contiguous)
+constexpr int LDR = BM + 4;                 // row stride of a [k][rows] tile (rows contiguous); BM == BN
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async16_ca(void* smem_dst, const void* gmem_src, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+}
+
+// Stage one [64 rows x 16 k] operand tile.  KMAJ: the operand is k-contiguous in global memory and is kept as
+// tile[row][k]; otherwise it is row-contiguous and kept as tile[k][row].
+//   elem(row, k) = base[row * rs + k * cs]
+template <bool KMAJ>
+__device__ __forceinline__ void stage_tile(float* tile, const float* __restrict__ base, int64_t rs, int64_t cs,
+                                           int row0, int nrows, int k0, int k_end, bool vec, int tid) {
+    if (vec) {
+        if (KMAJ) {
+            const int r = tid >> 2, kq = (tid & 3) * 4;
+            const int gr = row0 + r, gk = k0 + kq;
+            int bytes = 0;
+            if (gr < nrows && gk < k_end) bytes = min(4, k_end - gk) * 4;
+            const float* src = bytes ? base + (int64_t)gr * rs + gk : base;
+            cp_async16_ca(tile + r * LDK + kq, src, bytes);
+        } else {
+            const int k = tid >> 4, rq = (tid & 15) * 4;
+            const int gr = row0 + rq, gk = k0 + k;
+            int bytes = 0;
+            if (gk < k_end && gr < nrows) bytes = min(4, nrows - gr) * 4;
+            const float* src = bytes ? base + (int64_t)gk * cs + gr : base;
+            cp_async16_ca(tile + k * LDR + rq, src, bytes);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + i * NT;
+            int r, k;
+            if (KMAJ) { k = idx & (BK - 1); r = idx >> 4; } else { r = idx & (BM - 1); k = idx >> 6; }
+            const int gr = row0 + r, gk = k0 + k;
+            const bool ok = gr < nrows && gk < k_end;
+            const float* src = ok ? base + (int64_t)gr * rs + (int64_t)gk * cs : base;
+            cp_async4(KMAJ ? tile + r * LDK + k : tile + k * LDR + r, src, ok ? 4 : 0);
+        }
+    }
+}
+
+template <bool A_KMAJ, bool B_KMAJ>
+__global__ void __launch_bounds__(NT) gemm_kernel(GemmArgs p) {
+    constexpr int A_TILE = A_KMAJ ? BM * LDK : BK * LDR;
+    constexpr int B_TILE = B_KMAJ ? BN * LDK : BK * LDR;
+    __shared__ __align__(16) float As[STAGES][A_TILE];
+    __shared__ __align__(16) float Bs[STAGES][B_TILE];
 
     const int tid = threadIdx.x;
     const int tx = tid % (BN / TN), ty = tid / (BN / TN);
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
 
-    // K range of this split
     int k_begin = 0, k_end = p.K;
     if (p.splits > 1) {
         int chunk = (p.K + p.splits - 1) / p.splits;
@@ -39,8 +90,11 @@ gemm_kernel(GemmArgs p) {
         k_begin = blockIdx.z * chunk;
         k_end = min(p.K, k_begin + chunk);
     }
-    const bool a_kcontig = (p.a_cs == 1);
-    const bool b_kcontig = (p.b_rs == 1 && p.b_cs != 1);
+    // 16-byte copies need the contiguous dimension's base and leading stride 16-byte aligned
+    const bool a_vec = A_KMAJ ? (((p.a_rs & 3) == 0) && ((((uintptr_t)p.A) & 15) == 0) && ((k_begin & 3) == 0))
+                              : (((p.a_cs & 3) == 0) && ((((uintptr_t)p.A) & 15) == 0));
+    const bool b_vec = B_KMAJ ? (((p.b_cs & 3) == 0) && ((((uintptr_t)p.B) & 15) == 0) && ((k_begin & 3) == 0))
+                              : (((p.b_rs & 3) == 0) && ((((uintptr_t)p.B) & 15) == 0));
 
     float acc[TM][TN];
 #pragma unroll
@@ -52,78 +106,68 @@ gemm_kernel(GemmArgs p) {
     for (int j = 0; j < TN; ++j) csum[j] = 0.f;
     const bool do_colsum = (p.colsum != nullptr) && blockIdx.x == 0 && ty == 0;
 
-    float ra[LA], rb[LB];
-    auto load_tiles = [&](int k0) {
-#pragma unroll
-        for (int i = 0; i < LA; ++i) {
-            int idx = tid + i * NT;
-            int m, k;
-            if (a_kcontig) { k = idx % BK; m = idx / BK; } else { m = idx % BM; k = idx / BM; }
-            int gm = m0 + m, gk = k0 + k;
-            ra[i] = (gm < p.M && gk < k_end) ? __ldg(p.A + (int64_t)gm * p.a_rs + (int64_t)gk * p.a_cs) : 0.f;
+    const int nk = (k_end > k_begin) ? (k_end - k_begin + BK - 1) / BK : 0;
+    auto issue = [&](int kt) {
+        if (kt < nk) {
+            const int s = kt % STAGES, k0 = k_begin + kt * BK;
+            // A: rows = m, elem(m,k) = A[m*a_rs + k*a_cs];  B: rows = n, elem(n,k) = B[k*b_rs + n*b_cs]
+            stage_tile<A_KMAJ>(As[s], p.A, p.a_rs, p.a_cs, m0, p.M, k0, k_end, a_vec, tid);
+            stage_tile<B_KMAJ>(Bs[s], p.B, p.b_cs, p.b_rs, n0, p.N, k0, k_end, b_vec, tid);
         }
-#pragma unroll
-        for (int i = 0; i < LB; ++i) {
-            int idx = tid + i * NT;
-            int n, k;
-            if (b_kcontig) { k = idx % BK; n = idx / BK; } else { n = idx % BN; k = idx / BN; }
-            int gn = n0 + n, gk = k0 + k;
-            rb[i] = (gn < p.N && gk < k_end) ? __ldg(p.B + (int64_t)gk * p.b_rs + (int64_t)gn * p.b_cs) : 0.f;
-        }
+        cp_async_commit();
     };
-    auto store_tiles = [&]() {
 #pragma unroll
-        for (int i = 0; i < LA; ++i) {
-            int idx = tid + i * NT;
-            int m, k;
-            if (a_kcontig) { k = idx % BK; m = idx / BK; } else { m = idx % BM; k = idx / BM; }
-            As[k][m] = ra[i];
-        }
-#pragma unroll
-        for (int i = 0; i < LB; ++i) {
-            int idx = tid + i * NT;
-            int n, k;
-            if (b_kcontig) { k = idx % BK; n = idx / BK; } else { n = idx % BN; k = idx / BN; }
-            Bs[k][n] = rb[i];
-        }
-    };
+    for (int s = 0; s < STAGES - 1; ++s) issue(s);
 
-    if (k_begin < k_end) {
-        load_tiles(k_begin);
-        store_tiles();
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<STAGES - 2>();
         __syncthreads();
-        for (int k0 = k_begin; k0 < k_end; k0 += BK) {
-            const bool more = (k0 + BK) < k_end;
-            if (more) load_tiles(k0 + BK);
+        issue(kt + STAGES - 1);   // refills the stage consumed in iteration kt-1 (all threads passed the barrier)
+        const float* a_t = As[kt % STAGES];
+        const float* b_t = Bs[kt % STAGES];
 #pragma unroll
-            for (int k = 0; k < BK; ++k) {
-                float a[TM], b[TN];
+        for (int kk = 0; kk < BK; kk += 4) {
+            float a[4][TM], b[4][TN];   // [k][row]
+            if (A_KMAJ) {
 #pragma unroll
-                for (int i = 0; i < TM; i += 4) {
-                    float4 t = *reinterpret_cast<const float4*>(&As[k][ty * TM + i]);
-                    a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+                for (int i = 0; i < TM; ++i) {
+                    float4 t = *reinterpret_cast<const float4*>(a_t + (ty * TM + i) * LDK + kk);
+                    a[0][i] = t.x; a[1][i] = t.y; a[2][i] = t.z; a[3][i] = t.w;
                 }
+            } else {
 #pragma unroll
-                for (int j = 0; j < TN; j += 4) {
-                    float4 t = *reinterpret_cast<const float4*>(&Bs[k][tx * TN + j]);
-                    b[j] = t.x; b[j + 1] = t.y; b[j + 2] = t.z; b[j + 3] = t.w;
+                for (int k = 0; k < 4; ++k) {
+                    float4 t = *reinterpret_cast<const float4*>(a_t + (kk + k) * LDR + ty * TM);
+                    a[k][0] = t.x; a[k][1] = t.y; a[k][2] = t.z; a[k][3] = t.w;
                 }
+            }
+            if (B_KMAJ) {
+#pragma unroll
+                for (int j = 0; j < TN; ++j) {
+                    float4 t = *reinterpret_cast<const float4*>(b_t + (tx * TN + j) * LDK + kk);
+                    b[0][j] = t.x; b[1][j] = t.y; b[2][j] = t.z; b[3][j] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float4 t = *reinterpret_cast<const float4*>(b_t + (kk + k) * LDR + tx * TN);
+                    b[k][0] = t.x; b[k][1] = t.y; b[k][2] = t.z; b[k][3] = t.w;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
 #pragma unroll
                 for (int i = 0; i < TM; ++i)
 #pragma unroll
-                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[k][i], b[k][j], acc[i][j]);
                 if (do_colsum) {
 #pragma unroll
-                    for (int j = 0; j < TN; ++j) csum[j] += b[j];
+                    for (int j = 0; j < TN; ++j) csum[j] += b[k][j];
                 }
-            }
-            __syncthreads();
-            if (more) {
-                store_tiles();
-                __syncthreads();
             }
         }
     }
+    cp_async_wait<0>();
 
     // ---- epilogue
     float* C = p.C;
@@ -138,11 +182,11 @@ gemm_kernel(GemmArgs p) {
     }
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
-        int gm = m0 + ty * TM + i;
+        const int gm = m0 + ty * TM + i;
         if (gm >= p.M) continue;
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-            int gn = n0 + tx * TN + j;
+            const int gn = n0 + tx * TN + j;
             if (gn >= p.N) continue;
             float v = acc[i][j];
             float* dst = C + (int64_t)gm * p.c_rs + gn;
@@ -172,17 +216,24 @@ gemm_kernel(GemmArgs p) {
         float* cs = p.colsum + (int64_t)blockIdx.z * p.colsum_split_stride;
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-            int gn = n0 + tx * TN + j;
+            const int gn = n0 + tx * TN + j;
             if (gn < p.N) cs[gn] = csum[j];
         }
     }
 }
 
+}  // namespace
+
 void launch_gemm(cudaStream_t st, const GemmArgs& a) {
     if (a.M <= 0 || a.N <= 0) return;
-    constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
     dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, a.splits > 1 ? a.splits : 1);
-    gemm_kernel<BM, BN, BK, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, st>>>(a);
+    // orientation of each operand = its contiguous global dimension (k-contiguous wins a tie)
+    const bool a_kmaj = (a.a_cs == 1);
+    const bool b_kmaj = (a.b_rs == 1) && (a.b_cs != 1);
+    if (a_kmaj && b_kmaj) gemm_kernel<true, true><<<grid, NT, 0, st>>>(a);
+    else if (a_kmaj && !b_kmaj) gemm_kernel<true, false><<<grid, NT, 0, st>>>(a);
+    else if (!a_kmaj && b_kmaj) gemm_kernel<false, true><<<grid, NT, 0, st>>>(a);
+    else gemm_kernel<false, false><<<grid, NT, 0, st>>>(a);
     ++g_launch_count;
 }
 

@@ -36,7 +36,7 @@ struct Buf {
     void* ptr; size_t count; int dtype;   // 0 float32, 1 int32
 };
 
-enum Probe { PR_COATT_FWD = 0, PR_COATT_BWD, PR_EMB_UPDATE, PR_SORT, PR_STEP, PR_COUNT };
+enum Probe { PR_COATT_FWD = 0, PR_COATT_BWD, PR_EMB_UPDATE, PR_SORT, PR_STEP, PR_FWD_DENSE, PR_BWD_DENSE, PR_CATCHUP, PR_COUNT };
 
 }  // namespace
 
@@ -45,8 +45,10 @@ struct ScoreModel {
     int device = 0;
     std::string err;
     Dims dm;                        // dm.B / offsets are per call
-    cudaStream_t st = nullptr, st2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t st = nullptr, st2 = nullptr, st_w = nullptr;   // main, sort branch, weight-gradient branch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_l2 = nullptr, ev_w = nullptr;
+    cudaEvent_t ev_pool[16] = {nullptr}; int ev_next = 0;
+    bool side_w = false;   // a step is being enqueued with the weight-gradient branch forked
 
     // parameters
     std::vector<Tensor> tensors;
@@ -397,7 +399,12 @@ void gemm_bwd_weight(ScoreModel* h, const float* A, int lda, const float* dC, in
     g.splits = kSplits; g.c_split_stride = h->n_dense;
     g.colsum = (b_off >= 0) ? h->PG + b_off : nullptr; g.colsum_split_stride = h->n_dense;
     g.hp = h->hyper_dev;
-    launch_gemm(h->st, g);
+    // weight gradients are off the critical path: they only feed the final reduce, so they run on the
+    // side stream, ordered after the producer of dC by an event
+    cudaEvent_t e = h->ev_pool[h->ev_next++ & 15];
+    cudaEventRecord(e, h->st);
+    cudaStreamWaitEvent(h->st_w, e, 0);
+    launch_gemm(h->st_w, g);
 }
 
 void probe_begin(ScoreModel* h, int p, cudaStream_t s) {
@@ -418,7 +425,10 @@ void enqueue_forward(ScoreModel* h) {
     auto W = [&](const std::string& n) { return pp(h, (n + "/kernel").c_str()); };
     auto Bi = [&](const std::string& n) { return pp(h, (n + "/bias").c_str()); };
 
-    launch_l2_sum(h->st, h->P, h->flags, (int)h->n_dense, h->l2sum);
+    // 0.5*sum(v^2) only feeds the loss scalar: side stream
+    cudaStreamWaitEvent(h->st_w, h->ev_fork, 0);
+    launch_l2_sum(h->st_w, h->P, h->flags, (int)h->n_dense, h->l2sum);
+    cudaEventRecord(h->ev_l2, h->st_w);
 
     TargetArgs ta{};
     ta.emb = h->emb; ta.keys = h->keys;
@@ -435,6 +445,7 @@ void enqueue_forward(ScoreModel* h) {
     launch_coatt_fwd(h->st, dm, ca);
     probe_end(h, PR_COATT_FWD, h->st);
 
+    probe_begin(h, PR_FWD_DENSE, h->st);
     const char* sides[2] = {"gru_user_side", "gru_item_side"};
     GruArgs ga{};
     ga.length = h->length;
@@ -466,7 +477,9 @@ void enqueue_forward(ScoreModel* h) {
     gemm_fwd(h, h->g1, 200, pp(h, "fc2/kernel"), 80, pp(h, "fc2/bias"), h->g2, 80, B, 80, 200, EPI_BIAS_RELU_DROP, 2);
     launch_head(h->st, B, 80, h->g2, pp(h, "fc3/kernel"), pp(h, "fc3/bias"), h->label, h->hyper_dev, h->y, h->loss_b,
                 h->dlogit);
+    cudaStreamWaitEvent(h->st, h->ev_l2, 0);
     launch_loss_final(h->st, B, h->loss_b, h->l2sum, h->hyper_dev, h->loss_dev);
+    probe_end(h, PR_FWD_DENSE, h->st);
 }
 
 void enqueue_backward(ScoreModel* h) {
@@ -478,6 +491,7 @@ void enqueue_backward(ScoreModel* h) {
     auto Wo = [&](const std::string& n) { return po(h, (n + "/kernel").c_str()); };
     auto Bo = [&](const std::string& n) { return po(h, (n + "/bias").c_str()); };
 
+    probe_begin(h, PR_BWD_DENSE, h->st);
     cudaMemsetAsync(h->PG, 0, sizeof(float) * h->n_dense * kSplits, h->st);
 
     // prediction MLP
@@ -523,6 +537,7 @@ void enqueue_backward(ScoreModel* h) {
         gemm_bwd_data(h, h->dpx[s] + 2 * H, 3 * H, W(c), H, h->dx[s], Ds, M, Ds, H, EPI_ACCUM);
     }
 
+    probe_end(h, PR_BWD_DENSE, h->st);
     // co-attention + gather backward: per-position embedding gradient rows
     CoattBwdArgs cb{};
     cb.emb = h->emb; cb.keys = h->keys; cb.length = h->length;
@@ -540,6 +555,8 @@ void enqueue_backward(ScoreModel* h) {
     launch_coatt_grad_reduce(h->st, dm, h->coatt_part, h->n_coatt_part, h->target_part, h->n_target_part,
                              h->PG + Wo(nm.co_item), h->PG + Bo(nm.co_item), h->PG + Wo(nm.co_user),
                              h->PG + Bo(nm.co_user));
+    cudaEventRecord(h->ev_w, h->st_w);
+    cudaStreamWaitEvent(h->st, h->ev_w, 0);
     launch_reduce_partials(h->st, h->PG, kSplits, (int)h->n_dense, h->G);
 }
 
@@ -565,11 +582,14 @@ void enqueue_step(ScoreModel* h, int mode) {
     const bool need_bwd = (mode != MODE_EVAL);
     probe_begin(h, PR_STEP, h->st);
     launch_build_keys(h->st, dm, h->ids, h->length, h->keys, h->err_flag);
-    if (h->cfg.adam_mode == SCORE_ADAM_LAZY)
+    if (h->cfg.adam_mode == SCORE_ADAM_LAZY) {
+        probe_begin(h, PR_CATCHUP, h->st);
         launch_emb_catchup_rows(h->st, h->keys, dm.N, h->emb, h->emb_m, h->emb_v, h->last_step, dm.d, h->alpha_hist,
                                 h->hyper_dev);
+        probe_end(h, PR_CATCHUP, h->st);
+    }
+    cudaEventRecord(h->ev_fork, h->st);
     if (need_bwd) {   // the sort depends on ids only: run it on the side stream under forward/backward
-        cudaEventRecord(h->ev_fork, h->st);
         cudaStreamWaitEvent(h->st2, h->ev_fork, 0);
         probe_begin(h, PR_SORT, h->st2);
         h->sort_out = launch_sort_pairs(h->st2, h->sb, h->keys, dm.N, key_bits(dm.V));
@@ -757,7 +777,10 @@ int score_create(const ScoreConfig* cfg, int device, ScoreHandle* out) {
     }
     if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->st_w, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_l2, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_w, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         h->err = "stream/event creation failed";
         return die(SCORE_ERR_CUDA);
@@ -766,6 +789,7 @@ int score_create(const ScoreConfig* cfg, int device, ScoreHandle* out) {
         cudaEventCreate(&h->pr_beg[p]); cudaEventCreate(&h->pr_end[p]);
         h->pr_ms[p] = 0; h->pr_n[p] = 0;
     }
+    for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&h->ev_pool[i], cudaEventDisableTiming);
     build_registry(h);
     int rc = alloc_params(h);
     if (rc) return die(rc);
@@ -790,6 +814,10 @@ int score_destroy(ScoreHandle h) {
     if (h->err_host) cudaFreeHost(h->err_host);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_l2) cudaEventDestroy(h->ev_l2);
+    if (h->ev_w) cudaEventDestroy(h->ev_w);
+    for (int i = 0; i < 16; ++i) if (h->ev_pool[i]) cudaEventDestroy(h->ev_pool[i]);
+    if (h->st_w) cudaStreamDestroy(h->st_w);
     if (h->st) {
         for (int p = 0; p < PR_COUNT; ++p) { cudaEventDestroy(h->pr_beg[p]); cudaEventDestroy(h->pr_end[p]); }
         cudaStreamDestroy(h->st);
@@ -1126,7 +1154,8 @@ int score_enable_probes(ScoreHandle h, int on) {
     return SCORE_OK;
 }
 
-// out[2*p] = accumulated ms, out[2*p+1] = samples, for p in coatt_fwd, coatt_bwd, emb_update, sort, step
+// out[2*p] = accumulated ms, out[2*p+1] = samples, for p in coatt_fwd, coatt_bwd, emb_update, sort, step,
+// fwd_dense, bwd_dense, catchup
 int score_probe_times(ScoreHandle h, double* out, int n) {
     if (!h || !out) return SCORE_ERR_ARG;
     for (int p = 0; p < PR_COUNT && 2 * p + 1 < n; ++p) { out[2 * p] = h->pr_ms[p]; out[2 * p + 1] = (double)h->pr_n[p]; }

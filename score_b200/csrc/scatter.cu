@@ -100,7 +100,10 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 8;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
 
-size_t sort_hist_elems(int64_t n) { return (size_t)256 * ((n + SORT_TILE - 1) / SORT_TILE) + 1; }
+size_t sort_hist_elems(int64_t n) {
+    size_t total = (size_t)256 * ((n + SORT_TILE - 1) / SORT_TILE);
+    return total + (total + 1023) / 1024 + 1;   // histogram + one total per 1024-entry scan chunk
+}
 
 __global__ void sort_hist_kernel(const int32_t* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ hist,
                                  int nblocks) {
@@ -117,29 +120,40 @@ __global__ void sort_hist_kernel(const int32_t* __restrict__ keys, int64_t n, in
     hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
 }
 
-// in-place exclusive scan of `total` counters by one block of 1024 threads
-__global__ void sort_scan_kernel(uint32_t* __restrict__ hist, int total) {
-    __shared__ uint32_t sums[1024];
-    const int chunk = (total + 1023) / 1024;
-    const int lo = threadIdx.x * chunk, hi = min(total, lo + chunk);
-    uint32_t s = 0;
-    for (int i = lo; i < hi; ++i) s += hist[i];
-    sums[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {   // Hillis-Steele inclusive scan
-        uint32_t add = (threadIdx.x >= o) ? sums[threadIdx.x - o] : 0u;
-        __syncthreads();
-        sums[threadIdx.x] += add;
-        __syncthreads();
+// Exclusive scan of the (digit-major, tile-minor) histogram in two fully parallel kernels:
+//   sort_scan_local: each block of 1024 scans its own 1024-entry chunk in place and publishes the chunk total;
+//   the consumer (sort_scatter_kernel) adds the prefix of the chunk totals on the fly (<= a few hundred adds).
+__global__ void sort_scan_local_kernel(uint32_t* __restrict__ hist, int total, uint32_t* __restrict__ chunk_sums) {
+    __shared__ uint32_t wsum[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 1024 + threadIdx.x;
+    const uint32_t v = (i < total) ? hist[i] : 0u;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(FULL_MASK, x, o);
+        if (lane >= o) x += y;
     }
-    uint32_t run = (threadIdx.x == 0) ? 0u : sums[threadIdx.x - 1];
-    for (int i = lo; i < hi; ++i) { uint32_t c = hist[i]; hist[i] = run; run += c; }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(FULL_MASK, w, o);
+            if (lane >= o) w += y;
+        }
+        wsum[lane] = w;
+    }
+    __syncthreads();
+    if (i < total) hist[i] = (warp ? wsum[warp - 1] : 0u) + (x - v);
+    if (threadIdx.x == 1023) chunk_sums[blockIdx.x] = wsum[31];
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
                     int32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out, int64_t n, int shift,
-                    const uint32_t* __restrict__ hist, int nblocks) {
+                    const uint32_t* __restrict__ hist, int nblocks, const uint32_t* __restrict__ chunk_sums) {
     constexpr int WARPS = SORT_THREADS / 32;
     __shared__ uint32_t whist[WARPS][256];
     __shared__ uint32_t gbase[256];
@@ -170,7 +184,11 @@ sort_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restri
         uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) { uint32_t c = whist[w][dgt]; whist[w][dgt] = run; run += c; }
-        gbase[dgt] = hist[(int64_t)dgt * nblocks + blockIdx.x];
+        const int64_t hidx = (int64_t)dgt * nblocks + blockIdx.x;
+        uint32_t pre = 0;
+        const int chunk = (int)(hidx >> 10);
+        for (int c = 0; c < chunk; ++c) pre += chunk_sums[c];   // prefix of the 1024-entry chunk totals
+        gbase[dgt] = hist[hidx] + pre;
     }
     __syncthreads();
 #pragma unroll
@@ -195,9 +213,11 @@ int launch_sort_pairs(cudaStream_t st, SortBufs& sb, const int32_t* keys_in, int
     for (int p = 0; p < passes; ++p) {
         out = p & 1;
         sort_hist_kernel<<<nblocks, SORT_THREADS, 0, st>>>(kin, n, 8 * p, sb.hist, nblocks);
-        sort_scan_kernel<<<1, 1024, 0, st>>>(sb.hist, 256 * nblocks);
+        const int total = 256 * nblocks, nchunks = (total + 1023) / 1024;
+        uint32_t* chunk_sums = sb.hist + total;   // tail of the histogram allocation
+        sort_scan_local_kernel<<<nchunks, 1024, 0, st>>>(sb.hist, total, chunk_sums);
         sort_scatter_kernel<<<nblocks, SORT_THREADS, 0, st>>>(kin, vin, sb.keys[out], sb.vals[out], n, 8 * p, sb.hist,
-                                                             nblocks);
+                                                             nblocks, chunk_sums);
         g_launch_count += 3;
         kin = sb.keys[out];
         vin = sb.vals[out];
@@ -208,28 +228,59 @@ int launch_sort_pairs(cudaStream_t st, SortBufs& sb, const int32_t* keys_in, int
 // ------------------------------------------------------------------------------------------ segment reduce + row Adam
 // One group of d/4 lanes per sorted index; the group at the head of a run of equal keys sums the
 // run's gradient rows in sorted (= ascending position) order and updates the row.
-__global__ void emb_update_kernel(EmbUpdateArgs a) {
+__global__ void __launch_bounds__(256, 6) emb_update_kernel(EmbUpdateArgs a) {
     const int lpr = a.d >> 2;
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / lpr;
     const int sub = threadIdx.x % lpr;
     if (gid >= a.n) return;
-    const int32_t key = a.skeys[gid];
-    if (key == 0) return;
-    if (gid > 0 && a.skeys[gid - 1] == key) return;
+    // load batch 1 (independent): the previous key and the first four (key, position) pairs of the run
+    const int32_t k_prev = gid > 0 ? a.skeys[gid - 1] : -1;
+    int32_t kk[4], pp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int64_t idx = gid + u;
+        const bool in = idx < a.n;
+        kk[u] = in ? a.skeys[idx] : 0;
+        pp[u] = in ? a.spos[idx] : 0;
+    }
+    const int32_t key = kk[0];
+    if (key == 0 || k_prev == key) return;   // dummy / masked position, or not the head of its run
+    // load batch 2 (independent): the row's optimizer state and the run's gradient rows
+    const int64_t off = (int64_t)key * a.d + sub * 4;
+    float4 var, m, v;
+    if (a.mode == 0) {
+        var = *reinterpret_cast<const float4*>(a.emb + off);
+        m = *reinterpret_cast<const float4*>(a.m + off);
+        v = *reinterpret_cast<const float4*>(a.v + off);
+    }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t j = gid; j < a.n && a.skeys[j] == key; ++j) {
-        const float4 g = *reinterpret_cast<const float4*>(a.grad_rows + (int64_t)a.spos[j] * a.d + sub * 4);
-        acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+    // walk the run four entries at a time; the additions stay in sorted (= ascending position) order
+    for (int64_t j = gid;;) {
+        int cnt = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cnt += (cnt == u && kk[u] == key) ? 1 : 0;
+        float4 g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (u < cnt) g[u] = *reinterpret_cast<const float4*>(a.grad_rows + (int64_t)pp[u] * a.d + sub * 4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (u < cnt) { acc.x += g[u].x; acc.y += g[u].y; acc.z += g[u].z; acc.w += g[u].w; }
+        if (cnt < 4) break;
+        j += 4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t idx = j + u;
+            const bool in = idx < a.n;
+            kk[u] = in ? a.skeys[idx] : 0;
+            pp[u] = in ? a.spos[idx] : 0;
+        }
     }
     if (a.mode == 1) {
         *reinterpret_cast<float4*>(a.out_rows + gid * a.d + sub * 4) = acc;
         if (sub == 0) a.out_heads[gid] = key;
         return;
     }
-    const int64_t off = (int64_t)key * a.d + sub * 4;
-    float4 var = *reinterpret_cast<float4*>(a.emb + off);
-    float4 m = *reinterpret_cast<float4*>(a.m + off);
-    float4 v = *reinterpret_cast<float4*>(a.v + off);
     adam4(var, m, v, acc, a.hp->alpha);
     *reinterpret_cast<float4*>(a.emb + off) = var;
     *reinterpret_cast<float4*>(a.m + off) = m;
@@ -275,23 +326,29 @@ __device__ __forceinline__ void replay4(float4& var, float4& m, float4& v, int f
     for (int s = from + 1; s <= upto; ++s) adam4(var, m, v, z, alpha_hist[s]);
 }
 // one group per gathered position; the group that wins the atomic claim of the row replays it
-__global__ void emb_catchup_rows_kernel(const int32_t* __restrict__ keys, int64_t n, float* __restrict__ emb,
-                                        float* __restrict__ m, float* __restrict__ v, int32_t* __restrict__ last_step,
-                                        int d, const float* __restrict__ alpha_hist, const Hyper* hp) {
+__global__ void __launch_bounds__(256, 6)
+emb_catchup_rows_kernel(const int32_t* __restrict__ keys, int64_t n, float* __restrict__ emb,
+                        float* __restrict__ m, float* __restrict__ v, int32_t* __restrict__ last_step,
+                        int d, const float* __restrict__ alpha_hist, const Hyper* hp) {
     const int lpr = d >> 2;
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / lpr;
     const int sub = threadIdx.x % lpr;
     const int upto = hp->step - 1;
-    int32_t key = (gid < n) ? keys[gid] : 0;
+    const int32_t key = (gid < n) ? keys[gid] : 0;
+    // cheap pre-check (plain load) so that rows that are already current - every duplicate position after the
+    // first claim, and everything in the first step - skip the atomic and the state loads
+    int seen = upto;
+    if (key != 0 && sub == 0) seen = last_step[key];
+    seen = __shfl_sync(FULL_MASK, seen, 0, lpr);
     int old = upto;
-    if (key != 0 && sub == 0) old = atomicExch(&last_step[key], upto);
+    if (key != 0 && seen < upto && sub == 0) old = atomicExch(&last_step[key], upto);
     old = __shfl_sync(FULL_MASK, old, 0, lpr);
     if (key == 0 || old >= upto) return;
     const int64_t off = (int64_t)key * d + sub * 4;
     float4 mm = *reinterpret_cast<float4*>(m + off);
     float4 vv = *reinterpret_cast<float4*>(v + off);
-    if (all_zero(mm) && all_zero(vv)) return;
     float4 var = *reinterpret_cast<float4*>(emb + off);
+    if (all_zero(mm) && all_zero(vv)) return;
     replay4(var, mm, vv, old, upto, alpha_hist);
     *reinterpret_cast<float4*>(emb + off) = var;
     *reinterpret_cast<float4*>(m + off) = mm;

@@ -337,27 +337,36 @@ void launch_bn_fwd(cudaStream_t st, int B, int F, const float* x, const float* g
     bn_fwd_kernel<<<(n + 255) / 256, 256, 0, st>>>(B, F, x, gamma, beta, mean, var, z);
     ++g_launch_count;
 }
-// dx = dz * inv ; dgamma_c = sum_b dz (x - mean)/sqrt(var+eps) ; dbeta_c = sum_b dz   (one thread per column, fixed order)
+// dx = dz * inv ; dgamma_c = sum_b dz (x - mean)/sqrt(var+eps) ; dbeta_c = sum_b dz
+// block = 32 columns x 32 row groups; fixed-order tree over the row groups (deterministic)
 __global__ void bn_bwd_kernel(int B, int F, const float* __restrict__ x, const float* __restrict__ dz,
                               const float* __restrict__ gamma, const float* __restrict__ mean,
                               const float* __restrict__ var, float* __restrict__ dx, float* __restrict__ dgamma,
                               float* __restrict__ dbeta) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= F) return;
-    float rstd = 1.0f / sqrtf(var[c] + 1e-3f);
-    float inv = gamma[c] * rstd, mu = mean[c];
+    __shared__ float rg[32][33], rb[32][33];
+    const int c = blockIdx.x * 32 + threadIdx.x, ry = threadIdx.y;
     float sg = 0.f, sb = 0.f;
-    for (int b = 0; b < B; ++b) {
-        float d = dz[(int64_t)b * F + c];
-        sg += d * ((x[(int64_t)b * F + c] - mu) * rstd);
-        sb += d;
-        dx[(int64_t)b * F + c] = d * inv;
+    if (c < F) {
+        const float rstd = 1.0f / sqrtf(var[c] + 1e-3f);
+        const float inv = gamma[c] * rstd, mu = mean[c];
+        for (int b = ry; b < B; b += 32) {
+            const float d = dz[(int64_t)b * F + c];
+            sg += d * ((x[(int64_t)b * F + c] - mu) * rstd);
+            sb += d;
+            dx[(int64_t)b * F + c] = d * inv;
+        }
     }
-    dgamma[c] = sg; dbeta[c] = sb;
+    rg[ry][threadIdx.x] = sg; rb[ry][threadIdx.x] = sb;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) {
+        if (ry < o) { rg[ry][threadIdx.x] += rg[ry + o][threadIdx.x]; rb[ry][threadIdx.x] += rb[ry + o][threadIdx.x]; }
+        __syncthreads();
+    }
+    if (ry == 0 && c < F) { dgamma[c] = rg[0][threadIdx.x]; dbeta[c] = rb[0][threadIdx.x]; }
 }
 void launch_bn_bwd(cudaStream_t st, int B, int F, const float* x, const float* dz, const float* gamma,
                    const float* mean, const float* var, float* dx, float* dgamma, float* dbeta) {
-    bn_bwd_kernel<<<(F + 63) / 64, 64, 0, st>>>(B, F, x, dz, gamma, mean, var, dx, dgamma, dbeta);
+    bn_bwd_kernel<<<(F + 31) / 32, dim3(32, 32), 0, st>>>(B, F, x, dz, gamma, mean, var, dx, dgamma, dbeta);
     ++g_launch_count;
 }
 

@@ -201,9 +201,9 @@ class SCOREBASE(object):
         self._check(self._lib.score_enable_probes(self._h, 1 if on else 0))
 
     def probe_times(self):
-        out = np.zeros(10, np.float64)
-        self._lib.score_probe_times(self._h, out.ctypes.data, 10)
-        names = ["coatt_fwd", "coatt_bwd", "emb_update", "sort", "step"]
+        out = np.zeros(16, np.float64)
+        self._lib.score_probe_times(self._h, out.ctypes.data, 16)
+        names = ["coatt_fwd", "coatt_bwd", "emb_update", "sort", "step", "fwd_dense", "bwd_dense", "catchup"]
         return {n: (out[2 * i], int(out[2 * i + 1])) for i, n in enumerate(names)}
 
     def last_step_stats(self):

@@ -24,8 +24,6 @@ def _check_fb(rep, tol=pu.REL_TOL):
     for k, v in rep.items():
         if isinstance(v, bool):
             continue
-        if any(k == "grad/" + n for n in SHIFT_INVARIANT):
-            continue
         assert v <= tol, "%s: relative error %.3e" % (k, v)
 
 
