@@ -135,6 +135,21 @@ int score_restore(ScoreHandle h, const char* path);
 int score_eval_metrics(ScoreHandle h, const float* preds, const int32_t* target_iids,
                        const int32_t* labels, int64_t n, int32_t group, double* out9);
 
+/* Multi-GPU split step (one process per GPU; the collectives themselves are issued by the host side with
+ * torch.distributed / NCCL on score_stream(), between these calls).  There is no reference counterpart: the
+ * reference is single-device; the split keeps SCOREBASE.train's arithmetic.
+ *   data-parallel, replicated table:  score_step_begin -> all-reduce "dense_grad", all-gather "keys" and
+ *       "grad_rows" -> score_step_finish(gathered keys, gathered rows)  (identical update on every replica)
+ *   row-sharded table (owner = id % world):  score_prepare_batch -> all-to-all ids -> score_gather_rows on the
+ *       owners -> all-to-all rows -> score_step_begin(staged table) -> all-reduce "dense_grad", all-to-all
+ *       "grad_rows" to the owners -> score_step_finish(owned keys, owned rows).                              */
+int score_prepare_batch(ScoreHandle h, const ScoreBatch* batch);
+int score_device_buffer(ScoreHandle h, const char* name, void** dev_ptr, size_t* count);
+int score_gather_rows(ScoreHandle h, const int32_t* idx_dev, int64_t n, float* out_dev);
+int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg_lambda, float keep_prob,
+                     int32_t global_batch, int32_t train, const float* staged_table, const int32_t* staged_keys);
+int score_step_finish(ScoreHandle h, const int32_t* ext_keys, const float* ext_rows, int64_t n_ext, float* loss2);
+
 /* The CUDA stream every call of this handle is ordered on (a cudaStream_t). */
 int score_stream(ScoreHandle h, void** cuda_stream);
 
@@ -142,7 +157,8 @@ int score_stream(ScoreHandle h, void** cuda_stream);
  * score_launch_count: kernels launched by this library since the handle was created.
  * score_enable_probes / score_probe_times: CUDA-event timing of named kernels inside the timed
  *   train steps, on the stream they are launched on.  out[2*p] = accumulated ms, out[2*p+1] = number
- *   of samples, p = 0 coatt_fwd (gather), 1 coatt_bwd, 2 emb_update (scatter+Adam), 3 sort, 4 whole step.
+ *   of samples, p = 0 coatt_fwd (gather), 1 coatt_bwd, 2 emb_update (scatter+Adam), 3 sort, 4 whole step,
+ *   5 dense forward, 6 dense backward, 7 lazy catch-up.
  * score_last_step_stats: out3 = { positions N, live positions (non-zero key), unique rows U } of the
  *   last train step - the factors of the algorithmic byte counts in DESIGN.md. */
 int64_t score_launch_count(ScoreHandle h);

@@ -47,6 +47,11 @@ SYMBOLS = {
     "score_save": (C.c_int, [_H, C.c_char_p]),
     "score_restore": (C.c_int, [_H, C.c_char_p]),
     "score_eval_metrics": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "score_prepare_batch": (C.c_int, [_H, C.POINTER(ScoreBatch)]),
+    "score_device_buffer": (C.c_int, [_H, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "score_gather_rows": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p]),
+    "score_step_begin": (C.c_int, [_H, C.POINTER(ScoreBatch), _F, _F, _F, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "score_step_finish": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "score_stream": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "score_launch_count": (C.c_int64, [_H]),
     "score_enable_probes": (C.c_int, [_H, C.c_int]),

@@ -182,6 +182,7 @@ struct EmbUpdateArgs {
     const int32_t* skeys; const int32_t* spos; int64_t n;
     const float* grad_rows; int d;
     float* emb; float* m; float* v; int32_t* last_step;
+    const float* alpha_hist;       // LAZY: rows that are not current through step-1 are replayed first (may be null)
     const Hyper* hp;
     int mode;                      // 0: apply Adam, 1: export (seg sums to out_rows at head index, no update)
     float* out_rows; int32_t* out_heads;
@@ -197,6 +198,10 @@ void launch_emb_catchup_rows(cudaStream_t st, const int32_t* keys, int64_t n, fl
 // LAZY mode: bring the whole table up to `upto_step` (before read-back / save / eval of everything)
 void launch_emb_catchup_all(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d,
                             const float* alpha_hist, int upto_step);
+
+// out[i] = table[idx[i]] (idx 0 -> zeros; out-of-range -> zeros + error flag): owner side of a sharded gather
+void launch_gather_rows(cudaStream_t st, const float* table, const int32_t* idx, int64_t n, int d, int64_t V, float* out,
+                        int32_t* err_flag);
 
 // device-side TF-default initialisers
 void launch_init_trunc_normal(cudaStream_t st, float* p, int64_t n, uint64_t seed, uint32_t stream_id);

@@ -79,7 +79,7 @@ struct ScoreModel {
     int sort_out = 0;
     float *seg_rows = nullptr; int32_t* seg_heads = nullptr; int64_t seg_cap = 0;
     int64_t last_N = 0;
-    float *l2sum = nullptr, *loss_dev = nullptr;
+    float *l2sum = nullptr, *loss_dev = nullptr;   // loss_dev[0] = total loss, loss_dev[1] = reg_lambda * l2 part
     int32_t* err_flag = nullptr;
     Hyper* hyper_dev = nullptr;
     // pinned host staging
@@ -87,8 +87,12 @@ struct ScoreModel {
     float* loss_host = nullptr;
     int32_t* err_host = nullptr;
 
-    // external emb-grad source (multi-GPU replicated table)
-    const int32_t* ext_keys = nullptr; const float* ext_rows = nullptr; int64_t ext_n = 0;
+    // table / key list the forward and backward kernels read: the handle's own, or a staged per-batch
+    // mini-table when the embedding rows live on other ranks (row-sharded tables)
+    const float* emb_fwd = nullptr; const int32_t* keys_fwd = nullptr;
+    // sort buffers for externally supplied (key, gradient row) lists (multi-GPU finish)
+    SortBufs sb_ext{}; int64_t sb_ext_cap = 0;
+    bool begun = false; float begun_lr = 0.f;
 
     // graphs
     std::map<int, cudaGraphExec_t> graphs_train;
@@ -213,12 +217,12 @@ int alloc_params(ScoreModel* h) {
             for (int64_t i = 0; i < t.rows * t.cols; ++i) fl[t.off + i] = t.flags;
     CK(cudaMemcpy(h->flags, fl.data(), n, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&h->l2sum, sizeof(float)));
-    CK(cudaMalloc(&h->loss_dev, sizeof(float)));
+    CK(cudaMalloc(&h->loss_dev, 2 * sizeof(float)));
     CK(cudaMalloc(&h->err_flag, sizeof(int32_t)));
     CK(cudaMemsetAsync(h->err_flag, 0, sizeof(int32_t), h->st));
     CK(cudaMalloc(&h->hyper_dev, sizeof(Hyper)));
     CK(cudaMallocHost(&h->hyper_host, sizeof(Hyper)));
-    CK(cudaMallocHost(&h->loss_host, sizeof(float)));
+    CK(cudaMallocHost(&h->loss_host, 2 * sizeof(float)));
     CK(cudaMallocHost(&h->err_host, sizeof(int32_t)));
     if (h->cfg.adam_mode == SCORE_ADAM_LAZY) {
         h->alpha_cap = 1 << 20;
@@ -431,13 +435,13 @@ void enqueue_forward(ScoreModel* h) {
     cudaEventRecord(h->ev_l2, h->st_w);
 
     TargetArgs ta{};
-    ta.emb = h->emb; ta.keys = h->keys;
+    ta.emb = h->emb_fwd; ta.keys = h->keys_fwd;
     ta.w_item = W(nm.co_item); ta.b_item = Bi(nm.co_item); ta.w_user = W(nm.co_user); ta.b_user = Bi(nm.co_user);
     ta.q0 = h->q0; ta.fc_in = h->fc_in; ta.fc_off = Dfc - Ds; ta.c_item = h->c_item; ta.c_user = h->c_user;
     launch_target_fwd(h->st, dm, ta);
 
     CoattArgs ca{};
-    ca.emb = h->emb; ca.keys = h->keys; ca.length = h->length;
+    ca.emb = h->emb_fwd; ca.keys = h->keys_fwd; ca.length = h->length;
     ca.w_item = W(nm.co_item); ca.w_user = W(nm.co_user); ca.c_item = h->c_item; ca.c_user = h->c_user;
     ca.xhg_u = h->xhg[0]; ca.xhc_u = h->xhc[0]; ca.xhg_i = h->xhg[1]; ca.xhc_i = h->xhc[1];
     ca.key = h->key; ca.ldkey = Dk; ca.key_off = 2 * H; ca.save_r = h->save_r; ca.save_w = h->save_w;
@@ -540,7 +544,7 @@ void enqueue_backward(ScoreModel* h) {
     probe_end(h, PR_BWD_DENSE, h->st);
     // co-attention + gather backward: per-position embedding gradient rows
     CoattBwdArgs cb{};
-    cb.emb = h->emb; cb.keys = h->keys; cb.length = h->length;
+    cb.emb = h->emb_fwd; cb.keys = h->keys_fwd; cb.length = h->length;
     cb.w_item = W(nm.co_item); cb.w_user = W(nm.co_user); cb.save_r = h->save_r; cb.save_w = h->save_w;
     cb.dxu = h->dx[0]; cb.dxi = h->dx[1]; cb.dkey = h->dkey; cb.ldkey = Dk; cb.key_off = 2 * H;
     cb.grad_rows = h->grad_rows; cb.sdz = h->sdz; cb.partials = h->coatt_part; cb.n_partials = h->n_coatt_part;
@@ -580,6 +584,7 @@ void enqueue_step(ScoreModel* h, int mode) {
     const Dims& dm = h->dm;
     const bool train = (mode == MODE_TRAIN);
     const bool need_bwd = (mode != MODE_EVAL);
+    h->emb_fwd = h->emb; h->keys_fwd = h->keys;
     probe_begin(h, PR_STEP, h->st);
     launch_build_keys(h->st, dm, h->ids, h->length, h->keys, h->err_flag);
     if (h->cfg.adam_mode == SCORE_ADAM_LAZY) {
@@ -616,6 +621,7 @@ void enqueue_step(ScoreModel* h, int mode) {
         ea.skeys = h->sb.keys[h->sort_out]; ea.spos = h->sb.vals[h->sort_out]; ea.n = dm.N;
         ea.grad_rows = h->grad_rows; ea.d = dm.d;
         ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.last_step = h->last_step;
+        ea.alpha_hist = h->alpha_hist;
         ea.hp = h->hyper_dev; ea.mode = 0;
         probe_begin(h, PR_EMB_UPDATE, h->st);
         launch_emb_update(h->st, ea);
@@ -656,7 +662,7 @@ int flush_lazy(ScoreModel* h) {
 }
 
 int finish_sync(ScoreModel* h, float* loss_out) {
-    CK(cudaMemcpyAsync(h->loss_host, h->loss_dev, sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(h->loss_host, h->loss_dev, 2 * sizeof(float), cudaMemcpyDeviceToHost, h->st));
     CK(cudaMemcpyAsync(h->err_host, h->err_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     CK(cudaGetLastError());
@@ -1132,6 +1138,162 @@ int score_eval_metrics(ScoreHandle h, const float* preds, const int32_t* target_
     out9[8] = 0.0;
     return SCORE_OK;
 }
+
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------ multi-GPU split step
+namespace {
+
+int ensure_ext_sort(ScoreModel* h, int64_t n) {
+    if (n <= h->sb_ext_cap) return SCORE_OK;
+    for (int i = 0; i < 2; ++i) { if (h->sb_ext.keys[i]) cudaFree(h->sb_ext.keys[i]); if (h->sb_ext.vals[i]) cudaFree(h->sb_ext.vals[i]); }
+    if (h->sb_ext.hist) cudaFree(h->sb_ext.hist);
+    int64_t cap = n + n / 4 + 1024;
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaMalloc(&h->sb_ext.keys[i], sizeof(int32_t) * cap));
+        CK(cudaMalloc(&h->sb_ext.vals[i], sizeof(int32_t) * cap));
+    }
+    CK(cudaMalloc(&h->sb_ext.hist, sizeof(uint32_t) * sort_hist_elems(cap)));
+    h->sb_ext_cap = cap;
+    return SCORE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Upload a batch and build its sanitized key list (ids of masked slices -> 0, range check) without running the
+// model; afterwards score_device_buffer(h, "keys") is valid.  First stage of a row-sharded step.
+int score_prepare_batch(ScoreHandle h, const ScoreBatch* batch) {
+    if (!h) return SCORE_ERR_ARG;
+    int rc = check_batch(h, batch);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const int B = batch->batch_size;
+    rc = ensure_workspace(h, B > h->cfg.max_batch ? B : h->cfg.max_batch);
+    if (rc) return rc;
+    set_batch_dims(h, B);
+    rc = upload_batch(h, batch);
+    if (rc) return rc;
+    h->last_N = h->dm.N;
+    Dims dm = h->dm;
+    dm.V = ((int64_t)1 << 31) - 1;   // ids are GLOBAL row numbers here; the owner checks the range
+    launch_build_keys(h->st, dm, h->ids, h->length, h->keys, h->err_flag);
+    return SCORE_OK;
+}
+
+// Device pointers of per-step buffers for the host-side exchange (torch.distributed on score_stream()):
+// "keys" int32 [N], "grad_rows" float [N,d], "dense_grad" float [n_dense], "y_pred" float [B].
+int score_device_buffer(ScoreHandle h, const char* name, void** dev_ptr, size_t* count) {
+    if (!h || !name || !dev_ptr || !count) return SCORE_ERR_ARG;
+    std::string n(name);
+    if (n == "keys") { *dev_ptr = h->keys; *count = (size_t)h->last_N; }
+    else if (n == "grad_rows") { *dev_ptr = h->grad_rows; *count = (size_t)h->last_N * h->dm.d; }
+    else if (n == "dense_grad") { *dev_ptr = h->G; *count = (size_t)h->n_dense; }
+    else if (n == "y_pred") { *dev_ptr = h->y; *count = (size_t)h->dm.B; }
+    else return fail(h, SCORE_ERR_NAME, "unknown device buffer: " + n);
+    return SCORE_OK;
+}
+
+// Owner side of a row-sharded gather: out[i] = current value of local row idx[i] (idx 0 -> zeros).  In LAZY mode the
+// requested rows are first brought up to date.  All pointers are device pointers; ordered on score_stream().
+int score_gather_rows(ScoreHandle h, const int32_t* idx_dev, int64_t n, float* out_dev) {
+    if (!h || (n > 0 && (!idx_dev || !out_dev))) return SCORE_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (n == 0) return SCORE_OK;
+    fill_hyper(h, 1, 0.f, 0.f, 1.f, 0, 1);
+    CK(cudaMemcpyAsync(h->hyper_dev, h->hyper_host, sizeof(Hyper), cudaMemcpyHostToDevice, h->st));
+    if (h->cfg.adam_mode == SCORE_ADAM_LAZY)
+        launch_emb_catchup_rows(h->st, idx_dev, n, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.d, h->alpha_hist,
+                                h->hyper_dev);
+    launch_gather_rows(h->st, h->emb, idx_dev, n, h->dm.d, h->dm.V, out_dev, h->err_flag);
+    return SCORE_OK;
+}
+
+// Forward + backward of one local batch WITHOUT the optimizer update; the loss mean uses 1/global_batch.
+// batch == NULL reuses the batch of score_prepare_batch.  staged_table / staged_keys (device, may be NULL)
+// replace the handle's table and key list for the gathers: staged_keys[p] indexes staged_table rows.
+// Afterwards "dense_grad" and "grad_rows" hold this rank's contributions.
+int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg_lambda, float keep_prob,
+                     int32_t global_batch, int32_t train, const float* staged_table, const int32_t* staged_keys) {
+    if (!h) return SCORE_ERR_ARG;
+    if (h->dm.model_type != SCORE_MODEL_SCORE) return fail(h, SCORE_ERR_ARG, "model_type not implemented yet");
+    CK(cudaSetDevice(h->device));
+    if (batch) {
+        int rc = check_batch(h, batch);
+        if (rc) return rc;
+        const int B = batch->batch_size;
+        rc = ensure_workspace(h, B > h->cfg.max_batch ? B : h->cfg.max_batch);
+        if (rc) return rc;
+        set_batch_dims(h, B);
+        rc = upload_batch(h, batch);
+        if (rc) return rc;
+        h->last_N = h->dm.N;
+    } else if (h->dm.B <= 0) {
+        return fail(h, SCORE_ERR_ARG, "no prepared batch");
+    }
+    if (train && h->cfg.adam_mode == SCORE_ADAM_LAZY && h->step + 2 >= h->alpha_cap)
+        return fail(h, SCORE_ERR_ARG, "lazy Adam step history exhausted");
+    const Dims& dm = h->dm;
+    fill_hyper(h, dm.B, lr, reg_lambda, train ? keep_prob : 1.0f, train, global_batch);
+    CK(cudaMemcpyAsync(h->hyper_dev, h->hyper_host, sizeof(Hyper), cudaMemcpyHostToDevice, h->st));
+    h->last_mode = MODE_BEGIN;
+    cudaEventRecord(h->ev_fork, h->st);
+    if (staged_table) {
+        h->emb_fwd = staged_table; h->keys_fwd = staged_keys;
+    } else {
+        h->emb_fwd = h->emb; h->keys_fwd = h->keys;
+        if (batch) launch_build_keys(h->st, dm, h->ids, h->length, h->keys, h->err_flag);
+        if (h->cfg.adam_mode == SCORE_ADAM_LAZY)
+            launch_emb_catchup_rows(h->st, h->keys, dm.N, h->emb, h->emb_m, h->emb_v, h->last_step, dm.d,
+                                    h->alpha_hist, h->hyper_dev);
+    }
+    enqueue_forward(h);
+    if (train) enqueue_backward(h);
+    h->begun = train != 0;
+    h->begun_lr = lr;
+    CK(cudaGetLastError());
+    return SCORE_OK;
+}
+
+// Optimizer half of the split step: dense Adam on the (all-reduced) "dense_grad" buffer and the deterministic
+// sort + segment-reduce + row Adam over an externally assembled (key, gradient row) list - the concatenation of
+// every rank's positions for a replicated table, or the rows this rank owns for a sharded one.
+// loss2[0] = this rank's loss (data part uses 1/global_batch) incl. the L2 term, loss2[1] = the L2 term alone.
+int score_step_finish(ScoreHandle h, const int32_t* ext_keys, const float* ext_rows, int64_t n_ext, float* loss2) {
+    if (!h) return SCORE_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (h->begun) {
+        if (n_ext >= ((int64_t)1 << 31)) return fail(h, SCORE_ERR_ARG, "too many gradient rows for int32 positions");
+        launch_dense_adam(h->st, h->P, h->M1, h->V1, h->G, h->flags, (int)h->n_dense, h->hyper_dev, h->alpha_hist);
+        if (n_ext > 0) {
+            int rc = ensure_ext_sort(h, n_ext);
+            if (rc) return rc;
+            const int out = launch_sort_pairs(h->st, h->sb_ext, ext_keys, n_ext, key_bits(h->dm.V));
+            EmbUpdateArgs ea{};
+            ea.skeys = h->sb_ext.keys[out]; ea.spos = h->sb_ext.vals[out]; ea.n = n_ext;
+            ea.grad_rows = ext_rows; ea.d = h->dm.d;
+            ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.last_step = h->last_step;
+            ea.alpha_hist = h->alpha_hist; ea.hp = h->hyper_dev; ea.mode = 0;
+            launch_emb_update(h->st, ea);
+        }
+        if (h->cfg.adam_mode == SCORE_ADAM_DENSE)
+            launch_emb_dense_sweep(h->st, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.V, h->dm.d, h->hyper_dev);
+        h->step += 1;
+        h->beta1_power = h->beta1_power * 0.9f;
+        h->beta2_power = h->beta2_power * 0.999f;
+        h->begun = false;
+    }
+    float l = 0.f;
+    int rc = finish_sync(h, &l);
+    if (loss2) { loss2[0] = h->loss_host[0]; loss2[1] = h->loss_host[1]; }
+    return rc;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 int score_stream(ScoreHandle h, void** cuda_stream) {
     if (!h || !cuda_stream) return SCORE_ERR_ARG;

@@ -225,6 +225,12 @@ int launch_sort_pairs(cudaStream_t st, SortBufs& sb, const int32_t* keys_in, int
     return out;
 }
 
+// LAZY mode: replay the zero-gradient steps (from, upto] of one row chunk, same op sequence as the sweep.
+__device__ __forceinline__ void replay4(float4& var, float4& m, float4& v, int from, int upto,
+                                        const float* __restrict__ alpha_hist) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = from + 1; s <= upto; ++s) adam4(var, m, v, z, alpha_hist[s]);
+}
 // ------------------------------------------------------------------------------------------ segment reduce + row Adam
 // One group of d/4 lanes per sorted index; the group at the head of a run of equal keys sums the
 // run's gradient rows in sorted (= ascending position) order and updates the row.
@@ -281,7 +287,16 @@ __global__ void __launch_bounds__(256, 6) emb_update_kernel(EmbUpdateArgs a) {
         if (sub == 0) a.out_heads[gid] = key;
         return;
     }
+    if (a.alpha_hist) {   // LAZY: a row another rank gathered may not be current here yet
+        const int last = a.last_step[key], upto = a.hp->step - 1;
+        if (last < upto && !(all_zero(m) && all_zero(v))) replay4(var, m, v, last, upto, a.alpha_hist);
+    }
     adam4(var, m, v, acc, a.hp->alpha);
+    {   // every lane of the row group (identical control flow) has read last_step before lane 0 overwrites it
+        const int lane = threadIdx.x & 31;
+        const unsigned gmask = (lpr >= 32) ? FULL_MASK : (((1u << lpr) - 1u) << (lane & ~(lpr - 1)));
+        __syncwarp(gmask);
+    }
     *reinterpret_cast<float4*>(a.emb + off) = var;
     *reinterpret_cast<float4*>(a.m + off) = m;
     *reinterpret_cast<float4*>(a.v + off) = v;
@@ -319,12 +334,6 @@ void launch_emb_dense_sweep(cudaStream_t st, float* emb, float* m, float* v, int
     ++g_launch_count;
 }
 
-// LAZY mode: replay the zero-gradient steps (from, upto] of one row chunk, same op sequence as the sweep.
-__device__ __forceinline__ void replay4(float4& var, float4& m, float4& v, int from, int upto,
-                                        const float* __restrict__ alpha_hist) {
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = from + 1; s <= upto; ++s) adam4(var, m, v, z, alpha_hist[s]);
-}
 // one group per gathered position; the group that wins the atomic claim of the row replays it
 __global__ void __launch_bounds__(256, 6)
 emb_catchup_rows_kernel(const int32_t* __restrict__ keys, int64_t n, float* __restrict__ emb,
@@ -393,6 +402,27 @@ void launch_emb_catchup_all(cudaStream_t st, float* emb, float* m, float* v, int
     emb_catchup_all_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(emb, m, v, last_step, V, d, alpha_hist, upto);
     set_last_step_kernel<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(last_step, V, upto);
     g_launch_count += 2;
+}
+
+// ------------------------------------------------------------------------------------------ plain row gather
+__global__ void gather_rows_kernel(const float* __restrict__ table, const int32_t* __restrict__ idx, int64_t n, int d,
+                                   int64_t V, float* __restrict__ out, int32_t* __restrict__ err_flag) {
+    const int lpr = d >> 2;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = t / lpr;
+    const int sub = (int)(t - i * lpr);
+    if (i >= n) return;
+    int32_t id = idx[i];
+    if (id < 0 || id >= V) { atomicExch(err_flag, 1); id = 0; }
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (id != 0) v = *reinterpret_cast<const float4*>(table + (int64_t)id * d + sub * 4);
+    *reinterpret_cast<float4*>(out + i * d + sub * 4) = v;
+}
+void launch_gather_rows(cudaStream_t st, const float* table, const int32_t* idx, int64_t n, int d, int64_t V, float* out,
+                        int32_t* err_flag) {
+    const int64_t threads = n * (d >> 2);
+    gather_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(table, idx, n, d, V, out, err_flag);
+    ++g_launch_count;
 }
 
 // ------------------------------------------------------------------------------------------ initialisers

@@ -409,7 +409,11 @@ __global__ void loss_final_kernel(int B, const float* __restrict__ loss_b, const
         if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) loss[0] = red[0] * hp->inv_batch + hp->reg_lambda * l2sum[0];
+    if (threadIdx.x == 0) {
+        const float reg = hp->reg_lambda * l2sum[0];
+        loss[0] = red[0] * hp->inv_batch + reg;
+        loss[1] = reg;
+    }
 }
 void launch_loss_final(cudaStream_t st, int B, const float* loss_b, const float* l2sum, const Hyper* hp, float* loss) {
     loss_final_kernel<<<1, 256, 0, st>>>(B, loss_b, l2sum, hp, loss);

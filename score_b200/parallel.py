@@ -1,8 +1,193 @@
-"""Multi-GPU training of the SCoRe hot path: one process per GPU, torch.distributed (NCCL) for the exchange.
+"""Multi-GPU stepping of the SCoRe hot path: one process per GPU, torch.distributed (NCCL over
+NVLink/NVSwitch) for the exchanges, the C-ABI split step (score_step_begin / score_step_finish) for the math.
 
-Placeholder until the data-parallel step lands (multi-GPU)."""
+The reference is single-device; both schemes keep SCOREBASE.train's arithmetic
+(score.py:101-116) on the GLOBAL batch:
+
+* ``DataParallelTrainer`` - replicated table (Tmall / Taobao / CCMR sizes).  Samples are independent (BN runs in
+  inference mode, the loss is a batch mean), so each rank runs forward/backward on its shard with 1/global_B
+  scaling; dense gradients are summed with ONE all-reduce of one flat buffer; the per-position embedding
+  gradient rows and their keys are all-gathered and every replica applies the SAME deterministic
+  sort + segment-reduce + Adam, so replicas stay bit-identical without ever broadcasting the table.
+
+* ``ShardedEmbeddingTrainer`` - row-sharded table (large-vocab config): owner(id) = id % world, local row
+  = id // world + 1 (local row 0 is the dummy).  Forward: bucket ids by owner -> all-to-all ids -> owners gather
+  (lazy-Adam catch-up first) -> all-to-all rows back -> a per-batch staged mini-table feeds the unchanged
+  kernels.  Backward: all-to-all (local row, gradient row) to the owners -> owner-side sort / reduce / Adam.
+
+The pure-torch exchange helpers below run on CPU tensors with the gloo backend too (tests/test_parallel_cpu.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _capi
+from .model import TRAIN_KEEP_PROB, _Batch
 
 
-class DataParallelTrainer:
-    def __init__(self, model, world, rank):
-        raise NotImplementedError("data-parallel stepping is not implemented yet")
+# ------------------------------------------------------------------------------------------ exchange helpers
+class ExchangePlan:
+    """How one rank's flat position list is bucketed by owner for the all-to-all."""
+
+    def __init__(self, keys: torch.Tensor, world: int, group=None):
+        n = keys.numel()
+        k64 = keys.to(torch.int64)
+        nz = k64 != 0
+        owner = torch.where(nz, k64 % world, torch.full_like(k64, world))   # dummy positions -> bucket `world`
+        self.order = torch.argsort(owner, stable=True)                       # grouped by owner, position order inside
+        counts = torch.bincount(owner, minlength=world + 1)[:world]
+        recv = torch.empty_like(counts)
+        dist.all_to_all_single(recv, counts, group=group)
+        self.send_counts = counts.tolist()                                   # host sync: sizes of the exchange
+        self.recv_counts = recv.tolist()
+        self.n_valid = int(sum(self.send_counts))
+        self.n_recv = int(sum(self.recv_counts))
+        self.sel = self.order[:self.n_valid]                                 # positions that have a real row
+        self.send_local_rows = (k64[self.sel] // world + 1).to(torch.int32)  # owner-local row numbers
+        self.mini_keys = torch.where(nz, torch.arange(1, n + 1, device=keys.device), torch.zeros_like(k64)).to(torch.int32)
+        self.world, self.group, self.n = world, group, n
+
+    def exchange_ids(self):
+        """-> local row numbers this rank must serve, grouped by requesting rank."""
+        out = torch.empty(self.n_recv, dtype=torch.int32, device=self.send_local_rows.device)
+        dist.all_to_all_single(out, self.send_local_rows, self.recv_counts, self.send_counts, group=self.group)
+        return out
+
+    def return_rows(self, served_rows: torch.Tensor):
+        """owner -> requester: rows for `exchange_ids()` order come back in `sel` order; builds the staged table."""
+        d = served_rows.shape[1]
+        got = torch.empty(self.n_valid, d, dtype=served_rows.dtype, device=served_rows.device)
+        dist.all_to_all_single(got, served_rows, self.send_counts, self.recv_counts, group=self.group)
+        staged = torch.zeros(self.n + 1, d, dtype=served_rows.dtype, device=served_rows.device)
+        staged[self.sel + 1] = got
+        return staged
+
+    def send_grads(self, grad_rows: torch.Tensor):
+        """requester -> owner: per-position gradient rows, aligned with `exchange_ids()`."""
+        d = grad_rows.shape[1]
+        out = torch.empty(self.n_recv, d, dtype=grad_rows.dtype, device=grad_rows.device)
+        dist.all_to_all_single(out, grad_rows[self.sel].contiguous(), self.recv_counts, self.send_counts, group=self.group)
+        return out
+
+
+def shard_rows(n_rows_global: int, world: int) -> int:
+    """rows of one rank's local table (incl. the local dummy row 0)."""
+    return (n_rows_global + world - 1) // world + 1
+
+
+def global_to_local_table(table: torch.Tensor, world: int, rank: int) -> torch.Tensor:
+    """slice a global [V,d] table into rank's local layout (row 1 + v // world for v % world == rank)."""
+    mine = table[rank::world]
+    out = torch.zeros(shard_rows(table.shape[0], world), table.shape[1], dtype=table.dtype)
+    out[1:1 + mine.shape[0]] = mine
+    return out
+
+
+# ------------------------------------------------------------------------------------------ device plumbing
+class _DevView:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class _Base:
+    def __init__(self, model, world, rank, group=None):
+        self.m, self.world, self.rank, self.group = model, int(world), int(rank), group
+        self.lib = model._lib
+        self.h = model._h
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.stream = torch.cuda.ExternalStream(model.stream(), device=self.device)
+
+    def _dev(self, name, dtype):
+        ptr, cnt = C.c_void_p(), C.c_size_t()
+        self.m._check(self.lib.score_device_buffer(self.h, name.encode(), C.byref(ptr), C.byref(cnt)))
+        if cnt.value == 0:
+            return torch.empty(0, dtype=dtype, device=self.device)
+        ts = "<f4" if dtype == torch.float32 else "<i4"
+        return torch.as_tensor(_DevView(ptr.value, (cnt.value,), ts), device=self.device)
+
+    def _global_loss(self, loss2):
+        """sum over ranks of the data term (already scaled by 1/global_B) + the L2 term once."""
+        t = torch.tensor([loss2[0] - loss2[1]], dtype=torch.float64, device=self.device)
+        dist.all_reduce(t, group=self.group)
+        return float(t.item()) + float(loss2[1])
+
+
+class DataParallelTrainer(_Base):
+    """Dense data-parallel training with a replicated embedding table (BASELINE.json config 4)."""
+
+    def train(self, sess, batch_data, lr, reg_lambda, keep_prob=TRAIN_KEEP_PROB, want_loss=True):
+        b = _Batch(batch_data, self.m.cfg)
+        gb = b.B * self.world
+        with torch.cuda.stream(self.stream):
+            self.m._check(self.lib.score_step_begin(self.h, C.byref(b.struct), lr, reg_lambda, keep_prob, gb, 1, None, None))
+            g = self._dev("dense_grad", torch.float32)
+            dist.all_reduce(g, group=self.group)
+            keys = self._dev("keys", torch.int32)
+            rows = self._dev("grad_rows", torch.float32)
+            all_keys = torch.empty(self.world * keys.numel(), dtype=torch.int32, device=self.device)
+            all_rows = torch.empty(self.world * rows.numel(), dtype=torch.float32, device=self.device)
+            dist.all_gather_into_tensor(all_keys, keys, group=self.group)
+            dist.all_gather_into_tensor(all_rows, rows, group=self.group)
+            loss2 = (C.c_float * 2)()
+            self.m._check(self.lib.score_step_finish(self.h, all_keys.data_ptr(), all_rows.data_ptr(),
+                                                     all_keys.numel(), loss2))
+            return self._global_loss(loss2) if want_loss else None
+
+    def train_async(self, batch_data, lr, reg_lambda, keep_prob=TRAIN_KEEP_PROB):
+        self.train(None, batch_data, lr, reg_lambda, keep_prob, want_loss=False)
+
+    def eval(self, sess, batch_data, reg_lambda):
+        return self.m.eval(sess, batch_data, reg_lambda)   # replicas are identical
+
+
+class ShardedEmbeddingTrainer(_Base):
+    """Row-sharded embedding table + data-parallel dense part (BASELINE.json config 5).
+
+    ``model`` must have been built with feature_size = shard_rows(V_global, world)."""
+
+    def _fetch(self, b):
+        self.m._check(self.lib.score_prepare_batch(self.h, C.byref(b.struct)))
+        keys = self._dev("keys", torch.int32)
+        plan = ExchangePlan(keys, self.world, self.group)
+        want = plan.exchange_ids()
+        d = self.m.cfg["eb_dim"]
+        served = torch.empty(plan.n_recv, d, dtype=torch.float32, device=self.device)
+        self.m._check(self.lib.score_gather_rows(self.h, want.data_ptr(), plan.n_recv, served.data_ptr()))
+        staged = plan.return_rows(served)
+        return plan, want, staged
+
+    def train(self, sess, batch_data, lr, reg_lambda, keep_prob=TRAIN_KEEP_PROB, want_loss=True):
+        b = _Batch(batch_data, self.m.cfg)
+        gb = b.B * self.world
+        d = self.m.cfg["eb_dim"]
+        with torch.cuda.stream(self.stream):
+            plan, want, staged = self._fetch(b)
+            self.m._check(self.lib.score_step_begin(self.h, None, lr, reg_lambda, keep_prob, gb, 1,
+                                                    staged.data_ptr(), plan.mini_keys.data_ptr()))
+            g = self._dev("dense_grad", torch.float32)
+            dist.all_reduce(g, group=self.group)
+            grad_rows = self._dev("grad_rows", torch.float32).view(-1, d)
+            owned = plan.send_grads(grad_rows)
+            loss2 = (C.c_float * 2)()
+            self.m._check(self.lib.score_step_finish(self.h, want.data_ptr(), owned.data_ptr(), plan.n_recv, loss2))
+            return self._global_loss(loss2) if want_loss else None
+
+    def train_async(self, batch_data, lr, reg_lambda, keep_prob=TRAIN_KEEP_PROB):
+        self.train(None, batch_data, lr, reg_lambda, keep_prob, want_loss=False)
+
+    def eval(self, sess, batch_data, reg_lambda):
+        b = _Batch(batch_data, self.m.cfg)
+        with torch.cuda.stream(self.stream):
+            plan, want, staged = self._fetch(b)
+            self.m._check(self.lib.score_step_begin(self.h, None, 0.0, reg_lambda, 1.0, b.B, 0,
+                                                    staged.data_ptr(), plan.mini_keys.data_ptr()))
+            loss2 = (C.c_float * 2)()
+            self.m._check(self.lib.score_step_finish(self.h, None, None, 0, loss2))
+            preds = self._dev("y_pred", torch.float32).cpu().numpy().tolist()
+        lab = batch_data[6]
+        lab = lab.cpu().numpy() if hasattr(lab, "is_cuda") else lab
+        import numpy as np
+        return preds, np.asarray(lab).astype(np.int32).reshape(-1).tolist(), float(loss2[0])
