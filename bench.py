@@ -149,7 +149,10 @@ def workload_config(shape, args, global_batch):
             "global_batch": global_batch, "per_gpu_batch": shape.batch, "length": shape.length,
             "ids": "uniform" if not args.zipf else "zipf %.2f" % args.zipf,
             "adam": args.adam_mode, "cuda_graph": not args.no_graph,
-            "parallelism": "single GPU" if args.gpus == 1 else "dp%d (dense all-reduce + embedding-gradient all-gather)" % args.gpus,
+            "parallelism": {"single": "single GPU",
+                            "dp": "dp%d: replicated table, dense all-reduce + embedding-gradient all-gather" % args.gpus,
+                            "sharded": "dp%d dense + embedding rows sharded by id %% %d, all-to-all of ids / rows / gradient rows"
+                                       % (args.gpus, args.gpus)}[getattr(args, "par", "single")],
             "l2_policy": "inputs larger than L2: %.2f GB of embedding state (var+m+v), uniform-random rows, %d rotating "
                          "batches; no explicit flush" % (3 * shape.feature_size * shape.eb_dim * 4 / 1e9, POOL)}
 
@@ -166,6 +169,8 @@ def main():
     ap.add_argument("--zipf", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--parallel", default="auto", choices=["auto", "dp", "sharded"],
+                    help="N>1: dp = replicated table + gradient all-gather, sharded = row-sharded table + all-to-all")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -190,9 +195,16 @@ def main():
     from score_b200 import parallel
 
     B = shape.batch
-    m = sb.SCORE(*shape.ctor_args(), device=local, adam_mode=args.adam_mode, use_graph=not args.no_graph,
-                 seed=1111, max_batch=B)
-    trainer = parallel.DataParallelTrainer(m, world, rank) if world > 1 else None
+    par = args.parallel if args.parallel != "auto" else ("sharded" if shape.feature_size > 50_000_000 else "dp")
+    args.par = par if world > 1 else "single"
+    ctor = list(shape.ctor_args())
+    if world > 1 and par == "sharded":
+        ctor[0] = parallel.shard_rows(shape.feature_size, world)
+    m = sb.SCORE(*ctor, device=local, adam_mode=args.adam_mode, use_graph=(not args.no_graph) and world == 1,
+                 seed=1111 + (rank if par == "sharded" else 0), max_batch=B)
+    trainer = None
+    if world > 1:
+        trainer = (parallel.ShardedEmbeddingTrainer if par == "sharded" else parallel.DataParallelTrainer)(m, world, rank)
     stream = torch.cuda.ExternalStream(m.stream(), device=torch.device("cuda", local))
 
     host_pool = [make_batch(shape, batch=B, seed=1000 * (rank + 1) + i, zipf=args.zipf) for i in range(POOL)]

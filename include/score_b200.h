@@ -148,6 +148,8 @@ int score_device_buffer(ScoreHandle h, const char* name, void** dev_ptr, size_t*
 int score_gather_rows(ScoreHandle h, const int32_t* idx_dev, int64_t n, float* out_dev);
 int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg_lambda, float keep_prob,
                      int32_t global_batch, int32_t train, const float* staged_table, const int32_t* staged_keys);
+/* loss2 == NULL: enqueue only (no host synchronisation); otherwise loss2[0] = this rank's loss incl. the L2 term
+ * (data term scaled by 1/global_batch), loss2[1] = the L2 term alone. */
 int score_step_finish(ScoreHandle h, const int32_t* ext_keys, const float* ext_rows, int64_t n_ext, float* loss2);
 
 /* The CUDA stream every call of this handle is ordered on (a cudaStream_t). */

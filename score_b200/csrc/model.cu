@@ -82,7 +82,11 @@ struct ScoreModel {
     float *l2sum = nullptr, *loss_dev = nullptr;   // loss_dev[0] = total loss, loss_dev[1] = reg_lambda * l2 part
     int32_t* err_flag = nullptr;
     Hyper* hyper_dev = nullptr;
-    // pinned host staging
+    // pinned host staging.  hyper_ring: one slot per in-flight step so an asynchronous caller never overwrites a
+    // Hyper struct whose H2D copy has not executed yet; hyper_host points at the slot of the current call.
+    static constexpr int kHyperSlots = 32;
+    Hyper* hyper_ring = nullptr; cudaEvent_t hyper_ev[kHyperSlots] = {nullptr}; bool hyper_used[kHyperSlots] = {false};
+    int hyper_next = 0;
     Hyper* hyper_host = nullptr;
     float* loss_host = nullptr;
     int32_t* err_host = nullptr;
@@ -93,6 +97,7 @@ struct ScoreModel {
     // sort buffers for externally supplied (key, gradient row) lists (multi-GPU finish)
     SortBufs sb_ext{}; int64_t sb_ext_cap = 0;
     bool begun = false; float begun_lr = 0.f;
+    const int32_t* last_sorted = nullptr; int64_t last_sorted_n = 0;   // sorted key list of the last optimizer step
 
     // graphs
     std::map<int, cudaGraphExec_t> graphs_train;
@@ -221,7 +226,9 @@ int alloc_params(ScoreModel* h) {
     CK(cudaMalloc(&h->err_flag, sizeof(int32_t)));
     CK(cudaMemsetAsync(h->err_flag, 0, sizeof(int32_t), h->st));
     CK(cudaMalloc(&h->hyper_dev, sizeof(Hyper)));
-    CK(cudaMallocHost(&h->hyper_host, sizeof(Hyper)));
+    CK(cudaMallocHost(&h->hyper_ring, sizeof(Hyper) * ScoreModel::kHyperSlots));
+    for (int i = 0; i < ScoreModel::kHyperSlots; ++i) CK(cudaEventCreateWithFlags(&h->hyper_ev[i], cudaEventDisableTiming));
+    h->hyper_host = h->hyper_ring;
     CK(cudaMallocHost(&h->loss_host, 2 * sizeof(float)));
     CK(cudaMallocHost(&h->err_host, sizeof(int32_t)));
     if (h->cfg.adam_mode == SCORE_ADAM_LAZY) {
@@ -623,6 +630,7 @@ void enqueue_step(ScoreModel* h, int mode) {
         ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.last_step = h->last_step;
         ea.alpha_hist = h->alpha_hist;
         ea.hp = h->hyper_dev; ea.mode = 0;
+        h->last_sorted = ea.skeys; h->last_sorted_n = ea.n;
         probe_begin(h, PR_EMB_UPDATE, h->st);
         launch_emb_update(h->st, ea);
         probe_end(h, PR_EMB_UPDATE, h->st);
@@ -651,6 +659,18 @@ void fill_hyper(ScoreModel* h, int B, float lr, float reg_lambda, float keep_pro
     hp.inv_batch = 1.0f / (float)(global_batch > 0 ? global_batch : B);
     hp.seed_lo = (uint32_t)h->cfg.seed; hp.seed_hi = (uint32_t)(h->cfg.seed >> 32);
     hp.step = h->step + 1; hp.batch = B; hp.train = train; hp.pad0 = hp.pad1 = 0;
+}
+
+// fill the next ring slot and enqueue its H2D copy
+int upload_hyper(ScoreModel* h, int B, float lr, float reg_lambda, float keep_prob, int train, int global_batch) {
+    const int slot = h->hyper_next++ % ScoreModel::kHyperSlots;
+    if (h->hyper_used[slot]) CK(cudaEventSynchronize(h->hyper_ev[slot]));
+    h->hyper_host = h->hyper_ring + slot;
+    fill_hyper(h, B, lr, reg_lambda, keep_prob, train, global_batch);
+    CK(cudaMemcpyAsync(h->hyper_dev, h->hyper_host, sizeof(Hyper), cudaMemcpyHostToDevice, h->st));
+    CK(cudaEventRecord(h->hyper_ev[slot], h->st));
+    h->hyper_used[slot] = true;
+    return SCORE_OK;
 }
 
 int flush_lazy(ScoreModel* h) {
@@ -695,10 +715,10 @@ int run_step(ScoreModel* h, const ScoreBatch* b, int mode, float lr, float reg_l
     const bool train = (mode == MODE_TRAIN);
     if (train && h->cfg.adam_mode == SCORE_ADAM_LAZY && h->step + 2 >= h->alpha_cap)
         return fail(h, SCORE_ERR_ARG, "lazy Adam step history exhausted");
-    fill_hyper(h, B, lr, reg_lambda, (mode == MODE_EVAL) ? 1.0f : keep_prob, mode != MODE_EVAL, global_batch);
     rc = upload_batch(h, b);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h->hyper_dev, h->hyper_host, sizeof(Hyper), cudaMemcpyHostToDevice, h->st));
+    rc = upload_hyper(h, B, lr, reg_lambda, (mode == MODE_EVAL) ? 1.0f : keep_prob, mode != MODE_EVAL, global_batch);
+    if (rc) return rc;
     h->last_N = h->dm.N;
     h->last_mode = mode;
 
@@ -815,7 +835,8 @@ int score_destroy(ScoreHandle h) {
                     (void*)h->M1, (void*)h->V1, (void*)h->PG, (void*)h->flags, (void*)h->alpha_hist, (void*)h->l2sum,
                     (void*)h->loss_dev, (void*)h->err_flag, (void*)h->hyper_dev, (void*)h->seg_rows, (void*)h->seg_heads})
         if (p) cudaFree(p);
-    if (h->hyper_host) cudaFreeHost(h->hyper_host);
+    if (h->hyper_ring) cudaFreeHost(h->hyper_ring);
+    for (int i = 0; i < ScoreModel::kHyperSlots; ++i) if (h->hyper_ev[i]) cudaEventDestroy(h->hyper_ev[i]);
     if (h->loss_host) cudaFreeHost(h->loss_host);
     if (h->err_host) cudaFreeHost(h->err_host);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1202,8 +1223,10 @@ int score_gather_rows(ScoreHandle h, const int32_t* idx_dev, int64_t n, float* o
     if (!h || (n > 0 && (!idx_dev || !out_dev))) return SCORE_ERR_ARG;
     CK(cudaSetDevice(h->device));
     if (n == 0) return SCORE_OK;
-    fill_hyper(h, 1, 0.f, 0.f, 1.f, 0, 1);
-    CK(cudaMemcpyAsync(h->hyper_dev, h->hyper_host, sizeof(Hyper), cudaMemcpyHostToDevice, h->st));
+    {
+        int rc = upload_hyper(h, 1, 0.f, 0.f, 1.f, 0, 1);
+        if (rc) return rc;
+    }
     if (h->cfg.adam_mode == SCORE_ADAM_LAZY)
         launch_emb_catchup_rows(h->st, idx_dev, n, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.d, h->alpha_hist,
                                 h->hyper_dev);
@@ -1236,8 +1259,10 @@ int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg
     if (train && h->cfg.adam_mode == SCORE_ADAM_LAZY && h->step + 2 >= h->alpha_cap)
         return fail(h, SCORE_ERR_ARG, "lazy Adam step history exhausted");
     const Dims& dm = h->dm;
-    fill_hyper(h, dm.B, lr, reg_lambda, train ? keep_prob : 1.0f, train, global_batch);
-    CK(cudaMemcpyAsync(h->hyper_dev, h->hyper_host, sizeof(Hyper), cudaMemcpyHostToDevice, h->st));
+    {
+        int rc = upload_hyper(h, dm.B, lr, reg_lambda, train ? keep_prob : 1.0f, train, global_batch);
+        if (rc) return rc;
+    }
     h->last_mode = MODE_BEGIN;
     cudaEventRecord(h->ev_fork, h->st);
     if (staged_table) {
@@ -1276,6 +1301,7 @@ int score_step_finish(ScoreHandle h, const int32_t* ext_keys, const float* ext_r
             ea.grad_rows = ext_rows; ea.d = h->dm.d;
             ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.last_step = h->last_step;
             ea.alpha_hist = h->alpha_hist; ea.hp = h->hyper_dev; ea.mode = 0;
+            h->last_sorted = ea.skeys; h->last_sorted_n = ea.n;
             launch_emb_update(h->st, ea);
         }
         if (h->cfg.adam_mode == SCORE_ADAM_DENSE)
@@ -1285,9 +1311,10 @@ int score_step_finish(ScoreHandle h, const int32_t* ext_keys, const float* ext_r
         h->beta2_power = h->beta2_power * 0.999f;
         h->begun = false;
     }
+    if (!loss2) return SCORE_OK;   // asynchronous: the caller collects errors / the loss later with score_wait()
     float l = 0.f;
     int rc = finish_sync(h, &l);
-    if (loss2) { loss2[0] = h->loss_host[0]; loss2[1] = h->loss_host[1]; }
+    loss2[0] = h->loss_host[0]; loss2[1] = h->loss_host[1];
     return rc;
 }
 
@@ -1328,10 +1355,11 @@ int score_probe_times(ScoreHandle h, double* out, int n) {
 int score_last_step_stats(ScoreHandle h, int64_t* out3) {
     if (!h || !out3) return SCORE_ERR_ARG;
     CK(cudaSetDevice(h->device));
-    const int64_t N = h->last_N;
+    const int64_t N = h->last_sorted_n;
+    if (!h->last_sorted || N <= 0) return fail(h, SCORE_ERR_ARG, "no optimizer step has run yet");
     std::vector<int32_t> sk((size_t)N);
     CK(cudaStreamSynchronize(h->st));
-    CK(cudaMemcpy(sk.data(), h->sb.keys[h->sort_out], sizeof(int32_t) * N, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(sk.data(), h->last_sorted, sizeof(int32_t) * N, cudaMemcpyDeviceToHost));
     int64_t live = 0, uniq = 0;
     for (int64_t i = 0; i < N; ++i) {
         if (sk[i] == 0) continue;

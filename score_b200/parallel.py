@@ -123,15 +123,18 @@ class DataParallelTrainer(_Base):
         gb = b.B * self.world
         with torch.cuda.stream(self.stream):
             self.m._check(self.lib.score_step_begin(self.h, C.byref(b.struct), lr, reg_lambda, keep_prob, gb, 1, None, None))
+            self._keep_batch = b   # host id arrays stay alive until their H2D copies have run
             g = self._dev("dense_grad", torch.float32)
             dist.all_reduce(g, group=self.group)
             keys = self._dev("keys", torch.int32)
             rows = self._dev("grad_rows", torch.float32)
-            all_keys = torch.empty(self.world * keys.numel(), dtype=torch.int32, device=self.device)
-            all_rows = torch.empty(self.world * rows.numel(), dtype=torch.float32, device=self.device)
+            if getattr(self, "_all_keys", None) is None or self._all_keys.numel() != self.world * keys.numel():
+                self._all_keys = torch.empty(self.world * keys.numel(), dtype=torch.int32, device=self.device)
+                self._all_rows = torch.empty(self.world * rows.numel(), dtype=torch.float32, device=self.device)
+            all_keys, all_rows = self._all_keys, self._all_rows
             dist.all_gather_into_tensor(all_keys, keys, group=self.group)
             dist.all_gather_into_tensor(all_rows, rows, group=self.group)
-            loss2 = (C.c_float * 2)()
+            loss2 = (C.c_float * 2)() if want_loss else None
             self.m._check(self.lib.score_step_finish(self.h, all_keys.data_ptr(), all_rows.data_ptr(),
                                                      all_keys.numel(), loss2))
             return self._global_loss(loss2) if want_loss else None
@@ -165,14 +168,16 @@ class ShardedEmbeddingTrainer(_Base):
         d = self.m.cfg["eb_dim"]
         with torch.cuda.stream(self.stream):
             plan, want, staged = self._fetch(b)
+            self._keep_batch = b
             self.m._check(self.lib.score_step_begin(self.h, None, lr, reg_lambda, keep_prob, gb, 1,
                                                     staged.data_ptr(), plan.mini_keys.data_ptr()))
             g = self._dev("dense_grad", torch.float32)
             dist.all_reduce(g, group=self.group)
             grad_rows = self._dev("grad_rows", torch.float32).view(-1, d)
             owned = plan.send_grads(grad_rows)
-            loss2 = (C.c_float * 2)()
+            loss2 = (C.c_float * 2)() if want_loss else None
             self.m._check(self.lib.score_step_finish(self.h, want.data_ptr(), owned.data_ptr(), plan.n_recv, loss2))
+            self._keep = (plan, want, staged, owned)   # alive until the next step's kernels are enqueued behind them
             return self._global_loss(loss2) if want_loss else None
 
     def train_async(self, batch_data, lr, reg_lambda, keep_prob=TRAIN_KEEP_PROB):
