@@ -73,7 +73,11 @@ __device__ __forceinline__ void stage_tile(float* tile, const float* __restrict_
 }
 
 template <bool A_KMAJ, bool B_KMAJ>
-__global__ void __launch_bounds__(NT) gemm_kernel(GemmArgs p) {
+__global__ void __launch_bounds__(NT) gemm_kernel(GemmBatch batch) {
+    // blockIdx.z = problem * splits + split: independent problems of one launch share the grid
+    const int nsplit = batch.g[0].splits > 1 ? batch.g[0].splits : 1;
+    const GemmArgs& p = batch.g[blockIdx.z / nsplit];
+    const int split = blockIdx.z % nsplit;
     constexpr int A_TILE = A_KMAJ ? BM * LDK : BK * LDR;
     constexpr int B_TILE = B_KMAJ ? BN * LDK : BK * LDR;
     __shared__ __align__(16) float As[STAGES][A_TILE];
@@ -82,12 +86,13 @@ __global__ void __launch_bounds__(NT) gemm_kernel(GemmArgs p) {
     const int tid = threadIdx.x;
     const int tx = tid % (BN / TN), ty = tid / (BN / TN);
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    if (m0 >= p.M || n0 >= p.N) return;   // the grid is sized for the largest problem of the batch
 
     int k_begin = 0, k_end = p.K;
     if (p.splits > 1) {
         int chunk = (p.K + p.splits - 1) / p.splits;
         chunk = (chunk + BK - 1) / BK * BK;
-        k_begin = blockIdx.z * chunk;
+        k_begin = split * chunk;
         k_end = min(p.K, k_begin + chunk);
     }
     // 16-byte copies need the contiguous dimension's base and leading stride 16-byte aligned
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(NT) gemm_kernel(GemmArgs p) {
 
     // ---- epilogue
     float* C = p.C;
-    if (p.epi == EPI_SPLIT) C += (int64_t)blockIdx.z * p.c_split_stride;
+    if (p.epi == EPI_SPLIT) C += (int64_t)split * p.c_split_stride;
     float keep = 1.f;
     bool drop = false;
     uint32_t s_lo = 0, s_hi = 0, step = 0;
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(NT) gemm_kernel(GemmArgs p) {
         }
     }
     if (do_colsum) {
-        float* cs = p.colsum + (int64_t)blockIdx.z * p.colsum_split_stride;
+        float* cs = p.colsum + (int64_t)split * p.colsum_split_stride;
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
             const int gn = n0 + tx * TN + j;
@@ -224,17 +229,32 @@ __global__ void __launch_bounds__(NT) gemm_kernel(GemmArgs p) {
 
 }  // namespace
 
+// Independent problems with the same operand orientation and split count in ONE launch.
+void launch_gemm_batch(cudaStream_t st, const GemmArgs* list, int n) {
+    if (n <= 0) return;
+    GemmBatch b{};
+    int gm = 0, gn = 0;
+    const int nsplit = list[0].splits > 1 ? list[0].splits : 1;
+    for (int i = 0; i < n && i < 8; ++i) {
+        b.g[i] = list[i];
+        gm = max(gm, (list[i].M + BM - 1) / BM);
+        gn = max(gn, (list[i].N + BN - 1) / BN);
+    }
+    if (gm == 0 || gn == 0) return;
+    dim3 grid(gm, gn, n * nsplit);
+    // orientation of each operand = its contiguous global dimension (k-contiguous wins a tie)
+    const bool a_kmaj = (list[0].a_cs == 1);
+    const bool b_kmaj = (list[0].b_rs == 1) && (list[0].b_cs != 1);
+    if (a_kmaj && b_kmaj) gemm_kernel<true, true><<<grid, NT, 0, st>>>(b);
+    else if (a_kmaj && !b_kmaj) gemm_kernel<true, false><<<grid, NT, 0, st>>>(b);
+    else if (!a_kmaj && b_kmaj) gemm_kernel<false, true><<<grid, NT, 0, st>>>(b);
+    else gemm_kernel<false, false><<<grid, NT, 0, st>>>(b);
+    ++g_launch_count;
+}
+
 void launch_gemm(cudaStream_t st, const GemmArgs& a) {
     if (a.M <= 0 || a.N <= 0) return;
-    dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, a.splits > 1 ? a.splits : 1);
-    // orientation of each operand = its contiguous global dimension (k-contiguous wins a tie)
-    const bool a_kmaj = (a.a_cs == 1);
-    const bool b_kmaj = (a.b_rs == 1) && (a.b_cs != 1);
-    if (a_kmaj && b_kmaj) gemm_kernel<true, true><<<grid, NT, 0, st>>>(a);
-    else if (a_kmaj && !b_kmaj) gemm_kernel<true, false><<<grid, NT, 0, st>>>(a);
-    else if (!a_kmaj && b_kmaj) gemm_kernel<false, true><<<grid, NT, 0, st>>>(a);
-    else gemm_kernel<false, false><<<grid, NT, 0, st>>>(a);
-    ++g_launch_count;
+    launch_gemm_batch(st, &a, 1);
 }
 
 }  // namespace score

@@ -33,7 +33,10 @@ struct GemmArgs {
     float* colsum; int64_t colsum_split_stride;   // EPI_SPLIT: also sum_k B(k,n) -> bias gradient
     const Hyper* hp; uint32_t rng_stream;
 };
+struct GemmBatch { GemmArgs g[8]; };
 void launch_gemm(cudaStream_t st, const GemmArgs& a);
+// up to 8 independent problems (same operand orientation, same split count) in one launch
+void launch_gemm_batch(cudaStream_t st, const GemmArgs* list, int n);
 
 // ---------------------------------------------------------------- embedding front end (embed.cu)
 struct Dims {
@@ -129,7 +132,8 @@ void launch_att_inp_bwd(cudaStream_t st, const Dims& dm, const float* q, const f
 
 struct AttPoolArgs {
     const int32_t* length;
-    const float* f2;              // [M, 40]
+    const float* f2;              // [M, 40]   (used when s == nullptr)
+    const float* s;               // [M] raw scores precomputed by the fused attention chain, or nullptr
     const float* w3; const float* b3;
     const float* key; int ldkey;  // rep_t = key[:, 0:2H]
     float* score;                 // [B, T]
@@ -151,6 +155,43 @@ void launch_bn_fwd(cudaStream_t st, int B, int F, const float* x, const float* g
                    const float* mean, const float* var, float* z);
 void launch_bn_bwd(cudaStream_t st, int B, int F, const float* x, const float* dz, const float* gamma,
                    const float* mean, const float* var, float* dx, float* dgamma, float* dbeta);
+
+// fused prediction head (chain.cu): bn1 -> fc1 -> fc2 -> fc3 -> sigmoid -> per-sample loss and d loss / d logit
+struct FcArgs {
+    int B, F;
+    const float* fc_in; const float* gamma; const float* beta; const float* mean; const float* var;
+    const float* w1; const float* b1; const float* w2; const float* b2; const float* w3; const float* b3;
+    const int32_t* label; const Hyper* hp;
+    float* z0; float* g1; float* g2; float* y; float* loss_b; float* dlogit;
+};
+void launch_fc_fwd(cudaStream_t st, const FcArgs& a);
+struct FcBwdArgs {
+    int B, F;
+    const float* dlogit; const float* g2; const float* g1;
+    const float* w3; const float* w2; const float* w1; const float* gamma; const float* var;
+    const Hyper* hp;
+    float* dg2; float* dg1; float* dz0; float* dfc_in;
+};
+void launch_fc_bwd(cudaStream_t st, const FcBwdArgs& a);
+// fused attention MLP chain (chain.cu): forward writes a1 (for the first layer's weight gradient), f1, f2 and raw scores s
+struct AttChainArgs {
+    int64_t M; int T, Dk;
+    const float* q; const float* key;
+    const float* w1; const float* b1; const float* w2; const float* b2; const float* w3; const float* b3;
+    float* a1; float* f1; float* f2; float* s;
+};
+void launch_att_fwd(cudaStream_t st, const AttChainArgs& a);
+struct AttChainBwdArgs {
+    int64_t M; int T, Dk, acc_cols;
+    const float* ds; const float* f2; const float* f1; const float* q; const float* key;
+    const float* w3; const float* w2; const float* w1;
+    float* df2; float* df1; float* dkey; float* dq_row;
+};
+void launch_att_bwd(cudaStream_t st, const AttChainBwdArgs& a);   // requires Dk <= 128
+void launch_dq_reduce(cudaStream_t st, int B, int T, int Dk, const float* dq_row, float* dq);
+// dgamma / dbeta of the inference-mode batch norm (the dx part is produced by fc_bwd)
+void launch_bn_param_grads(cudaStream_t st, int B, int F, const float* x, const float* dz, const float* mean,
+                           const float* var, float* dgamma, float* dbeta);
 
 // logit = g2 . w3 + b3; y = sigmoid; per-sample log-loss (eps 1e-7) and d loss / d logit
 void launch_head(cudaStream_t st, int B, int F, const float* g2, const float* w3, const float* b3,

@@ -380,6 +380,15 @@ int upload_batch(ScoreModel* h, const ScoreBatch* b) {
 }
 
 // ------------------------------------------------------------------------------------------ GEMM helpers
+GemmArgs gemm_fwd_args(ScoreModel* h, const float* A, int lda, const float* W, int ldw, const float* bias, float* C,
+                       int ldc, int M, int N, int K, int epi, uint32_t rng_stream = 0) {
+    GemmArgs g{};
+    g.A = A; g.a_rs = lda; g.a_cs = 1;
+    g.B = W; g.b_rs = ldw; g.b_cs = 1;
+    g.C = C; g.c_rs = ldc; g.M = M; g.N = N; g.K = K; g.epi = epi; g.bias = bias;
+    g.splits = 1; g.hp = h->hyper_dev; g.rng_stream = rng_stream;
+    return g;
+}
 void gemm_fwd(ScoreModel* h, const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
               int M, int N, int K, int epi, uint32_t rng_stream = 0) {
     GemmArgs g{};
@@ -390,6 +399,15 @@ void gemm_fwd(ScoreModel* h, const float* A, int lda, const float* W, int ldw, c
     launch_gemm(h->st, g);
 }
 // dA[M, Kl] = dC[M, Nl] W[Kl, Nl]^T, optionally masked by the saved activation
+GemmArgs gemm_bwd_data_args(ScoreModel* h, const float* dC, int lddc, const float* W, int ldw, float* dA, int ldda, int M,
+                            int Kl, int Nl, int epi) {
+    GemmArgs g{};
+    g.A = dC; g.a_rs = lddc; g.a_cs = 1;
+    g.B = W; g.b_rs = 1; g.b_cs = ldw;
+    g.C = dA; g.c_rs = ldda; g.M = M; g.N = Kl; g.K = Nl; g.epi = epi;
+    g.splits = 1; g.hp = h->hyper_dev;
+    return g;
+}
 void gemm_bwd_data(ScoreModel* h, const float* dC, int lddc, const float* W, int ldw, float* dA, int ldda, int M,
                    int Kl, int Nl, int epi, const float* aux = nullptr, int aux_rs = 0, int mask_dropout = 0) {
     GemmArgs g{};
@@ -401,6 +419,24 @@ void gemm_bwd_data(ScoreModel* h, const float* dC, int lddc, const float* W, int
     launch_gemm(h->st, g);
 }
 // dW[Kl, Nl] (+ db[Nl]) = A[M, Kl]^T dC[M, Nl], into the kSplits partial planes of PG
+GemmArgs gemm_bwd_weight_args(ScoreModel* h, const float* A, int lda, const float* dC, int lddc, int64_t w_off,
+                              int64_t b_off, int M, int Kl, int Nl) {
+    GemmArgs g{};
+    g.A = A; g.a_rs = 1; g.a_cs = lda;
+    g.B = dC; g.b_rs = lddc; g.b_cs = 1;
+    g.C = h->PG + w_off; g.c_rs = Nl; g.M = Kl; g.N = Nl; g.K = M; g.epi = EPI_SPLIT;
+    g.splits = kSplits; g.c_split_stride = h->n_dense;
+    g.colsum = (b_off >= 0) ? h->PG + b_off : nullptr; g.colsum_split_stride = h->n_dense;
+    g.hp = h->hyper_dev;
+    return g;
+}
+// several weight-gradient problems in one side-stream launch
+void gemm_bwd_weight_batch(ScoreModel* h, const GemmArgs* list, int n) {
+    cudaEvent_t e = h->ev_pool[h->ev_next++ & 15];
+    cudaEventRecord(e, h->st);
+    cudaStreamWaitEvent(h->st_w, e, 0);
+    launch_gemm_batch(h->st_w, list, n);
+}
 void gemm_bwd_weight(ScoreModel* h, const float* A, int lda, const float* dC, int lddc, int64_t w_off, int64_t b_off,
                      int M, int Kl, int Nl) {
     GemmArgs g{};
@@ -460,34 +496,48 @@ void enqueue_forward(ScoreModel* h) {
     const char* sides[2] = {"gru_user_side", "gru_item_side"};
     GruArgs ga{};
     ga.length = h->length;
+    GemmArgs pxl[4];
     for (int s = 0; s < 2; ++s) {
         std::string g = std::string(sides[s]) + "/gru_cell/gates", c = std::string(sides[s]) + "/gru_cell/candidate";
-        // input part of both matmuls for all (b,t) rows at once: px = x [Wg_x | Wc_x]
-        gemm_fwd(h, h->xhg[s], ldx, W(g), 2 * H, nullptr, h->px[s], 3 * H, M, 2 * H, Ds, EPI_STORE);
-        gemm_fwd(h, h->xhg[s], ldx, W(c), H, nullptr, h->px[s] + 2 * H, 3 * H, M, H, Ds, EPI_STORE);
+        // input part of both matmuls for all (b,t) rows at once: px = x [Wg_x | Wc_x]  (4 problems, one launch)
+        pxl[2 * s] = gemm_fwd_args(h, h->xhg[s], ldx, W(g), 2 * H, nullptr, h->px[s], 3 * H, M, 2 * H, Ds, EPI_STORE);
+        pxl[2 * s + 1] = gemm_fwd_args(h, h->xhg[s], ldx, W(c), H, nullptr, h->px[s] + 2 * H, 3 * H, M, H, Ds, EPI_STORE);
         ga.px[s] = h->px[s]; ga.wg[s] = W(g); ga.bg[s] = Bi(g); ga.wc[s] = W(c); ga.bc[s] = Bi(c);
         ga.xhg[s] = h->xhg[s]; ga.xhc[s] = h->xhc[s]; ga.r[s] = h->gr[s]; ga.u[s] = h->gu[s]; ga.c[s] = h->gc[s];
     }
+    launch_gemm_batch(h->st, pxl, 4);
     ga.out = h->key; ga.ldout = Dk; ga.last = nullptr; ga.ldlast = 0;
     launch_gru_fwd(h->st, dm, ga);
 
     // attention over the T slices (score.py:169-186)
     gemm_fwd(h, h->q0, Ds, W(nm.att_q), Dk, Bi(nm.att_q), h->q, Dk, B, Dk, Ds, EPI_BIAS);
-    launch_att_inp_fwd(h->st, dm, h->q, h->key, h->a1);
-    gemm_fwd(h, h->a1, 4 * Dk, W(nm.att1), 80, Bi(nm.att1), h->f1, 80, M, 80, 4 * Dk, EPI_BIAS_RELU);
-    gemm_fwd(h, h->f1, 80, W(nm.att2), 40, Bi(nm.att2), h->f2, 40, M, 40, 80, EPI_BIAS_RELU);
+    // The fused forward chain (att_fwd_kernel) is correct but measured slower than three launches on B200
+    // (its 16x1 micro-tile is shared-memory-issue bound, profiles/README.md); it stays off until retiled.
+    const bool fused_att = false;
+    if (fused_att) {
+        AttChainArgs aa{};
+        aa.M = M; aa.T = T; aa.Dk = Dk; aa.q = h->q; aa.key = h->key;
+        aa.w1 = W(nm.att1); aa.b1 = Bi(nm.att1); aa.w2 = W(nm.att2); aa.b2 = Bi(nm.att2); aa.w3 = W(nm.att3); aa.b3 = Bi(nm.att3);
+        aa.a1 = h->a1; aa.f1 = h->f1; aa.f2 = h->f2; aa.s = h->ds;   // raw scores parked in the ds buffer until att_pool
+        launch_att_fwd(h->st, aa);
+    } else {
+        launch_att_inp_fwd(h->st, dm, h->q, h->key, h->a1);
+        gemm_fwd(h, h->a1, 4 * Dk, W(nm.att1), 80, Bi(nm.att1), h->f1, 80, M, 80, 4 * Dk, EPI_BIAS_RELU);
+        gemm_fwd(h, h->f1, 80, W(nm.att2), 40, Bi(nm.att2), h->f2, 40, M, 40, 80, EPI_BIAS_RELU);
+    }
     AttPoolArgs pa{};
-    pa.length = h->length; pa.f2 = h->f2; pa.w3 = W(nm.att3); pa.b3 = Bi(nm.att3);
+    pa.length = h->length; pa.f2 = h->f2; pa.s = fused_att ? h->ds : nullptr; pa.w3 = W(nm.att3); pa.b3 = Bi(nm.att3);
     pa.key = h->key; pa.ldkey = Dk; pa.score = h->score; pa.fc_in = h->fc_in; pa.ldfc = Dfc;
     launch_att_pool_fwd(h->st, dm, pa);
 
-    // build_fc_net + log-loss (score.py:68-81)
-    launch_bn_fwd(h->st, B, Dfc, h->fc_in, pp(h, "bn1/gamma"), pp(h, "bn1/beta"), pp(h, "bn1/moving_mean"),
-                  pp(h, "bn1/moving_variance"), h->z0);
-    gemm_fwd(h, h->z0, Dfc, pp(h, "fc1/kernel"), 200, pp(h, "fc1/bias"), h->g1, 200, B, 200, Dfc, EPI_BIAS_RELU_DROP, 1);
-    gemm_fwd(h, h->g1, 200, pp(h, "fc2/kernel"), 80, pp(h, "fc2/bias"), h->g2, 80, B, 80, 200, EPI_BIAS_RELU_DROP, 2);
-    launch_head(h->st, B, 80, h->g2, pp(h, "fc3/kernel"), pp(h, "fc3/bias"), h->label, h->hyper_dev, h->y, h->loss_b,
-                h->dlogit);
+    // build_fc_net + log-loss (score.py:68-81): one fused row-tile chain
+    FcArgs fa{};
+    fa.B = B; fa.F = Dfc; fa.fc_in = h->fc_in;
+    fa.gamma = pp(h, "bn1/gamma"); fa.beta = pp(h, "bn1/beta"); fa.mean = pp(h, "bn1/moving_mean"); fa.var = pp(h, "bn1/moving_variance");
+    fa.w1 = pp(h, "fc1/kernel"); fa.b1 = pp(h, "fc1/bias"); fa.w2 = pp(h, "fc2/kernel"); fa.b2 = pp(h, "fc2/bias");
+    fa.w3 = pp(h, "fc3/kernel"); fa.b3 = pp(h, "fc3/bias"); fa.label = h->label; fa.hp = h->hyper_dev;
+    fa.z0 = h->z0; fa.g1 = h->g1; fa.g2 = h->g2; fa.y = h->y; fa.loss_b = h->loss_b; fa.dlogit = h->dlogit;
+    launch_fc_fwd(h->st, fa);
     cudaStreamWaitEvent(h->st, h->ev_l2, 0);
     launch_loss_final(h->st, B, h->loss_b, h->l2sum, h->hyper_dev, h->loss_dev);
     probe_end(h, PR_FWD_DENSE, h->st);
@@ -505,28 +555,44 @@ void enqueue_backward(ScoreModel* h) {
     probe_begin(h, PR_BWD_DENSE, h->st);
     cudaMemsetAsync(h->PG, 0, sizeof(float) * h->n_dense * kSplits, h->st);
 
-    // prediction MLP
+    // prediction MLP: fused backward data chain on the main stream, weight gradients on the side stream
+    FcBwdArgs fb{};
+    fb.B = B; fb.F = Dfc; fb.dlogit = h->dlogit; fb.g2 = h->g2; fb.g1 = h->g1;
+    fb.w3 = W("fc3"); fb.w2 = W("fc2"); fb.w1 = W("fc1"); fb.gamma = pp(h, "bn1/gamma"); fb.var = pp(h, "bn1/moving_variance");
+    fb.hp = h->hyper_dev; fb.dg2 = h->dg2; fb.dg1 = h->dg1; fb.dz0 = h->dz0; fb.dfc_in = h->dfc_in;
+    launch_fc_bwd(h->st, fb);
     gemm_bwd_weight(h, h->g2, 80, h->dlogit, 1, Wo("fc3"), Bo("fc3"), B, 80, 1);
-    gemm_bwd_data(h, h->dlogit, 1, W("fc3"), 1, h->dg2, 80, B, 80, 1, EPI_MASK, h->g2, 80, 1);
     gemm_bwd_weight(h, h->g1, 200, h->dg2, 80, Wo("fc2"), Bo("fc2"), B, 200, 80);
-    gemm_bwd_data(h, h->dg2, 80, W("fc2"), 80, h->dg1, 200, B, 200, 80, EPI_MASK, h->g1, 200, 1);
     gemm_bwd_weight(h, h->z0, Dfc, h->dg1, 200, Wo("fc1"), Bo("fc1"), B, Dfc, 200);
-    gemm_bwd_data(h, h->dg1, 200, W("fc1"), 200, h->dz0, Dfc, B, Dfc, 200, EPI_STORE);
-    launch_bn_bwd(h->st, B, Dfc, h->fc_in, h->dz0, pp(h, "bn1/gamma"), pp(h, "bn1/moving_mean"),
-                  pp(h, "bn1/moving_variance"), h->dfc_in, h->PG + po(h, "bn1/gamma"), h->PG + po(h, "bn1/beta"));
+    launch_bn_param_grads(h->st_w, B, Dfc, h->fc_in, h->dz0, pp(h, "bn1/moving_mean"), pp(h, "bn1/moving_variance"),
+                          h->PG + po(h, "bn1/gamma"), h->PG + po(h, "bn1/beta"));
 
     // attention
     AttPoolBwdArgs pb{};
     pb.length = h->length; pb.score = h->score; pb.key = h->key; pb.ldkey = Dk; pb.dfc_in = h->dfc_in; pb.ldfc = Dfc;
     pb.ds = h->ds; pb.dkey = h->dkey;
     launch_att_pool_bwd(h->st, dm, pb);
-    gemm_bwd_weight(h, h->f2, 40, h->ds, 1, Wo(nm.att3), Bo(nm.att3), M, 40, 1);
-    gemm_bwd_data(h, h->ds, 1, W(nm.att3), 1, h->df2, 40, M, 40, 1, EPI_MASK, h->f2, 40, 0);
-    gemm_bwd_weight(h, h->f1, 80, h->df2, 40, Wo(nm.att2), Bo(nm.att2), M, 80, 40);
-    gemm_bwd_data(h, h->df2, 40, W(nm.att2), 40, h->df1, 80, M, 80, 40, EPI_MASK, h->f1, 80, 0);
-    gemm_bwd_weight(h, h->a1, 4 * Dk, h->df1, 80, Wo(nm.att1), Bo(nm.att1), M, 4 * Dk, 80);
-    gemm_bwd_data(h, h->df1, 80, W(nm.att1), 80, h->da1, 4 * Dk, M, 4 * Dk, 80, EPI_STORE);
-    launch_att_inp_bwd(h->st, dm, h->q, h->key, h->da1, h->dkey, h->dq, 2 * H);
+    if (Dk <= 128) {
+        // fused backward data chain; the three weight gradients stay SGEMMs on the side stream
+        AttChainBwdArgs ab{};
+        ab.M = M; ab.T = T; ab.Dk = Dk; ab.acc_cols = 2 * H;
+        ab.ds = h->ds; ab.f2 = h->f2; ab.f1 = h->f1; ab.q = h->q; ab.key = h->key;
+        ab.w3 = W(nm.att3); ab.w2 = W(nm.att2); ab.w1 = W(nm.att1);
+        ab.df2 = h->df2; ab.df1 = h->df1; ab.dkey = h->dkey; ab.dq_row = h->da1;   // da1 buffer reused as [M, Dk]
+        launch_att_bwd(h->st, ab);
+        launch_dq_reduce(h->st, B, T, Dk, h->da1, h->dq);
+        gemm_bwd_weight(h, h->f2, 40, h->ds, 1, Wo(nm.att3), Bo(nm.att3), M, 40, 1);
+        gemm_bwd_weight(h, h->f1, 80, h->df2, 40, Wo(nm.att2), Bo(nm.att2), M, 80, 40);
+        gemm_bwd_weight(h, h->a1, 4 * Dk, h->df1, 80, Wo(nm.att1), Bo(nm.att1), M, 4 * Dk, 80);
+    } else {
+        gemm_bwd_weight(h, h->f2, 40, h->ds, 1, Wo(nm.att3), Bo(nm.att3), M, 40, 1);
+        gemm_bwd_data(h, h->ds, 1, W(nm.att3), 1, h->df2, 40, M, 40, 1, EPI_MASK, h->f2, 40, 0);
+        gemm_bwd_weight(h, h->f1, 80, h->df2, 40, Wo(nm.att2), Bo(nm.att2), M, 80, 40);
+        gemm_bwd_data(h, h->df2, 40, W(nm.att2), 40, h->df1, 80, M, 80, 40, EPI_MASK, h->f1, 80, 0);
+        gemm_bwd_weight(h, h->a1, 4 * Dk, h->df1, 80, Wo(nm.att1), Bo(nm.att1), M, 4 * Dk, 80);
+        gemm_bwd_data(h, h->df1, 80, W(nm.att1), 80, h->da1, 4 * Dk, M, 4 * Dk, 80, EPI_STORE);
+        launch_att_inp_bwd(h->st, dm, h->q, h->key, h->da1, h->dkey, h->dq, 2 * H);
+    }
     gemm_bwd_weight(h, h->q0, Ds, h->dq, Dk, Wo(nm.att_q), Bo(nm.att_q), B, Ds, Dk);
     gemm_bwd_data(h, h->dq, Dk, W(nm.att_q), Dk, h->dq0, Ds, B, Ds, Dk, EPI_STORE);
 
@@ -540,14 +606,17 @@ void enqueue_backward(ScoreModel* h) {
         gb.r[s] = h->gr[s]; gb.u[s] = h->gu[s]; gb.c[s] = h->gc[s]; gb.dpx[s] = h->dpx[s];
     }
     launch_gru_bwd(h->st, dm, gb);
+    GemmArgs wl[4], d1[2], d2[2];
     for (int s = 0; s < 2; ++s) {
         std::string g = std::string(sides[s]) + "/gru_cell/gates", c = std::string(sides[s]) + "/gru_cell/candidate";
-        gemm_bwd_weight(h, h->xhg[s], ldx, h->dpx[s], 3 * H, Wo(g), Bo(g), M, ldx, 2 * H);
-        gemm_bwd_weight(h, h->xhc[s], ldx, h->dpx[s] + 2 * H, 3 * H, Wo(c), Bo(c), M, ldx, H);
-        gemm_bwd_data(h, h->dpx[s], 3 * H, W(g), 2 * H, h->dx[s], Ds, M, Ds, 2 * H, EPI_STORE);
-        gemm_bwd_data(h, h->dpx[s] + 2 * H, 3 * H, W(c), H, h->dx[s], Ds, M, Ds, H, EPI_ACCUM);
+        wl[2 * s] = gemm_bwd_weight_args(h, h->xhg[s], ldx, h->dpx[s], 3 * H, Wo(g), Bo(g), M, ldx, 2 * H);
+        wl[2 * s + 1] = gemm_bwd_weight_args(h, h->xhc[s], ldx, h->dpx[s] + 2 * H, 3 * H, Wo(c), Bo(c), M, ldx, H);
+        d1[s] = gemm_bwd_data_args(h, h->dpx[s], 3 * H, W(g), 2 * H, h->dx[s], Ds, M, Ds, 2 * H, EPI_STORE);
+        d2[s] = gemm_bwd_data_args(h, h->dpx[s] + 2 * H, 3 * H, W(c), H, h->dx[s], Ds, M, Ds, H, EPI_ACCUM);
     }
-
+    gemm_bwd_weight_batch(h, wl, 4);
+    launch_gemm_batch(h->st, d1, 2);   // dx  = dpx_gates Wg_x^T      (both sides)
+    launch_gemm_batch(h->st, d2, 2);   // dx += dpx_cand  Wc_x^T
     probe_end(h, PR_BWD_DENSE, h->st);
     // co-attention + gather backward: per-position embedding gradient rows
     CoattBwdArgs cb{};

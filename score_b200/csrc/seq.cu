@@ -242,12 +242,16 @@ __global__ void att_pool_fwd_kernel(Dims dm, AttPoolArgs a) {
     const int T = dm.T, H = dm.H;
     const int len = a.length[b];
     const float pad = -4294967296.0f;   // float32(-2**32 + 1)  score.py:180
-    for (int t = 0; t < T; ++t) {
-        const float* f = a.f2 + ((int64_t)b * T + t) * 40;
-        float p = 0.f;
-        for (int c = lane; c < 40; c += 32) p += f[c] * a.w3[c];
-        p = warp_sum(p) + a.b3[0];
-        if (lane == 0) sc[t] = (t < len) ? p : pad;
+    if (a.s) {
+        for (int t = lane; t < T; t += 32) sc[t] = (t < len) ? a.s[(int64_t)b * T + t] : pad;
+    } else {
+        for (int t = 0; t < T; ++t) {
+            const float* f = a.f2 + ((int64_t)b * T + t) * 40;
+            float p = 0.f;
+            for (int c = lane; c < 40; c += 32) p += f[c] * a.w3[c];
+            p = warp_sum(p) + a.b3[0];
+            if (lane == 0) sc[t] = (t < len) ? p : pad;
+        }
     }
     __syncwarp();
     float mx = -INFINITY;
@@ -367,6 +371,34 @@ __global__ void bn_bwd_kernel(int B, int F, const float* __restrict__ x, const f
 void launch_bn_bwd(cudaStream_t st, int B, int F, const float* x, const float* dz, const float* gamma,
                    const float* mean, const float* var, float* dx, float* dgamma, float* dbeta) {
     bn_bwd_kernel<<<(F + 31) / 32, dim3(32, 32), 0, st>>>(B, F, x, dz, gamma, mean, var, dx, dgamma, dbeta);
+    ++g_launch_count;
+}
+
+__global__ void bn_param_grads_kernel(int B, int F, const float* __restrict__ x, const float* __restrict__ dz,
+                                      const float* __restrict__ mean, const float* __restrict__ var,
+                                      float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ float rg[32][33], rb[32][33];
+    const int c = blockIdx.x * 32 + threadIdx.x, ry = threadIdx.y;
+    float sg = 0.f, sb = 0.f;
+    if (c < F) {
+        const float rstd = 1.0f / sqrtf(var[c] + 1e-3f), mu = mean[c];
+        for (int b = ry; b < B; b += 32) {
+            const float d = dz[(int64_t)b * F + c];
+            sg += d * ((x[(int64_t)b * F + c] - mu) * rstd);
+            sb += d;
+        }
+    }
+    rg[ry][threadIdx.x] = sg; rb[ry][threadIdx.x] = sb;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) {
+        if (ry < o) { rg[ry][threadIdx.x] += rg[ry + o][threadIdx.x]; rb[ry][threadIdx.x] += rb[ry + o][threadIdx.x]; }
+        __syncthreads();
+    }
+    if (ry == 0 && c < F) { dgamma[c] = rg[0][threadIdx.x]; dbeta[c] = rb[0][threadIdx.x]; }
+}
+void launch_bn_param_grads(cudaStream_t st, int B, int F, const float* x, const float* dz, const float* mean,
+                           const float* var, float* dgamma, float* dbeta) {
+    bn_param_grads_kernel<<<(F + 31) / 32, dim3(32, 32), 0, st>>>(B, F, x, dz, mean, var, dgamma, dbeta);
     ++g_launch_count;
 }
 
