@@ -125,31 +125,6 @@ struct GruBwdArgs {
 };
 void launch_gru_bwd(cudaStream_t st, const Dims& dm, const GruBwdArgs& a);
 
-// attention input [q, key, q-key, q*key] (score.py:174) and its backward
-void launch_att_inp_fwd(cudaStream_t st, const Dims& dm, const float* q, const float* key, float* a1);
-void launch_att_inp_bwd(cudaStream_t st, const Dims& dm, const float* q, const float* key, const float* da1,
-                        float* dkey, float* dq /* [B,Dk] */, int accumulate_cols /* first cols of dkey hold pooling grads */);
-
-struct AttPoolArgs {
-    const int32_t* length;
-    const float* f2;              // [M, 40]   (used when s == nullptr)
-    const float* s;               // [M] raw scores precomputed by the fused attention chain, or nullptr
-    const float* w3; const float* b3;
-    const float* key; int ldkey;  // rep_t = key[:, 0:2H]
-    float* score;                 // [B, T]
-    float* fc_in; int ldfc;       // user_final -> [0:H], item_final -> [H:2H] (model-type dependent)
-};
-void launch_att_pool_fwd(cudaStream_t st, const Dims& dm, const AttPoolArgs& a);
-
-struct AttPoolBwdArgs {
-    const int32_t* length;
-    const float* score; const float* key; int ldkey;
-    const float* dfc_in; int ldfc;
-    float* ds;                    // [M] gradient of the pre-softmax scores
-    float* dkey;                  // [M, ldkey]: cols 0:2H <- pooling gradient (overwritten)
-};
-void launch_att_pool_bwd(cudaStream_t st, const Dims& dm, const AttPoolBwdArgs& a);
-
 // batch-norm in inference mode (score.py:69): z = x * gamma/sqrt(var+eps) + (beta - mean*inv)
 void launch_bn_fwd(cudaStream_t st, int B, int F, const float* x, const float* gamma, const float* beta,
                    const float* mean, const float* var, float* z);
@@ -169,26 +144,11 @@ struct FcBwdArgs {
     int B, F;
     const float* dlogit; const float* g2; const float* g1;
     const float* w3; const float* w2; const float* w1; const float* gamma; const float* var;
+    const float* w2t; const float* w1t;   // derived transposes: fc2^T [80,200], fc1^T [200,F] (prep_weights)
     const Hyper* hp;
     float* dg2; float* dg1; float* dz0; float* dfc_in;
 };
 void launch_fc_bwd(cudaStream_t st, const FcBwdArgs& a);
-// fused attention MLP chain (chain.cu): forward writes a1 (for the first layer's weight gradient), f1, f2 and raw scores s
-struct AttChainArgs {
-    int64_t M; int T, Dk;
-    const float* q; const float* key;
-    const float* w1; const float* b1; const float* w2; const float* b2; const float* w3; const float* b3;
-    float* a1; float* f1; float* f2; float* s;
-};
-void launch_att_fwd(cudaStream_t st, const AttChainArgs& a);
-struct AttChainBwdArgs {
-    int64_t M; int T, Dk, acc_cols;
-    const float* ds; const float* f2; const float* f1; const float* q; const float* key;
-    const float* w3; const float* w2; const float* w1;
-    float* df2; float* df1; float* dkey; float* dq_row;
-};
-void launch_att_bwd(cudaStream_t st, const AttChainBwdArgs& a);   // requires Dk <= 128
-void launch_dq_reduce(cudaStream_t st, int B, int T, int Dk, const float* dq_row, float* dq);
 // dgamma / dbeta of the inference-mode batch norm (the dx part is produced by fc_bwd)
 void launch_bn_param_grads(cudaStream_t st, int B, int F, const float* x, const float* dz, const float* mean,
                            const float* var, float* dgamma, float* dbeta);
@@ -199,11 +159,67 @@ void launch_head(cudaStream_t st, int B, int F, const float* g2, const float* w3
 // loss = sum_b loss_b * inv_batch + reg_lambda * l2sum    (fixed-order reduction)
 void launch_loss_final(cudaStream_t st, int B, const float* loss_b, const float* l2sum, const Hyper* hp, float* loss);
 
+
+// ---------------------------------------------------------------- fused attention block (attn.cu)
+// Derived weights rebuilt once per step from the flat parameter buffer P into D:
+//   D[dst_off + r*ld_dst + c] = P[a_off + r*a_rs + c*a_cs] (+/-) P[b_off + r*a_rs + c*a_cs]     (b_off < 0: no second term)
+struct PrepOp { int64_t dst_off, a_off, b_off; int ld_dst, rows, cols, a_rs, a_cs, sign; };
+struct PrepOps { PrepOp op[12]; int n; };
+void launch_prep_weights(cudaStream_t st, const PrepOps& ops, const float* P, float* D);
+
+struct AttQArgs {
+    int B, Ds, Dk;
+    const float* q0;                       // [B, Ds] = [target_user || target_item]
+    const float* wq; const float* bq;      // query projection [Ds, Dk] (score.py:172)
+    const float* Wac; const float* b1;     // (Wa + Wc) [Dk, 80], bias of the first attention layer
+    float* q; float* U;                    // [B, Dk], [B, 80]
+};
+void launch_att_q(cudaStream_t st, const AttQArgs& a);
+
+struct AttFwd2Args {
+    int B, T, Dk, H, G;                    // G (samples per CTA) is set by the launcher
+    const int32_t* length;
+    const float* q; const float* U; const float* key;
+    const float* W1e;                      // [2*Dk, 80]: rows (Wb - Wc) | Wd
+    const float* w2; const float* b2; const float* w3; const float* b3;
+    float* qk;                             // [M, Dk] q*key (operand of the Wd weight gradient)
+    float* f1; float* f2;                  // [M, 80], [M, 40]
+    float* score;                          // [B, T]
+    float* fc_in; int ldfc; int model_type;
+};
+void launch_att_fwd2(cudaStream_t st, AttFwd2Args a);
+
+struct AttBwd2Args {
+    int B, T, Dk, H, G;
+    const int32_t* length;
+    const float* q; const float* key; const float* f1; const float* f2; const float* score;
+    const float* dfc_in; int ldfc; int model_type;
+    const float* w3;
+    const float* W2T;                      // [40, 80]
+    const float* W1eT;                     // [80, 2*Dk]: columns (Wb - Wc)^T | Wd^T
+    float* ds; float* df2; float* df1;     // [M], [M, 40], [M, 80]
+    float* dkey;                           // [M, Dk]
+    float* sdf1;                           // [B, 80]  sum_t d f1
+    float* dqD;                            // [B, Dk]  sum_t dD * key
+};
+void launch_att_bwd2(cudaStream_t st, AttBwd2Args a);
+
+struct AttQbArgs {
+    int B, Ds, Dk;
+    const float* sdf1; const float* dqD;
+    const float* WacT;                     // [80, Dk]
+    const float* WqT;                      // [Dk, Ds]
+    float* dq; float* dq0;                 // [B, Dk], [B, Ds]
+};
+void launch_att_qb(cudaStream_t st, const AttQbArgs& a);
+
 // ---------------------------------------------------------------- optimizer + scatter (scatter.cu)
 // sum of v*v/2 over L2-regularised dense parameters (flags bit0)
 void launch_l2_sum(cudaStream_t st, const float* params, const uint8_t* flags, int n, float* out);
 // G[i] = sum_s partial[s][i]
-void launch_reduce_partials(cudaStream_t st, const float* partials, int splits, int n, float* g);
+// optional derived range afterwards: g[dst + i] = g[a + i] - g[b + i], i < count  (dWc = dWa - dWb of the attention's first layer)
+void launch_reduce_partials(cudaStream_t st, const float* partials, int splits, int n, float* g,
+                            int64_t derive_dst = -1, int64_t derive_a = 0, int64_t derive_b = 0, int derive_count = 0);
 void launch_add_l2(cudaStream_t st, float* g, const float* p, const uint8_t* flags, int n, const Hyper* hp);
 // dense Adam on the flat parameter buffer: g = G + reg*p (flags bit0), skip non-trainables (flags bit1 clear)
 void launch_dense_adam(cudaStream_t st, float* p, float* m, float* v, const float* g, const uint8_t* flags,

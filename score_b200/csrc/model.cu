@@ -46,7 +46,7 @@ struct ScoreModel {
     std::string err;
     Dims dm;                        // dm.B / offsets are per call
     cudaStream_t st = nullptr, st2 = nullptr, st_w = nullptr;   // main, sort branch, weight-gradient branch
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_l2 = nullptr, ev_w = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_l2 = nullptr, ev_w = nullptr, ev_tgt = nullptr, ev_q = nullptr;
     cudaEvent_t ev_pool[16] = {nullptr}; int ev_next = 0;
     bool side_w = false;   // a step is being enqueued with the weight-gradient branch forked
 
@@ -58,6 +58,9 @@ struct ScoreModel {
     int32_t* last_step = nullptr;   // per-row step at which the row is current (DENSE / LAZY)
     float *P = nullptr, *G = nullptr, *M1 = nullptr, *V1 = nullptr, *PG = nullptr;
     uint8_t* flags = nullptr;
+    // derived weights of the fused dense chains (attn.cu, chain.cu), rebuilt from P at the start of every step
+    float* Dv = nullptr; int64_t n_derived = 0; PrepOps prep{};
+    int64_t dv_W1e = 0, dv_Wac = 0, dv_W1eT = 0, dv_WacT = 0, dv_W2T = 0, dv_WqT = 0, dv_fc1T = 0, dv_fc2T = 0;
     float* alpha_hist = nullptr; int64_t alpha_cap = 0;
     std::vector<float> alpha_host;
 
@@ -71,8 +74,8 @@ struct ScoreModel {
     std::map<std::string, Buf> bufs;
     int32_t *ids = nullptr, *label = nullptr, *length = nullptr, *keys = nullptr;
     float *q0, *c_item, *c_user, *xhg[2], *xhc[2], *key, *save_r, *save_w, *px[2], *gr[2], *gu[2], *gc[2];
-    float *q, *a1, *f1, *f2, *score, *fc_in, *z0, *g1, *g2, *y, *loss_b, *dlogit;
-    float *dg2, *dg1, *dz0, *dfc_in, *ds, *df2, *df1, *da1, *dkey, *dq, *dq0, *dpx[2], *dx[2], *sdz, *grad_rows;
+    float *q, *attU, *qk, *f1, *f2, *score, *fc_in, *z0, *g1, *g2, *y, *loss_b, *dlogit;
+    float *dg2, *dg1, *dz0, *dfc_in, *ds, *df2, *df1, *sdf1, *dqD, *dkey, *dq, *dq0, *dpx[2], *dx[2], *sdz, *grad_rows;
     float *coatt_part, *target_part;
     int n_coatt_part = 0, n_target_part = 0;
     SortBufs sb{};
@@ -191,6 +194,34 @@ void build_registry(ScoreModel* h) {
     add("bn1/moving_variance", 1, Dfc, 0);
     kb("fc1", Dfc, 200); kb("fc2", 200, 80); kb("fc3", 80, 1);
     h->n_dense = off;
+
+    // derived weights: combinations / transposes the fused chains stream (see attn.cu header)
+    int64_t doff = 0;
+    PrepOps& po_ = h->prep;
+    po_.n = 0;
+    auto reserve = [&](int64_t n) { int64_t o = doff; doff += (n + 3) / 4 * 4; return o; };
+    auto op = [&](int64_t dst, int ld, int rows, int cols, int64_t a, int64_t b, int a_rs, int a_cs, int sign) {
+        PrepOp& o = po_.op[po_.n++];
+        o.dst_off = dst; o.ld_dst = ld; o.rows = rows; o.cols = cols; o.a_off = a; o.b_off = b; o.a_rs = a_rs; o.a_cs = a_cs; o.sign = sign;
+    };
+    auto toff = [&](const std::string& name) { return h->tensors[h->tindex[name]].off; };
+    if (mt != SCORE_MODEL_RIA) {
+        const int64_t w1 = toff(nm.att1 + "/kernel"), blk = (int64_t)Dk * 80;   // row blocks Wa | Wb | Wc | Wd
+        h->dv_W1e = reserve(2 * blk); h->dv_Wac = reserve(blk); h->dv_W1eT = reserve(2 * blk); h->dv_WacT = reserve(blk);
+        h->dv_W2T = reserve(40 * 80); h->dv_WqT = reserve((int64_t)Dk * Ds);
+        op(h->dv_W1e, 80, Dk, 80, w1 + blk, w1 + 2 * blk, 80, 1, -1);              // Wb - Wc
+        op(h->dv_W1e + blk, 80, Dk, 80, w1 + 3 * blk, -1, 80, 1, 0);               // Wd
+        op(h->dv_Wac, 80, Dk, 80, w1, w1 + 2 * blk, 80, 1, +1);                    // Wa + Wc
+        op(h->dv_W1eT, 2 * Dk, 80, Dk, w1 + blk, w1 + 2 * blk, 1, 80, -1);         // (Wb - Wc)^T
+        op(h->dv_W1eT + Dk, 2 * Dk, 80, Dk, w1 + 3 * blk, -1, 1, 80, 0);           // Wd^T
+        op(h->dv_WacT, Dk, 80, Dk, w1, w1 + 2 * blk, 1, 80, +1);                   // (Wa + Wc)^T
+        op(h->dv_W2T, 80, 40, 80, toff(nm.att2 + "/kernel"), -1, 1, 40, 0);        // W2^T
+        op(h->dv_WqT, Ds, Dk, Ds, toff(nm.att_q + "/kernel"), -1, 1, Dk, 0);       // Wq^T
+    }
+    h->dv_fc1T = reserve((int64_t)200 * Dfc); h->dv_fc2T = reserve(80 * 200);
+    op(h->dv_fc1T, Dfc, 200, Dfc, toff("fc1/kernel"), -1, 1, 200, 0);              // fc1^T
+    op(h->dv_fc2T, 200, 80, 200, toff("fc2/kernel"), -1, 1, 80, 0);                // fc2^T
+    h->n_derived = doff;
 }
 
 int alloc_params(ScoreModel* h) {
@@ -212,6 +243,8 @@ int alloc_params(ScoreModel* h) {
     CK(cudaMalloc(&h->V1, sizeof(float) * n));
     CK(cudaMalloc(&h->PG, sizeof(float) * n * kSplits));
     CK(cudaMalloc(&h->flags, n));
+    CK(cudaMalloc(&h->Dv, sizeof(float) * (h->n_derived > 0 ? h->n_derived : 4)));
+    CK(cudaMemsetAsync(h->Dv, 0, sizeof(float) * (h->n_derived > 0 ? h->n_derived : 4), h->st));
     CK(cudaMemsetAsync(h->P, 0, sizeof(float) * n, h->st));
     CK(cudaMemsetAsync(h->G, 0, sizeof(float) * n, h->st));
     CK(cudaMemsetAsync(h->M1, 0, sizeof(float) * n, h->st));
@@ -322,13 +355,14 @@ int ensure_workspace(ScoreModel* h, int B) {
         WS(h->px[s], M * 3 * H, a.c_str()); WS(h->gr[s], M * H, b.c_str()); WS(h->gu[s], M * H, c.c_str());
         WS(h->gc[s], M * H, e.c_str()); WS(h->dpx[s], M * 3 * H, f.c_str()); WS(h->dx[s], M * Ds, g.c_str());
     }
-    WS(h->q, (int64_t)cap * Dk, "q"); WS(h->a1, M * 4 * Dk, "att_inp"); WS(h->f1, M * 80, "att_fc1");
+    WS(h->q, (int64_t)cap * Dk, "q"); WS(h->attU, (int64_t)cap * 80, "att_u"); WS(h->qk, M * Dk, "att_qk"); WS(h->f1, M * 80, "att_fc1");
     WS(h->f2, M * 40, "att_fc2"); WS(h->score, M, "score"); WS(h->fc_in, (int64_t)cap * Dfc, "fc_in");
     WS(h->z0, (int64_t)cap * Dfc, "bn1"); WS(h->g1, (int64_t)cap * 200, "fc1"); WS(h->g2, (int64_t)cap * 80, "fc2");
     WS(h->y, cap, "y_pred"); WS(h->loss_b, cap, "loss_b"); WS(h->dlogit, cap, "dlogit");
     WS(h->dg2, (int64_t)cap * 80, "d_fc2"); WS(h->dg1, (int64_t)cap * 200, "d_fc1"); WS(h->dz0, (int64_t)cap * Dfc, "d_bn1");
     WS(h->dfc_in, (int64_t)cap * Dfc, "d_fc_in"); WS(h->ds, M, "d_score"); WS(h->df2, M * 40, "d_att_fc2");
-    WS(h->df1, M * 80, "d_att_fc1"); WS(h->da1, M * 4 * Dk, "d_att_inp"); WS(h->dkey, M * Dk, "d_key");
+    WS(h->df1, M * 80, "d_att_fc1"); WS(h->sdf1, (int64_t)cap * 80, "d_att_fc1_sum"); WS(h->dqD, (int64_t)cap * Dk, "d_q_keyside");
+    WS(h->dkey, M * Dk, "d_key");
     WS(h->dq, (int64_t)cap * Dk, "d_q"); WS(h->dq0, (int64_t)cap * Ds, "d_q0"); WS(h->sdz, M * 2, "sdz");
     WS(h->grad_rows, N * dm.d, "grad_rows");
     h->n_coatt_part = coatt_bwd_num_ctas();
@@ -472,8 +506,9 @@ void enqueue_forward(ScoreModel* h) {
     auto W = [&](const std::string& n) { return pp(h, (n + "/kernel").c_str()); };
     auto Bi = [&](const std::string& n) { return pp(h, (n + "/bias").c_str()); };
 
-    // 0.5*sum(v^2) only feeds the loss scalar: side stream
+    // side stream: derived weights of the fused chains, then 0.5*sum(v^2) (only feeds the loss scalar)
     cudaStreamWaitEvent(h->st_w, h->ev_fork, 0);
+    launch_prep_weights(h->st_w, h->prep, h->P, h->Dv);
     launch_l2_sum(h->st_w, h->P, h->flags, (int)h->n_dense, h->l2sum);
     cudaEventRecord(h->ev_l2, h->st_w);
 
@@ -482,6 +517,15 @@ void enqueue_forward(ScoreModel* h) {
     ta.w_item = W(nm.co_item); ta.b_item = Bi(nm.co_item); ta.w_user = W(nm.co_user); ta.b_user = Bi(nm.co_user);
     ta.q0 = h->q0; ta.fc_in = h->fc_in; ta.fc_off = Dfc - Ds; ta.c_item = h->c_item; ta.c_user = h->c_user;
     launch_target_fwd(h->st, dm, ta);
+    {   // query side of the attention (per sample): off the critical path, next to the gather and the GRUs
+        cudaEventRecord(h->ev_tgt, h->st);
+        cudaStreamWaitEvent(h->st_w, h->ev_tgt, 0);
+        AttQArgs qa{};
+        qa.B = B; qa.Ds = Ds; qa.Dk = Dk; qa.q0 = h->q0; qa.wq = W(nm.att_q); qa.bq = Bi(nm.att_q);
+        qa.Wac = h->Dv + h->dv_Wac; qa.b1 = Bi(nm.att1); qa.q = h->q; qa.U = h->attU;
+        launch_att_q(h->st_w, qa);
+        cudaEventRecord(h->ev_q, h->st_w);
+    }
 
     CoattArgs ca{};
     ca.emb = h->emb_fwd; ca.keys = h->keys_fwd; ca.length = h->length;
@@ -509,26 +553,14 @@ void enqueue_forward(ScoreModel* h) {
     ga.out = h->key; ga.ldout = Dk; ga.last = nullptr; ga.ldlast = 0;
     launch_gru_fwd(h->st, dm, ga);
 
-    // attention over the T slices (score.py:169-186)
-    gemm_fwd(h, h->q0, Ds, W(nm.att_q), Dk, Bi(nm.att_q), h->q, Dk, B, Dk, Ds, EPI_BIAS);
-    // The fused forward chain (att_fwd_kernel) is correct but measured slower than three launches on B200
-    // (its 16x1 micro-tile is shared-memory-issue bound, profiles/README.md); it stays off until retiled.
-    const bool fused_att = false;
-    if (fused_att) {
-        AttChainArgs aa{};
-        aa.M = M; aa.T = T; aa.Dk = Dk; aa.q = h->q; aa.key = h->key;
-        aa.w1 = W(nm.att1); aa.b1 = Bi(nm.att1); aa.w2 = W(nm.att2); aa.b2 = Bi(nm.att2); aa.w3 = W(nm.att3); aa.b3 = Bi(nm.att3);
-        aa.a1 = h->a1; aa.f1 = h->f1; aa.f2 = h->f2; aa.s = h->ds;   // raw scores parked in the ds buffer until att_pool
-        launch_att_fwd(h->st, aa);
-    } else {
-        launch_att_inp_fwd(h->st, dm, h->q, h->key, h->a1);
-        gemm_fwd(h, h->a1, 4 * Dk, W(nm.att1), 80, Bi(nm.att1), h->f1, 80, M, 80, 4 * Dk, EPI_BIAS_RELU);
-        gemm_fwd(h, h->f1, 80, W(nm.att2), 40, Bi(nm.att2), h->f2, 40, M, 40, 80, EPI_BIAS_RELU);
-    }
-    AttPoolArgs pa{};
-    pa.length = h->length; pa.f2 = h->f2; pa.s = fused_att ? h->ds : nullptr; pa.w3 = W(nm.att3); pa.b3 = Bi(nm.att3);
-    pa.key = h->key; pa.ldkey = Dk; pa.score = h->score; pa.fc_in = h->fc_in; pa.ldfc = Dfc;
-    launch_att_pool_fwd(h->st, dm, pa);
+    // attention over the T slices + attentive pooling (score.py:169-186, 214-216): one fused row-tile chain
+    cudaStreamWaitEvent(h->st, h->ev_q, 0);
+    AttFwd2Args fa2{};
+    fa2.B = B; fa2.T = T; fa2.Dk = Dk; fa2.H = H; fa2.length = h->length; fa2.q = h->q; fa2.U = h->attU; fa2.key = h->key;
+    fa2.W1e = h->Dv + h->dv_W1e; fa2.w2 = W(nm.att2); fa2.b2 = Bi(nm.att2); fa2.w3 = W(nm.att3); fa2.b3 = Bi(nm.att3);
+    fa2.qk = h->qk; fa2.f1 = h->f1; fa2.f2 = h->f2; fa2.score = h->score; fa2.fc_in = h->fc_in; fa2.ldfc = Dfc;
+    fa2.model_type = dm.model_type;
+    launch_att_fwd2(h->st, fa2);
 
     // build_fc_net + log-loss (score.py:68-81): one fused row-tile chain
     FcArgs fa{};
@@ -559,6 +591,7 @@ void enqueue_backward(ScoreModel* h) {
     FcBwdArgs fb{};
     fb.B = B; fb.F = Dfc; fb.dlogit = h->dlogit; fb.g2 = h->g2; fb.g1 = h->g1;
     fb.w3 = W("fc3"); fb.w2 = W("fc2"); fb.w1 = W("fc1"); fb.gamma = pp(h, "bn1/gamma"); fb.var = pp(h, "bn1/moving_variance");
+    fb.w2t = h->Dv + h->dv_fc2T; fb.w1t = h->Dv + h->dv_fc1T;
     fb.hp = h->hyper_dev; fb.dg2 = h->dg2; fb.dg1 = h->dg1; fb.dz0 = h->dz0; fb.dfc_in = h->dfc_in;
     launch_fc_bwd(h->st, fb);
     gemm_bwd_weight(h, h->g2, 80, h->dlogit, 1, Wo("fc3"), Bo("fc3"), B, 80, 1);
@@ -567,34 +600,28 @@ void enqueue_backward(ScoreModel* h) {
     launch_bn_param_grads(h->st_w, B, Dfc, h->fc_in, h->dz0, pp(h, "bn1/moving_mean"), pp(h, "bn1/moving_variance"),
                           h->PG + po(h, "bn1/gamma"), h->PG + po(h, "bn1/beta"));
 
-    // attention
-    AttPoolBwdArgs pb{};
-    pb.length = h->length; pb.score = h->score; pb.key = h->key; pb.ldkey = Dk; pb.dfc_in = h->dfc_in; pb.ldfc = Dfc;
-    pb.ds = h->ds; pb.dkey = h->dkey;
-    launch_att_pool_bwd(h->st, dm, pb);
-    if (Dk <= 128) {
-        // fused backward data chain; the three weight gradients stay SGEMMs on the side stream
-        AttChainBwdArgs ab{};
-        ab.M = M; ab.T = T; ab.Dk = Dk; ab.acc_cols = 2 * H;
-        ab.ds = h->ds; ab.f2 = h->f2; ab.f1 = h->f1; ab.q = h->q; ab.key = h->key;
-        ab.w3 = W(nm.att3); ab.w2 = W(nm.att2); ab.w1 = W(nm.att1);
-        ab.df2 = h->df2; ab.df1 = h->df1; ab.dkey = h->dkey; ab.dq_row = h->da1;   // da1 buffer reused as [M, Dk]
-        launch_att_bwd(h->st, ab);
-        launch_dq_reduce(h->st, B, T, Dk, h->da1, h->dq);
+    // attention: pooling + softmax + MLP backward in one fused chain, then the per-sample query side
+    const int64_t blk = (int64_t)Dk * 80;   // dense_3/kernel row blocks: Wa | Wb | Wc | Wd
+    {
+        AttBwd2Args ab{};
+        ab.B = B; ab.T = T; ab.Dk = Dk; ab.H = H; ab.length = h->length; ab.q = h->q; ab.key = h->key; ab.f1 = h->f1;
+        ab.f2 = h->f2; ab.score = h->score; ab.dfc_in = h->dfc_in; ab.ldfc = Dfc; ab.model_type = dm.model_type;
+        ab.w3 = W(nm.att3); ab.W2T = h->Dv + h->dv_W2T; ab.W1eT = h->Dv + h->dv_W1eT;
+        ab.ds = h->ds; ab.df2 = h->df2; ab.df1 = h->df1; ab.dkey = h->dkey; ab.sdf1 = h->sdf1; ab.dqD = h->dqD;
+        launch_att_bwd2(h->st, ab);
         gemm_bwd_weight(h, h->f2, 40, h->ds, 1, Wo(nm.att3), Bo(nm.att3), M, 40, 1);
         gemm_bwd_weight(h, h->f1, 80, h->df2, 40, Wo(nm.att2), Bo(nm.att2), M, 80, 40);
-        gemm_bwd_weight(h, h->a1, 4 * Dk, h->df1, 80, Wo(nm.att1), Bo(nm.att1), M, 4 * Dk, 80);
-    } else {
-        gemm_bwd_weight(h, h->f2, 40, h->ds, 1, Wo(nm.att3), Bo(nm.att3), M, 40, 1);
-        gemm_bwd_data(h, h->ds, 1, W(nm.att3), 1, h->df2, 40, M, 40, 1, EPI_MASK, h->f2, 40, 0);
-        gemm_bwd_weight(h, h->f1, 80, h->df2, 40, Wo(nm.att2), Bo(nm.att2), M, 80, 40);
-        gemm_bwd_data(h, h->df2, 40, W(nm.att2), 40, h->df1, 80, M, 80, 40, EPI_MASK, h->f1, 80, 0);
-        gemm_bwd_weight(h, h->a1, 4 * Dk, h->df1, 80, Wo(nm.att1), Bo(nm.att1), M, 4 * Dk, 80);
-        gemm_bwd_data(h, h->df1, 80, W(nm.att1), 80, h->da1, 4 * Dk, M, 4 * Dk, 80, EPI_STORE);
-        launch_att_inp_bwd(h->st, dm, h->q, h->key, h->da1, h->dkey, h->dq, 2 * H);
+        GemmArgs w1l[2];
+        w1l[0] = gemm_bwd_weight_args(h, h->key, Dk, h->df1, 80, Wo(nm.att1) + blk, -1, M, Dk, 80);      // dWb = key^T df1
+        w1l[1] = gemm_bwd_weight_args(h, h->qk, Dk, h->df1, 80, Wo(nm.att1) + 3 * blk, -1, M, Dk, 80);   // dWd = (q*key)^T df1
+        gemm_bwd_weight_batch(h, w1l, 2);
+        AttQbArgs qb{};
+        qb.B = B; qb.Ds = Ds; qb.Dk = Dk; qb.sdf1 = h->sdf1; qb.dqD = h->dqD; qb.WacT = h->Dv + h->dv_WacT;
+        qb.WqT = h->Dv + h->dv_WqT; qb.dq = h->dq; qb.dq0 = h->dq0;
+        launch_att_qb(h->st, qb);
+        gemm_bwd_weight(h, h->q, Dk, h->sdf1, 80, Wo(nm.att1), Bo(nm.att1), B, Dk, 80);                  // dWa = q^T sum_t df1
+        gemm_bwd_weight(h, h->q0, Ds, h->dq, Dk, Wo(nm.att_q), Bo(nm.att_q), B, Ds, Dk);
     }
-    gemm_bwd_weight(h, h->q0, Ds, h->dq, Dk, Wo(nm.att_q), Bo(nm.att_q), B, Ds, Dk);
-    gemm_bwd_data(h, h->dq, Dk, W(nm.att_q), Dk, h->dq0, Ds, B, Ds, Dk, EPI_STORE);
 
     // GRUs
     const char* sides[2] = {"gru_user_side", "gru_item_side"};
@@ -637,7 +664,10 @@ void enqueue_backward(ScoreModel* h) {
                              h->PG + Bo(nm.co_user));
     cudaEventRecord(h->ev_w, h->st_w);
     cudaStreamWaitEvent(h->st, h->ev_w, 0);
-    launch_reduce_partials(h->st, h->PG, kSplits, (int)h->n_dense, h->G);
+    {   // dWc = dWa - dWb (attn.cu header)
+        const int64_t w1 = po(h, (nm.att1 + "/kernel").c_str()), blk = (int64_t)Dk * 80;
+        launch_reduce_partials(h->st, h->PG, kSplits, (int)h->n_dense, h->G, w1 + 2 * blk, w1, w1 + blk, (int)blk);
+    }
 }
 
 int key_bits(int64_t V) {
@@ -876,6 +906,8 @@ int score_create(const ScoreConfig* cfg, int device, ScoreHandle* out) {
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_l2, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_w, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_tgt, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_q, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         h->err = "stream/event creation failed";
         return die(SCORE_ERR_CUDA);
@@ -901,7 +933,7 @@ int score_destroy(ScoreHandle h) {
     if (h->st) cudaStreamSynchronize(h->st);
     free_workspace(h);
     for (void* p : {(void*)h->emb, (void*)h->emb_m, (void*)h->emb_v, (void*)h->last_step, (void*)h->P, (void*)h->G,
-                    (void*)h->M1, (void*)h->V1, (void*)h->PG, (void*)h->flags, (void*)h->alpha_hist, (void*)h->l2sum,
+                    (void*)h->M1, (void*)h->V1, (void*)h->PG, (void*)h->flags, (void*)h->Dv, (void*)h->alpha_hist, (void*)h->l2sum,
                     (void*)h->loss_dev, (void*)h->err_flag, (void*)h->hyper_dev, (void*)h->seg_rows, (void*)h->seg_heads})
         if (p) cudaFree(p);
     if (h->hyper_ring) cudaFreeHost(h->hyper_ring);
@@ -912,6 +944,8 @@ int score_destroy(ScoreHandle h) {
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_l2) cudaEventDestroy(h->ev_l2);
     if (h->ev_w) cudaEventDestroy(h->ev_w);
+    if (h->ev_tgt) cudaEventDestroy(h->ev_tgt);
+    if (h->ev_q) cudaEventDestroy(h->ev_q);
     for (int i = 0; i < 16; ++i) if (h->ev_pool[i]) cudaEventDestroy(h->ev_pool[i]);
     if (h->st_w) cudaStreamDestroy(h->st_w);
     if (h->st) {

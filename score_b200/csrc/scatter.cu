@@ -49,15 +49,26 @@ void launch_l2_sum(cudaStream_t st, const float* params, const uint8_t* flags, i
     ++g_launch_count;
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, int splits, int n, float* __restrict__ g) {
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int splits, int n, float* __restrict__ g,
+                                       int64_t d_dst, int64_t d_a, int64_t d_b, int d_count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float s = 0.f;
+    if (d_dst >= 0 && i >= d_dst && i < d_dst + d_count) {
+        // derived range: the same fixed-order sums its two source elements get, then their difference
+        const int64_t ia = d_a + (i - d_dst), ib = d_b + (i - d_dst);
+        float sb = 0.f;
+        for (int k = 0; k < splits; ++k) { s += partials[(int64_t)k * n + ia]; sb += partials[(int64_t)k * n + ib]; }
+        g[i] = s - sb;
+        return;
+    }
     for (int k = 0; k < splits; ++k) s += partials[(int64_t)k * n + i];
     g[i] = s;
 }
-void launch_reduce_partials(cudaStream_t st, const float* partials, int splits, int n, float* g) {
-    reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(partials, splits, n, g);
+void launch_reduce_partials(cudaStream_t st, const float* partials, int splits, int n, float* g, int64_t derive_dst,
+                            int64_t derive_a, int64_t derive_b, int derive_count) {
+    reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(partials, splits, n, g, derive_dst, derive_a, derive_b,
+                                                            derive_count);
     ++g_launch_count;
 }
 

@@ -5,8 +5,7 @@
 //           copied through for t >= length.  The input part of both matmuls is hoisted out of the
 //           time loop into one SGEMM over all B*T rows (px); this kernel runs the recurrence with
 //           the state-side weights resident in shared memory.
-//   attention()  [q, key, q-key, q*key] -> 80 -> 40 -> 1 -> mask -> softmax over T  score.py:169-186
-//   pooling + build_fc_net + log-loss                                       score.py:214-217, 68-81
+//   (attention() + pooling live in attn.cu, build_fc_net + log-loss in chain.cu)
 #include "kernels.h"
 
 namespace score {
@@ -181,147 +180,6 @@ void launch_gru_bwd(cudaStream_t st, const Dims& dm, const GruBwdArgs& a) {
     }
     dim3 block(2 * dm.H, RB), grid((dm.B + RB - 1) / RB, 2);
     gru_bwd_kernel<<<grid, block, smem, st>>>(dm, a, RB);
-    ++g_launch_count;
-}
-
-// ------------------------------------------------------------------------------------------ attention input
-// a1[m] = [q_b | key_m | q_b - key_m | q_b * key_m]
-__global__ void att_inp_fwd_kernel(int64_t M, int T, int Dk, const float* __restrict__ q,
-                                   const float* __restrict__ key, float* __restrict__ a1) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= M * Dk) return;
-    int64_t m = idx / Dk; int c = (int)(idx - m * Dk);
-    int64_t b = m / T;
-    float qv = q[b * Dk + c], kv = key[m * Dk + c];
-    float* o = a1 + m * 4 * Dk;
-    o[c] = qv; o[Dk + c] = kv; o[2 * Dk + c] = qv - kv; o[3 * Dk + c] = qv * kv;
-}
-void launch_att_inp_fwd(cudaStream_t st, const Dims& dm, const float* q, const float* key, float* a1) {
-    int64_t n = (int64_t)dm.B * dm.T * dm.Dk;
-    att_inp_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int64_t)dm.B * dm.T, dm.T, dm.Dk, q, key, a1);
-    ++g_launch_count;
-}
-
-// da1 = [dA | dB | dC | dD]:  dq_b = sum_t (dA + dC + dD*key),  dkey = dB - dC + dD*q (+ pooling grad in cols < acc_cols)
-// one thread per (b, c): loops over t in fixed order
-__global__ void att_inp_bwd_kernel(int B, int T, int Dk, const float* __restrict__ q, const float* __restrict__ key,
-                                   const float* __restrict__ da1, float* __restrict__ dkey, float* __restrict__ dq,
-                                   int acc_cols) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= B * Dk) return;
-    int b = idx / Dk, c = idx - b * Dk;
-    float qv = q[idx];
-    float s = 0.f;
-    for (int t = 0; t < T; ++t) {
-        int64_t m = (int64_t)b * T + t;
-        const float* g = da1 + m * 4 * Dk;
-        float kv = key[m * Dk + c];
-        float dA = g[c], dBv = g[Dk + c], dC = g[2 * Dk + c], dD = g[3 * Dk + c];
-        s += dA + dC + dD * kv;
-        float dk = dBv - dC + dD * qv;
-        if (c < acc_cols) dk += dkey[m * Dk + c];
-        dkey[m * Dk + c] = dk;
-    }
-    dq[idx] = s;
-}
-void launch_att_inp_bwd(cudaStream_t st, const Dims& dm, const float* q, const float* key, const float* da1,
-                        float* dkey, float* dq, int accumulate_cols) {
-    int n = dm.B * dm.Dk;
-    att_inp_bwd_kernel<<<(n + 127) / 128, 128, 0, st>>>(dm.B, dm.T, dm.Dk, q, key, da1, dkey, dq, accumulate_cols);
-    ++g_launch_count;
-}
-
-// ------------------------------------------------------------------------------------------ attention pooling
-// one warp per sample: s_t = f2[m] . w3 + b3 ; masked softmax over T ; final = sum_t rep_t * score_t
-__global__ void att_pool_fwd_kernel(Dims dm, AttPoolArgs a) {
-    extern __shared__ float sm[];
-    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* sc = sm + warp * dm.T;
-    const int b = blockIdx.x * warps + warp;
-    if (b >= dm.B) return;
-    const int T = dm.T, H = dm.H;
-    const int len = a.length[b];
-    const float pad = -4294967296.0f;   // float32(-2**32 + 1)  score.py:180
-    if (a.s) {
-        for (int t = lane; t < T; t += 32) sc[t] = (t < len) ? a.s[(int64_t)b * T + t] : pad;
-    } else {
-        for (int t = 0; t < T; ++t) {
-            const float* f = a.f2 + ((int64_t)b * T + t) * 40;
-            float p = 0.f;
-            for (int c = lane; c < 40; c += 32) p += f[c] * a.w3[c];
-            p = warp_sum(p) + a.b3[0];
-            if (lane == 0) sc[t] = (t < len) ? p : pad;
-        }
-    }
-    __syncwarp();
-    float mx = -INFINITY;
-    for (int t = lane; t < T; t += 32) mx = fmaxf(mx, sc[t]);
-    mx = warp_max(mx);
-    float den = 0.f;
-    for (int t = lane; t < T; t += 32) den += expf(sc[t] - mx);
-    den = warp_sum(den);
-    __syncwarp();
-    for (int t = lane; t < T; t += 32) {
-        float w = expf(sc[t] - mx) / den;
-        sc[t] = w;
-        a.score[(int64_t)b * T + t] = w;
-    }
-    __syncwarp();
-    // pooled states; destination layout depends on the model type (score.py:217, 325, 362)
-    const int mt = dm.model_type;
-    for (int c = lane; c < 2 * H; c += 32) {
-        float s = 0.f;
-        for (int t = 0; t < T; ++t) s += a.key[((int64_t)b * T + t) * a.ldkey + c] * sc[t];
-        int dst = c;
-        if (mt == 3) { if (c >= H) continue; }            // SCORE_USER keeps only the user state
-        else if (mt == 4) { if (c < H) continue; dst = c - H; }   // SCORE_ITEM keeps only the item state
-        a.fc_in[(int64_t)b * a.ldfc + dst] = s;
-    }
-}
-void launch_att_pool_fwd(cudaStream_t st, const Dims& dm, const AttPoolArgs& a) {
-    const int warps = 4;
-    att_pool_fwd_kernel<<<(dm.B + warps - 1) / warps, warps * 32, warps * dm.T * sizeof(float), st>>>(dm, a);
-    ++g_launch_count;
-}
-
-// backward: dscore_t = d_final . rep_t ; ds_t = score_t (dscore_t - sum score dscore) for live t ;
-// dkey[:, 0:2H] = score_t * d_final
-__global__ void att_pool_bwd_kernel(Dims dm, AttPoolBwdArgs a) {
-    extern __shared__ float sm[];
-    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* dsc = sm + warp * dm.T;
-    const int b = blockIdx.x * warps + warp;
-    if (b >= dm.B) return;
-    const int T = dm.T, H = dm.H, mt = dm.model_type;
-    const int len = a.length[b];
-    const float* dfc = a.dfc_in + (int64_t)b * a.ldfc;
-    for (int t = 0; t < T; ++t) {
-        const int64_t m = (int64_t)b * T + t;
-        const float sct = a.score[m];
-        float p = 0.f;
-        for (int c = lane; c < 2 * H; c += 32) {
-            float d;
-            if (mt == 3) d = (c < H) ? dfc[c] : 0.f;
-            else if (mt == 4) d = (c >= H) ? dfc[c - H] : 0.f;
-            else d = dfc[c];
-            p += d * a.key[m * a.ldkey + c];
-            a.dkey[m * a.ldkey + c] = d * sct;
-        }
-        p = warp_sum(p);
-        if (lane == 0) dsc[t] = p;
-    }
-    __syncwarp();
-    float dot = 0.f;
-    for (int t = lane; t < T; t += 32) dot += a.score[(int64_t)b * T + t] * dsc[t];
-    dot = warp_sum(dot);
-    for (int t = lane; t < T; t += 32) {
-        float s = a.score[(int64_t)b * T + t];
-        a.ds[(int64_t)b * T + t] = (t < len) ? s * (dsc[t] - dot) : 0.f;   // tf.where blocks the gradient of padded slots
-    }
-}
-void launch_att_pool_bwd(cudaStream_t st, const Dims& dm, const AttPoolBwdArgs& a) {
-    const int warps = 4;
-    att_pool_bwd_kernel<<<(dm.B + warps - 1) / warps, warps * 32, warps * dm.T * sizeof(float), st>>>(dm, a);
     ++g_launch_count;
 }
 
