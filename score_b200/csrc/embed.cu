@@ -20,31 +20,83 @@ namespace score {
 // ------------------------------------------------------------------------------------------
 // keys[p] = sanitized id of flat position p: 0 for masked slices (t >= length[b]) and ids that
 // are out of range (flagged).  Positions: [user_1hop | user_2hop | item_1hop | item_2hop | tu | ti].
+// Four positions per thread (one 16-byte id load, four independent dependent chains).  In LAZY optimizer mode the
+// same pass claims the stale rows among the keys (atomic exchange on last_step, plain pre-check first) and appends
+// (row, last step) to the compact list emb_replay_kernel works through (scatter.cu).
+__device__ __forceinline__ bool position_live(const Dims& dm, int64_t p, const int32_t* __restrict__ length) {
+    if (p >= dm.off_tu) return true;
+    int64_t local; int f;
+    if (p < dm.off_u2) { local = p - dm.off_u1; f = dm.fi; }
+    else if (p < dm.off_i1) { local = p - dm.off_u2; f = dm.fu; }
+    else if (p < dm.off_i2) { local = p - dm.off_i1; f = dm.fu; }
+    else { local = p - dm.off_i2; f = dm.fi; }
+    const int64_t slice = local / ((int64_t)dm.K * f);
+    const int b = (int)(slice / dm.T), t = (int)(slice % dm.T);
+    return t < length[b];
+}
+
 __global__ void build_keys_kernel(Dims dm, const int32_t* __restrict__ ids, const int32_t* __restrict__ length,
-                                  int32_t* __restrict__ keys, int32_t* __restrict__ err_flag) {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= dm.N) return;
-    int32_t id = ids[p];
-    bool live = true;
-    if (p < dm.off_tu) {
-        int64_t local; int f;
-        if (p < dm.off_u2) { local = p - dm.off_u1; f = dm.fi; }
-        else if (p < dm.off_i1) { local = p - dm.off_u2; f = dm.fu; }
-        else if (p < dm.off_i2) { local = p - dm.off_i1; f = dm.fu; }
-        else { local = p - dm.off_i2; f = dm.fi; }
-        int64_t slice = local / ((int64_t)dm.K * f);
-        int b = (int)(slice / dm.T), t = (int)(slice % dm.T);
-        live = t < length[b];
+                                  int32_t* __restrict__ keys, int32_t* __restrict__ err_flag, ClaimArgs ca) {
+    const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int lane = threadIdx.x & 31;
+    int32_t id[4] = {0, 0, 0, 0};
+    if (p0 + 3 < dm.N) {
+        const int4 v = *reinterpret_cast<const int4*>(ids + p0);
+        id[0] = v.x; id[1] = v.y; id[2] = v.z; id[3] = v.w;
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (p0 + u < dm.N) id[u] = ids[p0 + u];
     }
-    if (id < 0 || (int64_t)id >= dm.V) { atomicExch(err_flag, 1); id = 0; }
-    keys[p] = live ? id : 0;
+    bool bad = false;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if (p0 + u >= dm.N) { id[u] = 0; continue; }
+        if (id[u] < 0 || (int64_t)id[u] >= dm.V) { bad = true; id[u] = 0; }
+        if (id[u] != 0 && !position_live(dm, p0 + u, length)) id[u] = 0;
+    }
+    if (bad) atomicExch(err_flag, 1);
+    if (p0 + 3 < dm.N) *reinterpret_cast<int4*>(keys + p0) = make_int4(id[0], id[1], id[2], id[3]);
+    else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (p0 + u < dm.N) keys[p0 + u] = id[u];
+    }
+    if (!ca.last_step) return;   // uniform
+    const int upto = ca.hp->step - 1;
+    int seen[4], old[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) seen[u] = id[u] != 0 ? ca.last_step[id[u]] : upto;   // four independent loads
+    int nwin = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        old[u] = upto;
+        if (seen[u] < upto) old[u] = atomicExch(&ca.last_step[id[u]], upto);
+        nwin += old[u] < upto ? 1 : 0;
+    }
+    // warp-aggregated append
+    int incl = nwin;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(FULL_MASK, incl, o);
+        if (lane >= o) incl += y;
+    }
+    const int total = __shfl_sync(FULL_MASK, incl, 31);
+    if (total == 0) return;
+    int base = 0;
+    if (lane == 31) base = atomicAdd(ca.counter, total);
+    base = __shfl_sync(FULL_MASK, base, 31);
+    int idx = base + incl - nwin;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (old[u] < upto) { ca.list[2 * idx] = id[u]; ca.list[2 * idx + 1] = old[u]; ++idx; }
 }
 
 void launch_build_keys(cudaStream_t st, const Dims& dm, const int32_t* ids, const int32_t* length,
-                       int32_t* keys, int32_t* err_flag) {
-    int threads = 256;
-    int64_t blocks = (dm.N + threads - 1) / threads;
-    build_keys_kernel<<<(unsigned)blocks, threads, 0, st>>>(dm, ids, length, keys, err_flag);
+                       int32_t* keys, int32_t* err_flag, const ClaimArgs* claim) {
+    ClaimArgs ca{};
+    if (claim) { ca = *claim; cudaMemsetAsync(ca.counter, 0, sizeof(int32_t), st); }
+    const int threads = 256;
+    const int64_t blocks = ((dm.N + 3) / 4 + threads - 1) / threads;
+    build_keys_kernel<<<(unsigned)blocks, threads, 0, st>>>(dm, ids, length, keys, err_flag, ca);
     ++g_launch_count;
 }
 

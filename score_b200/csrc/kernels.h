@@ -48,8 +48,13 @@ struct Dims {
     int model_type;
 };
 
+// LAZY optimizer mode: claim the stale rows among the keys while they are built (see scatter.cu: emb_replay_kernel)
+struct ClaimArgs { int32_t* last_step; const Hyper* hp; int32_t* list; int32_t* counter; };
 void launch_build_keys(cudaStream_t st, const Dims& dm, const int32_t* ids, const int32_t* length,
-                       int32_t* keys, int32_t* err_flag);
+                       int32_t* keys, int32_t* err_flag, const ClaimArgs* claim = nullptr);
+// replay the rows of a claim list (2 int32 per entry: row, last step); *counter entries
+void launch_emb_replay(cudaStream_t st, const int32_t* claim_list, const int32_t* claim_counter, int64_t max_rows, float* emb,
+                       float* m, float* v, int d, const float* alpha_hist, const Hyper* hp);
 
 struct TargetArgs {
     const float* emb; const int32_t* keys;
@@ -151,7 +156,7 @@ struct FcBwdArgs {
 void launch_fc_bwd(cudaStream_t st, const FcBwdArgs& a);
 // dgamma / dbeta of the inference-mode batch norm (the dx part is produced by fc_bwd)
 void launch_bn_param_grads(cudaStream_t st, int B, int F, const float* x, const float* dz, const float* mean,
-                           const float* var, float* dgamma, float* dbeta);
+                           const float* var, float* dgamma, float* dbeta, int splits, int64_t split_stride);
 
 // logit = g2 . w3 + b3; y = sigmoid; per-sample log-loss (eps 1e-7) and d loss / d logit
 void launch_head(cudaStream_t st, int B, int F, const float* g2, const float* w3, const float* b3,
@@ -235,8 +240,11 @@ size_t sort_hist_elems(int64_t n);
 // returns the index (0/1) of the ping-pong buffer that holds the result
 int launch_sort_pairs(cudaStream_t st, SortBufs& sb, const int32_t* keys_in, int64_t n, int key_bits);
 
+// compact list of the sorted indices that start a run of equal non-zero keys (order arbitrary); *counter = their number
+void launch_emb_heads(cudaStream_t st, const int32_t* skeys, int64_t n, int32_t* heads, int32_t* counter);
 struct EmbUpdateArgs {
     const int32_t* skeys; const int32_t* spos; int64_t n;
+    const int32_t* heads; const int32_t* n_heads;   // from launch_emb_heads
     const float* grad_rows; int d;
     float* emb; float* m; float* v; int32_t* last_step;
     const float* alpha_hist;       // LAZY: rows that are not current through step-1 are replayed first (may be null)
@@ -249,9 +257,11 @@ void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a);
 void launch_emb_dense_sweep(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d,
                             const Hyper* hp);
 // LAZY mode: replay skipped zero-gradient steps of the rows about to be gathered (keys in position order;
-// duplicates are resolved by an atomic claim on last_step, the replay result does not depend on the winner)
-void launch_emb_catchup_rows(cudaStream_t st, const int32_t* keys, int64_t n, float* emb, float* m, float* v,
-                             int32_t* last_step, int d, const float* alpha_hist, const Hyper* hp);
+// duplicates are resolved by an atomic claim on last_step, the replay result does not depend on the winner).
+// claim_list: 2*n int32 of scratch, claim_counter: one int32.
+void launch_emb_catchup_rows(cudaStream_t st, const int32_t* keys, int64_t n, int64_t V, float* emb, float* m, float* v,
+                             int32_t* last_step, int d, const float* alpha_hist, const Hyper* hp, int32_t* claim_list,
+                             int32_t* claim_counter);
 // LAZY mode: bring the whole table up to `upto_step` (before read-back / save / eval of everything)
 void launch_emb_catchup_all(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d,
                             const float* alpha_hist, int upto_step);

@@ -22,7 +22,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr int kSplits = 16;   // fixed number of batch-row chunks for weight gradients (deterministic two-stage sum)
+constexpr int kSplits = 32;   // fixed number of batch-row chunks for weight gradients (deterministic two-stage sum)
 
 struct Tensor {
     std::string name;
@@ -82,6 +82,9 @@ struct ScoreModel {
     int sort_out = 0;
     float *seg_rows = nullptr; int32_t* seg_heads = nullptr; int64_t seg_cap = 0;
     int64_t last_N = 0;
+    int32_t* claim_list = nullptr; int32_t* claim_ext = nullptr; int64_t claim_ext_cap = 0;   // LAZY catch-up scratch
+    int32_t* claim_counter = nullptr;
+    int32_t* n_heads_dev = nullptr;   // number of run heads in the sorted key list (emb_heads_kernel)
     float *l2sum = nullptr, *loss_dev = nullptr;   // loss_dev[0] = total loss, loss_dev[1] = reg_lambda * l2 part
     int32_t* err_flag = nullptr;
     Hyper* hyper_dev = nullptr;
@@ -254,6 +257,9 @@ int alloc_params(ScoreModel* h) {
         if (!t.is_emb)
             for (int64_t i = 0; i < t.rows * t.cols; ++i) fl[t.off + i] = t.flags;
     CK(cudaMemcpy(h->flags, fl.data(), n, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->claim_counter, sizeof(int32_t)));
+    CK(cudaMalloc(&h->n_heads_dev, sizeof(int32_t)));
+    CK(cudaMemsetAsync(h->n_heads_dev, 0, sizeof(int32_t), h->st));
     CK(cudaMalloc(&h->l2sum, sizeof(float)));
     CK(cudaMalloc(&h->loss_dev, 2 * sizeof(float)));
     CK(cudaMalloc(&h->err_flag, sizeof(int32_t)));
@@ -369,6 +375,7 @@ int ensure_workspace(ScoreModel* h, int B) {
     h->n_target_part = target_bwd_num_ctas();
     WS(h->coatt_part, (int64_t)h->n_coatt_part * (2 * dm.Di + 2 * dm.Du), nullptr);
     WS(h->target_part, (int64_t)h->n_target_part * (dm.Di + dm.Du + 2), nullptr);
+    WSI(h->claim_list, 2 * N, nullptr);
     WSI(h->sb.keys[0], N, nullptr); WSI(h->sb.keys[1], N, nullptr);
     WSI(h->sb.vals[0], N, nullptr); WSI(h->sb.vals[1], N, nullptr);
     {
@@ -498,7 +505,7 @@ void probe_end(ScoreModel* h, int p, cudaStream_t s) {
 enum StepMode { MODE_TRAIN = 0, MODE_EVAL = 1, MODE_FWDBWD = 2, MODE_BEGIN = 3 };
 
 // forward graph of class SCORE (score.py:188-224); everything enqueued on h->st
-void enqueue_forward(ScoreModel* h) {
+void enqueue_forward(ScoreModel* h, bool will_bwd) {
     const Dims& dm = h->dm;
     const int B = dm.B, T = dm.T, H = dm.H, Ds = dm.Ds, Dk = dm.Dk, Dfc = dm.Dfc, ldx = dm.ldx;
     const int M = B * T;
@@ -508,6 +515,7 @@ void enqueue_forward(ScoreModel* h) {
 
     // side stream: derived weights of the fused chains, then 0.5*sum(v^2) (only feeds the loss scalar)
     cudaStreamWaitEvent(h->st_w, h->ev_fork, 0);
+    if (will_bwd) cudaMemsetAsync(h->PG, 0, sizeof(float) * h->n_dense * kSplits, h->st_w);   // weight-gradient partial planes
     launch_prep_weights(h->st_w, h->prep, h->P, h->Dv);
     launch_l2_sum(h->st_w, h->P, h->flags, (int)h->n_dense, h->l2sum);
     cudaEventRecord(h->ev_l2, h->st_w);
@@ -585,7 +593,6 @@ void enqueue_backward(ScoreModel* h) {
     auto Bo = [&](const std::string& n) { return po(h, (n + "/bias").c_str()); };
 
     probe_begin(h, PR_BWD_DENSE, h->st);
-    cudaMemsetAsync(h->PG, 0, sizeof(float) * h->n_dense * kSplits, h->st);
 
     // prediction MLP: fused backward data chain on the main stream, weight gradients on the side stream
     FcBwdArgs fb{};
@@ -594,11 +601,15 @@ void enqueue_backward(ScoreModel* h) {
     fb.w2t = h->Dv + h->dv_fc2T; fb.w1t = h->Dv + h->dv_fc1T;
     fb.hp = h->hyper_dev; fb.dg2 = h->dg2; fb.dg1 = h->dg1; fb.dz0 = h->dz0; fb.dfc_in = h->dfc_in;
     launch_fc_bwd(h->st, fb);
-    gemm_bwd_weight(h, h->g2, 80, h->dlogit, 1, Wo("fc3"), Bo("fc3"), B, 80, 1);
-    gemm_bwd_weight(h, h->g1, 200, h->dg2, 80, Wo("fc2"), Bo("fc2"), B, 200, 80);
-    gemm_bwd_weight(h, h->z0, Dfc, h->dg1, 200, Wo("fc1"), Bo("fc1"), B, Dfc, 200);
+    {   // weight gradients go to the side stream in groups: one launch per group of problems that become ready together
+        GemmArgs l[3];
+        l[0] = gemm_bwd_weight_args(h, h->z0, Dfc, h->dg1, 200, Wo("fc1"), Bo("fc1"), B, Dfc, 200);
+        l[1] = gemm_bwd_weight_args(h, h->g1, 200, h->dg2, 80, Wo("fc2"), Bo("fc2"), B, 200, 80);
+        l[2] = gemm_bwd_weight_args(h, h->g2, 80, h->dlogit, 1, Wo("fc3"), Bo("fc3"), B, 80, 1);
+        gemm_bwd_weight_batch(h, l, 3);
+    }
     launch_bn_param_grads(h->st_w, B, Dfc, h->fc_in, h->dz0, pp(h, "bn1/moving_mean"), pp(h, "bn1/moving_variance"),
-                          h->PG + po(h, "bn1/gamma"), h->PG + po(h, "bn1/beta"));
+                          h->PG + po(h, "bn1/gamma"), h->PG + po(h, "bn1/beta"), kSplits, h->n_dense);
 
     // attention: pooling + softmax + MLP backward in one fused chain, then the per-sample query side
     const int64_t blk = (int64_t)Dk * 80;   // dense_3/kernel row blocks: Wa | Wb | Wc | Wd
@@ -609,18 +620,20 @@ void enqueue_backward(ScoreModel* h) {
         ab.w3 = W(nm.att3); ab.W2T = h->Dv + h->dv_W2T; ab.W1eT = h->Dv + h->dv_W1eT;
         ab.ds = h->ds; ab.df2 = h->df2; ab.df1 = h->df1; ab.dkey = h->dkey; ab.sdf1 = h->sdf1; ab.dqD = h->dqD;
         launch_att_bwd2(h->st, ab);
-        gemm_bwd_weight(h, h->f2, 40, h->ds, 1, Wo(nm.att3), Bo(nm.att3), M, 40, 1);
-        gemm_bwd_weight(h, h->f1, 80, h->df2, 40, Wo(nm.att2), Bo(nm.att2), M, 80, 40);
-        GemmArgs w1l[2];
+        GemmArgs w1l[4];
         w1l[0] = gemm_bwd_weight_args(h, h->key, Dk, h->df1, 80, Wo(nm.att1) + blk, -1, M, Dk, 80);      // dWb = key^T df1
         w1l[1] = gemm_bwd_weight_args(h, h->qk, Dk, h->df1, 80, Wo(nm.att1) + 3 * blk, -1, M, Dk, 80);   // dWd = (q*key)^T df1
-        gemm_bwd_weight_batch(h, w1l, 2);
+        w1l[2] = gemm_bwd_weight_args(h, h->f1, 80, h->df2, 40, Wo(nm.att2), Bo(nm.att2), M, 80, 40);
+        w1l[3] = gemm_bwd_weight_args(h, h->f2, 40, h->ds, 1, Wo(nm.att3), Bo(nm.att3), M, 40, 1);
+        gemm_bwd_weight_batch(h, w1l, 4);
         AttQbArgs qb{};
         qb.B = B; qb.Ds = Ds; qb.Dk = Dk; qb.sdf1 = h->sdf1; qb.dqD = h->dqD; qb.WacT = h->Dv + h->dv_WacT;
         qb.WqT = h->Dv + h->dv_WqT; qb.dq = h->dq; qb.dq0 = h->dq0;
         launch_att_qb(h->st, qb);
-        gemm_bwd_weight(h, h->q, Dk, h->sdf1, 80, Wo(nm.att1), Bo(nm.att1), B, Dk, 80);                  // dWa = q^T sum_t df1
-        gemm_bwd_weight(h, h->q0, Ds, h->dq, Dk, Wo(nm.att_q), Bo(nm.att_q), B, Ds, Dk);
+        GemmArgs wql[2];
+        wql[0] = gemm_bwd_weight_args(h, h->q, Dk, h->sdf1, 80, Wo(nm.att1), Bo(nm.att1), B, Dk, 80);    // dWa = q^T sum_t df1
+        wql[1] = gemm_bwd_weight_args(h, h->q0, Ds, h->dq, Dk, Wo(nm.att_q), Bo(nm.att_q), B, Ds, Dk);
+        gemm_bwd_weight_batch(h, wql, 2);
     }
 
     // GRUs
@@ -692,22 +705,26 @@ void enqueue_step(ScoreModel* h, int mode) {
     const bool need_bwd = (mode != MODE_EVAL);
     h->emb_fwd = h->emb; h->keys_fwd = h->keys;
     probe_begin(h, PR_STEP, h->st);
-    launch_build_keys(h->st, dm, h->ids, h->length, h->keys, h->err_flag);
     if (h->cfg.adam_mode == SCORE_ADAM_LAZY) {
         probe_begin(h, PR_CATCHUP, h->st);
-        launch_emb_catchup_rows(h->st, h->keys, dm.N, h->emb, h->emb_m, h->emb_v, h->last_step, dm.d, h->alpha_hist,
-                                h->hyper_dev);
+        ClaimArgs ca{h->last_step, h->hyper_dev, h->claim_list, h->claim_counter};
+        launch_build_keys(h->st, dm, h->ids, h->length, h->keys, h->err_flag, &ca);
+        launch_emb_replay(h->st, h->claim_list, h->claim_counter, dm.N, h->emb, h->emb_m, h->emb_v, dm.d, h->alpha_hist,
+                          h->hyper_dev);
         probe_end(h, PR_CATCHUP, h->st);
+    } else {
+        launch_build_keys(h->st, dm, h->ids, h->length, h->keys, h->err_flag);
     }
     cudaEventRecord(h->ev_fork, h->st);
     if (need_bwd) {   // the sort depends on ids only: run it on the side stream under forward/backward
         cudaStreamWaitEvent(h->st2, h->ev_fork, 0);
         probe_begin(h, PR_SORT, h->st2);
         h->sort_out = launch_sort_pairs(h->st2, h->sb, h->keys, dm.N, key_bits(dm.V));
+        launch_emb_heads(h->st2, h->sb.keys[h->sort_out], dm.N, h->sb.keys[1 - h->sort_out], h->n_heads_dev);
         probe_end(h, PR_SORT, h->st2);
         cudaEventRecord(h->ev_join, h->st2);
     }
-    enqueue_forward(h);
+    enqueue_forward(h, need_bwd);
     if (need_bwd) {
         enqueue_backward(h);
         cudaStreamWaitEvent(h->st, h->ev_join, 0);
@@ -717,6 +734,7 @@ void enqueue_step(ScoreModel* h, int mode) {
         cudaMemsetAsync(h->seg_heads, 0, sizeof(int32_t) * dm.N, h->st);
         EmbUpdateArgs ea{};
         ea.skeys = h->sb.keys[h->sort_out]; ea.spos = h->sb.vals[h->sort_out]; ea.n = dm.N;
+        ea.heads = h->sb.keys[1 - h->sort_out]; ea.n_heads = h->n_heads_dev;
         ea.grad_rows = h->grad_rows; ea.d = dm.d; ea.hp = h->hyper_dev; ea.mode = 1;
         ea.out_rows = h->seg_rows; ea.out_heads = h->seg_heads;
         launch_emb_update(h->st, ea);
@@ -725,6 +743,7 @@ void enqueue_step(ScoreModel* h, int mode) {
         launch_dense_adam(h->st, h->P, h->M1, h->V1, h->G, h->flags, (int)h->n_dense, h->hyper_dev, h->alpha_hist);
         EmbUpdateArgs ea{};
         ea.skeys = h->sb.keys[h->sort_out]; ea.spos = h->sb.vals[h->sort_out]; ea.n = dm.N;
+        ea.heads = h->sb.keys[1 - h->sort_out]; ea.n_heads = h->n_heads_dev;
         ea.grad_rows = h->grad_rows; ea.d = dm.d;
         ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.last_step = h->last_step;
         ea.alpha_hist = h->alpha_hist;
@@ -933,7 +952,7 @@ int score_destroy(ScoreHandle h) {
     if (h->st) cudaStreamSynchronize(h->st);
     free_workspace(h);
     for (void* p : {(void*)h->emb, (void*)h->emb_m, (void*)h->emb_v, (void*)h->last_step, (void*)h->P, (void*)h->G,
-                    (void*)h->M1, (void*)h->V1, (void*)h->PG, (void*)h->flags, (void*)h->Dv, (void*)h->alpha_hist, (void*)h->l2sum,
+                    (void*)h->M1, (void*)h->V1, (void*)h->PG, (void*)h->flags, (void*)h->Dv, (void*)h->n_heads_dev, (void*)h->claim_counter, (void*)h->claim_ext, (void*)h->alpha_hist, (void*)h->l2sum,
                     (void*)h->loss_dev, (void*)h->err_flag, (void*)h->hyper_dev, (void*)h->seg_rows, (void*)h->seg_heads})
         if (p) cudaFree(p);
     if (h->hyper_ring) cudaFreeHost(h->hyper_ring);
@@ -1330,9 +1349,17 @@ int score_gather_rows(ScoreHandle h, const int32_t* idx_dev, int64_t n, float* o
         int rc = upload_hyper(h, 1, 0.f, 0.f, 1.f, 0, 1);
         if (rc) return rc;
     }
-    if (h->cfg.adam_mode == SCORE_ADAM_LAZY)
-        launch_emb_catchup_rows(h->st, idx_dev, n, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.d, h->alpha_hist,
-                                h->hyper_dev);
+    if (h->cfg.adam_mode == SCORE_ADAM_LAZY) {
+        if (n > h->claim_ext_cap) {
+            CK(cudaStreamSynchronize(h->st));
+            if (h->claim_ext) cudaFree(h->claim_ext);
+            h->claim_ext = nullptr; h->claim_ext_cap = 0;
+            CK(cudaMalloc(&h->claim_ext, sizeof(int32_t) * 2 * (n + n / 4)));
+            h->claim_ext_cap = n + n / 4;
+        }
+        launch_emb_catchup_rows(h->st, idx_dev, n, h->dm.V, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.d, h->alpha_hist,
+                                h->hyper_dev, h->claim_ext, h->claim_counter);
+    }
     launch_gather_rows(h->st, h->emb, idx_dev, n, h->dm.d, h->dm.V, out_dev, h->err_flag);
     return SCORE_OK;
 }
@@ -1374,10 +1401,10 @@ int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg
         h->emb_fwd = h->emb; h->keys_fwd = h->keys;
         if (batch) launch_build_keys(h->st, dm, h->ids, h->length, h->keys, h->err_flag);
         if (h->cfg.adam_mode == SCORE_ADAM_LAZY)
-            launch_emb_catchup_rows(h->st, h->keys, dm.N, h->emb, h->emb_m, h->emb_v, h->last_step, dm.d,
-                                    h->alpha_hist, h->hyper_dev);
+            launch_emb_catchup_rows(h->st, h->keys, dm.N, dm.V, h->emb, h->emb_m, h->emb_v, h->last_step, dm.d,
+                                    h->alpha_hist, h->hyper_dev, h->claim_list, h->claim_counter);
     }
-    enqueue_forward(h);
+    enqueue_forward(h, train != 0);
     if (train) enqueue_backward(h);
     h->begun = train != 0;
     h->begun_lr = lr;
@@ -1400,7 +1427,9 @@ int score_step_finish(ScoreHandle h, const int32_t* ext_keys, const float* ext_r
             if (rc) return rc;
             const int out = launch_sort_pairs(h->st, h->sb_ext, ext_keys, n_ext, key_bits(h->dm.V));
             EmbUpdateArgs ea{};
+            launch_emb_heads(h->st, h->sb_ext.keys[out], n_ext, h->sb_ext.keys[1 - out], h->n_heads_dev);
             ea.skeys = h->sb_ext.keys[out]; ea.spos = h->sb_ext.vals[out]; ea.n = n_ext;
+            ea.heads = h->sb_ext.keys[1 - out]; ea.n_heads = h->n_heads_dev;
             ea.grad_rows = ext_rows; ea.d = h->dm.d;
             ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.last_step = h->last_step;
             ea.alpha_hist = h->alpha_hist; ea.hp = h->hyper_dev; ea.mode = 0;

@@ -243,80 +243,120 @@ __device__ __forceinline__ void replay4(float4& var, float4& m, float4& v, int f
     for (int s = from + 1; s <= upto; ++s) adam4(var, m, v, z, alpha_hist[s]);
 }
 // ------------------------------------------------------------------------------------------ segment reduce + row Adam
-// One group of d/4 lanes per sorted index; the group at the head of a run of equal keys sums the
-// run's gradient rows in sorted (= ascending position) order and updates the row.
-__global__ void __launch_bounds__(256, 6) emb_update_kernel(EmbUpdateArgs a) {
+// Step 1 (emb_heads_kernel, on the sort stream): compact list of the sorted indices that start a run of equal non-zero
+// keys.  The list order comes from atomics and only decides which thread group serves which row - every row's
+// arithmetic is fixed, so the result is deterministic.
+// Step 2 (emb_update_kernel): one group of d/4 lanes per run head, grid-stride over the compact list, so every lane of
+// every resident warp has a row in flight (a group-per-sorted-index layout leaves ~60 % of the groups idle: they sit
+// on non-head indices).  The group loads the row's optimizer state early, walks the run four entries at a time
+// (independent loads, additions in ascending position order - no float atomics) and applies TF-form Adam.
+__global__ void emb_heads_kernel(const int32_t* __restrict__ skeys, int64_t n, int32_t* __restrict__ heads,
+                                 int32_t* __restrict__ counter) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int32_t key = 0, prev = -1;
+    if (i < n) { key = skeys[i]; prev = i > 0 ? skeys[i - 1] : -1; }
+    const bool head = (i < n) && key != 0 && key != prev;
+    const unsigned mask = __ballot_sync(FULL_MASK, head);
+    if (mask == 0) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(FULL_MASK, base, 0);
+    if (head) heads[base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)i;
+}
+void launch_emb_heads(cudaStream_t st, const int32_t* skeys, int64_t n, int32_t* heads, int32_t* counter) {
+    cudaMemsetAsync(counter, 0, sizeof(int32_t), st);
+    emb_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(skeys, n, heads, counter);
+    ++g_launch_count;
+}
+
+template <bool EXPORT>
+__global__ void __launch_bounds__(256, 4) emb_update_kernel(EmbUpdateArgs a) {
     const int lpr = a.d >> 2;
-    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / lpr;
     const int sub = threadIdx.x % lpr;
-    if (gid >= a.n) return;
-    // load batch 1 (independent): the previous key and the first four (key, position) pairs of the run
-    const int32_t k_prev = gid > 0 ? a.skeys[gid - 1] : -1;
-    int32_t kk[4], pp[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const int64_t idx = gid + u;
-        const bool in = idx < a.n;
-        kk[u] = in ? a.skeys[idx] : 0;
-        pp[u] = in ? a.spos[idx] : 0;
-    }
-    const int32_t key = kk[0];
-    if (key == 0 || k_prev == key) return;   // dummy / masked position, or not the head of its run
-    // load batch 2 (independent): the row's optimizer state and the run's gradient rows
-    const int64_t off = (int64_t)key * a.d + sub * 4;
-    float4 var, m, v;
-    if (a.mode == 0) {
-        var = *reinterpret_cast<const float4*>(a.emb + off);
-        m = *reinterpret_cast<const float4*>(a.m + off);
-        v = *reinterpret_cast<const float4*>(a.v + off);
-    }
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    // walk the run four entries at a time; the additions stay in sorted (= ascending position) order
-    for (int64_t j = gid;;) {
-        int cnt = 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) cnt += (cnt == u && kk[u] == key) ? 1 : 0;
-        float4 g[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (u < cnt) g[u] = *reinterpret_cast<const float4*>(a.grad_rows + (int64_t)pp[u] * a.d + sub * 4);
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (u < cnt) { acc.x += g[u].x; acc.y += g[u].y; acc.z += g[u].z; acc.w += g[u].w; }
-        if (cnt < 4) break;
-        j += 4;
+    const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / lpr;
+    const int nheads = *a.n_heads;
+    for (int64_t h = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / lpr; h < nheads; h += ngroups) {
+        const int64_t gid = a.heads[h];
+        // load batch 1 (independent): the first four (key, position) pairs of the run
+        int32_t kk[4], pp[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int64_t idx = j + u;
+            const int64_t idx = gid + u;
             const bool in = idx < a.n;
             kk[u] = in ? a.skeys[idx] : 0;
             pp[u] = in ? a.spos[idx] : 0;
         }
+        const int32_t key = kk[0];
+        // load batch 2 (independent): the row's optimizer state and the run's gradient rows
+        const int64_t off = (int64_t)key * a.d + sub * 4;
+        float4 var, m, v;
+        if (!EXPORT) {
+            var = *reinterpret_cast<const float4*>(a.emb + off);
+            m = *reinterpret_cast<const float4*>(a.m + off);
+            v = *reinterpret_cast<const float4*>(a.v + off);
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // walk the run four entries at a time; the additions stay in sorted (= ascending position) order
+        for (int64_t j = gid;;) {
+            int cnt = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cnt += (cnt == u && kk[u] == key) ? 1 : 0;
+            float4 g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (u < cnt) g[u] = *reinterpret_cast<const float4*>(a.grad_rows + (int64_t)pp[u] * a.d + sub * 4);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (u < cnt) { acc.x += g[u].x; acc.y += g[u].y; acc.z += g[u].z; acc.w += g[u].w; }
+            if (cnt < 4) break;
+            j += 4;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t idx = j + u;
+                const bool in = idx < a.n;
+                kk[u] = in ? a.skeys[idx] : 0;
+                pp[u] = in ? a.spos[idx] : 0;
+            }
+        }
+        if (EXPORT) {
+            *reinterpret_cast<float4*>(a.out_rows + gid * a.d + sub * 4) = acc;
+            if (sub == 0) a.out_heads[gid] = key;
+            continue;
+        }
+        if (a.alpha_hist) {   // LAZY: a row another rank gathered may not be current here yet
+            const int last = a.last_step[key], upto = a.hp->step - 1;
+            if (last < upto && !(all_zero(m) && all_zero(v))) replay4(var, m, v, last, upto, a.alpha_hist);
+        }
+        adam4(var, m, v, acc, a.hp->alpha);
+        {   // every lane of the row group (identical control flow) has read last_step before lane 0 overwrites it
+            const int lane = threadIdx.x & 31;
+            const unsigned gmask = (lpr >= 32) ? FULL_MASK : (((1u << lpr) - 1u) << (lane & ~(lpr - 1)));
+            __syncwarp(gmask);
+        }
+        *reinterpret_cast<float4*>(a.emb + off) = var;
+        *reinterpret_cast<float4*>(a.m + off) = m;
+        *reinterpret_cast<float4*>(a.v + off) = v;
+        if (sub == 0 && a.last_step) a.last_step[key] = a.hp->step;
     }
-    if (a.mode == 1) {
-        *reinterpret_cast<float4*>(a.out_rows + gid * a.d + sub * 4) = acc;
-        if (sub == 0) a.out_heads[gid] = key;
-        return;
-    }
-    if (a.alpha_hist) {   // LAZY: a row another rank gathered may not be current here yet
-        const int last = a.last_step[key], upto = a.hp->step - 1;
-        if (last < upto && !(all_zero(m) && all_zero(v))) replay4(var, m, v, last, upto, a.alpha_hist);
-    }
-    adam4(var, m, v, acc, a.hp->alpha);
-    {   // every lane of the row group (identical control flow) has read last_step before lane 0 overwrites it
-        const int lane = threadIdx.x & 31;
-        const unsigned gmask = (lpr >= 32) ? FULL_MASK : (((1u << lpr) - 1u) << (lane & ~(lpr - 1)));
-        __syncwarp(gmask);
-    }
-    *reinterpret_cast<float4*>(a.emb + off) = var;
-    *reinterpret_cast<float4*>(a.m + off) = m;
-    *reinterpret_cast<float4*>(a.v + off) = v;
-    if (sub == 0 && a.last_step) a.last_step[key] = a.hp->step;
 }
 void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
     const int lpr = a.d >> 2;
-    int64_t threads = a.n * lpr;
-    emb_update_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a);
+    // one group per head when at most half of the sorted indices start a run (groups past the head count exit at once;
+    // the grid-stride loop covers the rest): many short CTAs keep the SMs evenly loaded, one persistent wave does not
+    int64_t want = (a.n * lpr + 255) / 256;
+    int64_t half = (want + 1) / 2, cap = (int64_t)sms * 6;
+    unsigned grid = (unsigned)(half > cap ? half : (want < cap ? want : cap));
+    if (grid == 0) grid = 1;
+    if (a.mode == 1) emb_update_kernel<true><<<grid, 256, 0, st>>>(a);
+    else emb_update_kernel<false><<<grid, 256, 0, st>>>(a);
     ++g_launch_count;
 }
 
@@ -345,42 +385,80 @@ void launch_emb_dense_sweep(cudaStream_t st, float* emb, float* m, float* v, int
     ++g_launch_count;
 }
 
-// one group per gathered position; the group that wins the atomic claim of the row replays it
-__global__ void __launch_bounds__(256, 6)
-emb_catchup_rows_kernel(const int32_t* __restrict__ keys, int64_t n, float* __restrict__ emb,
-                        float* __restrict__ m, float* __restrict__ v, int32_t* __restrict__ last_step,
-                        int d, const float* __restrict__ alpha_hist, const Hyper* hp) {
-    const int lpr = d >> 2;
-    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / lpr;
-    const int sub = threadIdx.x % lpr;
+// LAZY catch-up of the rows about to be gathered, in two kernels:
+//   emb_claim_kernel   one thread per gathered position; the thread that wins the atomic claim of a stale row appends
+//                      (row, last step) to a compact list (plain pre-check first: duplicates and current rows skip the atomic);
+//   emb_replay_kernel  one thread per ELEMENT of a claimed row replays the skipped zero-gradient steps.
+// The replay is a serial chain of IEEE div/sqrt per element, i.e. instruction-bound; a group-per-position layout leaves
+// the lanes of unclaimed positions idle and makes a warp wait for the longest of its eight replays.  The compact list
+// keeps every lane busy and only two rows share a warp.  The replay result does not depend on which duplicate wins.
+__global__ void emb_claim_kernel(const int32_t* __restrict__ keys, int64_t n, int64_t V, int32_t* __restrict__ last_step,
+                                 const Hyper* hp, int32_t* __restrict__ list, int32_t* __restrict__ counter) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const int upto = hp->step - 1;
-    const int32_t key = (gid < n) ? keys[gid] : 0;
-    // cheap pre-check (plain load) so that rows that are already current - every duplicate position after the
-    // first claim, and everything in the first step - skip the atomic and the state loads
-    int seen = upto;
-    if (key != 0 && sub == 0) seen = last_step[key];
-    seen = __shfl_sync(FULL_MASK, seen, 0, lpr);
+    const int32_t key = (i < n) ? keys[i] : 0;
+    bool win = false;
     int old = upto;
-    if (key != 0 && seen < upto && sub == 0) old = atomicExch(&last_step[key], upto);
-    old = __shfl_sync(FULL_MASK, old, 0, lpr);
-    if (key == 0 || old >= upto) return;
-    const int64_t off = (int64_t)key * d + sub * 4;
-    float4 mm = *reinterpret_cast<float4*>(m + off);
-    float4 vv = *reinterpret_cast<float4*>(v + off);
-    float4 var = *reinterpret_cast<float4*>(emb + off);
-    if (all_zero(mm) && all_zero(vv)) return;
-    replay4(var, mm, vv, old, upto, alpha_hist);
-    *reinterpret_cast<float4*>(emb + off) = var;
-    *reinterpret_cast<float4*>(m + off) = mm;
-    *reinterpret_cast<float4*>(v + off) = vv;
+    if (key > 0 && (int64_t)key < V) {
+        const int seen = last_step[key];
+        if (seen < upto) {
+            old = atomicExch(&last_step[key], upto);
+            win = old < upto;
+        }
+    }
+    const unsigned mask = __ballot_sync(FULL_MASK, win);
+    if (mask == 0) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(FULL_MASK, base, 0);
+    if (win) {
+        const int idx = base + __popc(mask & ((1u << lane) - 1u));
+        list[2 * idx] = key;
+        list[2 * idx + 1] = old;
+    }
 }
-void launch_emb_catchup_rows(cudaStream_t st, const int32_t* keys, int64_t n, float* emb, float* m, float* v,
-                             int32_t* last_step, int d, const float* alpha_hist, const Hyper* hp) {
-    const int lpr = d >> 2;
-    int64_t threads = n * lpr;
-    emb_catchup_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(keys, n, emb, m, v, last_step, d,
-                                                                               alpha_hist, hp);
+__global__ void __launch_bounds__(256) emb_replay_kernel(const int32_t* __restrict__ list, const int32_t* __restrict__ counter,
+                                                         float* __restrict__ emb, float* __restrict__ m, float* __restrict__ v,
+                                                         int d, const float* __restrict__ alpha_hist, const Hyper* hp) {
+    const int upto = hp->step - 1;
+    const int64_t total = (int64_t)(*counter) * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / d;
+        const int c = (int)(e - r * d);
+        const int32_t key = list[2 * r], old = list[2 * r + 1];
+        const int64_t off = (int64_t)key * d + c;
+        float mm = m[off], vv = v[off];
+        if (mm == 0.f && vv == 0.f) continue;   // never touched: every replayed step is exactly a no-op
+        float var = emb[off];
+        for (int s = old + 1; s <= upto; ++s) adam_elem(var, mm, vv, 0.f, alpha_hist[s]);
+        emb[off] = var; m[off] = mm; v[off] = vv;
+    }
+}
+static int num_sms_cached() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+void launch_emb_replay(cudaStream_t st, const int32_t* claim_list, const int32_t* claim_counter, int64_t max_rows, float* emb,
+                       float* m, float* v, int d, const float* alpha_hist, const Hyper* hp) {
+    int64_t want = (max_rows * d + 255) / 256, cap = (int64_t)num_sms_cached() * 8;
+    if (want < 1) want = 1;
+    emb_replay_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(claim_list, claim_counter, emb, m, v, d, alpha_hist, hp);
     ++g_launch_count;
+}
+void launch_emb_catchup_rows(cudaStream_t st, const int32_t* keys, int64_t n, int64_t V, float* emb, float* m, float* v,
+                             int32_t* last_step, int d, const float* alpha_hist, const Hyper* hp, int32_t* claim_list,
+                             int32_t* claim_counter) {
+    cudaMemsetAsync(claim_counter, 0, sizeof(int32_t), st);
+    emb_claim_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, n, V, last_step, hp, claim_list, claim_counter);
+    ++g_launch_count;
+    launch_emb_replay(st, claim_list, claim_counter, n, emb, m, v, d, alpha_hist, hp);
 }
 __global__ void emb_catchup_all_kernel(float* __restrict__ emb, float* __restrict__ m, float* __restrict__ v,
                                        int32_t* __restrict__ last_step, int64_t V, int d,

@@ -232,15 +232,19 @@ void launch_bn_bwd(cudaStream_t st, int B, int F, const float* x, const float* d
     ++g_launch_count;
 }
 
+// dgamma_c = sum_b dz (x - mean)/sqrt(var+eps), dbeta_c = sum_b dz: batch rows split over blockIdx.y, each split writes its
+// own partial plane (reduced in fixed order by reduce_partials)
 __global__ void bn_param_grads_kernel(int B, int F, const float* __restrict__ x, const float* __restrict__ dz,
                                       const float* __restrict__ mean, const float* __restrict__ var,
-                                      float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t split_stride) {
     __shared__ float rg[32][33], rb[32][33];
     const int c = blockIdx.x * 32 + threadIdx.x, ry = threadIdx.y;
+    const int chunk = (B + gridDim.y - 1) / gridDim.y;
+    const int b_lo = blockIdx.y * chunk, b_hi = min(B, b_lo + chunk);
     float sg = 0.f, sb = 0.f;
     if (c < F) {
         const float rstd = 1.0f / sqrtf(var[c] + 1e-3f), mu = mean[c];
-        for (int b = ry; b < B; b += 32) {
+        for (int b = b_lo + ry; b < b_hi; b += 32) {
             const float d = dz[(int64_t)b * F + c];
             sg += d * ((x[(int64_t)b * F + c] - mu) * rstd);
             sb += d;
@@ -252,11 +256,15 @@ __global__ void bn_param_grads_kernel(int B, int F, const float* __restrict__ x,
         if (ry < o) { rg[ry][threadIdx.x] += rg[ry + o][threadIdx.x]; rb[ry][threadIdx.x] += rb[ry + o][threadIdx.x]; }
         __syncthreads();
     }
-    if (ry == 0 && c < F) { dgamma[c] = rg[0][threadIdx.x]; dbeta[c] = rb[0][threadIdx.x]; }
+    if (ry == 0 && c < F) {
+        dgamma[(int64_t)blockIdx.y * split_stride + c] = rg[0][threadIdx.x];
+        dbeta[(int64_t)blockIdx.y * split_stride + c] = rb[0][threadIdx.x];
+    }
 }
 void launch_bn_param_grads(cudaStream_t st, int B, int F, const float* x, const float* dz, const float* mean,
-                           const float* var, float* dgamma, float* dbeta) {
-    bn_param_grads_kernel<<<(F + 31) / 32, dim3(32, 32), 0, st>>>(B, F, x, dz, mean, var, dgamma, dbeta);
+                           const float* var, float* dgamma, float* dbeta, int splits, int64_t split_stride) {
+    bn_param_grads_kernel<<<dim3((F + 31) / 32, splits), dim3(32, 32), 0, st>>>(B, F, x, dz, mean, var, dgamma, dbeta,
+                                                                                  split_stride);
     ++g_launch_count;
 }
 
