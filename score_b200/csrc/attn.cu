@@ -518,3 +518,65 @@ void launch_att_qb(cudaStream_t st, const AttQbArgs& a) {
 }
 
 }  // namespace score
+
+// ------------------------------------------------------------------------------------------ generic row-tile product
+// out[m, :N] (+)= X[m, :K] W[:K, :N] (+ bias) for up to 4 independent problems in one launch (blockIdx.y): the GRU input
+// projections of both sides (score.py:205-208, the x part of [x, h] W hoisted out of the time loop) and their
+// backward dx = dpx [Wg_x | Wc_x]^T.  32 rows per CTA on tile_layer.
+namespace score {
+
+__global__ void __launch_bounds__(TL_CT) rowgemm_kernel(RowGemmBatch batch) {
+    constexpr int RT = 32;
+    using G = TileGeom<RT>;
+    extern __shared__ __align__(16) float sm[];
+    const RowGemmArgs& p = batch.p[blockIdx.y];
+    const int tid = threadIdx.x, K = p.K;
+    const int row0 = blockIdx.x * RT;
+    if (row0 >= p.M) return;
+    float* Xs = sm;               // [K][RT]
+    float* wbuf = Xs + K * RT;
+    int rg, cg;
+    tile_coords<RT>(tid, rg, cg);
+    tile_for_each_chunk<RT>(K, tid, [&](int r, int c4) {
+        const int m = row0 + r;
+        const float4 v = m < p.M ? *reinterpret_cast<const float4*>(p.X + (int64_t)m * p.ldx + 4 * c4)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        tile_put4(Xs, RT, 4 * c4, r, v);
+    });
+    __syncthreads();
+    float acc[4][4];
+    for (int cb = 0; cb < p.N; cb += G::NP) {
+        const int nb = min(G::NP, p.N - cb);
+        tile_zero(acc);
+        tile_layer<RT>(Xs, K, p.W + cb, p.ldw, nb, acc, wbuf, tid);
+        if (4 * cg < nb) {
+            const int c = cb + 4 * cg;
+            float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bias = *reinterpret_cast<const float4*>(p.bias + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = row0 + 4 * rg + i;
+                if (m < p.M)
+                    *reinterpret_cast<float4*>(p.out + (int64_t)m * p.ldo + c) =
+                        make_float4(acc[i][0] + bias.x, acc[i][1] + bias.y, acc[i][2] + bias.z, acc[i][3] + bias.w);
+            }
+        }
+    }
+}
+
+void launch_rowgemm(cudaStream_t st, const RowGemmArgs* list, int n) {
+    if (n <= 0) return;
+    RowGemmBatch b{};
+    int maxM = 0, maxK = 0;
+    for (int i = 0; i < n && i < 4; ++i) { b.p[i] = list[i]; maxM = max(maxM, list[i].M); maxK = max(maxK, list[i].K); }
+    const size_t smem = ((size_t)maxK * 32 + TileGeom<32>::WBUF) * sizeof(float);
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+        cudaFuncSetAttribute(rowgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = smem;
+    }
+    rowgemm_kernel<<<dim3((maxM + 31) / 32, n), TL_CT, smem, st>>>(b);
+    ++g_launch_count;
+}
+
+}  // namespace score

@@ -169,7 +169,7 @@ void launch_loss_final(cudaStream_t st, int B, const float* loss_b, const float*
 // Derived weights rebuilt once per step from the flat parameter buffer P into D:
 //   D[dst_off + r*ld_dst + c] = P[a_off + r*a_rs + c*a_cs] (+/-) P[b_off + r*a_rs + c*a_cs]     (b_off < 0: no second term)
 struct PrepOp { int64_t dst_off, a_off, b_off; int ld_dst, rows, cols, a_rs, a_cs, sign; };
-struct PrepOps { PrepOp op[12]; int n; };
+struct PrepOps { PrepOp op[24]; int n; };
 void launch_prep_weights(cudaStream_t st, const PrepOps& ops, const float* P, float* D);
 
 struct AttQArgs {
@@ -218,8 +218,14 @@ struct AttQbArgs {
 };
 void launch_att_qb(cudaStream_t st, const AttQbArgs& a);
 
+// out[m, :N] = X[m, :K] W[:K, :N] (+ bias); K, N, ldx, ldw, ldo multiples of 4, 16-byte aligned bases; up to 4 problems
+struct RowGemmArgs { const float* X; int ldx; const float* W; int ldw; const float* bias; float* out; int ldo; int M, K, N; };
+struct RowGemmBatch { RowGemmArgs p[4]; };
+void launch_rowgemm(cudaStream_t st, const RowGemmArgs* list, int n);
+
 // ---------------------------------------------------------------- optimizer + scatter (scatter.cu)
-// sum of v*v/2 over L2-regularised dense parameters (flags bit0)
+// partial sums of v*v/2 over L2-regularised dense parameters (flags bit0): out[L2_PARTS]
+constexpr int L2_PARTS = 32;
 void launch_l2_sum(cudaStream_t st, const float* params, const uint8_t* flags, int n, float* out);
 // G[i] = sum_s partial[s][i]
 // optional derived range afterwards: g[dst + i] = g[a + i] - g[b + i], i < count  (dWc = dWa - dWb of the attention's first layer)

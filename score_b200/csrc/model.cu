@@ -46,7 +46,7 @@ struct ScoreModel {
     std::string err;
     Dims dm;                        // dm.B / offsets are per call
     cudaStream_t st = nullptr, st2 = nullptr, st_w = nullptr;   // main, sort branch, weight-gradient branch
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_l2 = nullptr, ev_w = nullptr, ev_tgt = nullptr, ev_q = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_l2 = nullptr, ev_w = nullptr, ev_tgt = nullptr, ev_q = nullptr, ev_prep = nullptr;
     cudaEvent_t ev_pool[16] = {nullptr}; int ev_next = 0;
     bool side_w = false;   // a step is being enqueued with the weight-gradient branch forked
 
@@ -61,6 +61,7 @@ struct ScoreModel {
     // derived weights of the fused dense chains (attn.cu, chain.cu), rebuilt from P at the start of every step
     float* Dv = nullptr; int64_t n_derived = 0; PrepOps prep{};
     int64_t dv_W1e = 0, dv_Wac = 0, dv_W1eT = 0, dv_WacT = 0, dv_W2T = 0, dv_WqT = 0, dv_fc1T = 0, dv_fc2T = 0;
+    int64_t dv_Wx[2] = {0, 0}, dv_WxT[2] = {0, 0};   // GRU input-side kernels [Wg_x | Wc_x] ([Ds,3H]) and their transpose
     float* alpha_hist = nullptr; int64_t alpha_cap = 0;
     std::vector<float> alpha_host;
 
@@ -221,6 +222,18 @@ void build_registry(ScoreModel* h) {
         op(h->dv_W2T, 80, 40, 80, toff(nm.att2 + "/kernel"), -1, 1, 40, 0);        // W2^T
         op(h->dv_WqT, Ds, Dk, Ds, toff(nm.att_q + "/kernel"), -1, 1, Dk, 0);       // Wq^T
     }
+    {
+        const char* sides[2] = {"gru_user_side", "gru_item_side"};
+        for (int sd = 0; sd < 2; ++sd) {
+            const int64_t wg = toff(std::string(sides[sd]) + "/gru_cell/gates/kernel");        // [Ds+H, 2H]
+            const int64_t wc = toff(std::string(sides[sd]) + "/gru_cell/candidate/kernel");    // [Ds+H, H]
+            h->dv_Wx[sd] = reserve((int64_t)Ds * 3 * H); h->dv_WxT[sd] = reserve((int64_t)3 * H * Ds);
+            op(h->dv_Wx[sd], 3 * H, Ds, 2 * H, wg, -1, 2 * H, 1, 0);
+            op(h->dv_Wx[sd] + 2 * H, 3 * H, Ds, H, wc, -1, H, 1, 0);
+            op(h->dv_WxT[sd], Ds, 2 * H, Ds, wg, -1, 1, 2 * H, 0);
+            op(h->dv_WxT[sd] + (int64_t)2 * H * Ds, Ds, H, Ds, wc, -1, 1, H, 0);
+        }
+    }
     h->dv_fc1T = reserve((int64_t)200 * Dfc); h->dv_fc2T = reserve(80 * 200);
     op(h->dv_fc1T, Dfc, 200, Dfc, toff("fc1/kernel"), -1, 1, 200, 0);              // fc1^T
     op(h->dv_fc2T, 200, 80, 200, toff("fc2/kernel"), -1, 1, 80, 0);                // fc2^T
@@ -260,7 +273,7 @@ int alloc_params(ScoreModel* h) {
     CK(cudaMalloc(&h->claim_counter, sizeof(int32_t)));
     CK(cudaMalloc(&h->n_heads_dev, sizeof(int32_t)));
     CK(cudaMemsetAsync(h->n_heads_dev, 0, sizeof(int32_t), h->st));
-    CK(cudaMalloc(&h->l2sum, sizeof(float)));
+    CK(cudaMalloc(&h->l2sum, sizeof(float) * L2_PARTS));
     CK(cudaMalloc(&h->loss_dev, 2 * sizeof(float)));
     CK(cudaMalloc(&h->err_flag, sizeof(int32_t)));
     CK(cudaMemsetAsync(h->err_flag, 0, sizeof(int32_t), h->st));
@@ -517,6 +530,7 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
     cudaStreamWaitEvent(h->st_w, h->ev_fork, 0);
     if (will_bwd) cudaMemsetAsync(h->PG, 0, sizeof(float) * h->n_dense * kSplits, h->st_w);   // weight-gradient partial planes
     launch_prep_weights(h->st_w, h->prep, h->P, h->Dv);
+    cudaEventRecord(h->ev_prep, h->st_w);
     launch_l2_sum(h->st_w, h->P, h->flags, (int)h->n_dense, h->l2sum);
     cudaEventRecord(h->ev_l2, h->st_w);
 
@@ -548,16 +562,16 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
     const char* sides[2] = {"gru_user_side", "gru_item_side"};
     GruArgs ga{};
     ga.length = h->length;
-    GemmArgs pxl[4];
+    RowGemmArgs pxl[2];
     for (int s = 0; s < 2; ++s) {
         std::string g = std::string(sides[s]) + "/gru_cell/gates", c = std::string(sides[s]) + "/gru_cell/candidate";
-        // input part of both matmuls for all (b,t) rows at once: px = x [Wg_x | Wc_x]  (4 problems, one launch)
-        pxl[2 * s] = gemm_fwd_args(h, h->xhg[s], ldx, W(g), 2 * H, nullptr, h->px[s], 3 * H, M, 2 * H, Ds, EPI_STORE);
-        pxl[2 * s + 1] = gemm_fwd_args(h, h->xhg[s], ldx, W(c), H, nullptr, h->px[s] + 2 * H, 3 * H, M, H, Ds, EPI_STORE);
+        // input part of both matmuls for all (b,t) rows at once: px = x [Wg_x | Wc_x]  (both sides, one launch)
+        pxl[s] = RowGemmArgs{h->xhg[s], ldx, h->Dv + h->dv_Wx[s], 3 * H, nullptr, h->px[s], 3 * H, M, Ds, 3 * H};
         ga.px[s] = h->px[s]; ga.wg[s] = W(g); ga.bg[s] = Bi(g); ga.wc[s] = W(c); ga.bc[s] = Bi(c);
         ga.xhg[s] = h->xhg[s]; ga.xhc[s] = h->xhc[s]; ga.r[s] = h->gr[s]; ga.u[s] = h->gu[s]; ga.c[s] = h->gc[s];
     }
-    launch_gemm_batch(h->st, pxl, 4);
+    cudaStreamWaitEvent(h->st, h->ev_prep, 0);   // the derived weights are rebuilt on the side stream
+    launch_rowgemm(h->st, pxl, 2);
     ga.out = h->key; ga.ldout = Dk; ga.last = nullptr; ga.ldlast = 0;
     launch_gru_fwd(h->st, dm, ga);
 
@@ -646,17 +660,17 @@ void enqueue_backward(ScoreModel* h) {
         gb.r[s] = h->gr[s]; gb.u[s] = h->gu[s]; gb.c[s] = h->gc[s]; gb.dpx[s] = h->dpx[s];
     }
     launch_gru_bwd(h->st, dm, gb);
-    GemmArgs wl[4], d1[2], d2[2];
+    GemmArgs wl[4];
+    RowGemmArgs dxl[2];
     for (int s = 0; s < 2; ++s) {
         std::string g = std::string(sides[s]) + "/gru_cell/gates", c = std::string(sides[s]) + "/gru_cell/candidate";
         wl[2 * s] = gemm_bwd_weight_args(h, h->xhg[s], ldx, h->dpx[s], 3 * H, Wo(g), Bo(g), M, ldx, 2 * H);
         wl[2 * s + 1] = gemm_bwd_weight_args(h, h->xhc[s], ldx, h->dpx[s] + 2 * H, 3 * H, Wo(c), Bo(c), M, ldx, H);
-        d1[s] = gemm_bwd_data_args(h, h->dpx[s], 3 * H, W(g), 2 * H, h->dx[s], Ds, M, Ds, 2 * H, EPI_STORE);
-        d2[s] = gemm_bwd_data_args(h, h->dpx[s] + 2 * H, 3 * H, W(c), H, h->dx[s], Ds, M, Ds, H, EPI_ACCUM);
+        // dx = dpx [Wg_x | Wc_x]^T
+        dxl[s] = RowGemmArgs{h->dpx[s], 3 * H, h->Dv + h->dv_WxT[s], Ds, nullptr, h->dx[s], Ds, M, 3 * H, Ds};
     }
     gemm_bwd_weight_batch(h, wl, 4);
-    launch_gemm_batch(h->st, d1, 2);   // dx  = dpx_gates Wg_x^T      (both sides)
-    launch_gemm_batch(h->st, d2, 2);   // dx += dpx_cand  Wc_x^T
+    launch_rowgemm(h->st, dxl, 2);
     probe_end(h, PR_BWD_DENSE, h->st);
     // co-attention + gather backward: per-position embedding gradient rows
     CoattBwdArgs cb{};
@@ -927,6 +941,7 @@ int score_create(const ScoreConfig* cfg, int device, ScoreHandle* out) {
         cudaEventCreateWithFlags(&h->ev_w, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_tgt, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_q, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_prep, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         h->err = "stream/event creation failed";
         return die(SCORE_ERR_CUDA);
@@ -965,6 +980,7 @@ int score_destroy(ScoreHandle h) {
     if (h->ev_w) cudaEventDestroy(h->ev_w);
     if (h->ev_tgt) cudaEventDestroy(h->ev_tgt);
     if (h->ev_q) cudaEventDestroy(h->ev_q);
+    if (h->ev_prep) cudaEventDestroy(h->ev_prep);
     for (int i = 0; i < 16; ++i) if (h->ev_pool[i]) cudaEventDestroy(h->ev_pool[i]);
     if (h->st_w) cudaStreamDestroy(h->st_w);
     if (h->st) {

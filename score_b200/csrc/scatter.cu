@@ -30,22 +30,23 @@ __device__ __forceinline__ void adam4(float4& var, float4& m, float4& v, const f
 __device__ __forceinline__ bool all_zero(const float4& a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f && a.w == 0.f; }
 
 // ------------------------------------------------------------------------------------------ dense parameters
-// 0.5 * sum v^2 over L2-regularised parameters; single block, fixed-shape tree (deterministic)
+// 0.5 * sum v^2 over L2-regularised parameters: L2_PARTS blocks, fixed-shape tree per block; loss_final adds the
+// per-block partials in index order (deterministic)
 __global__ void l2_sum_kernel(const float* __restrict__ p, const uint8_t* __restrict__ flags, int n, float* out) {
-    __shared__ float red[1024];
+    __shared__ float red[256];
     float s = 0.f;
-    for (int i = threadIdx.x; i < n; i += 1024)
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
         if (flags[i] & 1) s += p[i] * p[i];
     red[threadIdx.x] = s;
     __syncthreads();
-    for (int o = 512; o > 0; o >>= 1) {
+    for (int o = 128; o > 0; o >>= 1) {
         if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[0] = red[0] * 0.5f;
+    if (threadIdx.x == 0) out[blockIdx.x] = red[0] * 0.5f;
 }
 void launch_l2_sum(cudaStream_t st, const float* params, const uint8_t* flags, int n, float* out) {
-    l2_sum_kernel<<<1, 1024, 0, st>>>(params, flags, n, out);
+    l2_sum_kernel<<<L2_PARTS, 256, 0, st>>>(params, flags, n, out);
     ++g_launch_count;
 }
 

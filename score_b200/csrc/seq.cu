@@ -11,9 +11,12 @@
 namespace score {
 
 // ------------------------------------------------------------------------------------------ GRU forward
-// block = (2H threads) x (RB rows); grid = (ceil(B/RB), 2 sides)
+// block = (2H threads) x (RB rows); grid = (ceil(B/RB), 2 sides).  The recurrence is a latency chain (T dependent
+// steps), so the only global loads inside it - the hoisted input projections px - are prefetched one step ahead, and
+// the loop stops at the longest length of the CTA's rows (later steps only store the zero outputs).
 __global__ void gru_fwd_kernel(Dims dm, GruArgs a, int RB) {
     extern __shared__ float sm[];
+    __shared__ int s_tmax;
     const int H = dm.H, H2 = 2 * dm.H, T = dm.T;
     const int side = blockIdx.y;
     const int j = threadIdx.x, r = threadIdx.y;
@@ -26,21 +29,35 @@ __global__ void gru_fwd_kernel(Dims dm, GruArgs a, int RB) {
     float* us = rh + RB * H;                     // [RB][H]   update gate
     const float* wg = a.wg[side] + (int64_t)dm.Ds * H2;
     const float* wc = a.wc[side] + (int64_t)dm.Ds * H;
+    if (tid == 0) s_tmax = 0;
     for (int i = tid; i < H * H2; i += nthreads) Wg[(i / H2) * sg + (i % H2)] = wg[i];
     for (int i = tid; i < H * H; i += nthreads) Wc[(i / H) * sc + (i % H)] = wc[i];
     for (int i = tid; i < RB * H; i += nthreads) hs[i] = 0.f;
     __syncthreads();
     const int b = blockIdx.x * RB + r;
     const bool row_ok = b < dm.B;
-    const int len = row_ok ? a.length[b] : 0;
+    const int len = row_ok ? min(a.length[b], T) : 0;
+    if (j == 0) atomicMax(&s_tmax, len);
+    __syncthreads();
+    const int tmax = s_tmax;
     const float bgj = a.bg[side][j];
     const float bcj = (j < H) ? a.bc[side][j] : 0.f;
     const float* px = a.px[side];
-    for (int t = 0; t < T; ++t) {
+    float pg = 0.f, pc = 0.f;
+    if (row_ok && tmax > 0) {
+        pg = px[(int64_t)b * T * 3 * H + j];
+        if (j < H) pc = px[(int64_t)b * T * 3 * H + H2 + j];
+    }
+    for (int t = 0; t < tmax; ++t) {
         const int64_t m = (int64_t)b * T + t;
+        float pg_n = 0.f, pc_n = 0.f;
+        if (row_ok && t + 1 < tmax) {
+            pg_n = px[(m + 1) * 3 * H + j];
+            if (j < H) pc_n = px[(m + 1) * 3 * H + H2 + j];
+        }
         float val = 0.f;
         if (row_ok) {
-            float acc = px[m * 3 * H + j] + bgj;
+            float acc = pg + bgj;
             const float* h = hs + r * H;
             for (int k = 0; k < H; ++k) acc = fmaf(h[k], Wg[k * sg + j], acc);
             val = sigmoidf_acc(acc);
@@ -50,7 +67,7 @@ __global__ void gru_fwd_kernel(Dims dm, GruArgs a, int RB) {
         __syncthreads();
         float hn = 0.f;
         if (row_ok && j < H) {
-            float acc = px[m * 3 * H + H2 + j] + bcj;
+            float acc = pc + bcj;
             const float* q = rh + r * H;
             for (int k = 0; k < H; ++k) acc = fmaf(q[k], Wc[k * sc + j], acc);
             float c = tanhf(acc);
@@ -67,7 +84,10 @@ __global__ void gru_fwd_kernel(Dims dm, GruArgs a, int RB) {
         __syncthreads();
         if (row_ok && j < H) hs[r * H + j] = hn;
         __syncthreads();
+        pg = pg_n; pc = pc_n;
     }
+    if (row_ok && j < H)
+        for (int t = tmax; t < T; ++t) a.out[((int64_t)b * T + t) * a.ldout + side * H + j] = 0.f;
     if (a.last && row_ok && j < H) a.last[(int64_t)b * a.ldlast + side * H + j] = hs[r * H + j];
 }
 
@@ -95,8 +115,11 @@ void launch_gru_fwd(cudaStream_t st, const Dims& dm, const GruArgs& a) {
 
 // ------------------------------------------------------------------------------------------ GRU backward (BPTT)
 //   h' = u h + (1-u) c ;  c = tanh(px_c + (r h) Wc_h + bc) ;  [r,u] = sigmoid(px_g + h Wg_h + bg)
+// Same latency structure as the forward pass: the saved activations of step t-1 are prefetched while step t runs, and
+// steps beyond the longest length of the CTA's rows only store their zero gradients.
 __global__ void gru_bwd_kernel(Dims dm, GruBwdArgs a, int RB) {
     extern __shared__ float sm[];
+    __shared__ int s_tmax;
     const int H = dm.H, H2 = 2 * dm.H, T = dm.T;
     const int side = blockIdx.y;
     const int j = threadIdx.x, r = threadIdx.y;
@@ -110,26 +133,48 @@ __global__ void gru_bwd_kernel(Dims dm, GruBwdArgs a, int RB) {
     float* dhd = dg + RB * H2;                   // [RB][H]  direct part of d h_{t-1}
     const float* wg = a.wg[side] + (int64_t)dm.Ds * H2;
     const float* wc = a.wc[side] + (int64_t)dm.Ds * H;
+    if (tid == 0) s_tmax = 0;
     for (int i = tid; i < H * H2; i += nthreads) Wg[(i / H2) * sg + (i % H2)] = wg[i];
     for (int i = tid; i < H * H; i += nthreads) Wc[(i / H) * sc + (i % H)] = wc[i];
     const int b = blockIdx.x * RB + r;
     const bool row_ok = b < dm.B;
-    const int len = row_ok ? a.length[b] : 0;
+    const int len = row_ok ? min(a.length[b], T) : 0;
     if (j < H) dh[r * H + j] = (a.dlast && row_ok) ? a.dlast[(int64_t)b * a.lddlast + side * H + j] : 0.f;
     __syncthreads();
+    if (j == 0) atomicMax(&s_tmax, len);
+    __syncthreads();
+    const int tmax = s_tmax;
     float* dpx = a.dpx[side];
-    for (int t = T - 1; t >= 0; --t) {
+    if (row_ok && j < H)
+        for (int t = tmax; t < T; ++t) {
+            const int64_t m = (int64_t)b * T + t;
+            dpx[m * 3 * H + j] = 0.f; dpx[m * 3 * H + H + j] = 0.f; dpx[m * 3 * H + H2 + j] = 0.f;
+        }
+    // saved activations of the current step (threads j < H): d out, u, c, h_{t-1}, r
+    float c_do = 0.f, c_u = 0.f, c_c = 0.f, c_hp = 0.f, c_r = 0.f;
+    auto fetch = [&](int t, float& f_do, float& f_u, float& f_c, float& f_hp, float& f_r) {
+        f_do = f_u = f_c = f_hp = f_r = 0.f;
+        if (j < H && row_ok && t >= 0 && t < len) {
+            const int64_t m = (int64_t)b * T + t;
+            f_do = a.dout ? a.dout[m * a.lddout + side * H + j] : 0.f;
+            f_u = a.u[side][m * H + j]; f_c = a.c[side][m * H + j];
+            f_hp = a.xhg[side][m * dm.ldx + dm.Ds + j];
+            f_r = a.r[side][m * H + j];
+        }
+    };
+    fetch(tmax - 1, c_do, c_u, c_c, c_hp, c_r);
+    for (int t = tmax - 1; t >= 0; --t) {
         const int64_t m = (int64_t)b * T + t;
         const bool alive = row_ok && (t < len);
-        float hp = 0.f, rr = 0.f;
+        float n_do, n_u, n_c, n_hp, n_r;
+        fetch(t - 1, n_do, n_u, n_c, n_hp, n_r);
+        const float hp = c_hp, rr = c_r;
         // phase A: through h' = u h + (1-u) c
         if (j < H) {
             float dcpv = 0.f, dguv = 0.f, direct = dh[r * H + j];
             if (alive) {
-                float dhn = dh[r * H + j] + (a.dout ? a.dout[m * a.lddout + side * H + j] : 0.f);
-                float u = a.u[side][m * H + j], c = a.c[side][m * H + j];
-                hp = a.xhg[side][m * dm.ldx + dm.Ds + j];
-                rr = a.r[side][m * H + j];
+                float dhn = dh[r * H + j] + c_do;
+                float u = c_u, c = c_c;
                 float du = dhn * (hp - c);
                 float dc = dhn * (1.f - u);
                 direct = dhn * u;
@@ -167,6 +212,7 @@ __global__ void gru_bwd_kernel(Dims dm, GruBwdArgs a, int RB) {
             dh[r * H + j] = v;
         }
         __syncthreads();
+        c_do = n_do; c_u = n_u; c_c = n_c; c_hp = n_hp; c_r = n_r;
     }
 }
 
@@ -308,7 +354,9 @@ __global__ void loss_final_kernel(int B, const float* __restrict__ loss_b, const
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        const float reg = hp->reg_lambda * l2sum[0];
+        float l2 = 0.f;
+        for (int i = 0; i < L2_PARTS; ++i) l2 += l2sum[i];
+        const float reg = hp->reg_lambda * l2;
         loss[0] = red[0] * hp->inv_batch + reg;
         loss[1] = reg;
     }
