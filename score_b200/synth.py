@@ -50,6 +50,8 @@ SHAPES = {
     "ccmr_k20": Shape("ccmr_k20", 1 + 4920695 + 190129 + 80172 + 213482 + 63 + 1044, 16, 32, 40, 20, 1, 5,
                       4920695, 190129, 1024, 38),
     "large_vocab": Shape("large_vocab", 200000001, 64, 128, 8, 10, 1, 1, 100000000, 100000000, 1024, 6),
+    # one rank's shard of the large-vocab table at 8 GPUs (25 M rows, d=64: 19.2 GB of var+m+v) for 1-GPU kernel runs
+    "large_vocab_shard": Shape("large_vocab_shard", 25000001, 64, 128, 8, 10, 1, 1, 12500000, 12500000, 1024, 6),
     # small shapes for tests / smoke
     "tiny": Shape("tiny", 5000, 16, 32, 6, 10, 3, 4, 1000, 3000, 24, 4),
     "tiny_tb": Shape("tiny_tb", 6000, 16, 32, 8, 10, 1, 2, 2000, 3500, 64, 6),
