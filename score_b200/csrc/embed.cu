@@ -9,50 +9,60 @@
 //   rel[b,t,i,j] = relu(Wt.target + W1.seq1[i] + W2.seq2[i] + bias) =: r_i        (independent of j)
 //   seq1_weights[i] = softmax_i(r_i)        seq2_weights[j] = 1/K
 //   atten_info = [K*r_i (K values) || (sum_i r_i) repeated K times]
-// One warp owns one (b, t) time slice: it stages the slice's K*(2*if + 2*uf) table rows in shared
-// memory with cp.async (HBM-bound phase, many slices in flight per SM), then does the dot
-// products with warp-shuffle reductions.  Slices with t >= length[b] are skipped: they reach
-// neither the GRU output nor the attention (score.py:179-181, 205-208).
+//
+// Position space.  Every id of a batch owns one "position" p in [0, N): the sanitized id lives at keys[p], its
+// embedding-gradient row at grad_rows[p*d ..].  Positions are SLICE-MAJOR: the NROWS = K*(2*if + 2*uf) ids of the
+// (b,t) slice s sit at [s*NROWS, (s+1)*NROWS) in the order
+//   seg0 = user_1hop (K*if) | seg1 = item_2hop (K*if) | seg2 = user_2hop (K*uf) | seg3 = item_1hop (K*uf)
+// (co-attention #1 = (seg0, seg1, target_item), #2 = (seg2, seg3, target_user), score.py:196-197), followed by
+// target_user [B*uf] and target_item [B*if].  One warp owns one slice: its ids are one contiguous run, its table rows
+// land in shared memory in the same order, and its gradient rows leave as one contiguous block.
+//
+// The kernels are instruction-bound before they are bandwidth-bound (ncu, profiles/: 1 650 warp instructions per
+// Taobao slice with run-time geometry), so they are compiled once per geometry (K, if, uf, d) of the reference's data
+// sets - every index computation folds to constants, every loop unrolls - with a run-time-geometry instance as the
+// fallback for any other configuration.
 #include "kernels.h"
 
 namespace score {
 
 // ------------------------------------------------------------------------------------------
-// keys[p] = sanitized id of flat position p: 0 for masked slices (t >= length[b]) and ids that
-// are out of range (flagged).  Positions: [user_1hop | user_2hop | item_1hop | item_2hop | tu | ti].
-// Four positions per thread (one 16-byte id load, four independent dependent chains).  In LAZY optimizer mode the
-// same pass claims the stale rows among the keys (atomic exchange on last_step, plain pre-check first) and appends
-// (row, last step) to the compact list emb_replay_kernel works through (scatter.cu).
-__device__ __forceinline__ bool position_live(const Dims& dm, int64_t p, const int32_t* __restrict__ length) {
-    if (p >= dm.off_tu) return true;
-    int64_t local; int f;
-    if (p < dm.off_u2) { local = p - dm.off_u1; f = dm.fi; }
-    else if (p < dm.off_i1) { local = p - dm.off_u2; f = dm.fu; }
-    else if (p < dm.off_i2) { local = p - dm.off_i1; f = dm.fu; }
-    else { local = p - dm.off_i2; f = dm.fi; }
-    const int64_t slice = local / ((int64_t)dm.K * f);
-    const int b = (int)(slice / dm.T), t = (int)(slice % dm.T);
-    return t < length[b];
-}
-
-__global__ void build_keys_kernel(Dims dm, const int32_t* __restrict__ ids, const int32_t* __restrict__ length,
-                                  int32_t* __restrict__ keys, int32_t* __restrict__ err_flag, ClaimArgs ca) {
-    const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int lane = threadIdx.x & 31;
-    int32_t id[4] = {0, 0, 0, 0};
-    if (p0 + 3 < dm.N) {
-        const int4 v = *reinterpret_cast<const int4*>(ids + p0);
-        id[0] = v.x; id[1] = v.y; id[2] = v.z; id[3] = v.w;
-    } else {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) if (p0 + u < dm.N) id[u] = ids[p0 + u];
+// keys[p] = sanitized id of position p: 0 for masked slices (t >= length[b]) and ids that are out of range (flagged).
+// The six id tensors are read where they lie (device batches: the caller's tensors, no staging copy) through a pointer
+// table in device memory, so a captured graph stays valid from batch to batch.  Four positions per thread.  In LAZY
+// optimizer mode the same pass claims the stale rows among the keys (atomic exchange on last_step, plain pre-check
+// first) and appends (row, last step) to the compact list emb_replay_kernel works through (scatter.cu).
+__global__ void build_keys_kernel(Dims dm, const BatchPtrs* __restrict__ bpp, int32_t* __restrict__ keys,
+                                  int32_t* __restrict__ label_out, int32_t* __restrict__ length_out,
+                                  int32_t* __restrict__ err_flag, ClaimArgs ca) {
+    const BatchPtrs bp = *bpp;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gtid < dm.B) {
+        const int32_t lb = bp.label[gtid], ln = bp.length[gtid];
+        label_out[gtid] = lb; length_out[gtid] = ln;
     }
+    const int64_t p0 = gtid * 4;
+    const int lane = threadIdx.x & 31;
+    const uint32_t nrows = (uint32_t)dm.nrows, nfi = (uint32_t)(dm.K * dm.fi), nfu = (uint32_t)(dm.K * dm.fu);
+    int32_t id[4] = {0, 0, 0, 0};
     bool bad = false;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        if (p0 + u >= dm.N) { id[u] = 0; continue; }
-        if (id[u] < 0 || (int64_t)id[u] >= dm.V) { bad = true; id[u] = 0; }
-        if (id[u] != 0 && !position_live(dm, p0 + u, length)) id[u] = 0;
+        const int64_t p = p0 + u;
+        int32_t v = 0;
+        if (p < dm.off_tu) {
+            const uint32_t slice = (uint32_t)p / nrows, r = (uint32_t)p - slice * nrows;
+            const uint32_t b = slice / (uint32_t)dm.T, t = slice - b * (uint32_t)dm.T;
+            if ((int32_t)t < bp.length[b]) {
+                if (r < nfi) v = bp.u1[(int64_t)slice * nfi + r];
+                else if (r < 2 * nfi) v = bp.i2[(int64_t)slice * nfi + (r - nfi)];
+                else if (r < 2 * nfi + nfu) v = bp.u2[(int64_t)slice * nfu + (r - 2 * nfi)];
+                else v = bp.i1[(int64_t)slice * nfu + (r - 2 * nfi - nfu)];
+            }
+        } else if (p < dm.off_ti) v = bp.tu[p - dm.off_tu];
+        else if (p < dm.N) v = bp.ti[p - dm.off_ti];
+        if (v < 0 || (int64_t)v >= dm.V) { bad = true; v = 0; }
+        id[u] = v;
     }
     if (bad) atomicExch(err_flag, 1);
     if (p0 + 3 < dm.N) *reinterpret_cast<int4*>(keys + p0) = make_int4(id[0], id[1], id[2], id[3]);
@@ -90,19 +100,21 @@ __global__ void build_keys_kernel(Dims dm, const int32_t* __restrict__ ids, cons
         if (old[u] < upto) { ca.list[2 * idx] = id[u]; ca.list[2 * idx + 1] = old[u]; ++idx; }
 }
 
-void launch_build_keys(cudaStream_t st, const Dims& dm, const int32_t* ids, const int32_t* length,
-                       int32_t* keys, int32_t* err_flag, const ClaimArgs* claim) {
+void launch_build_keys(cudaStream_t st, const Dims& dm, const BatchPtrs* bp_dev, int32_t* keys, int32_t* label_out,
+                       int32_t* length_out, int32_t* err_flag, const ClaimArgs* claim) {
     ClaimArgs ca{};
     if (claim) { ca = *claim; cudaMemsetAsync(ca.counter, 0, sizeof(int32_t), st); }
     const int threads = 256;
-    const int64_t blocks = ((dm.N + 3) / 4 + threads - 1) / threads;
-    build_keys_kernel<<<(unsigned)blocks, threads, 0, st>>>(dm, ids, length, keys, err_flag, ca);
+    int64_t work = (dm.N + 3) / 4;
+    if (work < dm.B) work = dm.B;
+    const int64_t blocks = (work + threads - 1) / threads;
+    build_keys_kernel<<<(unsigned)blocks, threads, 0, st>>>(dm, bp_dev, keys, label_out, length_out, err_flag, ca);
     ++g_launch_count;
 }
 
 // ------------------------------------------------------------------------------------------
-// stage `nrows` table rows (ids at key_ptr[0..nrows), global or shared) into smem dst[nrows][d]; whole warp
-// cooperates, consecutive lanes fetch consecutive 16-byte chunks (a d=16 row is 4 lanes, 64 B contiguous).
+// stage `nrows` table rows (ids at key_ptr[0..nrows)) into smem dst[nrows][d]; whole warp cooperates, consecutive
+// lanes fetch consecutive 16-byte chunks (a d=16 row is 4 lanes, 64 B contiguous).
 __device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ emb, const int32_t* key_ptr,
                                            int nrows, int d, int lane) {
     const int cpr = d >> 2;   // 16-byte chunks per row
@@ -154,159 +166,222 @@ void launch_target_fwd(cudaStream_t st, const Dims& dm, const TargetArgs& a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Co-attention kernels.  One warp owns one (b, t) slice.
-//
-// Shared memory per warp: the slice's table rows (16-byte chunks, XOR-swizzled by row so that a lane-per-row
-// read of the same chunk index is bank-conflict free), its ids, one dot product per row, the K softmax
-// weights / relatedness gradients of both co-attentions, and (backward) the slice's incoming gradients and
-// the warp's accumulators for the co-attention kernel gradient.
-//
-// Row order in shared memory:  seg0 = user_1hop (K*fi rows) | seg1 = item_2hop (K*fi) | seg2 = user_2hop (K*fu)
-// | seg3 = item_1hop (K*fu).  Co-attention #1 = (seg0, seg1, target_item), #2 = (seg2, seg3, target_user)
-// (score.py:196-197).  The instruction budget matters as much as the bytes here (ncu: the first version
-// of this kernel was issue-bound at 2 750 warp instructions per slice), hence lane-per-row float4 dot
-// products and lane-per-chunk pooling instead of lane-per-element loops with a shuffle tree per neighbor.
+// Slice geometry: compile-time for the reference's data sets, run-time otherwise.  Same accessors, so the kernels
+// below are written once.
+template <int K_, int FI_, int FU_, int D_>
+struct GeomS {
+    static constexpr bool kStatic = true;
+    __device__ __forceinline__ explicit GeomS(const Dims&) {}
+    __device__ __forceinline__ constexpr int K() const { return K_; }
+    __device__ __forceinline__ constexpr int FI() const { return FI_; }
+    __device__ __forceinline__ constexpr int FU() const { return FU_; }
+    __device__ __forceinline__ constexpr int D() const { return D_; }
+    __device__ __forceinline__ constexpr int cpr() const { return D_ / 4; }
+    __device__ __forceinline__ constexpr int logcpr() const {
+        return D_ == 4 ? 0 : D_ == 8 ? 1 : D_ == 16 ? 2 : D_ == 32 ? 3 : D_ == 64 ? 4 : 5;
+    }
+};
+struct GeomD {
+    static constexpr bool kStatic = false;
+    int k, fi, fu, d, lc;
+    __device__ __forceinline__ explicit GeomD(const Dims& dm) : k(dm.K), fi(dm.fi), fu(dm.fu), d(dm.d) { lc = 31 - __clz(dm.d >> 2); }
+    __device__ __forceinline__ int K() const { return k; }
+    __device__ __forceinline__ int FI() const { return fi; }
+    __device__ __forceinline__ int FU() const { return fu; }
+    __device__ __forceinline__ int D() const { return d; }
+    __device__ __forceinline__ int cpr() const { return d >> 2; }
+    __device__ __forceinline__ int logcpr() const { return lc; }
+};
+// first row, number of rows and fields per node of segment `seg`; float offset of the segment's slice of the
+// co-attention kernels in the CTA's weight buffer [Wt_item | W1_item | W2_item | Wt_user | W1_user | W2_user]
+template <class G>
+__device__ __forceinline__ void seg_geom(const G& g, int seg, int& row0, int& nrow, int& F, int& wofs) {
+    const int nfi = g.K() * g.FI(), nfu = g.K() * g.FU(), Di = g.FI() * g.D(), Du = g.FU() * g.D();
+    row0 = seg == 0 ? 0 : seg == 1 ? nfi : seg == 2 ? 2 * nfi : 2 * nfi + nfu;
+    nrow = seg < 2 ? nfi : nfu;
+    F = seg < 2 ? g.FI() : g.FU();
+    wofs = seg == 0 ? Di : seg == 1 ? 2 * Di : seg == 2 ? 3 * Di + Du : 3 * Di + 2 * Du;
+}
+
+// Shared memory per warp: the slice's table rows in position order (linear 16-byte chunks: chunk q of the slice at
+// float offset 4q, so lane-per-chunk reads are conflict free), one dot product per row, the per-neighbor weights of
+// both co-attentions, and (backward) the slice's incoming gradients and the warp's accumulators for the
+// co-attention kernel gradient.
 struct CoattSmem {
     int w_off;        // [3*Di + 3*Du] co-attention kernels (CTA-shared)
     int warp_off;     // per-warp region start (floats)
     int warp_stride;  // per-warp floats
-    int rows;         // nrows * d
     int nrows;        // K * (2*fi + 2*fu)
-    // per-warp layout (floats): rows | kbuf[nrows] | dots[nrows] | wts[4*K pad 4*32] | (bwd) dbuf[2*Ds + 4K] | (bwd) acc[2*Di+2*Du]
-    int kbuf_off, dots_off, wts_off, dbuf_off, acc_off;
+    // per-warp layout (floats): rows[nrows*d] | dots[nrows] | wts[4*32] | (bwd) dbuf[2*Ds + 4K] | (bwd) acc[2*Di+2*Du]
+    int dots_off, wts_off, dbuf_off, acc_off;
 };
 __host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
 
-struct SliceGeom {
-    int nfi, nfu, nrows, cpr, swz;
-};
-__device__ __forceinline__ SliceGeom slice_geom(const Dims& dm) {
-    SliceGeom g;
-    g.nfi = dm.K * dm.fi; g.nfu = dm.K * dm.fu; g.nrows = 2 * g.nfi + 2 * g.nfu;
-    g.cpr = dm.d >> 2; g.swz = min(g.cpr - 1, 7);
-    return g;
-}
-// physical float offset of 16-byte chunk c4 of row r
-__device__ __forceinline__ int chunk_off(const SliceGeom& g, int r, int c4) { return (r * g.cpr + (c4 ^ (r & g.swz))) << 2; }
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
-// Gather one (b,t) slice: first ALL of its ids in one batch of independent loads (one global latency), then
-// all of its table rows with cp.async (a second latency) - never an id load in front of each row.
-__device__ __forceinline__ void stage_slice(float* rows, int32_t* kbuf, const Dims& dm, const SliceGeom& g,
-                                            const float* __restrict__ emb, const int32_t* __restrict__ keys,
-                                            int64_t slice, int lane) {
-    const int32_t* g0 = keys + dm.off_u1 + slice * g.nfi;
-    const int32_t* g1 = keys + dm.off_i2 + slice * g.nfi;
-    const int32_t* g2 = keys + dm.off_u2 + slice * g.nfu;
-    const int32_t* g3 = keys + dm.off_i1 + slice * g.nfu;
-    for (int r = lane; r < g.nfi; r += 32) { kbuf[r] = __ldg(g0 + r); kbuf[g.nfi + r] = __ldg(g1 + r); }
-    for (int r = lane; r < g.nfu; r += 32) { kbuf[2 * g.nfi + r] = __ldg(g2 + r); kbuf[2 * g.nfi + g.nfu + r] = __ldg(g3 + r); }
-    __syncwarp();
-    const int total = g.nrows * g.cpr;
-    const int shift = 31 - __clz(g.cpr);   // cpr is a power of two
-    for (int q = lane; q < total; q += 32) {
-        const int r = q >> shift, c4 = q & (g.cpr - 1);
-        const int32_t id = kbuf[r];
-        const float* src = emb + (int64_t)id * dm.d + c4 * 4;
-        cp_async16(rows + chunk_off(g, r, c4), id != 0 ? src : emb, id != 0 ? 16 : 0);
+// Gather one (b,t) slice: every lane fetches its 16-byte chunks with cp.async; the id of a row is read by the lanes
+// that need it (one broadcast load per row, all of them independent), never staged first.
+template <class G>
+__device__ __forceinline__ void stage_slice(const G& g, float* rows, const float* __restrict__ emb,
+                                            const int32_t* __restrict__ ks, int nrows, int lane) {
+    const int total = nrows << g.logcpr();
+    const int D = g.D();
+#pragma unroll
+    for (int q0 = 0; q0 < total; q0 += 32) {
+        const int q = q0 + lane;
+        if (q < total) {
+            const int r = q >> g.logcpr(), c4 = q & (g.cpr() - 1);
+            const int32_t id = __ldg(ks + r);
+            const float* src = emb + (int64_t)id * D + c4 * 4;
+            cp_async16(rows + q * 4, id != 0 ? src : emb, id != 0 ? 16 : 0);
+        }
     }
     cp_async_commit();
 }
 
-// segment of a row and its position inside it
-__device__ __forceinline__ void row_decode(const SliceGeom& g, const Dims& dm, int r, int& seg, int& i, int& field) {
-    int rl, f;
-    if (r < g.nfi) { seg = 0; rl = r; f = dm.fi; }
-    else if (r < 2 * g.nfi) { seg = 1; rl = r - g.nfi; f = dm.fi; }
-    else if (r < 2 * g.nfi + g.nfu) { seg = 2; rl = r - 2 * g.nfi; f = dm.fu; }
-    else { seg = 3; rl = r - 2 * g.nfi - g.nfu; f = dm.fu; }
-    i = rl / f; field = rl - i * f;
+// dots[row] = <row, vec[(row's field) * d ..]> for every row of segment `seg`: lane per 16-byte chunk, then a
+// shuffle tree over the chunks of a row
+template <class G>
+__device__ __forceinline__ void seg_dots(const G& g, int seg, const float* rows, const float* vec, float* dots, int lane) {
+    int row0, nrow, F, wofs;
+    seg_geom(g, seg, row0, nrow, F, wofs);
+    const int nch = nrow << g.logcpr(), fmod = F << g.logcpr();
+    const float4* r4 = reinterpret_cast<const float4*>(rows) + (row0 << g.logcpr());
+    const float4* v4 = reinterpret_cast<const float4*>(vec);
+#pragma unroll
+    for (int q0 = 0; q0 < nch; q0 += 32) {
+        const int q = q0 + lane;
+        float p = 0.f;
+        if (q < nch) p = dot4(r4[q], v4[q % fmod]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            if (o < g.cpr()) p += __shfl_xor_sync(FULL_MASK, p, o);
+        if (q < nch && (q & (g.cpr() - 1)) == 0) dots[row0 + (q >> g.logcpr())] = p;
+    }
 }
-__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
-// softmax over the first K lanes of `r`; returns the weight of this lane (0 for lanes >= K)
-__device__ __forceinline__ float softmax_k(float r, int lane, int K) {
-    float x = (lane < K) ? r : -INFINITY;
-    float mx = warp_max(x);
-    float e = (lane < K) ? expf(x - mx) : 0.f;
-    return e / warp_sum(e);
+// reductions over the 16-lane half of a warp (both co-attentions side by side when K <= 16)
+__device__ __forceinline__ float half_sum(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ float half_max(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
 }
 
-__global__ void coatt_fwd_kernel(Dims dm, CoattArgs a, CoattSmem sp) {
+template <class G>
+__global__ void __launch_bounds__(128) coatt_fwd_kernel(Dims dm, CoattArgs a, CoattSmem sp) {
     extern __shared__ __align__(16) float sm[];
+    const G g(dm);
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K = g.K(), D = g.D(), Di = g.FI() * D, Du = g.FU() * D, Ds = Di + Du;
+    const int nfi = K * g.FI(), nfu = K * g.FU(), nrows = 2 * nfi + 2 * nfu;
     float* Wsm = sm + sp.w_off;
-    for (int i = threadIdx.x; i < 3 * dm.Di; i += blockDim.x) Wsm[i] = a.w_item[i];
-    for (int i = threadIdx.x; i < 3 * dm.Du; i += blockDim.x) Wsm[3 * dm.Di + i] = a.w_user[i];
-    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * Di; i += blockDim.x) Wsm[i] = a.w_item[i];
+    for (int i = threadIdx.x; i < 3 * Du; i += blockDim.x) Wsm[3 * Di + i] = a.w_user[i];
     float* rows = sm + sp.warp_off + warp * sp.warp_stride;
-    int32_t* kbuf = reinterpret_cast<int32_t*>(rows + sp.kbuf_off);
     float* dots = rows + sp.dots_off;
-    float* wts = rows + sp.wts_off;
-    const SliceGeom g = slice_geom(dm);
-    const int K = dm.K, Di = dm.Di, Du = dm.Du, Ds = dm.Ds, d = dm.d;
+    float* wts = rows + sp.wts_off;      // w1[32] | w2[32] | 1/K [32]
     const float invK = 1.0f / (float)K;
-    const int64_t M = (int64_t)dm.B * dm.T;
-    for (int64_t slice = (int64_t)blockIdx.x * warps + warp; slice < M; slice += (int64_t)gridDim.x * warps) {
-        const int b = (int)(slice / dm.T), t = (int)(slice - (int64_t)b * dm.T);
-        float* xu_g = a.xhg_u + slice * dm.ldx; float* xu_c = a.xhc_u + slice * dm.ldx;
-        float* xi_g = a.xhg_i + slice * dm.ldx; float* xi_c = a.xhc_i + slice * dm.ldx;
-        float* info = a.key + slice * a.ldkey + a.key_off;
+    wts[64 + lane] = invK;
+    __syncthreads();
+    const int M = dm.B * dm.T;
+    for (int slice = blockIdx.x * warps + warp; slice < M; slice += gridDim.x * warps) {
+        const int b = slice / dm.T, t = slice - b * dm.T;
+        float* xu_g = a.xhg_u + (int64_t)slice * dm.ldx; float* xu_c = a.xhc_u + (int64_t)slice * dm.ldx;
+        float* xi_g = a.xhg_i + (int64_t)slice * dm.ldx; float* xi_c = a.xhc_i + (int64_t)slice * dm.ldx;
+        float* info = a.key + (int64_t)slice * a.ldkey + a.key_off;
         if (t >= a.length[b]) {   // dead slice: nothing downstream reads it, keep buffers finite
             for (int c = lane; c < Ds; c += 32) { xu_g[c] = 0.f; xu_c[c] = 0.f; xi_g[c] = 0.f; xi_c[c] = 0.f; }
             for (int c = lane; c < 4 * K; c += 32) info[c] = 0.f;
             continue;
         }
-        stage_slice(rows, kbuf, dm, g, a.emb, a.keys, slice, lane);
+        stage_slice(g, rows, a.emb, a.keys + (int64_t)slice * nrows, nrows, lane);
+        const float cz1 = a.c_item[b], cz2 = a.c_user[b];
         cp_async_wait<0>();
         __syncwarp();
         // (1) one dot product per row with its slice of the co-attention kernel (W1 for seq1 rows, W2 for seq2 rows)
-        for (int r = lane; r < g.nrows; r += 32) {
-            int seg, i, field;
-            row_decode(g, dm, r, seg, i, field);
-            const int woff = (seg == 0 ? Di : seg == 1 ? 2 * Di : seg == 2 ? 3 * Di + Du : 3 * Di + 2 * Du) + field * d;
-            const float4* wv = reinterpret_cast<const float4*>(Wsm + woff);
-            float acc = 0.f;
-            for (int c4 = 0; c4 < g.cpr; ++c4)
-                acc += dot4(*reinterpret_cast<const float4*>(rows + chunk_off(g, r, c4)), wv[c4]);
-            dots[r] = acc;
+#pragma unroll
+        for (int seg = 0; seg < 4; ++seg) {
+            int row0, nrow, F, wofs;
+            seg_geom(g, seg, row0, nrow, F, wofs);
+            seg_dots(g, seg, rows, Wsm + wofs, dots, lane);
         }
         __syncwarp();
         // (2) relatedness r_i = relu(target part + seq1[i] part + seq2[i] part), softmax over the K neighbors
-        float z1 = a.c_item[b], z2 = a.c_user[b];
-        if (lane < K) {
-            for (int f = 0; f < dm.fi; ++f) z1 += dots[lane * dm.fi + f] + dots[g.nfi + lane * dm.fi + f];
-            for (int f = 0; f < dm.fu; ++f) z2 += dots[2 * g.nfi + lane * dm.fu + f] + dots[2 * g.nfi + g.nfu + lane * dm.fu + f];
-        }
-        const float r1 = (lane < K) ? fmaxf(z1, 0.f) : 0.f, r2 = (lane < K) ? fmaxf(z2, 0.f) : 0.f;
-        const float w1 = softmax_k(r1, lane, K), w2 = softmax_k(r2, lane, K);
-        const float s1 = warp_sum(r1), s2 = warp_sum(r2);
-        if (lane < K) {
-            wts[lane] = w1; wts[K + lane] = w2;
-            info[lane] = (float)K * r1; info[K + lane] = s1;            // atten_info of co-attention #1 (score.py:165-166)
-            info[2 * K + lane] = (float)K * r2; info[3 * K + lane] = s2;   // ... of co-attention #2
-            float* sr = a.save_r + slice * 2 * K; float* sw = a.save_w + slice * 2 * K;
-            sr[lane] = r1; sr[K + lane] = r2; sw[lane] = w1; sw[K + lane] = w2;
+        float* sr = a.save_r + (int64_t)slice * 2 * K; float* sw = a.save_w + (int64_t)slice * 2 * K;
+        if (K <= 16) {   // lanes 0..15: co-attention #1, lanes 16..31: co-attention #2
+            const int half = lane >> 4, i = lane & 15;
+            const bool act = i < K;
+            const int F = half ? g.FU() : g.FI();
+            const int base = half ? 2 * nfi : 0, nf = half ? nfu : nfi;
+            float z = half ? cz2 : cz1;
+            if (act) {
+                const int fmax = g.FI() > g.FU() ? g.FI() : g.FU();
+#pragma unroll
+                for (int f = 0; f < fmax; ++f)
+                    if (f < F) z += dots[base + i * F + f] + dots[base + nf + i * F + f];
+            }
+            const float r = act ? fmaxf(z, 0.f) : 0.f;
+            const float mx = half_max(act ? r : -INFINITY);
+            const float e = act ? expf(r - mx) : 0.f;
+            const float w = e / half_sum(e);
+            const float s = half_sum(r);
+            if (act) {
+                wts[half * 32 + i] = w;
+                info[half * 2 * K + i] = (float)K * r;     // atten_info (score.py:165-166)
+                info[half * 2 * K + K + i] = s;
+                sr[half * K + i] = r; sw[half * K + i] = w;
+            }
+        } else {
+            float z1 = cz1, z2 = cz2;
+            if (lane < K) {
+                for (int f = 0; f < g.FI(); ++f) z1 += dots[lane * g.FI() + f] + dots[nfi + lane * g.FI() + f];
+                for (int f = 0; f < g.FU(); ++f) z2 += dots[2 * nfi + lane * g.FU() + f] + dots[2 * nfi + nfu + lane * g.FU() + f];
+            }
+            const bool act = lane < K;
+            const float r1 = act ? fmaxf(z1, 0.f) : 0.f, r2 = act ? fmaxf(z2, 0.f) : 0.f;
+            const float m1 = warp_max(act ? r1 : -INFINITY), m2 = warp_max(act ? r2 : -INFINITY);
+            const float e1 = act ? expf(r1 - m1) : 0.f, e2 = act ? expf(r2 - m2) : 0.f;
+            const float w1 = e1 / warp_sum(e1), w2 = e2 / warp_sum(e2);
+            const float s1 = warp_sum(r1), s2 = warp_sum(r2);
+            if (act) {
+                wts[lane] = w1; wts[32 + lane] = w2;
+                info[lane] = (float)K * r1; info[K + lane] = s1;
+                info[2 * K + lane] = (float)K * r2; info[3 * K + lane] = s2;
+                sr[lane] = r1; sr[K + lane] = r2; sw[lane] = w1; sw[K + lane] = w2;
+            }
         }
         __syncwarp();
         // (3) pooling, one 16-byte output chunk per lane:
         //   user_side = [sum_i w1_i user_1hop[i] | sum_i w2_i user_2hop[i]],  item_side = [mean item_1hop | mean item_2hop]
         const int nchunk = (2 * Ds) >> 2;
-        for (int e4 = lane; e4 < nchunk; e4 += 32) {
-            const int e = e4 << 2;
-            int segbase, f, c, wsel; float* dst0; float* dst1;
-            if (e < Di) { segbase = 0; f = dm.fi; c = e; wsel = 0; dst0 = xu_g + c; dst1 = xu_c + c; }
-            else if (e < Ds) { segbase = 2 * g.nfi; f = dm.fu; c = e - Di; wsel = 1; dst0 = xu_g + Di + c; dst1 = xu_c + Di + c; }
-            else if (e < Ds + Du) { segbase = 2 * g.nfi + g.nfu; f = dm.fu; c = e - Ds; wsel = 2; dst0 = xi_g + c; dst1 = xi_c + c; }
-            else { segbase = g.nfi; f = dm.fi; c = e - Ds - Du; wsel = 2; dst0 = xi_g + Du + c; dst1 = xi_c + Du + c; }
-            const int field = c / d, c4 = (c - field * d) >> 2;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int i = 0; i < K; ++i) {
-                const float4 v = *reinterpret_cast<const float4*>(rows + chunk_off(g, segbase + i * f + field, c4));
-                const float w = wsel == 2 ? invK : wts[wsel * K + i];
-                acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+        const float4* r4 = reinterpret_cast<const float4*>(rows);
+#pragma unroll
+        for (int e0 = 0; e0 < nchunk; e0 += 32) {
+            const int e4 = e0 + lane;
+            if (e4 < nchunk) {
+                const int e = e4 << 2;
+                int row0, F, c, wsel; float* dst0; float* dst1;
+                if (e < Di) { row0 = 0; F = g.FI(); c = e; wsel = 0; dst0 = xu_g + e; dst1 = xu_c + e; }
+                else if (e < Ds) { row0 = 2 * nfi; F = g.FU(); c = e - Di; wsel = 32; dst0 = xu_g + e; dst1 = xu_c + e; }
+                else if (e < Ds + Du) { row0 = 2 * nfi + nfu; F = g.FU(); c = e - Ds; wsel = 64; dst0 = xi_g + c; dst1 = xi_c + c; }
+                else { row0 = nfi; F = g.FI(); c = e - Ds - Du; wsel = 64; dst0 = xi_g + Du + c; dst1 = xi_c + Du + c; }
+                const float4* src = r4 + (row0 << g.logcpr()) + (c >> 2);   // chunk (field, c4) of neighbor 0
+                const int stride = F << g.logcpr();
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    const float4 v = src[i * stride];
+                    const float w = wts[wsel + i];
+                    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                }
+                *reinterpret_cast<float4*>(dst0) = acc;
+                *reinterpret_cast<float4*>(dst1) = acc;
             }
-            dst0[0] = acc.x; dst0[1] = acc.y; dst0[2] = acc.z; dst0[3] = acc.w;
-            dst1[0] = acc.x; dst1[1] = acc.y; dst1[2] = acc.z; dst1[3] = acc.w;
         }
         __syncwarp();
     }
@@ -317,9 +392,7 @@ static CoattSmem coatt_plan(const Dims& dm, int warps, bool bwd, size_t* bytes) 
     sp.w_off = 0;
     sp.warp_off = round4(3 * dm.Di + 3 * dm.Du);
     sp.nrows = dm.K * (2 * dm.fi + 2 * dm.fu);
-    sp.rows = sp.nrows * dm.d;
-    sp.kbuf_off = sp.rows;
-    sp.dots_off = sp.kbuf_off + round4(sp.nrows);
+    sp.dots_off = sp.nrows * dm.d;
     sp.wts_off = sp.dots_off + round4(sp.nrows);
     sp.dbuf_off = sp.wts_off + 4 * 32;
     sp.acc_off = sp.dbuf_off + (bwd ? round4(2 * dm.Ds + 4 * dm.K) : 0);
@@ -339,20 +412,36 @@ static int num_sms() {
     return g_num_sms;
 }
 
-void launch_coatt_fwd(cudaStream_t st, const Dims& dm, const CoattArgs& a) {
+template <class G>
+static void coatt_fwd_launch(cudaStream_t st, const Dims& dm, const CoattArgs& a) {
     const int warps = 4;
     size_t smem;
     CoattSmem sp = coatt_plan(dm, warps, false, &smem);
     static size_t attr_set = 0;
     if (smem > 48 * 1024 && smem > attr_set) {
-        cudaFuncSetAttribute(coatt_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(coatt_fwd_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = smem;
     }
     int64_t M = (int64_t)dm.B * dm.T;
     int64_t want = (M + warps - 1) / warps;
     int64_t cap = (int64_t)num_sms() * 32;
     int grid = (int)(want < cap ? want : cap);
-    coatt_fwd_kernel<<<grid, warps * 32, smem, st>>>(dm, a, sp);
+    coatt_fwd_kernel<G><<<grid, warps * 32, smem, st>>>(dm, a, sp);
+}
+
+// geometries of the reference's data sets (train_score.py:23-54) + the large-vocab config; anything else: run-time
+#define SCORE_GEOM_DISPATCH(FN, ...)                                                                         \
+    do {                                                                                                     \
+        if (dm.K == 10 && dm.fi == 2 && dm.fu == 1 && dm.d == 16) FN<GeomS<10, 2, 1, 16>>(__VA_ARGS__);      \
+        else if (dm.K == 10 && dm.fi == 4 && dm.fu == 3 && dm.d == 16) FN<GeomS<10, 4, 3, 16>>(__VA_ARGS__); \
+        else if (dm.K == 10 && dm.fi == 5 && dm.fu == 1 && dm.d == 16) FN<GeomS<10, 5, 1, 16>>(__VA_ARGS__); \
+        else if (dm.K == 20 && dm.fi == 5 && dm.fu == 1 && dm.d == 16) FN<GeomS<20, 5, 1, 16>>(__VA_ARGS__); \
+        else if (dm.K == 10 && dm.fi == 1 && dm.fu == 1 && dm.d == 64) FN<GeomS<10, 1, 1, 64>>(__VA_ARGS__); \
+        else FN<GeomD>(__VA_ARGS__);                                                                         \
+    } while (0)
+
+void launch_coatt_fwd(cudaStream_t st, const Dims& dm, const CoattArgs& a) {
+    SCORE_GEOM_DISPATCH(coatt_fwd_launch, st, dm, a);
     ++g_launch_count;
 }
 
@@ -362,123 +451,155 @@ void launch_coatt_fwd(cudaStream_t st, const Dims& dm, const CoattArgs& a) {
 //   dw_i = dout1 . seq1[i]                    dr_i = K*dinfo[i] + sum_j dinfo[K+j] + w_i (dw_i - sum_k w_k dw_k)
 //   dz_i = dr_i [r_i > 0]                     dseq1[i] = w_i dout1 + dz_i W1      dseq2[i] = dout2 / K + dz_i W2
 //   dW1 += sum_i dz_i seq1[i]                 dW2 += sum_i dz_i seq2[i]           sdz = sum_i dz_i
-__global__ void coatt_bwd_kernel(Dims dm, CoattBwdArgs a, CoattSmem sp) {
+template <class G>
+__global__ void __launch_bounds__(128) coatt_bwd_kernel(Dims dm, CoattBwdArgs a, CoattSmem sp) {
     extern __shared__ __align__(16) float sm[];
+    const G g(dm);
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K = g.K(), D = g.D(), Di = g.FI() * D, Du = g.FU() * D, Ds = Di + Du;
+    const int nfi = K * g.FI(), nfu = K * g.FU(), nrows = 2 * nfi + 2 * nfu;
     float* Wsm = sm + sp.w_off;
-    for (int i = threadIdx.x; i < 3 * dm.Di; i += blockDim.x) Wsm[i] = a.w_item[i];
-    for (int i = threadIdx.x; i < 3 * dm.Du; i += blockDim.x) Wsm[3 * dm.Di + i] = a.w_user[i];
+    for (int i = threadIdx.x; i < 3 * Di; i += blockDim.x) Wsm[i] = a.w_item[i];
+    for (int i = threadIdx.x; i < 3 * Du; i += blockDim.x) Wsm[3 * Di + i] = a.w_user[i];
     float* rows = sm + sp.warp_off + warp * sp.warp_stride;
-    int32_t* kbuf = reinterpret_cast<int32_t*>(rows + sp.kbuf_off);
     float* dots = rows + sp.dots_off;
-    float* wts = rows + sp.wts_off;      // w1[K] | w2[K] | dz1[K] | dz2[K]   (strides of 32)
+    float* wts = rows + sp.wts_off;      // a1[32] (w1) | a2[32] (w2) | dz1[32] | dz2[32]
     float* dbuf = rows + sp.dbuf_off;    // d user_side [Ds] | d item_side [Ds] | d atten_info [4K]
     float* acc = rows + sp.acc_off;      // dW1_item [Di] | dW2_item [Di] | dW1_user [Du] | dW2_user [Du]
-    const SliceGeom g = slice_geom(dm);
-    const int K = dm.K, Di = dm.Di, Du = dm.Du, Ds = dm.Ds, d = dm.d;
     const int nacc = 2 * Di + 2 * Du;
     const float invK = 1.0f / (float)K;
     for (int c = lane; c < nacc; c += 32) acc[c] = 0.f;
     __syncthreads();
-    const int64_t M = (int64_t)dm.B * dm.T;
-    for (int64_t slice = (int64_t)blockIdx.x * warps + warp; slice < M; slice += (int64_t)gridDim.x * warps) {
-        const int b = (int)(slice / dm.T), t = (int)(slice - (int64_t)b * dm.T);
+    const int M = dm.B * dm.T;
+    for (int slice = blockIdx.x * warps + warp; slice < M; slice += gridDim.x * warps) {
+        const int b = slice / dm.T, t = slice - b * dm.T;
         if (t >= a.length[b]) {
-            if (lane == 0) { a.sdz[slice * 2] = 0.f; a.sdz[slice * 2 + 1] = 0.f; }
+            if (lane == 0) { a.sdz[(int64_t)slice * 2] = 0.f; a.sdz[(int64_t)slice * 2 + 1] = 0.f; }
             continue;   // positions of dead slices carry key 0: their gradient rows are never read
         }
-        stage_slice(rows, kbuf, dm, g, a.emb, a.keys, slice, lane);
+        stage_slice(g, rows, a.emb, a.keys + (int64_t)slice * nrows, nrows, lane);
         {   // incoming gradients of this slice (overlaps the row gather)
-            const float* dxu = a.dxu + slice * Ds; const float* dxi = a.dxi + slice * Ds;
-            const float* dinfo = a.dkey + slice * a.ldkey + a.key_off;
-            for (int c = lane; c < Ds; c += 32) { dbuf[c] = dxu[c]; dbuf[Ds + c] = dxi[c]; }
+            const float4* dxu = reinterpret_cast<const float4*>(a.dxu + (int64_t)slice * Ds);
+            const float4* dxi = reinterpret_cast<const float4*>(a.dxi + (int64_t)slice * Ds);
+            const float* dinfo = a.dkey + (int64_t)slice * a.ldkey + a.key_off;
+            float4* d4 = reinterpret_cast<float4*>(dbuf);
+            for (int c = lane; c < (Ds >> 2); c += 32) { d4[c] = dxu[c]; d4[(Ds >> 2) + c] = dxi[c]; }
             for (int c = lane; c < 4 * K; c += 32) dbuf[2 * Ds + c] = dinfo[c];
         }
-        float w1 = 0.f, w2 = 0.f, r1 = 0.f, r2 = 0.f;
-        if (lane < K) {
-            const float* sr = a.save_r + slice * 2 * K; const float* sw = a.save_w + slice * 2 * K;
+        const float* sr = a.save_r + (int64_t)slice * 2 * K; const float* sw = a.save_w + (int64_t)slice * 2 * K;
+        float w_h = 0.f, r_h = 0.f, w1 = 0.f, w2 = 0.f, r1 = 0.f, r2 = 0.f;
+        if (K <= 16) {
+            const int half = lane >> 4, i = lane & 15;
+            if (i < K) { w_h = sw[half * K + i]; r_h = sr[half * K + i]; }
+        } else if (lane < K) {
             r1 = sr[lane]; r2 = sr[K + lane]; w1 = sw[lane]; w2 = sw[K + lane];
         }
         cp_async_wait<0>();
         __syncwarp();
         // (1) dw: dot of every seq1 row (seg0, seg2) with its field's slice of dout1
-        for (int r = lane; r < g.nrows; r += 32) {
-            int seg, i, field;
-            row_decode(g, dm, r, seg, i, field);
-            if (seg == 0 || seg == 2) {
-                const float4* dv = reinterpret_cast<const float4*>(dbuf + (seg == 0 ? 0 : Di) + field * d);
-                float s = 0.f;
-                for (int c4 = 0; c4 < g.cpr; ++c4)
-                    s += dot4(*reinterpret_cast<const float4*>(rows + chunk_off(g, r, c4)), dv[c4]);
-                dots[r] = s;
-            }
-        }
+        seg_dots(g, 0, rows, dbuf, dots, lane);
+        seg_dots(g, 2, rows, dbuf + Di, dots, lane);
         __syncwarp();
         // (2) per-neighbor scalars in lanes
-        float dw1 = 0.f, dw2 = 0.f;
-        if (lane < K) {
-            for (int f = 0; f < dm.fi; ++f) dw1 += dots[lane * dm.fi + f];
-            for (int f = 0; f < dm.fu; ++f) dw2 += dots[2 * g.nfi + lane * dm.fu + f];
-        }
         const float* dinf = dbuf + 2 * Ds;
-        const float dot1 = warp_sum(w1 * dw1), dot2 = warp_sum(w2 * dw2);
-        const float tail1 = warp_sum(lane < K ? dinf[K + lane] : 0.f), tail2 = warp_sum(lane < K ? dinf[3 * K + lane] : 0.f);
-        float dz1 = 0.f, dz2 = 0.f;
-        if (lane < K) {
-            const float dr1 = (float)K * dinf[lane] + tail1 + w1 * (dw1 - dot1);
-            const float dr2 = (float)K * dinf[2 * K + lane] + tail2 + w2 * (dw2 - dot2);
-            dz1 = r1 > 0.f ? dr1 : 0.f;
-            dz2 = r2 > 0.f ? dr2 : 0.f;
-            wts[lane] = w1; wts[32 + lane] = w2; wts[64 + lane] = dz1; wts[96 + lane] = dz2;
+        if (K <= 16) {
+            const int half = lane >> 4, i = lane & 15;
+            const bool act = i < K;
+            const int F = half ? g.FU() : g.FI();
+            const int base = half ? 2 * nfi : 0;
+            float dw = 0.f;
+            if (act) {
+                const int fmax = g.FI() > g.FU() ? g.FI() : g.FU();
+#pragma unroll
+                for (int f = 0; f < fmax; ++f)
+                    if (f < F) dw += dots[base + i * F + f];
+            }
+            const float* di = dinf + half * 2 * K;
+            const float dotw = half_sum(w_h * dw);
+            const float tail = half_sum(act ? di[K + i] : 0.f);
+            float dz = 0.f;
+            if (act) {
+                const float dr = (float)K * di[i] + tail + w_h * (dw - dotw);
+                dz = r_h > 0.f ? dr : 0.f;
+                wts[half * 32 + i] = w_h; wts[64 + half * 32 + i] = dz;
+            }
+            const float sdz = half_sum(dz);
+            if (i == 0) a.sdz[(int64_t)slice * 2 + half] = sdz;
+        } else {
+            float dw1 = 0.f, dw2 = 0.f;
+            if (lane < K) {
+                for (int f = 0; f < g.FI(); ++f) dw1 += dots[lane * g.FI() + f];
+                for (int f = 0; f < g.FU(); ++f) dw2 += dots[2 * nfi + lane * g.FU() + f];
+            }
+            const float dot1 = warp_sum(w1 * dw1), dot2 = warp_sum(w2 * dw2);
+            const float tail1 = warp_sum(lane < K ? dinf[K + lane] : 0.f), tail2 = warp_sum(lane < K ? dinf[3 * K + lane] : 0.f);
+            float dz1 = 0.f, dz2 = 0.f;
+            if (lane < K) {
+                const float dr1 = (float)K * dinf[lane] + tail1 + w1 * (dw1 - dot1);
+                const float dr2 = (float)K * dinf[2 * K + lane] + tail2 + w2 * (dw2 - dot2);
+                dz1 = r1 > 0.f ? dr1 : 0.f;
+                dz2 = r2 > 0.f ? dr2 : 0.f;
+                wts[lane] = w1; wts[32 + lane] = w2; wts[64 + lane] = dz1; wts[96 + lane] = dz2;
+            }
+            const float sdz1 = warp_sum(dz1), sdz2 = warp_sum(dz2);
+            if (lane == 0) { a.sdz[(int64_t)slice * 2] = sdz1; a.sdz[(int64_t)slice * 2 + 1] = sdz2; }
         }
-        const float sdz1 = warp_sum(dz1), sdz2 = warp_sum(dz2);
-        if (lane == 0) { a.sdz[slice * 2] = sdz1; a.sdz[slice * 2 + 1] = sdz2; }
         __syncwarp();
-        // (3) per-position gradient rows, one 16-byte chunk per lane, written in position order (coalesced)
+        // (3) per-position gradient rows, one 16-byte chunk per lane; the slice's rows are one contiguous block
         {
-            const int total = g.nrows * g.cpr;
-            const int shift = 31 - __clz(g.cpr);
-            float* gr = a.grad_rows;
-            float* gb0 = gr + (dm.off_u1 + slice * g.nfi) * d;
-            float* gb1 = gr + (dm.off_i2 + slice * g.nfi) * d;
-            float* gb2 = gr + (dm.off_u2 + slice * g.nfu) * d;
-            float* gb3 = gr + (dm.off_i1 + slice * g.nfu) * d;
-            for (int q = lane; q < total; q += 32) {
-                const int r = q >> shift, c4 = q & (g.cpr - 1);
-                int seg, i, field;
-                row_decode(g, dm, r, seg, i, field);
-                const int col = field * d + c4 * 4;
-                float a_i, dz; const float* dv; const float* wv; float* dst;
-                if (seg == 0) { a_i = wts[i]; dz = wts[64 + i]; dv = dbuf + col; wv = Wsm + Di + col; dst = gb0 + (int64_t)r * d; }
-                else if (seg == 1) { a_i = invK; dz = wts[64 + i]; dv = dbuf + Ds + Du + col; wv = Wsm + 2 * Di + col; dst = gb1 + (int64_t)(r - g.nfi) * d; }
-                else if (seg == 2) { a_i = wts[32 + i]; dz = wts[96 + i]; dv = dbuf + Di + col; wv = Wsm + 3 * Di + Du + col; dst = gb2 + (int64_t)(r - 2 * g.nfi) * d; }
-                else { a_i = invK; dz = wts[96 + i]; dv = dbuf + Ds + col; wv = Wsm + 3 * Di + 2 * Du + col; dst = gb3 + (int64_t)(r - 2 * g.nfi - g.nfu) * d; }
-                const float4 dvv = *reinterpret_cast<const float4*>(dv);
-                const float4 wvv = *reinterpret_cast<const float4*>(wv);
-                float4 o;
-                o.x = a_i * dvv.x + dz * wvv.x; o.y = a_i * dvv.y + dz * wvv.y;
-                o.z = a_i * dvv.z + dz * wvv.z; o.w = a_i * dvv.w + dz * wvv.w;
-                *reinterpret_cast<float4*>(dst + c4 * 4) = o;
+            float4* gout = reinterpret_cast<float4*>(a.grad_rows) + ((int64_t)slice * nrows << g.logcpr());
+#pragma unroll
+            for (int seg = 0; seg < 4; ++seg) {
+                int row0, nrow, F, wofs;
+                seg_geom(g, seg, row0, nrow, F, wofs);
+                const int nch = nrow << g.logcpr(), fmod = F << g.logcpr();
+                // d(pooled output) of this segment and its slice of the co-attention kernel
+                const float4* dv4 = reinterpret_cast<const float4*>(dbuf + (seg == 0 ? 0 : seg == 1 ? Ds + Du : seg == 2 ? Di : Ds));
+                const float4* wv4 = reinterpret_cast<const float4*>(Wsm + wofs);
+                const float* ai = wts + (seg == 0 ? 0 : 32);        // softmax weights (seq1 segments)
+                const float* dzi = wts + (seg < 2 ? 64 : 96);
+                float4* go = gout + (row0 << g.logcpr());
+#pragma unroll
+                for (int q0 = 0; q0 < nch; q0 += 32) {
+                    const int q = q0 + lane;
+                    if (q < nch) {
+                        const int i = q / fmod, fc = q - i * fmod;
+                        const float a_i = (seg == 0 || seg == 2) ? ai[i] : invK;
+                        const float dz = dzi[i];
+                        const float4 dvv = dv4[fc], wvv = wv4[fc];
+                        float4 o;
+                        o.x = a_i * dvv.x + dz * wvv.x; o.y = a_i * dvv.y + dz * wvv.y;
+                        o.z = a_i * dvv.z + dz * wvv.z; o.w = a_i * dvv.w + dz * wvv.w;
+                        go[q] = o;
+                    }
+                }
             }
         }
         // (4) co-attention kernel gradient: dW1 += sum_i dz_i seq1[i], dW2 += sum_i dz_i seq2[i] (per-warp accumulators)
         {
             const int nchunk = nacc >> 2;
-            for (int e4 = lane; e4 < nchunk; e4 += 32) {
-                const int e = e4 << 2;
-                int segbase, f, c, zsel;
-                if (e < Di) { segbase = 0; f = dm.fi; c = e; zsel = 64; }
-                else if (e < 2 * Di) { segbase = g.nfi; f = dm.fi; c = e - Di; zsel = 64; }
-                else if (e < 2 * Di + Du) { segbase = 2 * g.nfi; f = dm.fu; c = e - 2 * Di; zsel = 96; }
-                else { segbase = 2 * g.nfi + g.nfu; f = dm.fu; c = e - 2 * Di - Du; zsel = 96; }
-                const int field = c / d, c4 = (c - field * d) >> 2;
-                float4 s = *reinterpret_cast<float4*>(acc + e);
-                for (int i = 0; i < K; ++i) {
-                    const float4 v = *reinterpret_cast<const float4*>(rows + chunk_off(g, segbase + i * f + field, c4));
-                    const float z = wts[zsel + i];
-                    s.x = fmaf(z, v.x, s.x); s.y = fmaf(z, v.y, s.y); s.z = fmaf(z, v.z, s.z); s.w = fmaf(z, v.w, s.w);
+            const float4* r4 = reinterpret_cast<const float4*>(rows);
+#pragma unroll
+            for (int e0 = 0; e0 < nchunk; e0 += 32) {
+                const int e4 = e0 + lane;
+                if (e4 < nchunk) {
+                    const int e = e4 << 2;
+                    int row0, F, c, zsel;
+                    if (e < Di) { row0 = 0; F = g.FI(); c = e; zsel = 64; }
+                    else if (e < 2 * Di) { row0 = nfi; F = g.FI(); c = e - Di; zsel = 64; }
+                    else if (e < 2 * Di + Du) { row0 = 2 * nfi; F = g.FU(); c = e - 2 * Di; zsel = 96; }
+                    else { row0 = 2 * nfi + nfu; F = g.FU(); c = e - 2 * Di - Du; zsel = 96; }
+                    const float4* src = r4 + (row0 << g.logcpr()) + (c >> 2);
+                    const int stride = F << g.logcpr();
+                    float4 s = *reinterpret_cast<float4*>(acc + e);
+#pragma unroll
+                    for (int i = 0; i < K; ++i) {
+                        const float4 v = src[i * stride];
+                        const float z = wts[zsel + i];
+                        s.x = fmaf(z, v.x, s.x); s.y = fmaf(z, v.y, s.y); s.z = fmaf(z, v.z, s.z); s.w = fmaf(z, v.w, s.w);
+                    }
+                    *reinterpret_cast<float4*>(acc + e) = s;
                 }
-                *reinterpret_cast<float4*>(acc + e) = s;
             }
         }
         __syncwarp();
@@ -494,16 +615,21 @@ __global__ void coatt_bwd_kernel(Dims dm, CoattBwdArgs a, CoattSmem sp) {
 
 int coatt_bwd_num_ctas() { return num_sms() * 8; }
 
-void launch_coatt_bwd(cudaStream_t st, const Dims& dm, const CoattBwdArgs& a) {
+template <class G>
+static void coatt_bwd_launch(cudaStream_t st, const Dims& dm, const CoattBwdArgs& a) {
     const int warps = 4;
     size_t smem;
     CoattSmem sp = coatt_plan(dm, warps, true, &smem);
     static size_t attr_set = 0;
     if (smem > 48 * 1024 && smem > attr_set) {
-        cudaFuncSetAttribute(coatt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(coatt_bwd_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = smem;
     }
-    coatt_bwd_kernel<<<a.n_partials, warps * 32, smem, st>>>(dm, a, sp);
+    coatt_bwd_kernel<G><<<a.n_partials, warps * 32, smem, st>>>(dm, a, sp);
+}
+
+void launch_coatt_bwd(cudaStream_t st, const Dims& dm, const CoattBwdArgs& a) {
+    SCORE_GEOM_DISPATCH(coatt_bwd_launch, st, dm, a);
     ++g_launch_count;
 }
 

@@ -44,14 +44,22 @@ struct Dims {
     int B, T, K, d, H, fu, fi;
     int Du, Di, Ds, Dk, Dfc;      // user/item node width, GRU input width, key width, fc input width
     int ldx;                       // Ds + H: leading dim of the [x || h] buffers
-    int64_t off_u1, off_u2, off_i1, off_i2, off_tu, off_ti, N;  // position offsets in the flat id list
+    int nrows;                     // K * (2*fi + 2*fu): positions (ids) per (b,t) slice
+    int64_t off_tu, off_ti, N;     // slice-major position space (embed.cu): B*T*nrows history positions, then the targets
     int model_type;
+};
+
+// Where the eight tensors of the current batch lie (device memory): the handle's staging buffers for a host batch,
+// the caller's own tensors for a device batch.  Lives in device memory so a captured graph follows it.
+struct BatchPtrs {
+    const int32_t* u1; const int32_t* u2; const int32_t* i1; const int32_t* i2;   // user_1hop, user_2hop, item_1hop, item_2hop
+    const int32_t* tu; const int32_t* ti; const int32_t* label; const int32_t* length;
 };
 
 // LAZY optimizer mode: claim the stale rows among the keys while they are built (see scatter.cu: emb_replay_kernel)
 struct ClaimArgs { int32_t* last_step; const Hyper* hp; int32_t* list; int32_t* counter; };
-void launch_build_keys(cudaStream_t st, const Dims& dm, const int32_t* ids, const int32_t* length,
-                       int32_t* keys, int32_t* err_flag, const ClaimArgs* claim = nullptr);
+void launch_build_keys(cudaStream_t st, const Dims& dm, const BatchPtrs* bp_dev, int32_t* keys, int32_t* label_out,
+                       int32_t* length_out, int32_t* err_flag, const ClaimArgs* claim = nullptr);
 // replay the rows of a claim list (2 int32 per entry: row, last step); *counter entries
 void launch_emb_replay(cudaStream_t st, const int32_t* claim_list, const int32_t* claim_counter, int64_t max_rows, float* emb,
                        float* m, float* v, int d, const float* alpha_hist, const Hyper* hp);
@@ -239,6 +247,8 @@ void launch_dense_adam(cudaStream_t st, float* p, float* m, float* v, const floa
 struct SortBufs {
     int32_t* keys[2]; int32_t* vals[2];   // ping-pong
     uint32_t* hist;                        // [256 * nblocks]
+    int32_t* runs;                         // [8 * n_cap] short-run descriptors of the sorted list (launch_emb_runs)
+    int32_t* runs_long;                    // [4 * emb_runs_long_cap(n_cap)] medium / long run descriptors
     int n_cap;
 };
 size_t sort_hist_elems(int64_t n);
@@ -246,11 +256,17 @@ size_t sort_hist_elems(int64_t n);
 // returns the index (0/1) of the ping-pong buffer that holds the result
 int launch_sort_pairs(cudaStream_t st, SortBufs& sb, const int32_t* keys_in, int64_t n, int key_bits);
 
-// compact list of the sorted indices that start a run of equal non-zero keys (order arbitrary); *counter = their number
-void launch_emb_heads(cudaStream_t st, const int32_t* skeys, int64_t n, int32_t* heads, int32_t* counter);
+// Run descriptors of the sorted (key, position) list, three tiers by run length (scatter.cu):
+//   runs       8 int32 per run of <= 4 entries: {key, start, n, pos0, pos1, pos2, pos3, 0}           (capacity n runs)
+//   runs_long  4 int32 per longer run {key, start, count, 0}: runs of <= 512 entries from the front, longer ones from
+//              the back of a buffer of emb_runs_long_cap(n) descriptors
+//   counters   4 int32: number of short / medium / long runs, and of all runs (= unique rows)
+int64_t emb_runs_long_cap(int64_t n);
+void launch_emb_runs(cudaStream_t st, const int32_t* skeys, const int32_t* spos, int64_t n, int32_t* runs,
+                     int32_t* runs_long, int32_t* counters);
 struct EmbUpdateArgs {
     const int32_t* skeys; const int32_t* spos; int64_t n;
-    const int32_t* heads; const int32_t* n_heads;   // from launch_emb_heads
+    const int32_t* runs; const int32_t* runs_long; int64_t long_cap; const int32_t* counters;   // from launch_emb_runs
     const float* grad_rows; int d;
     float* emb; float* m; float* v; int32_t* last_step;
     const float* alpha_hist;       // LAZY: rows that are not current through step-1 are replayed first (may be null)

@@ -88,11 +88,17 @@ struct ScoreModel {
     int32_t* n_heads_dev = nullptr;   // number of run heads in the sorted key list (emb_heads_kernel)
     float *l2sum = nullptr, *loss_dev = nullptr;   // loss_dev[0] = total loss, loss_dev[1] = reg_lambda * l2 part
     int32_t* err_flag = nullptr;
-    Hyper* hyper_dev = nullptr;
+    // Per-step parameters the kernels read from device memory (one H2D copy per step; captured graphs stay valid):
+    // the hyper-parameters and the pointer table of the current batch.
+    struct StepParams { Hyper hp; BatchPtrs bp; };
+    StepParams* step_dev = nullptr;
+    Hyper* hyper_dev = nullptr;        // &step_dev->hp
+    BatchPtrs* bp_dev = nullptr;       // &step_dev->bp
+    BatchPtrs bp_cur{};                // pointer table of the batch uploaded last (host copy)
     // pinned host staging.  hyper_ring: one slot per in-flight step so an asynchronous caller never overwrites a
-    // Hyper struct whose H2D copy has not executed yet; hyper_host points at the slot of the current call.
+    // struct whose H2D copy has not executed yet; hyper_host points at the slot of the current call.
     static constexpr int kHyperSlots = 32;
-    Hyper* hyper_ring = nullptr; cudaEvent_t hyper_ev[kHyperSlots] = {nullptr}; bool hyper_used[kHyperSlots] = {false};
+    StepParams* hyper_ring = nullptr; cudaEvent_t hyper_ev[kHyperSlots] = {nullptr}; bool hyper_used[kHyperSlots] = {false};
     int hyper_next = 0;
     Hyper* hyper_host = nullptr;
     float* loss_host = nullptr;
@@ -271,16 +277,18 @@ int alloc_params(ScoreModel* h) {
             for (int64_t i = 0; i < t.rows * t.cols; ++i) fl[t.off + i] = t.flags;
     CK(cudaMemcpy(h->flags, fl.data(), n, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&h->claim_counter, sizeof(int32_t)));
-    CK(cudaMalloc(&h->n_heads_dev, sizeof(int32_t)));
-    CK(cudaMemsetAsync(h->n_heads_dev, 0, sizeof(int32_t), h->st));
+    CK(cudaMalloc(&h->n_heads_dev, 4 * sizeof(int32_t)));
+    CK(cudaMemsetAsync(h->n_heads_dev, 0, 4 * sizeof(int32_t), h->st));
     CK(cudaMalloc(&h->l2sum, sizeof(float) * L2_PARTS));
     CK(cudaMalloc(&h->loss_dev, 2 * sizeof(float)));
     CK(cudaMalloc(&h->err_flag, sizeof(int32_t)));
     CK(cudaMemsetAsync(h->err_flag, 0, sizeof(int32_t), h->st));
-    CK(cudaMalloc(&h->hyper_dev, sizeof(Hyper)));
-    CK(cudaMallocHost(&h->hyper_ring, sizeof(Hyper) * ScoreModel::kHyperSlots));
+    CK(cudaMalloc(&h->step_dev, sizeof(ScoreModel::StepParams)));
+    h->hyper_dev = &h->step_dev->hp;
+    h->bp_dev = &h->step_dev->bp;
+    CK(cudaMallocHost(&h->hyper_ring, sizeof(ScoreModel::StepParams) * ScoreModel::kHyperSlots));
     for (int i = 0; i < ScoreModel::kHyperSlots; ++i) CK(cudaEventCreateWithFlags(&h->hyper_ev[i], cudaEventDisableTiming));
-    h->hyper_host = h->hyper_ring;
+    h->hyper_host = &h->hyper_ring[0].hp;
     CK(cudaMallocHost(&h->loss_host, 2 * sizeof(float)));
     CK(cudaMallocHost(&h->err_host, sizeof(int32_t)));
     if (h->cfg.adam_mode == SCORE_ADAM_LAZY) {
@@ -391,6 +399,8 @@ int ensure_workspace(ScoreModel* h, int B) {
     WSI(h->claim_list, 2 * N, nullptr);
     WSI(h->sb.keys[0], N, nullptr); WSI(h->sb.keys[1], N, nullptr);
     WSI(h->sb.vals[0], N, nullptr); WSI(h->sb.vals[1], N, nullptr);
+    WSI(h->sb.runs, 8 * N, nullptr);
+    WSI(h->sb.runs_long, 4 * emb_runs_long_cap(N), nullptr);
     {
         uint32_t* hist = nullptr;
         int rc = ws_alloc(h, &hist, sort_hist_elems(N), nullptr);
@@ -407,29 +417,38 @@ void set_batch_dims(ScoreModel* h, int B) {
     Dims& dm = h->dm;
     dm.B = B;
     const int64_t M = (int64_t)B * dm.T;
-    dm.off_u1 = 0;
-    dm.off_u2 = dm.off_u1 + M * dm.K * dm.fi;
-    dm.off_i1 = dm.off_u2 + M * dm.K * dm.fu;
-    dm.off_i2 = dm.off_i1 + M * dm.K * dm.fu;
-    dm.off_tu = dm.off_i2 + M * dm.K * dm.fi;
+    dm.nrows = dm.K * (2 * dm.fi + 2 * dm.fu);
+    dm.off_tu = M * dm.nrows;
     dm.off_ti = dm.off_tu + (int64_t)B * dm.fu;
     dm.N = dm.off_ti + (int64_t)B * dm.fi;
 }
 
+// Make the batch visible to the device.  A device batch is consumed where it lies (pointer table only); a host batch
+// is copied into the handle's staging buffers first.  The table reaches the device with the next upload_hyper().
 int upload_batch(ScoreModel* h, const ScoreBatch* b) {
     const Dims& dm = h->dm;
     const int B = b->batch_size;
     const int64_t M = (int64_t)B * dm.T;
-    const cudaMemcpyKind kind = b->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    BatchPtrs& bp = h->bp_cur;
+    if (b->on_device) {
+        bp.u1 = b->user_1hop; bp.u2 = b->user_2hop; bp.i1 = b->item_1hop; bp.i2 = b->item_2hop;
+        bp.tu = b->target_user; bp.ti = b->target_item; bp.label = b->label; bp.length = b->length;
+        return SCORE_OK;
+    }
     const size_t s_i = sizeof(int32_t);
-    CK(cudaMemcpyAsync(h->ids + dm.off_u1, b->user_1hop, s_i * M * dm.K * dm.fi, kind, h->st));
-    CK(cudaMemcpyAsync(h->ids + dm.off_u2, b->user_2hop, s_i * M * dm.K * dm.fu, kind, h->st));
-    CK(cudaMemcpyAsync(h->ids + dm.off_i1, b->item_1hop, s_i * M * dm.K * dm.fu, kind, h->st));
-    CK(cudaMemcpyAsync(h->ids + dm.off_i2, b->item_2hop, s_i * M * dm.K * dm.fi, kind, h->st));
-    CK(cudaMemcpyAsync(h->ids + dm.off_tu, b->target_user, s_i * B * dm.fu, kind, h->st));
-    CK(cudaMemcpyAsync(h->ids + dm.off_ti, b->target_item, s_i * B * dm.fi, kind, h->st));
-    CK(cudaMemcpyAsync(h->label, b->label, s_i * B, kind, h->st));
-    CK(cudaMemcpyAsync(h->length, b->length, s_i * B, kind, h->st));
+    const int64_t n_i = M * dm.K * dm.fi, n_u = M * dm.K * dm.fu;
+    int32_t* st_u1 = h->ids; int32_t* st_u2 = st_u1 + n_i; int32_t* st_i1 = st_u2 + n_u; int32_t* st_i2 = st_i1 + n_u;
+    int32_t* st_tu = st_i2 + n_i; int32_t* st_ti = st_tu + (int64_t)B * dm.fu;
+    CK(cudaMemcpyAsync(st_u1, b->user_1hop, s_i * n_i, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(st_u2, b->user_2hop, s_i * n_u, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(st_i1, b->item_1hop, s_i * n_u, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(st_i2, b->item_2hop, s_i * n_i, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(st_tu, b->target_user, s_i * B * dm.fu, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(st_ti, b->target_item, s_i * B * dm.fi, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->label, b->label, s_i * B, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->length, b->length, s_i * B, cudaMemcpyHostToDevice, h->st));
+    bp.u1 = st_u1; bp.u2 = st_u2; bp.i1 = st_i1; bp.i2 = st_i2; bp.tu = st_tu; bp.ti = st_ti;
+    bp.label = h->label; bp.length = h->length;
     return SCORE_OK;
 }
 
@@ -722,19 +741,19 @@ void enqueue_step(ScoreModel* h, int mode) {
     if (h->cfg.adam_mode == SCORE_ADAM_LAZY) {
         probe_begin(h, PR_CATCHUP, h->st);
         ClaimArgs ca{h->last_step, h->hyper_dev, h->claim_list, h->claim_counter};
-        launch_build_keys(h->st, dm, h->ids, h->length, h->keys, h->err_flag, &ca);
+        launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag, &ca);
         launch_emb_replay(h->st, h->claim_list, h->claim_counter, dm.N, h->emb, h->emb_m, h->emb_v, dm.d, h->alpha_hist,
                           h->hyper_dev);
         probe_end(h, PR_CATCHUP, h->st);
     } else {
-        launch_build_keys(h->st, dm, h->ids, h->length, h->keys, h->err_flag);
+        launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag);
     }
     cudaEventRecord(h->ev_fork, h->st);
     if (need_bwd) {   // the sort depends on ids only: run it on the side stream under forward/backward
         cudaStreamWaitEvent(h->st2, h->ev_fork, 0);
         probe_begin(h, PR_SORT, h->st2);
         h->sort_out = launch_sort_pairs(h->st2, h->sb, h->keys, dm.N, key_bits(dm.V));
-        launch_emb_heads(h->st2, h->sb.keys[h->sort_out], dm.N, h->sb.keys[1 - h->sort_out], h->n_heads_dev);
+        launch_emb_runs(h->st2, h->sb.keys[h->sort_out], h->sb.vals[h->sort_out], dm.N, h->sb.runs, h->sb.runs_long, h->n_heads_dev);
         probe_end(h, PR_SORT, h->st2);
         cudaEventRecord(h->ev_join, h->st2);
     }
@@ -748,7 +767,7 @@ void enqueue_step(ScoreModel* h, int mode) {
         cudaMemsetAsync(h->seg_heads, 0, sizeof(int32_t) * dm.N, h->st);
         EmbUpdateArgs ea{};
         ea.skeys = h->sb.keys[h->sort_out]; ea.spos = h->sb.vals[h->sort_out]; ea.n = dm.N;
-        ea.heads = h->sb.keys[1 - h->sort_out]; ea.n_heads = h->n_heads_dev;
+        ea.runs = h->sb.runs; ea.runs_long = h->sb.runs_long; ea.long_cap = emb_runs_long_cap(dm.N); ea.counters = h->n_heads_dev;
         ea.grad_rows = h->grad_rows; ea.d = dm.d; ea.hp = h->hyper_dev; ea.mode = 1;
         ea.out_rows = h->seg_rows; ea.out_heads = h->seg_heads;
         launch_emb_update(h->st, ea);
@@ -757,7 +776,7 @@ void enqueue_step(ScoreModel* h, int mode) {
         launch_dense_adam(h->st, h->P, h->M1, h->V1, h->G, h->flags, (int)h->n_dense, h->hyper_dev, h->alpha_hist);
         EmbUpdateArgs ea{};
         ea.skeys = h->sb.keys[h->sort_out]; ea.spos = h->sb.vals[h->sort_out]; ea.n = dm.N;
-        ea.heads = h->sb.keys[1 - h->sort_out]; ea.n_heads = h->n_heads_dev;
+        ea.runs = h->sb.runs; ea.runs_long = h->sb.runs_long; ea.long_cap = emb_runs_long_cap(dm.N); ea.counters = h->n_heads_dev;
         ea.grad_rows = h->grad_rows; ea.d = dm.d;
         ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.last_step = h->last_step;
         ea.alpha_hist = h->alpha_hist;
@@ -797,9 +816,10 @@ void fill_hyper(ScoreModel* h, int B, float lr, float reg_lambda, float keep_pro
 int upload_hyper(ScoreModel* h, int B, float lr, float reg_lambda, float keep_prob, int train, int global_batch) {
     const int slot = h->hyper_next++ % ScoreModel::kHyperSlots;
     if (h->hyper_used[slot]) CK(cudaEventSynchronize(h->hyper_ev[slot]));
-    h->hyper_host = h->hyper_ring + slot;
+    h->hyper_host = &h->hyper_ring[slot].hp;
     fill_hyper(h, B, lr, reg_lambda, keep_prob, train, global_batch);
-    CK(cudaMemcpyAsync(h->hyper_dev, h->hyper_host, sizeof(Hyper), cudaMemcpyHostToDevice, h->st));
+    h->hyper_ring[slot].bp = h->bp_cur;
+    CK(cudaMemcpyAsync(h->step_dev, h->hyper_ring + slot, sizeof(ScoreModel::StepParams), cudaMemcpyHostToDevice, h->st));
     CK(cudaEventRecord(h->hyper_ev[slot], h->st));
     h->hyper_used[slot] = true;
     return SCORE_OK;
@@ -968,7 +988,7 @@ int score_destroy(ScoreHandle h) {
     free_workspace(h);
     for (void* p : {(void*)h->emb, (void*)h->emb_m, (void*)h->emb_v, (void*)h->last_step, (void*)h->P, (void*)h->G,
                     (void*)h->M1, (void*)h->V1, (void*)h->PG, (void*)h->flags, (void*)h->Dv, (void*)h->n_heads_dev, (void*)h->claim_counter, (void*)h->claim_ext, (void*)h->alpha_hist, (void*)h->l2sum,
-                    (void*)h->loss_dev, (void*)h->err_flag, (void*)h->hyper_dev, (void*)h->seg_rows, (void*)h->seg_heads})
+                    (void*)h->loss_dev, (void*)h->err_flag, (void*)h->step_dev, (void*)h->seg_rows, (void*)h->seg_heads})
         if (p) cudaFree(p);
     if (h->hyper_ring) cudaFreeHost(h->hyper_ring);
     for (int i = 0; i < ScoreModel::kHyperSlots; ++i) if (h->hyper_ev[i]) cudaEventDestroy(h->hyper_ev[i]);
@@ -1308,12 +1328,16 @@ int ensure_ext_sort(ScoreModel* h, int64_t n) {
     if (n <= h->sb_ext_cap) return SCORE_OK;
     for (int i = 0; i < 2; ++i) { if (h->sb_ext.keys[i]) cudaFree(h->sb_ext.keys[i]); if (h->sb_ext.vals[i]) cudaFree(h->sb_ext.vals[i]); }
     if (h->sb_ext.hist) cudaFree(h->sb_ext.hist);
+    if (h->sb_ext.runs) cudaFree(h->sb_ext.runs);
+    if (h->sb_ext.runs_long) cudaFree(h->sb_ext.runs_long);
     int64_t cap = n + n / 4 + 1024;
     for (int i = 0; i < 2; ++i) {
         CK(cudaMalloc(&h->sb_ext.keys[i], sizeof(int32_t) * cap));
         CK(cudaMalloc(&h->sb_ext.vals[i], sizeof(int32_t) * cap));
     }
     CK(cudaMalloc(&h->sb_ext.hist, sizeof(uint32_t) * sort_hist_elems(cap)));
+    CK(cudaMalloc(&h->sb_ext.runs, sizeof(int32_t) * 8 * cap));
+    CK(cudaMalloc(&h->sb_ext.runs_long, sizeof(int32_t) * 4 * emb_runs_long_cap(cap)));
     h->sb_ext_cap = cap;
     return SCORE_OK;
 }
@@ -1338,7 +1362,9 @@ int score_prepare_batch(ScoreHandle h, const ScoreBatch* batch) {
     h->last_N = h->dm.N;
     Dims dm = h->dm;
     dm.V = ((int64_t)1 << 31) - 1;   // ids are GLOBAL row numbers here; the owner checks the range
-    launch_build_keys(h->st, dm, h->ids, h->length, h->keys, h->err_flag);
+    rc = upload_hyper(h, B, 0.f, 0.f, 1.f, 0, 0);   // carries the batch's pointer table
+    if (rc) return rc;
+    launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag);
     return SCORE_OK;
 }
 
@@ -1411,11 +1437,11 @@ int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg
     }
     h->last_mode = MODE_BEGIN;
     cudaEventRecord(h->ev_fork, h->st);
+    if (batch) launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag);
     if (staged_table) {
         h->emb_fwd = staged_table; h->keys_fwd = staged_keys;
     } else {
         h->emb_fwd = h->emb; h->keys_fwd = h->keys;
-        if (batch) launch_build_keys(h->st, dm, h->ids, h->length, h->keys, h->err_flag);
         if (h->cfg.adam_mode == SCORE_ADAM_LAZY)
             launch_emb_catchup_rows(h->st, h->keys, dm.N, dm.V, h->emb, h->emb_m, h->emb_v, h->last_step, dm.d,
                                     h->alpha_hist, h->hyper_dev, h->claim_list, h->claim_counter);
@@ -1443,9 +1469,9 @@ int score_step_finish(ScoreHandle h, const int32_t* ext_keys, const float* ext_r
             if (rc) return rc;
             const int out = launch_sort_pairs(h->st, h->sb_ext, ext_keys, n_ext, key_bits(h->dm.V));
             EmbUpdateArgs ea{};
-            launch_emb_heads(h->st, h->sb_ext.keys[out], n_ext, h->sb_ext.keys[1 - out], h->n_heads_dev);
+            launch_emb_runs(h->st, h->sb_ext.keys[out], h->sb_ext.vals[out], n_ext, h->sb_ext.runs, h->sb_ext.runs_long, h->n_heads_dev);
             ea.skeys = h->sb_ext.keys[out]; ea.spos = h->sb_ext.vals[out]; ea.n = n_ext;
-            ea.heads = h->sb_ext.keys[1 - out]; ea.n_heads = h->n_heads_dev;
+            ea.runs = h->sb_ext.runs; ea.runs_long = h->sb_ext.runs_long; ea.long_cap = emb_runs_long_cap(n_ext); ea.counters = h->n_heads_dev;
             ea.grad_rows = ext_rows; ea.d = h->dm.d;
             ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.last_step = h->last_step;
             ea.alpha_hist = h->alpha_hist; ea.hp = h->hyper_dev; ea.mode = 0;

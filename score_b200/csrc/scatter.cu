@@ -244,102 +244,253 @@ __device__ __forceinline__ void replay4(float4& var, float4& m, float4& v, int f
     for (int s = from + 1; s <= upto; ++s) adam4(var, m, v, z, alpha_hist[s]);
 }
 // ------------------------------------------------------------------------------------------ segment reduce + row Adam
-// Step 1 (emb_heads_kernel, on the sort stream): compact list of the sorted indices that start a run of equal non-zero
-// keys.  The list order comes from atomics and only decides which thread group serves which row - every row's
-// arithmetic is fixed, so the result is deterministic.
-// Step 2 (emb_update_kernel): one group of d/4 lanes per run head, grid-stride over the compact list, so every lane of
-// every resident warp has a row in flight (a group-per-sorted-index layout leaves ~60 % of the groups idle: they sit
-// on non-head indices).  The group loads the row's optimizer state early, walks the run four entries at a time
-// (independent loads, additions in ascending position order - no float atomics) and applies TF-form Adam.
-__global__ void emb_heads_kernel(const int32_t* __restrict__ skeys, int64_t n, int32_t* __restrict__ heads,
-                                 int32_t* __restrict__ counter) {
+// Real batches hold very hot rows next to cold ones: a side-feature id (category, gender, genre ...) occurs hundreds to
+// thousands of times in one batch, a user or item id once or twice.  A serial walk of the hot runs would set the kernel
+// time (ncu: with one thread group per run the Taobao-shape update took 60-75 us, all of it the 207-entry runs), so the
+// runs of the sorted list are split into three tiers by length and every tier has its own fixed summation tree:
+//   S  (<= 4 entries)     one group of d/4 lanes per run; the 32-byte descriptor holds the run's positions, so the
+//                         optimizer state and all gradient rows are ONE batch of independent 16-byte loads;
+//   M  (5 .. 512)         one team of 16 lanes (d <= 32) or one warp per run: group g of the team adds entries g, g+G,
+//                         g+2G ... in ascending order, the G partial sums are added in group order (shuffles);
+//   L  (> 512)            one CTA per run: the same with 256/LPR groups, the warps' sums added in warp order (smem).
+// No float atomics anywhere; the tree of a run depends only on its length, so results are reproducible.
+// emb_runs_kernel (on the sort stream, off the critical path) builds the three descriptor lists; the order inside a
+// list comes from atomics and only decides which threads serve which run.
+constexpr int RUN_S_MAX = 4;
+constexpr int RUN_M_MAX = 512;
+
+__global__ void emb_runs_kernel(const int32_t* __restrict__ skeys, const int32_t* __restrict__ spos, int64_t n,
+                                int4* __restrict__ runs, int4* __restrict__ runs_long, int64_t long_cap,
+                                int32_t* __restrict__ counters) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int32_t key = 0, prev = -1;
     if (i < n) { key = skeys[i]; prev = i > 0 ? skeys[i - 1] : -1; }
     const bool head = (i < n) && key != 0 && key != prev;
-    const unsigned mask = __ballot_sync(FULL_MASK, head);
-    if (mask == 0) return;
+    const unsigned hmask = __ballot_sync(FULL_MASK, head);
+    if (hmask == 0) return;
+    if (lane == 0) atomicAdd(counters + 3, __popc(hmask));   // total number of runs (= unique rows)
+    int32_t k[4] = {0, 0, 0, 0}, p[4] = {0, 0, 0, 0};
+    if (head) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {   // independent loads
+            k[u] = (i + 1 + u < n) ? skeys[i + 1 + u] : 0;
+            p[u] = (i + u < n) ? spos[i + u] : 0;
+        }
+    }
+    int n4 = 1;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) n4 += (n4 == u + 1 && k[u] == key) ? 1 : 0;
+    const bool more = head && n4 == 4 && k[3] == key;
+    const bool is_s = head && !more;
+    const unsigned smask = __ballot_sync(FULL_MASK, is_s);
     int base = 0;
-    if (lane == 0) base = atomicAdd(counter, __popc(mask));
+    if (lane == 0 && smask) base = atomicAdd(counters, __popc(smask));
     base = __shfl_sync(FULL_MASK, base, 0);
-    if (head) heads[base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)i;
+    if (is_s) {
+        const int64_t slot = base + __popc(smask & ((1u << lane) - 1u));
+        runs[2 * slot] = make_int4(key, (int32_t)i, n4, p[0]);
+        runs[2 * slot + 1] = make_int4(p[1], p[2], p[3], 0);
+    }
+    if (!more) return;
+    // long run: entries i .. i+4 carry the key; gallop, then bisect, to the first index that does not
+    int64_t lo = i + 4, stepw = 4;
+    while (lo + stepw < n && skeys[lo + stepw] == key) { lo += stepw; stepw <<= 1; }
+    int64_t hi = lo + stepw < n ? lo + stepw : n;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (skeys[mid] == key) lo = mid; else hi = mid;
+    }
+    const int32_t cnt = (int32_t)(hi - i);
+    if (cnt <= RUN_M_MAX) {
+        const int slot = atomicAdd(counters + 1, 1);
+        runs_long[slot] = make_int4(key, (int32_t)i, cnt, 0);              // M list grows from the front
+    } else {
+        const int slot = atomicAdd(counters + 2, 1);
+        runs_long[long_cap - 1 - slot] = make_int4(key, (int32_t)i, cnt, 0);   // L list grows from the back
+    }
 }
-void launch_emb_heads(cudaStream_t st, const int32_t* skeys, int64_t n, int32_t* heads, int32_t* counter) {
-    cudaMemsetAsync(counter, 0, sizeof(int32_t), st);
-    emb_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(skeys, n, heads, counter);
+int64_t emb_runs_long_cap(int64_t n) { return n / (RUN_S_MAX + 1) + n / (RUN_M_MAX + 1) + 8; }
+void launch_emb_runs(cudaStream_t st, const int32_t* skeys, const int32_t* spos, int64_t n, int32_t* runs,
+                     int32_t* runs_long, int32_t* counters) {
+    cudaMemsetAsync(counters, 0, 4 * sizeof(int32_t), st);
+    emb_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(skeys, spos, n, reinterpret_cast<int4*>(runs),
+                                                                 reinterpret_cast<int4*>(runs_long), emb_runs_long_cap(n),
+                                                                 counters);
     ++g_launch_count;
 }
 
-template <bool EXPORT>
-__global__ void __launch_bounds__(256, 4) emb_update_kernel(EmbUpdateArgs a) {
-    const int lpr = a.d >> 2;
-    const int sub = threadIdx.x % lpr;
-    const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / lpr;
-    const int nheads = *a.n_heads;
-    for (int64_t h = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / lpr; h < nheads; h += ngroups) {
-        const int64_t gid = a.heads[h];
-        // load batch 1 (independent): the first four (key, position) pairs of the run
-        int32_t kk[4], pp[4];
+__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+// optimizer step of one row by one group of LPR lanes (all of them active here, identical control flow)
+template <bool EXPORT, int LPR>
+__device__ __forceinline__ void emb_apply_row(const EmbUpdateArgs& a, int32_t key, int32_t start, const float4& acc,
+                                              float4 var, float4 m, float4 v, int last, int sub, float alpha, int step) {
+    constexpr int D = LPR * 4;
+    if (EXPORT) {
+        *reinterpret_cast<float4*>(a.out_rows + (int64_t)start * D + sub * 4) = acc;
+        if (sub == 0) a.out_heads[start] = key;
+        return;
+    }
+    const int64_t off = (int64_t)key * D + sub * 4;
+    if (a.alpha_hist) {   // LAZY: a row another rank gathered may not be current here yet
+        const int upto = step - 1;
+        if (last < upto && !(all_zero(m) && all_zero(v))) replay4(var, m, v, last, upto, a.alpha_hist);
+    }
+    adam4(var, m, v, acc, alpha);
+    {   // every lane of the row group has read last_step before lane 0 overwrites it
+        const int lane = threadIdx.x & 31;
+        const unsigned gmask = (LPR >= 32) ? FULL_MASK : (((1u << LPR) - 1u) << (lane & ~(LPR - 1)));
+        __syncwarp(gmask);
+    }
+    *reinterpret_cast<float4*>(a.emb + off) = var;
+    *reinterpret_cast<float4*>(a.m + off) = m;
+    *reinterpret_cast<float4*>(a.v + off) = v;
+    if (sub == 0 && a.last_step) a.last_step[key] = step;
+}
+
+// entries gi, gi+NG, gi+2NG ... of the run, four independent loads at a time, additions in ascending order
+template <int LPR>
+__device__ __forceinline__ float4 emb_strided_sum(const EmbUpdateArgs& a, int32_t start, int32_t cnt, int gi, int NG, int sub) {
+    constexpr int D = LPR * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = gi; e < cnt; e += 4 * NG) {
+        int32_t pp[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int64_t idx = gid + u;
-            const bool in = idx < a.n;
-            kk[u] = in ? a.skeys[idx] : 0;
-            pp[u] = in ? a.spos[idx] : 0;
-        }
-        const int32_t key = kk[0];
-        // load batch 2 (independent): the row's optimizer state and the run's gradient rows
-        const int64_t off = (int64_t)key * a.d + sub * 4;
-        float4 var, m, v;
-        if (!EXPORT) {
+        for (int u = 0; u < 4; ++u) pp[u] = (e + u * NG < cnt) ? a.spos[(int64_t)start + e + u * NG] : -1;
+        float4 g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            g[u] = pp[u] >= 0 ? *reinterpret_cast<const float4*>(a.grad_rows + (int64_t)pp[u] * D + sub * 4)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (pp[u] >= 0) add4(acc, g[u]);
+    }
+    return acc;
+}
+// sum of the group partials of a team of TL lanes (TL/LPR groups) in group order; every lane of the team ends up with
+// the total of its sub-chunk
+template <int LPR, int TL>
+__device__ __forceinline__ float4 emb_team_combine(const float4& part, int lane) {
+    constexpr int GT = TL / LPR;
+    const int src0 = (lane & ~(TL - 1)) + (lane % LPR);
+    float4 tot;
+    tot.x = __shfl_sync(FULL_MASK, part.x, src0); tot.y = __shfl_sync(FULL_MASK, part.y, src0);
+    tot.z = __shfl_sync(FULL_MASK, part.z, src0); tot.w = __shfl_sync(FULL_MASK, part.w, src0);
+#pragma unroll
+    for (int g = 1; g < GT; ++g) {
+        float4 o;
+        o.x = __shfl_sync(FULL_MASK, part.x, src0 + g * LPR); o.y = __shfl_sync(FULL_MASK, part.y, src0 + g * LPR);
+        o.z = __shfl_sync(FULL_MASK, part.z, src0 + g * LPR); o.w = __shfl_sync(FULL_MASK, part.w, src0 + g * LPR);
+        add4(tot, o);
+    }
+    return tot;
+}
+
+template <bool EXPORT, int LPR>
+__global__ void __launch_bounds__(256) emb_update_kernel(EmbUpdateArgs a) {
+    constexpr int D = LPR * 4;
+    constexpr int G = 32 / LPR;          // groups per warp
+    constexpr int NGC = 256 / LPR;       // groups per CTA
+    __shared__ float4 red[8][LPR];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = threadIdx.x % LPR;
+    const int nS = a.counters[0], nM = a.counters[1], nL = a.counters[2];
+    const float alpha = a.hp->alpha;
+    const int step = a.hp->step;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int4* __restrict__ runs_long = reinterpret_cast<const int4*>(a.runs_long);
+
+    // ---- tier L: one CTA per run
+    for (int r = blockIdx.x; r < nL; r += gridDim.x) {
+        const int4 dsc = runs_long[a.long_cap - 1 - r];
+        const int32_t key = dsc.x, start = dsc.y, cnt = dsc.z;
+        const bool owner = threadIdx.x < LPR;
+        float4 var = z4, m = z4, v = z4; int last = 0;
+        if (owner && !EXPORT) {
+            const int64_t off = (int64_t)key * D + sub * 4;
             var = *reinterpret_cast<const float4*>(a.emb + off);
             m = *reinterpret_cast<const float4*>(a.m + off);
             v = *reinterpret_cast<const float4*>(a.v + off);
+            if (a.alpha_hist) last = a.last_step[key];
         }
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        // walk the run four entries at a time; the additions stay in sorted (= ascending position) order
-        for (int64_t j = gid;;) {
-            int cnt = 0;
+        const float4 part = emb_strided_sum<LPR>(a, start, cnt, threadIdx.x / LPR, NGC, sub);
+        const float4 wtot = emb_team_combine<LPR, 32>(part, lane);
+        if (lane < LPR) red[warp][lane] = wtot;
+        __syncthreads();
+        if (owner) {
+            float4 acc = red[0][sub];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) cnt += (cnt == u && kk[u] == key) ? 1 : 0;
-            float4 g[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (u < cnt) g[u] = *reinterpret_cast<const float4*>(a.grad_rows + (int64_t)pp[u] * a.d + sub * 4);
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (u < cnt) { acc.x += g[u].x; acc.y += g[u].y; acc.z += g[u].z; acc.w += g[u].w; }
-            if (cnt < 4) break;
-            j += 4;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t idx = j + u;
-                const bool in = idx < a.n;
-                kk[u] = in ? a.skeys[idx] : 0;
-                pp[u] = in ? a.spos[idx] : 0;
-            }
+            for (int w = 1; w < 8; ++w) add4(acc, red[w][sub]);
+            emb_apply_row<EXPORT, LPR>(a, key, start, acc, var, m, v, last, sub, alpha, step);
         }
-        if (EXPORT) {
-            *reinterpret_cast<float4*>(a.out_rows + gid * a.d + sub * 4) = acc;
-            if (sub == 0) a.out_heads[gid] = key;
-            continue;
-        }
-        if (a.alpha_hist) {   // LAZY: a row another rank gathered may not be current here yet
-            const int last = a.last_step[key], upto = a.hp->step - 1;
-            if (last < upto && !(all_zero(m) && all_zero(v))) replay4(var, m, v, last, upto, a.alpha_hist);
-        }
-        adam4(var, m, v, acc, a.hp->alpha);
-        {   // every lane of the row group (identical control flow) has read last_step before lane 0 overwrites it
-            const int lane = threadIdx.x & 31;
-            const unsigned gmask = (lpr >= 32) ? FULL_MASK : (((1u << lpr) - 1u) << (lane & ~(lpr - 1)));
-            __syncwarp(gmask);
-        }
-        *reinterpret_cast<float4*>(a.emb + off) = var;
-        *reinterpret_cast<float4*>(a.m + off) = m;
-        *reinterpret_cast<float4*>(a.v + off) = v;
-        if (sub == 0 && a.last_step) a.last_step[key] = a.hp->step;
+        __syncthreads();
     }
+    // ---- tier M: one team of TL lanes per run (half a warp for narrow rows: two runs per warp in flight)
+    {
+        constexpr int TL = LPR <= 8 ? 16 : 32;
+        constexpr int TPW = 32 / TL;         // teams per warp
+        const int tw = lane / TL, tl = lane % TL;
+        const int gwarp = blockIdx.x * 8 + warp, nwarps = gridDim.x * 8;
+        for (int r0 = gwarp * TPW; r0 < nM; r0 += nwarps * TPW) {   // warp-uniform trip count
+            const int r = r0 + tw;
+            const bool valid = r < nM;
+            int4 dsc = make_int4(0, 0, 0, 0);
+            if (valid) dsc = runs_long[r];
+            const int32_t key = dsc.x, start = dsc.y, cnt = dsc.z;
+            const bool owner = valid && tl < LPR;
+            float4 var = z4, m = z4, v = z4; int last = 0;
+            if (owner && !EXPORT) {
+                const int64_t off = (int64_t)key * D + sub * 4;
+                var = *reinterpret_cast<const float4*>(a.emb + off);
+                m = *reinterpret_cast<const float4*>(a.m + off);
+                v = *reinterpret_cast<const float4*>(a.v + off);
+                if (a.alpha_hist) last = a.last_step[key];
+            }
+            const float4 part = emb_strided_sum<LPR>(a, start, cnt, tl / LPR, TL / LPR, sub);
+            __syncwarp();
+            const float4 acc = emb_team_combine<LPR, TL>(part, lane);
+            if (owner) emb_apply_row<EXPORT, LPR>(a, key, start, acc, var, m, v, last, sub, alpha, step);
+            __syncwarp();
+        }
+    }
+    // ---- tier S: one group per run, next descriptor prefetched
+    const int ngroups = (int)((gridDim.x * blockDim.x) / LPR);
+    const int4* __restrict__ runs = reinterpret_cast<const int4*>(a.runs);
+    int h = (int)((blockIdx.x * blockDim.x + threadIdx.x) / LPR);
+    if (h >= nS) return;
+    int4 d0 = runs[2 * h], d1 = runs[2 * h + 1];
+    for (; h < nS; h += ngroups) {
+        const int32_t key = d0.x, start = d0.y, n4 = d0.z;
+        const int32_t pos[4] = {d0.w, d1.x, d1.y, d1.z};
+        {   // clamped: the last iteration re-reads its own descriptor
+            const int hn = (h + ngroups < nS) ? h + ngroups : h;
+            d0 = runs[2 * hn]; d1 = runs[2 * hn + 1];
+        }
+        float4 var = z4, m = z4, v = z4; int last = 0;
+        if (!EXPORT) {
+            const int64_t off = (int64_t)key * D + sub * 4;
+            var = *reinterpret_cast<const float4*>(a.emb + off);
+            m = *reinterpret_cast<const float4*>(a.m + off);
+            v = *reinterpret_cast<const float4*>(a.v + off);
+            if (a.alpha_hist) last = a.last_step[key];
+        }
+        float4 g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            g[u] = (u < n4) ? *reinterpret_cast<const float4*>(a.grad_rows + (int64_t)pos[u] * D + sub * 4) : z4;
+        float4 acc = g[0];
+#pragma unroll
+        for (int u = 1; u < 4; ++u)
+            if (u < n4) add4(acc, g[u]);
+        emb_apply_row<EXPORT, LPR>(a, key, start, acc, var, m, v, last, sub, alpha, step);
+    }
+}
+template <int LPR>
+static void emb_update_launch(cudaStream_t st, const EmbUpdateArgs& a, unsigned grid) {
+    if (a.mode == 1) emb_update_kernel<true, LPR><<<grid, 256, 0, st>>>(a);
+    else emb_update_kernel<false, LPR><<<grid, 256, 0, st>>>(a);
 }
 void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a) {
     static int sms = 0;
@@ -350,14 +501,20 @@ void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a) {
         if (sms <= 0) sms = 148;
     }
     const int lpr = a.d >> 2;
-    // one group per head when at most half of the sorted indices start a run (groups past the head count exit at once;
-    // the grid-stride loop covers the rest): many short CTAs keep the SMs evenly loaded, one persistent wave does not
-    int64_t want = (a.n * lpr + 255) / 256;
-    int64_t half = (want + 1) / 2, cap = (int64_t)sms * 6;
-    unsigned grid = (unsigned)(half > cap ? half : (want < cap ? want : cap));
+    // the run counts live on the device: size the grid for one group per sorted index, capped at a few resident waves
+    // (groups past the run count exit at once; the grid-stride loops cover the rest)
+    int64_t want = (a.n * lpr + 255) / 256, cap = (int64_t)sms * 16;
+    unsigned grid = (unsigned)(want < cap ? want : cap);
     if (grid == 0) grid = 1;
-    if (a.mode == 1) emb_update_kernel<true><<<grid, 256, 0, st>>>(a);
-    else emb_update_kernel<false><<<grid, 256, 0, st>>>(a);
+    switch (lpr) {
+        case 1: emb_update_launch<1>(st, a, grid); break;
+        case 2: emb_update_launch<2>(st, a, grid); break;
+        case 4: emb_update_launch<4>(st, a, grid); break;
+        case 8: emb_update_launch<8>(st, a, grid); break;
+        case 16: emb_update_launch<16>(st, a, grid); break;
+        case 32: emb_update_launch<32>(st, a, grid); break;
+        default: break;   // score_create rejects other widths
+    }
     ++g_launch_count;
 }
 

@@ -105,17 +105,16 @@ def forward_backward_report(shape: Shape, batch, seed=7, reg_lambda=1e-4, keep_p
 
 
 def expected_keys(batch, cfg):
-    """ids in flat position order [u1|u2|i1|i2|tu|ti], zeroed where t >= length (masked slices)."""
+    """ids in the slice-major position order of embed.cu - per (b,t) slice [user_1hop | item_2hop | user_2hop |
+    item_1hop], then target_user, target_item - zeroed where t >= length (masked slices)."""
     T = cfg.max_time_len
+    B = np.asarray(batch[0]).shape[0]
     live = (np.arange(T)[None, :] < np.asarray(batch[7])[:, None])
-    parts = []
-    for x in batch[:4]:
-        a = np.asarray(x).astype(np.int32).copy()
-        a[~live] = 0
-        parts.append(a.reshape(-1))
-    parts.append(np.asarray(batch[4]).astype(np.int32).reshape(-1))
-    parts.append(np.asarray(batch[5]).astype(np.int32).reshape(-1))
-    return np.concatenate(parts)
+    u1, u2, i1, i2 = (np.asarray(x).astype(np.int32).reshape(B, T, -1) for x in batch[:4])
+    hist = np.concatenate([u1, i2, u2, i1], axis=2).copy()
+    hist[~live] = 0
+    return np.concatenate([hist.reshape(-1), np.asarray(batch[4]).astype(np.int32).reshape(-1),
+                           np.asarray(batch[5]).astype(np.int32).reshape(-1)])
 
 
 def train_steps_report(shape: Shape, batches, seed=7, lr=5e-4, reg_lambda=1e-4, adam_mode="dense",

@@ -62,6 +62,16 @@ def test_forward_backward_wide_rows_d64_h128():
     _check_fb(rep)
 
 
+@pytest.mark.parametrize("geom", [(7, 2, 2, 32), (18, 1, 2, 8), (10, 3, 2, 16)])
+def test_forward_backward_runtime_geometry_fallback(geom):
+    """geometries outside the compiled-in table (embed.cu: SCORE_GEOM_DISPATCH) take the run-time-geometry kernels;
+    K > 16 also takes the unpacked softmax path"""
+    K, fi, fu, d = geom
+    shape = Shape("odd", 30000, d, 32, 5, K, fu, fi, 12000, 15000, 10, 4)
+    rep = pu.forward_backward_report(shape, make_batch(shape, seed=21))
+    _check_fb(rep)
+
+
 def test_ragged_lengths_dummy_slices_and_single_sample():
     shape = SHAPES["tiny"]
     b = list(make_batch(shape, seed=12, batch=9, dummy_frac=0.4))
