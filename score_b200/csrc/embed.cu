@@ -212,10 +212,13 @@ struct CoattSmem {
     int warp_off;     // per-warp region start (floats)
     int warp_stride;  // per-warp floats
     int nrows;        // K * (2*fi + 2*fu)
-    // per-warp layout (floats): rows[nrows*d] | dots[nrows] | wts[4*32] | (bwd) dbuf[2*Ds + 4K] | (bwd) acc[2*Di+2*Du]
+    // per-warp layout (floats): rows[nrows*d] | dots[nrows] | wts[4*WS] | (bwd) dbuf[2*Ds + 4K] | (bwd) acc[2*Di+2*Du]
     int dots_off, wts_off, dbuf_off, acc_off;
 };
 __host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
+// stride between the per-neighbor weight arrays of a warp: 8 banks apart, so lanes that read entry i of different
+// arrays (pooling: one array per segment) do not collide
+constexpr int WS = 40;
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
@@ -280,13 +283,17 @@ __global__ void __launch_bounds__(128) coatt_fwd_kernel(Dims dm, CoattArgs a, Co
     const int K = g.K(), D = g.D(), Di = g.FI() * D, Du = g.FU() * D, Ds = Di + Du;
     const int nfi = K * g.FI(), nfu = K * g.FU(), nrows = 2 * nfi + 2 * nfu;
     float* Wsm = sm + sp.w_off;
-    for (int i = threadIdx.x; i < 3 * Di; i += blockDim.x) Wsm[i] = a.w_item[i];
-    for (int i = threadIdx.x; i < 3 * Du; i += blockDim.x) Wsm[3 * Di + i] = a.w_user[i];
+    const bool sum_pool = a.sum_pool != 0;
+    if (!sum_pool) {
+        for (int i = threadIdx.x; i < 3 * Di; i += blockDim.x) Wsm[i] = a.w_item[i];
+        for (int i = threadIdx.x; i < 3 * Du; i += blockDim.x) Wsm[3 * Di + i] = a.w_user[i];
+    }
     float* rows = sm + sp.warp_off + warp * sp.warp_stride;
     float* dots = rows + sp.dots_off;
-    float* wts = rows + sp.wts_off;      // w1[32] | w2[32] | 1/K [32]
+    float* wts = rows + sp.wts_off;      // w1[32] | w2[32] | weight of the seq2 neighbors [32]
     const float invK = 1.0f / (float)K;
-    wts[64 + lane] = invK;
+    wts[lane] = 1.0f; wts[WS + lane] = 1.0f;          // sum_pool: every neighbor counts once
+    wts[2 * WS + lane] = sum_pool ? 1.0f : invK;
     __syncthreads();
     const int M = dm.B * dm.T;
     for (int slice = blockIdx.x * warps + warp; slice < M; slice += gridDim.x * warps) {
@@ -296,13 +303,14 @@ __global__ void __launch_bounds__(128) coatt_fwd_kernel(Dims dm, CoattArgs a, Co
         float* info = a.key + (int64_t)slice * a.ldkey + a.key_off;
         if (t >= a.length[b]) {   // dead slice: nothing downstream reads it, keep buffers finite
             for (int c = lane; c < Ds; c += 32) { xu_g[c] = 0.f; xu_c[c] = 0.f; xi_g[c] = 0.f; xi_c[c] = 0.f; }
-            for (int c = lane; c < 4 * K; c += 32) info[c] = 0.f;
+            if (!sum_pool) for (int c = lane; c < 4 * K; c += 32) info[c] = 0.f;
             continue;
         }
         stage_slice(g, rows, a.emb, a.keys + (int64_t)slice * nrows, nrows, lane);
-        const float cz1 = a.c_item[b], cz2 = a.c_user[b];
+        const float cz1 = sum_pool ? 0.f : a.c_item[b], cz2 = sum_pool ? 0.f : a.c_user[b];
         cp_async_wait<0>();
         __syncwarp();
+        if (!sum_pool) {
         // (1) one dot product per row with its slice of the co-attention kernel (W1 for seq1 rows, W2 for seq2 rows)
 #pragma unroll
         for (int seg = 0; seg < 4; ++seg) {
@@ -331,7 +339,7 @@ __global__ void __launch_bounds__(128) coatt_fwd_kernel(Dims dm, CoattArgs a, Co
             const float w = e / half_sum(e);
             const float s = half_sum(r);
             if (act) {
-                wts[half * 32 + i] = w;
+                wts[half * WS + i] = w;
                 info[half * 2 * K + i] = (float)K * r;     // atten_info (score.py:165-166)
                 info[half * 2 * K + K + i] = s;
                 sr[half * K + i] = r; sw[half * K + i] = w;
@@ -349,12 +357,13 @@ __global__ void __launch_bounds__(128) coatt_fwd_kernel(Dims dm, CoattArgs a, Co
             const float w1 = e1 / warp_sum(e1), w2 = e2 / warp_sum(e2);
             const float s1 = warp_sum(r1), s2 = warp_sum(r2);
             if (act) {
-                wts[lane] = w1; wts[32 + lane] = w2;
+                wts[lane] = w1; wts[WS + lane] = w2;
                 info[lane] = (float)K * r1; info[K + lane] = s1;
                 info[2 * K + lane] = (float)K * r2; info[3 * K + lane] = s2;
                 sr[lane] = r1; sr[K + lane] = r2; sw[lane] = w1; sw[K + lane] = w2;
             }
         }
+        }   // !sum_pool
         __syncwarp();
         // (3) pooling, one 16-byte output chunk per lane:
         //   user_side = [sum_i w1_i user_1hop[i] | sum_i w2_i user_2hop[i]],  item_side = [mean item_1hop | mean item_2hop]
@@ -367,9 +376,9 @@ __global__ void __launch_bounds__(128) coatt_fwd_kernel(Dims dm, CoattArgs a, Co
                 const int e = e4 << 2;
                 int row0, F, c, wsel; float* dst0; float* dst1;
                 if (e < Di) { row0 = 0; F = g.FI(); c = e; wsel = 0; dst0 = xu_g + e; dst1 = xu_c + e; }
-                else if (e < Ds) { row0 = 2 * nfi; F = g.FU(); c = e - Di; wsel = 32; dst0 = xu_g + e; dst1 = xu_c + e; }
-                else if (e < Ds + Du) { row0 = 2 * nfi + nfu; F = g.FU(); c = e - Ds; wsel = 64; dst0 = xi_g + c; dst1 = xi_c + c; }
-                else { row0 = nfi; F = g.FI(); c = e - Ds - Du; wsel = 64; dst0 = xi_g + Du + c; dst1 = xi_c + Du + c; }
+                else if (e < Ds) { row0 = 2 * nfi; F = g.FU(); c = e - Di; wsel = WS; dst0 = xu_g + e; dst1 = xu_c + e; }
+                else if (e < Ds + Du) { row0 = 2 * nfi + nfu; F = g.FU(); c = e - Ds; wsel = 2 * WS; dst0 = xi_g + c; dst1 = xi_c + c; }
+                else { row0 = nfi; F = g.FI(); c = e - Ds - Du; wsel = 2 * WS; dst0 = xi_g + Du + c; dst1 = xi_c + Du + c; }
                 const float4* src = r4 + (row0 << g.logcpr()) + (c >> 2);   // chunk (field, c4) of neighbor 0
                 const int stride = F << g.logcpr();
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -394,7 +403,7 @@ static CoattSmem coatt_plan(const Dims& dm, int warps, bool bwd, size_t* bytes) 
     sp.nrows = dm.K * (2 * dm.fi + 2 * dm.fu);
     sp.dots_off = sp.nrows * dm.d;
     sp.wts_off = sp.dots_off + round4(sp.nrows);
-    sp.dbuf_off = sp.wts_off + 4 * 32;
+    sp.dbuf_off = sp.wts_off + 4 * WS;
     sp.acc_off = sp.dbuf_off + (bwd ? round4(2 * dm.Ds + 4 * dm.K) : 0);
     sp.warp_stride = sp.acc_off + (bwd ? round4(2 * dm.Di + 2 * dm.Du) : 0);
     *bytes = (size_t)(sp.warp_off + warps * sp.warp_stride) * sizeof(float);
@@ -459,15 +468,17 @@ __global__ void __launch_bounds__(128) coatt_bwd_kernel(Dims dm, CoattBwdArgs a,
     const int K = g.K(), D = g.D(), Di = g.FI() * D, Du = g.FU() * D, Ds = Di + Du;
     const int nfi = K * g.FI(), nfu = K * g.FU(), nrows = 2 * nfi + 2 * nfu;
     float* Wsm = sm + sp.w_off;
-    for (int i = threadIdx.x; i < 3 * Di; i += blockDim.x) Wsm[i] = a.w_item[i];
-    for (int i = threadIdx.x; i < 3 * Du; i += blockDim.x) Wsm[3 * Di + i] = a.w_user[i];
+    const bool sum_pool = a.sum_pool != 0;
+    for (int i = threadIdx.x; i < 3 * Di; i += blockDim.x) Wsm[i] = sum_pool ? 0.f : a.w_item[i];
+    for (int i = threadIdx.x; i < 3 * Du; i += blockDim.x) Wsm[3 * Di + i] = sum_pool ? 0.f : a.w_user[i];
     float* rows = sm + sp.warp_off + warp * sp.warp_stride;
     float* dots = rows + sp.dots_off;
     float* wts = rows + sp.wts_off;      // a1[32] (w1) | a2[32] (w2) | dz1[32] | dz2[32]
+    wts[lane] = 1.0f; wts[WS + lane] = 1.0f; wts[2 * WS + lane] = 0.f; wts[3 * WS + lane] = 0.f;   // the sum_pool constants
     float* dbuf = rows + sp.dbuf_off;    // d user_side [Ds] | d item_side [Ds] | d atten_info [4K]
     float* acc = rows + sp.acc_off;      // dW1_item [Di] | dW2_item [Di] | dW1_user [Du] | dW2_user [Du]
     const int nacc = 2 * Di + 2 * Du;
-    const float invK = 1.0f / (float)K;
+    const float invK = sum_pool ? 1.0f : 1.0f / (float)K;   // weight of a seq2 neighbor in its pooled output
     for (int c = lane; c < nacc; c += 32) acc[c] = 0.f;
     __syncthreads();
     const int M = dm.B * dm.T;
@@ -481,14 +492,19 @@ __global__ void __launch_bounds__(128) coatt_bwd_kernel(Dims dm, CoattBwdArgs a,
         {   // incoming gradients of this slice (overlaps the row gather)
             const float4* dxu = reinterpret_cast<const float4*>(a.dxu + (int64_t)slice * Ds);
             const float4* dxi = reinterpret_cast<const float4*>(a.dxi + (int64_t)slice * Ds);
-            const float* dinfo = a.dkey + (int64_t)slice * a.ldkey + a.key_off;
             float4* d4 = reinterpret_cast<float4*>(dbuf);
             for (int c = lane; c < (Ds >> 2); c += 32) { d4[c] = dxu[c]; d4[(Ds >> 2) + c] = dxi[c]; }
-            for (int c = lane; c < 4 * K; c += 32) dbuf[2 * Ds + c] = dinfo[c];
+            if (a.dkey) {
+                const float* dinfo = a.dkey + (int64_t)slice * a.ldkey + a.key_off;
+                for (int c = lane; c < 4 * K; c += 32) dbuf[2 * Ds + c] = dinfo[c];
+            } else {
+                for (int c = lane; c < 4 * K; c += 32) dbuf[2 * Ds + c] = 0.f;
+            }
         }
         const float* sr = a.save_r + (int64_t)slice * 2 * K; const float* sw = a.save_w + (int64_t)slice * 2 * K;
         float w_h = 0.f, r_h = 0.f, w1 = 0.f, w2 = 0.f, r1 = 0.f, r2 = 0.f;
-        if (K <= 16) {
+        if (sum_pool) {
+        } else if (K <= 16) {
             const int half = lane >> 4, i = lane & 15;
             if (i < K) { w_h = sw[half * K + i]; r_h = sr[half * K + i]; }
         } else if (lane < K) {
@@ -496,6 +512,9 @@ __global__ void __launch_bounds__(128) coatt_bwd_kernel(Dims dm, CoattBwdArgs a,
         }
         cp_async_wait<0>();
         __syncwarp();
+        if (sum_pool) {
+            if (lane == 0) { a.sdz[(int64_t)slice * 2] = 0.f; a.sdz[(int64_t)slice * 2 + 1] = 0.f; }
+        } else {
         // (1) dw: dot of every seq1 row (seg0, seg2) with its field's slice of dout1
         seg_dots(g, 0, rows, dbuf, dots, lane);
         seg_dots(g, 2, rows, dbuf + Di, dots, lane);
@@ -521,7 +540,7 @@ __global__ void __launch_bounds__(128) coatt_bwd_kernel(Dims dm, CoattBwdArgs a,
             if (act) {
                 const float dr = (float)K * di[i] + tail + w_h * (dw - dotw);
                 dz = r_h > 0.f ? dr : 0.f;
-                wts[half * 32 + i] = w_h; wts[64 + half * 32 + i] = dz;
+                wts[half * WS + i] = w_h; wts[2 * WS + half * WS + i] = dz;
             }
             const float sdz = half_sum(dz);
             if (i == 0) a.sdz[(int64_t)slice * 2 + half] = sdz;
@@ -539,11 +558,12 @@ __global__ void __launch_bounds__(128) coatt_bwd_kernel(Dims dm, CoattBwdArgs a,
                 const float dr2 = (float)K * dinf[2 * K + lane] + tail2 + w2 * (dw2 - dot2);
                 dz1 = r1 > 0.f ? dr1 : 0.f;
                 dz2 = r2 > 0.f ? dr2 : 0.f;
-                wts[lane] = w1; wts[32 + lane] = w2; wts[64 + lane] = dz1; wts[96 + lane] = dz2;
+                wts[lane] = w1; wts[WS + lane] = w2; wts[2 * WS + lane] = dz1; wts[3 * WS + lane] = dz2;
             }
             const float sdz1 = warp_sum(dz1), sdz2 = warp_sum(dz2);
             if (lane == 0) { a.sdz[(int64_t)slice * 2] = sdz1; a.sdz[(int64_t)slice * 2 + 1] = sdz2; }
         }
+        }   // !sum_pool
         __syncwarp();
         // (3) per-position gradient rows, one 16-byte chunk per lane; the slice's rows are one contiguous block
         {
@@ -556,8 +576,8 @@ __global__ void __launch_bounds__(128) coatt_bwd_kernel(Dims dm, CoattBwdArgs a,
                 // d(pooled output) of this segment and its slice of the co-attention kernel
                 const float4* dv4 = reinterpret_cast<const float4*>(dbuf + (seg == 0 ? 0 : seg == 1 ? Ds + Du : seg == 2 ? Di : Ds));
                 const float4* wv4 = reinterpret_cast<const float4*>(Wsm + wofs);
-                const float* ai = wts + (seg == 0 ? 0 : 32);        // softmax weights (seq1 segments)
-                const float* dzi = wts + (seg < 2 ? 64 : 96);
+                const float* ai = wts + (seg == 0 ? 0 : WS);        // softmax weights (seq1 segments)
+                const float* dzi = wts + (seg < 2 ? 2 * WS : 3 * WS);
                 float4* go = gout + (row0 << g.logcpr());
 #pragma unroll
                 for (int q0 = 0; q0 < nch; q0 += 32) {
@@ -576,7 +596,7 @@ __global__ void __launch_bounds__(128) coatt_bwd_kernel(Dims dm, CoattBwdArgs a,
             }
         }
         // (4) co-attention kernel gradient: dW1 += sum_i dz_i seq1[i], dW2 += sum_i dz_i seq2[i] (per-warp accumulators)
-        {
+        if (!sum_pool) {
             const int nchunk = nacc >> 2;
             const float4* r4 = reinterpret_cast<const float4*>(rows);
 #pragma unroll
@@ -585,10 +605,10 @@ __global__ void __launch_bounds__(128) coatt_bwd_kernel(Dims dm, CoattBwdArgs a,
                 if (e4 < nchunk) {
                     const int e = e4 << 2;
                     int row0, F, c, zsel;
-                    if (e < Di) { row0 = 0; F = g.FI(); c = e; zsel = 64; }
-                    else if (e < 2 * Di) { row0 = nfi; F = g.FI(); c = e - Di; zsel = 64; }
-                    else if (e < 2 * Di + Du) { row0 = 2 * nfi; F = g.FU(); c = e - 2 * Di; zsel = 96; }
-                    else { row0 = 2 * nfi + nfu; F = g.FU(); c = e - 2 * Di - Du; zsel = 96; }
+                    if (e < Di) { row0 = 0; F = g.FI(); c = e; zsel = 2 * WS; }
+                    else if (e < 2 * Di) { row0 = nfi; F = g.FI(); c = e - Di; zsel = 2 * WS; }
+                    else if (e < 2 * Di + Du) { row0 = 2 * nfi; F = g.FU(); c = e - 2 * Di; zsel = 3 * WS; }
+                    else { row0 = 2 * nfi + nfu; F = g.FU(); c = e - 2 * Di - Du; zsel = 3 * WS; }
                     const float4* src = r4 + (row0 << g.logcpr()) + (c >> 2);
                     const int stride = F << g.logcpr();
                     float4 s = *reinterpret_cast<float4*>(acc + e);

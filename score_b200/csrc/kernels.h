@@ -81,6 +81,7 @@ struct CoattArgs {
     float* xhg_u; float* xhc_u; float* xhg_i; float* xhc_i;   // [M, ldx], x part written here
     float* key; int ldkey; int key_off;                       // atten_info -> key[:, key_off : key_off+4K]
     float* save_r; float* save_w;                             // [M, 2K]
+    int sum_pool;   // RCA (score.py:266-269): plain sum over the K neighbors, no relatedness, no atten_info
 };
 void launch_coatt_fwd(cudaStream_t st, const Dims& dm, const CoattArgs& a);
 
@@ -89,7 +90,8 @@ struct CoattBwdArgs {
     const float* w_item; const float* w_user;
     const float* save_r; const float* save_w;
     const float* dxu; const float* dxi;        // [M, Ds]
-    const float* dkey; int ldkey; int key_off; // d atten_info
+    const float* dkey; int ldkey; int key_off; // d atten_info (NULL: atten_info has no consumer - RIA)
+    int sum_pool;                              // RCA: backward of the plain neighbor sum
     float* grad_rows;                          // [N, d] per-position embedding gradient rows
     float* sdz;                                // [M, 2]  sum_i d z_i per slice and co-attention
     float* partials; int n_partials;           // [n_partials, 2*Di + 2*Du] per-CTA dW1|dW2 (item), dW1|dW2 (user)

@@ -553,12 +553,15 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
     launch_l2_sum(h->st_w, h->P, h->flags, (int)h->n_dense, h->l2sum);
     cudaEventRecord(h->ev_l2, h->st_w);
 
+    const int mt = dm.model_type;
+    const bool has_coatt = mt != SCORE_MODEL_RCA;   // RCA sums the neighbors (score.py:266-269)
+    const bool has_att = mt != SCORE_MODEL_RIA;     // RIA feeds the final GRU states to the MLP (score.py:244-249)
     TargetArgs ta{};
     ta.emb = h->emb_fwd; ta.keys = h->keys_fwd;
-    ta.w_item = W(nm.co_item); ta.b_item = Bi(nm.co_item); ta.w_user = W(nm.co_user); ta.b_user = Bi(nm.co_user);
+    if (has_coatt) { ta.w_item = W(nm.co_item); ta.b_item = Bi(nm.co_item); ta.w_user = W(nm.co_user); ta.b_user = Bi(nm.co_user); }
     ta.q0 = h->q0; ta.fc_in = h->fc_in; ta.fc_off = Dfc - Ds; ta.c_item = h->c_item; ta.c_user = h->c_user;
     launch_target_fwd(h->st, dm, ta);
-    {   // query side of the attention (per sample): off the critical path, next to the gather and the GRUs
+    if (has_att) {   // query side of the attention (per sample): off the critical path, next to the gather and the GRUs
         cudaEventRecord(h->ev_tgt, h->st);
         cudaStreamWaitEvent(h->st_w, h->ev_tgt, 0);
         AttQArgs qa{};
@@ -570,7 +573,9 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
 
     CoattArgs ca{};
     ca.emb = h->emb_fwd; ca.keys = h->keys_fwd; ca.length = h->length;
-    ca.w_item = W(nm.co_item); ca.w_user = W(nm.co_user); ca.c_item = h->c_item; ca.c_user = h->c_user;
+    if (has_coatt) { ca.w_item = W(nm.co_item); ca.w_user = W(nm.co_user); }
+    ca.sum_pool = has_coatt ? 0 : 1;
+    ca.c_item = h->c_item; ca.c_user = h->c_user;
     ca.xhg_u = h->xhg[0]; ca.xhc_u = h->xhc[0]; ca.xhg_i = h->xhg[1]; ca.xhc_i = h->xhc[1];
     ca.key = h->key; ca.ldkey = Dk; ca.key_off = 2 * H; ca.save_r = h->save_r; ca.save_w = h->save_w;
     probe_begin(h, PR_COATT_FWD, h->st);
@@ -591,10 +596,12 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
     }
     cudaStreamWaitEvent(h->st, h->ev_prep, 0);   // the derived weights are rebuilt on the side stream
     launch_rowgemm(h->st, pxl, 2);
-    ga.out = h->key; ga.ldout = Dk; ga.last = nullptr; ga.ldlast = 0;
+    ga.out = h->key; ga.ldout = Dk;
+    ga.last = has_att ? nullptr : h->fc_in; ga.ldlast = has_att ? 0 : Dfc;   // RIA: fc_in = [user_last | item_last | ...]
     launch_gru_fwd(h->st, dm, ga);
 
     // attention over the T slices + attentive pooling (score.py:169-186, 214-216): one fused row-tile chain
+    if (has_att) {
     cudaStreamWaitEvent(h->st, h->ev_q, 0);
     AttFwd2Args fa2{};
     fa2.B = B; fa2.T = T; fa2.Dk = Dk; fa2.H = H; fa2.length = h->length; fa2.q = h->q; fa2.U = h->attU; fa2.key = h->key;
@@ -602,6 +609,7 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
     fa2.qk = h->qk; fa2.f1 = h->f1; fa2.f2 = h->f2; fa2.score = h->score; fa2.fc_in = h->fc_in; fa2.ldfc = Dfc;
     fa2.model_type = dm.model_type;
     launch_att_fwd2(h->st, fa2);
+    }
 
     // build_fc_net + log-loss (score.py:68-81): one fused row-tile chain
     FcArgs fa{};
@@ -645,8 +653,10 @@ void enqueue_backward(ScoreModel* h) {
                           h->PG + po(h, "bn1/gamma"), h->PG + po(h, "bn1/beta"), kSplits, h->n_dense);
 
     // attention: pooling + softmax + MLP backward in one fused chain, then the per-sample query side
+    const int mt = dm.model_type;
+    const bool has_coatt = mt != SCORE_MODEL_RCA, has_att = mt != SCORE_MODEL_RIA;
     const int64_t blk = (int64_t)Dk * 80;   // dense_3/kernel row blocks: Wa | Wb | Wc | Wd
-    {
+    if (has_att) {
         AttBwd2Args ab{};
         ab.B = B; ab.T = T; ab.Dk = Dk; ab.H = H; ab.length = h->length; ab.q = h->q; ab.key = h->key; ab.f1 = h->f1;
         ab.f2 = h->f2; ab.score = h->score; ab.dfc_in = h->dfc_in; ab.ldfc = Dfc; ab.model_type = dm.model_type;
@@ -672,7 +682,9 @@ void enqueue_backward(ScoreModel* h) {
     // GRUs
     const char* sides[2] = {"gru_user_side", "gru_item_side"};
     GruBwdArgs gb{};
-    gb.length = h->length; gb.dout = h->dkey; gb.lddout = Dk; gb.dlast = nullptr; gb.lddlast = 0;
+    gb.length = h->length;
+    gb.dout = has_att ? h->dkey : nullptr; gb.lddout = Dk;                       // RIA: only the final states are consumed
+    gb.dlast = has_att ? nullptr : h->dfc_in; gb.lddlast = has_att ? 0 : Dfc;
     for (int s = 0; s < 2; ++s) {
         std::string g = std::string(sides[s]) + "/gru_cell/gates", c = std::string(sides[s]) + "/gru_cell/candidate";
         gb.wg[s] = W(g); gb.wc[s] = W(c); gb.xhg[s] = h->xhg[s];
@@ -694,25 +706,34 @@ void enqueue_backward(ScoreModel* h) {
     // co-attention + gather backward: per-position embedding gradient rows
     CoattBwdArgs cb{};
     cb.emb = h->emb_fwd; cb.keys = h->keys_fwd; cb.length = h->length;
-    cb.w_item = W(nm.co_item); cb.w_user = W(nm.co_user); cb.save_r = h->save_r; cb.save_w = h->save_w;
-    cb.dxu = h->dx[0]; cb.dxi = h->dx[1]; cb.dkey = h->dkey; cb.ldkey = Dk; cb.key_off = 2 * H;
+    if (has_coatt) { cb.w_item = W(nm.co_item); cb.w_user = W(nm.co_user); }
+    cb.sum_pool = has_coatt ? 0 : 1;
+    cb.save_r = h->save_r; cb.save_w = h->save_w;
+    cb.dxu = h->dx[0]; cb.dxi = h->dx[1];
+    cb.dkey = (has_att && has_coatt) ? h->dkey : nullptr;   // RIA never consumes atten_info; RCA has none
+    cb.ldkey = Dk; cb.key_off = 2 * H;
     cb.grad_rows = h->grad_rows; cb.sdz = h->sdz; cb.partials = h->coatt_part; cb.n_partials = h->n_coatt_part;
     probe_begin(h, PR_COATT_BWD, h->st);
     launch_coatt_bwd(h->st, dm, cb);
     probe_end(h, PR_COATT_BWD, h->st);
     TargetBwdArgs tb{};
-    tb.length = h->length; tb.w_item = W(nm.co_item); tb.w_user = W(nm.co_user); tb.q0 = h->q0; tb.dq0 = h->dq0;
+    tb.length = h->length;
+    if (has_coatt) { tb.w_item = W(nm.co_item); tb.w_user = W(nm.co_user); }
+    tb.q0 = h->q0; tb.dq0 = has_att ? h->dq0 : nullptr;
     tb.dfc_in = h->dfc_in; tb.fc_off = Dfc - Ds; tb.ldfc = Dfc; tb.sdz = h->sdz; tb.grad_rows = h->grad_rows;
     tb.partials = h->target_part; tb.n_partials = h->n_target_part;
     launch_target_bwd(h->st, dm, tb);
-    launch_coatt_grad_reduce(h->st, dm, h->coatt_part, h->n_coatt_part, h->target_part, h->n_target_part,
-                             h->PG + Wo(nm.co_item), h->PG + Bo(nm.co_item), h->PG + Wo(nm.co_user),
-                             h->PG + Bo(nm.co_user));
+    if (has_coatt)
+        launch_coatt_grad_reduce(h->st, dm, h->coatt_part, h->n_coatt_part, h->target_part, h->n_target_part,
+                                 h->PG + Wo(nm.co_item), h->PG + Bo(nm.co_item), h->PG + Wo(nm.co_user),
+                                 h->PG + Bo(nm.co_user));
     cudaEventRecord(h->ev_w, h->st_w);
     cudaStreamWaitEvent(h->st, h->ev_w, 0);
-    {   // dWc = dWa - dWb (attn.cu header)
+    if (has_att) {   // dWc = dWa - dWb (attn.cu header)
         const int64_t w1 = po(h, (nm.att1 + "/kernel").c_str()), blk = (int64_t)Dk * 80;
         launch_reduce_partials(h->st, h->PG, kSplits, (int)h->n_dense, h->G, w1 + 2 * blk, w1, w1 + blk, (int)blk);
+    } else {
+        launch_reduce_partials(h->st, h->PG, kSplits, (int)h->n_dense, h->G);
     }
 }
 
@@ -857,7 +878,6 @@ int run_step(ScoreModel* h, const ScoreBatch* b, int mode, float lr, float reg_l
              int global_batch, bool sync, float* loss_out) {
     int rc = check_batch(h, b);
     if (rc) return rc;
-    if (h->dm.model_type != SCORE_MODEL_SCORE) return fail(h, SCORE_ERR_ARG, "model_type not implemented yet");
     CK(cudaSetDevice(h->device));
     const int B = b->batch_size;
     rc = ensure_workspace(h, B > h->cfg.max_batch ? B : h->cfg.max_batch);
@@ -953,9 +973,12 @@ int score_create(const ScoreConfig* cfg, int device, ScoreHandle* out) {
         h->err = "this build contains sm_100a kernels only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
         return die(SCORE_ERR_CUDA);
     }
-    if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->st_w, cudaStreamNonBlocking) != cudaSuccess ||
+    // the main stream carries the critical path; the sort / weight-gradient branches only fill idle SMs
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->st2, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->st_w, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_l2, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_w, cudaEventDisableTiming) != cudaSuccess ||
@@ -1413,7 +1436,6 @@ int score_gather_rows(ScoreHandle h, const int32_t* idx_dev, int64_t n, float* o
 int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg_lambda, float keep_prob,
                      int32_t global_batch, int32_t train, const float* staged_table, const int32_t* staged_keys) {
     if (!h) return SCORE_ERR_ARG;
-    if (h->dm.model_type != SCORE_MODEL_SCORE) return fail(h, SCORE_ERR_ARG, "model_type not implemented yet");
     CK(cudaSetDevice(h->device));
     if (batch) {
         int rc = check_batch(h, batch);

@@ -54,17 +54,26 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int s
                                        int64_t d_dst, int64_t d_a, int64_t d_b, int d_count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float s = 0.f;
+    // fixed-order sum over the planes, eight independent loads in flight
+    auto plane_sum = [&](int64_t col) {
+        float s = 0.f;
+        int k = 0;
+        for (; k + 8 <= splits; k += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = partials[(int64_t)(k + u) * n + col];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; k < splits; ++k) s += partials[(int64_t)k * n + col];
+        return s;
+    };
     if (d_dst >= 0 && i >= d_dst && i < d_dst + d_count) {
         // derived range: the same fixed-order sums its two source elements get, then their difference
-        const int64_t ia = d_a + (i - d_dst), ib = d_b + (i - d_dst);
-        float sb = 0.f;
-        for (int k = 0; k < splits; ++k) { s += partials[(int64_t)k * n + ia]; sb += partials[(int64_t)k * n + ib]; }
-        g[i] = s - sb;
+        g[i] = plane_sum(d_a + (i - d_dst)) - plane_sum(d_b + (i - d_dst));
         return;
     }
-    for (int k = 0; k < splits; ++k) s += partials[(int64_t)k * n + i];
-    g[i] = s;
+    g[i] = plane_sum(i);
 }
 void launch_reduce_partials(cudaStream_t st, const float* partials, int splits, int n, float* g, int64_t derive_dst,
                             int64_t derive_a, int64_t derive_b, int derive_count) {

@@ -17,7 +17,7 @@ from oracle import score_ref as ref
 from score_b200.synth import SHAPES
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CUDA_MODEL_TYPES = ("SCORE",)   # extended as the ablation classes land on the CUDA path
+CUDA_MODEL_TYPES = ("SCORE", "RIA", "RCA", "SCORE_USER", "SCORE_ITEM")
 
 
 def _load(name):

@@ -72,6 +72,25 @@ def test_forward_backward_runtime_geometry_fallback(geom):
     _check_fb(rep)
 
 
+@pytest.mark.parametrize("model_type", ["RIA", "RCA", "SCORE_USER", "SCORE_ITEM"])
+@pytest.mark.parametrize("name", ["tiny", "tiny_tb"])
+def test_forward_backward_ablation_classes(model_type, name):
+    """score.py:226-369: the four ablation classes run through the same kernels (flags), parity like SCORE."""
+    shape = SHAPES[name]
+    rep = pu.forward_backward_report(shape, make_batch(shape, seed=31), model_type=model_type)
+    _check_fb(rep)
+
+
+@pytest.mark.parametrize("model_type", ["RIA", "RCA", "SCORE_USER", "SCORE_ITEM"])
+def test_train_steps_ablation_classes(model_type):
+    shape = SHAPES["tiny"]
+    batches = [make_batch(shape, seed=40 + i) for i in range(3)]
+    rep = pu.train_steps_report(shape, batches, adam_mode="lazy", model_type=model_type)
+    for k, v in rep.items():
+        if k.startswith("loss"):
+            assert v <= 1e-5, (k, v)
+
+
 def test_ragged_lengths_dummy_slices_and_single_sample():
     shape = SHAPES["tiny"]
     b = list(make_batch(shape, seed=12, batch=9, dummy_frac=0.4))
