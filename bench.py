@@ -51,6 +51,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(workload, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json, written by
+    tools/ncu_traffic.py); None when no capture of this workload exists."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        e = json.load(open(path))[workload][kernel]
+        return e["traffic_bytes"], e["source"]
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -297,14 +308,22 @@ def main():
             return tot / n if n else None
 
         t_g, t_s = per_launch("coatt_fwd"), per_launch("emb_update")
+        tr_g, src_g = ncu_traffic(shape.name, "coatt_fwd")
+        tr_s, src_s = ncu_traffic(shape.name, "emb_update")
         roof = {"bound": "hbm", "kernel": "coatt_fwd_kernel (fused embedding gather + co-attention + pooling)",
                 "achieved": gather_bytes / (t_g * 1e-3) / 1e9 if t_g else None, "peak": peak, "unit": "GB/s",
-                "frac": gather_bytes / (t_g * 1e-3) / 1e9 / peak if t_g else None, "traffic": None,
+                "frac": gather_bytes / (t_g * 1e-3) / 1e9 / peak if t_g else None, "traffic": tr_g,
+                "traffic_source": src_g,
                 "peak_source": peak_src, "bytes_per_launch": gather_bytes, "ms_per_launch": t_g,
-                "bytes_rule": "live non-zero ids x (4 + 4d)"}
+                "bytes_rule": "live non-zero ids x (4 + 4d); every index counted, no credit for the duplicates the "
+                              "loader's cyclic padding and the 1+neg user-side replication create (those hit L2, "
+                              "which is why traffic < bytes_per_launch)",
+                "timing": "CUDA events around the kernel on its own stream inside the timed steps (the sort / "
+                          "weight-gradient streams run concurrently)"}
         roof_s = {"bound": "hbm", "kernel": "emb_update_kernel (segment-reduce + fused row Adam)",
                   "achieved": scatter_bytes / (t_s * 1e-3) / 1e9 if t_s else None, "peak": peak, "unit": "GB/s",
-                  "frac": scatter_bytes / (t_s * 1e-3) / 1e9 / peak if t_s else None, "traffic": None,
+                  "frac": scatter_bytes / (t_s * 1e-3) / 1e9 / peak if t_s else None, "traffic": tr_s,
+                  "traffic_source": src_s,
                   "bytes_per_launch": scatter_bytes, "ms_per_launch": t_s, "unique_rows": uniq,
                   "bytes_rule": "live ids x (4 + 4d) + unique rows x 6 x 4d"}
         line = {"metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,

@@ -168,6 +168,40 @@ int score_enable_probes(ScoreHandle h, int on);
 int score_probe_times(ScoreHandle h, double* out, int n);
 int score_last_step_stats(ScoreHandle h, int64_t* out3);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * On-GPU graph store + neighbor sampler: replaces GraphHandler / GraphLoader
+ * (code/score/graph_loader.py:94-277 neighbor selection, :340-385 batch assembly) for callers that keep the
+ * interaction graph in HBM.  The graph is the content of the reference's per-node Mongo documents
+ * (graph_storage.py:153-245) as two CSR arrays indexed by node * n_slices + slice; nodes are the unified ids
+ * 1..n_user (users) and n_user+1..n_user+n_item (items), row 0 is unused.  All arrays are HOST pointers, copied once. */
+typedef struct ScoreGraph* ScoreGraphHandle;
+typedef struct ScoreGraphDesc {
+    int32_t n_user, n_item, n_slices;
+    int32_t user_fnum, item_fnum;  /* fields per node incl. the id (graph_loader.py:186-191)                   */
+    const int64_t* hop1_off;       /* [(n_user+n_item+1)*n_slices + 1]  doc['1hop'][slice]                      */
+    const int32_t* hop1_ids;
+    const int64_t* hop2_off;       /* same shape                        doc['2hop'][slice] (<= 100 ids)         */
+    const int32_t* hop2_ids;
+    const int32_t* hop2_deg;       /* doc['degrees'][slice], parallel to hop2_ids; may be NULL ('rs' mode only) */
+    const int32_t* user_feat;      /* [(n_user+1) * (user_fnum-1)]  user_feat_dict[str(uid)]; NULL if user_fnum == 1 */
+    const int32_t* item_feat;      /* [(n_item+1) * (item_fnum-1)]  row iid - n_user; NULL if item_fnum == 1   */
+} ScoreGraphDesc;
+int score_graph_create(const ScoreGraphDesc* desc, int device, ScoreGraphHandle* out);
+int score_graph_destroy(ScoreGraphHandle g);
+const char* score_graph_last_error(ScoreGraphHandle g);
+/* One batch, as GraphLoader.worker assembles it (graph_loader.py:340-385): uids[ceil(B/group)] target users,
+ * iids[B] target items (group = 1 + neg_sample_num consecutive items per user), histories of slices
+ * start_time..pred_time-1 padded to max_time_len with copies of the last one.  mode 0 = 'rs' (uniform with
+ * replacement, the mode train_score.py uses), 1 = 'is' (softmax of 1/(degree-1)).  uids / iids: host or device.
+ * *out receives DEVICE pointers (on_device = 1) owned by the graph handle, valid until the next sample call; pass it
+ * to score_train_step / score_eval.  Work is enqueued on cuda_stream (a cudaStream_t; NULL = the graph's own). */
+int score_graph_sample(ScoreGraphHandle g, const int32_t* uids, const int32_t* iids, int32_t batch_size,
+                       int32_t group, int32_t start_time, int32_t pred_time, int32_t max_time_len,
+                       int32_t obj_per_time_slice, int32_t mode, uint64_t seed, uint32_t draw_id, void* cuda_stream,
+                       ScoreBatch* out);
+int score_graph_sync(ScoreGraphHandle g, void* cuda_stream);   /* waits; SCORE_ERR_ID_RANGE if a target was unknown */
+int score_copy_to_host(void* dst_host, const void* src_device, size_t bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,12 @@ class ScoreBatch(C.Structure):
                 ("on_device", C.c_int32)]
 
 
+class ScoreGraphDesc(C.Structure):
+    _fields_ = [("n_user", C.c_int32), ("n_item", C.c_int32), ("n_slices", C.c_int32), ("user_fnum", C.c_int32),
+                ("item_fnum", C.c_int32), ("hop1_off", C.c_void_p), ("hop1_ids", C.c_void_p), ("hop2_off", C.c_void_p),
+                ("hop2_ids", C.c_void_p), ("hop2_deg", C.c_void_p), ("user_feat", C.c_void_p), ("item_feat", C.c_void_p)]
+
+
 # every symbol include/score_b200.h declares: (restype, argtypes)
 _H = C.c_void_p
 _F = C.c_float
@@ -57,6 +63,13 @@ SYMBOLS = {
     "score_enable_probes": (C.c_int, [_H, C.c_int]),
     "score_probe_times": (C.c_int, [_H, C.c_void_p, C.c_int]),
     "score_last_step_stats": (C.c_int, [_H, C.c_void_p]),
+    "score_graph_create": (C.c_int, [C.POINTER(ScoreGraphDesc), C.c_int, C.POINTER(_H)]),
+    "score_graph_destroy": (C.c_int, [_H]),
+    "score_graph_last_error": (C.c_char_p, [_H]),
+    "score_graph_sample": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(ScoreBatch)]),
+    "score_graph_sync": (C.c_int, [_H, C.c_void_p]),
+    "score_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
 }
 
 ERR_ARG, ERR_CUDA, ERR_ID_RANGE, ERR_IO, ERR_NAME = 1, 2, 3, 4, 5

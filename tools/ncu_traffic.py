@@ -1,0 +1,42 @@
+"""Record the DRAM traffic per launch of the HBM-side kernels from an `ncu --set full` report into
+profiles/traffic.json (bench.py copies it into roofline.traffic).  Usage: tools/ncu_traffic.py <report.ncu-rep> <workload> <label>"""
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KERNELS = {"coatt_fwd": "coatt_fwd_kernel", "coatt_bwd": "coatt_bwd_kernel", "emb_update": "emb_update_kernel",
+           "emb_replay": "emb_replay_kernel", "build_keys": "build_keys_kernel"}
+
+
+def to_bytes(v, unit):
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+    return float(v.replace(",", "")) * scale
+
+
+def main():
+    rep, workload, label = sys.argv[1:4]
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    h, units = rows[0], rows[1]
+    ir, iw, it, ik = (h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"),
+                      h.index("gpu__time_duration.sum"), h.index("Kernel Name"))
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    entry = data.setdefault(workload, {})
+    for key, sub in KERNELS.items():
+        inst = [r for r in rows[2:] if sub in r[ik]]
+        if not inst:
+            continue
+        r = inst[-1]   # the latest captured launch (steady state of the lazy optimizer)
+        rd, wr = to_bytes(r[ir], units[ir]), to_bytes(r[iw], units[iw])
+        entry[key] = {"traffic_bytes": rd + wr, "dram_read_bytes": rd, "dram_write_bytes": wr,
+                      "ncu_duration_us": float(r[it].replace(",", "")), "source": label}
+    json.dump(data, open(path, "w"), indent=1, sort_keys=True)
+    print(json.dumps(entry, indent=1))
+
+
+if __name__ == "__main__":
+    main()
