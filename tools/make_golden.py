@@ -99,6 +99,135 @@ def make_metrics(reference_root):
     print("metrics_reference.npz:", names)
 
 
+# ------------------------------------------------------------------------------------------ loader (graph_loader.py)
+class _FakeColl(object):
+    def __init__(self, docs, key):
+        self.docs, self.key = docs, key
+
+    def find(self, q):
+        import copy
+        return [copy.deepcopy(self.docs[q[self.key]])]   # a Mongo query returns a fresh document every time
+
+
+class _FakeDB(object):
+    def __init__(self, user_docs, item_docs):
+        self.user_docs, self.item_docs = user_docs, item_docs
+
+    def __getitem__(self, name):
+        return _FakeColl(self.user_docs, 'uid') if name.startswith('user_') else _FakeColl(self.item_docs, 'iid')
+
+
+class _FakeMongo(object):
+    def __init__(self, user_docs, item_docs):
+        self.db = _FakeDB(user_docs, item_docs)
+
+    def MongoClient(self, url):
+        return {None: self.db}.get(None) and type("C", (), {"__getitem__": lambda s_, n: self.db})()
+
+
+class _Ctx(object):
+    side = 1; ent = 0; queue = None; seed = 0; draw_id = 0; T = 0; K = 0
+
+
+def _np_proxy(ctx):
+    """numpy with np.random.choice replaced: the K uniforms come from the Philox stream of the CUDA sampler (keyed by
+    the draw the harness announced), the index rule is NumPy's own"""
+    from oracle import loader_ref as L
+
+    def choice(a, size=None, replace=True, p=None):
+        ts = ctx.queue.pop(0)
+        u = L.draw_uniforms(ctx.seed, ctx.draw_id, ctx.side, ctx.ent, ts, ctx.T, ctx.K)[:size]
+        a = np.asarray(a)
+        if p is None:
+            idx = np.minimum((u * np.float32(len(a))).astype(np.int64), len(a) - 1)   # stands in for randint(0, n)
+        else:
+            cdf = np.asarray(p, np.float64).cumsum()
+            cdf /= cdf[-1]
+            idx = np.minimum(cdf.searchsorted(u.astype(np.float64), side='right'), len(a) - 1)   # numpy/random/mtrand.pyx choice()
+        return a[idx]
+
+    class _Random(object):
+        pass
+    rnd = _Random()
+    rnd.choice = choice
+
+    class _NP(object):
+        random = rnd
+
+        def __getattr__(self, name):
+            return getattr(np, name)
+    return _NP()
+
+
+def load_reference_graph_handler(reference_root, ns):
+    path = os.path.join(reference_root, "code", "score", "graph_loader.py")
+    tree = ast.parse(open(path).read())
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == "GraphHandler":
+            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    return ns["GraphHandler"]
+
+
+LOADER_CASES = [
+    # name, n_user, n_item, time_slice_num, start, pred, K, uf, if, mode, neg, n_groups
+    ("rs_plain", 30, 40, 9, 0, 6, 10, 1, 1, "rs", 1, 6),
+    ("rs_tmall_fields", 25, 35, 12, 0, 9, 10, 3, 4, "rs", 1, 5),
+    ("rs_start2_neg3", 20, 30, 10, 2, 7, 5, 1, 2, "rs", 3, 4),
+    ("is_taobao_fields", 30, 40, 9, 0, 7, 10, 1, 2, "is", 1, 6),
+    ("rs_eval_last_slice", 20, 30, 9, 0, 8, 10, 1, 5, "rs", 9, 2),
+]
+
+
+def make_loader(reference_root):
+    from oracle import loader_ref as L
+    from score_b200.graph import docs_to_csr, feat_table
+    out = {"source": np.array("reference: GraphHandler.gen_user_history / gen_item_history of code/score/graph_loader.py:"
+                              "40-277 executed unmodified (ast-extracted class; MongoDB replaced by in-memory documents; "
+                              "np.random.choice fed the Philox uniforms of csrc/sampler.cu), batch assembled in the order "
+                              "of GraphLoader.worker :340-385")}
+    names = []
+    for ci, (name, nu, ni, tsn, start, pred, K, uf, fi, mode, neg, n_groups) in enumerate(LOADER_CASES):
+        rng = np.random.default_rng(500 + ci)
+        user_docs, item_docs, ufd, ifd = L.random_graph(rng, nu, ni, tsn, user_fnum=uf, item_fnum=fi)
+        T = tsn - start - 1
+        ctx = _Ctx()
+        ctx.seed, ctx.draw_id, ctx.T, ctx.K = 777 + ci, ci, T, K
+        ns = {"pymongo": _FakeMongo(user_docs, item_docs), "np": _np_proxy(ctx), "pkl": None}
+        GH = load_reference_graph_handler(reference_root, ns)
+        gh = GH(tsn, "db", K, nu, ni, start, 7, 11, mode, None, None, uf, fi)
+        gh.user_feat_dict, gh.item_feat_dict = ufd, ifd
+        grp = neg + 1
+        uids = rng.integers(1, nu + 1, n_groups).tolist()
+        iids = rng.integers(nu + 1, nu + ni + 1, n_groups * grp).tolist()
+        cols = [[] for _ in range(8)]
+        for i, uid in enumerate(uids):      # GraphLoader.worker, graph_loader.py:357-382
+            ctx.side, ctx.ent = 1, i
+            ctx.queue = [t for t in range(pred - start) if user_docs[uid]['2hop'][start + t] != []]
+            u1, u2 = gh.gen_user_history(uid, pred)
+            for j in range(i * grp, (i + 1) * grp):
+                ctx.side, ctx.ent = 2, n_groups + j
+                ctx.queue = [t for t in range(pred - start) if item_docs[iids[j]]['2hop'][start + t] != []]
+                i1, i2 = gh.gen_item_history(iids[j], pred)
+                cols[0].append(u1); cols[1].append(u2); cols[2].append(i1); cols[3].append(i2)
+                cols[4].append([uid] if ufd is None else [uid] + ufd[str(uid)])
+                cols[5].append([iids[j]] if ifd is None else [iids[j]] + ifd[str(iids[j])])
+                cols[6].append(1 if j % grp == 0 else 0)
+                cols[7].append(pred - start)
+        off1, ids1, off2, ids2, deg2 = docs_to_csr(user_docs, item_docs, nu, ni, tsn)
+        pre = name + "/"
+        out[pre + "params"] = np.array([nu, ni, tsn, start, pred, K, uf, fi, 0 if mode == "rs" else 1, neg, 777 + ci, ci], np.int64)
+        out[pre + "hop1_off"], out[pre + "hop1_ids"], out[pre + "hop2_off"], out[pre + "hop2_ids"], out[pre + "hop2_deg"] = off1, ids1, off2, ids2, deg2
+        out[pre + "user_feat"] = feat_table(ufd, 1, nu, uf - 1)
+        out[pre + "item_feat"] = feat_table(ifd, nu + 1, ni, fi - 1)
+        out[pre + "uids"], out[pre + "iids"] = np.asarray(uids, np.int32), np.asarray(iids, np.int32)
+        for k in range(8):
+            out[pre + "batch/%d" % k] = np.asarray(cols[k]).astype(np.int32)    # feeding int32 placeholders casts (score.py:21-30)
+        names.append(name)
+        print("loader case %s: B=%d T=%d, %d 2-hop draws unused" % (name, len(cols[6]), T, len(ctx.queue)))
+    out["cases"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "loader_reference.npz"), **out)
+
+
 def params_digest(params):
     h = hashlib.sha256()
     for k, v in params.items():
@@ -176,6 +305,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     if not args.only or args.only == "metrics":
         make_metrics(args.reference)
+    if not args.only or args.only == "loader":
+        make_loader(args.reference)
     for c in MODEL_CASES:
         if not args.only or args.only == c[0]:
             make_model_case(*c)
