@@ -228,6 +228,27 @@ def make_loader(reference_root):
     np.savez_compressed(os.path.join(OUT, "loader_reference.npz"), **out)
 
 
+def make_tmall(reference_root):
+    """BASELINE.json config 1: the reference's bundled Tmall sample as a derived fixture (graph CSR + feature tables +
+    target lines); the raw log itself stays in the reference tree"""
+    from score_b200 import tmall_sample as ts
+    from score_b200.graph import docs_to_csr, feat_table
+    d = ts.build(os.path.join(reference_root, "score-data", "Tmall", "raw_data", "user_log_format1.csv"))
+    off1, ids1, off2, ids2, deg2 = docs_to_csr(d["user_docs"], d["item_docs"], d["n_user"], d["n_item"], d["n_slices"])
+    np.savez_compressed(
+        os.path.join(OUT, "tmall_sample.npz"),
+        source=np.array("derived from the reference's score-data/Tmall/raw_data/user_log_format1.csv by "
+                        "score_b200/tmall_sample.py (restated feateng_tmall.py / graph_storage.py / gen_target.py; "
+                        "age and gender synthesised: user_info_format1.csv is not shipped)"),
+        dims=np.array([d["n_user"], d["n_item"], d["feature_size"], d["n_slices"]], np.int64),
+        hop1_off=off1, hop1_ids=ids1, hop2_off=off2, hop2_ids=ids2, hop2_deg=deg2,
+        user_feat=feat_table(d["user_feat"], 1, d["n_user"], 2),
+        item_feat=feat_table(d["item_feat"], d["n_user"] + 1, d["n_item"], 3),
+        target_9=d["targets"][9], target_10=d["targets"][10], target_11=d["targets"][11])
+    print("tmall_sample.npz: %d users, %d items, V=%d, targets %s" % (
+        d["n_user"], d["n_item"], d["feature_size"], {k: len(v) for k, v in d["targets"].items()}))
+
+
 def params_digest(params):
     h = hashlib.sha256()
     for k, v in params.items():
@@ -307,6 +328,8 @@ def main():
         make_metrics(args.reference)
     if not args.only or args.only == "loader":
         make_loader(args.reference)
+    if not args.only or args.only == "tmall":
+        make_tmall(args.reference)
     for c in MODEL_CASES:
         if not args.only or args.only == c[0]:
             make_model_case(*c)
