@@ -211,7 +211,7 @@ def main():
     ctor = list(shape.ctor_args())
     if world > 1 and par == "sharded":
         ctor[0] = parallel.shard_rows(shape.feature_size, world)
-    m = sb.SCORE(*ctor, device=local, adam_mode=args.adam_mode, use_graph=(not args.no_graph) and world == 1,
+    m = sb.SCORE(*ctor, device=local, adam_mode=args.adam_mode, use_graph=(not args.no_graph) and (world == 1 or par == "dp"),
                  seed=1111 + (rank if par == "sharded" else 0), max_batch=B)
     trainer = None
     if world > 1:

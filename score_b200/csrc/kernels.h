@@ -273,7 +273,8 @@ struct EmbUpdateArgs {
     float* emb; float* m; float* v; int32_t* last_step;
     const float* alpha_hist;       // LAZY: rows that are not current through step-1 are replayed first (may be null)
     const Hyper* hp;
-    int mode;                      // 0: apply Adam, 1: export (seg sums to out_rows at head index, no update)
+    int mode;                      // 0: apply Adam; 1 / 2: export the run sums to out_rows / out_heads at the run's first sorted
+                                   // index / at its compact slot (0 .. runs-1), no update
     float* out_rows; int32_t* out_heads;
 };
 void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a);

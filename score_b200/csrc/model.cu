@@ -109,6 +109,9 @@ struct ScoreModel {
     const float* emb_fwd = nullptr; const int32_t* keys_fwd = nullptr;
     // sort buffers for externally supplied (key, gradient row) lists (multi-GPU finish)
     SortBufs sb_ext{}; int64_t sb_ext_cap = 0;
+    bool local_sorted = false;   // score_step_begin sorted this rank's own keys (side stream)
+    std::map<int, cudaGraphExec_t> graphs_begin; std::map<int, int64_t> graph_kernels_begin; std::map<int, int> warm_begin;
+    cudaEvent_t ev_keys = nullptr;
     bool begun = false; float begun_lr = 0.f;
     const int32_t* last_sorted = nullptr; int64_t last_sorted_n = 0;   // sorted key list of the last optimizer step
 
@@ -332,6 +335,10 @@ void free_workspace(ScoreModel* h) {
     h->graphs_train.clear();
     h->warm_train.clear();
     h->graph_kernels.clear();
+    for (auto& kv : h->graphs_begin) cudaGraphExecDestroy(kv.second);
+    h->graphs_begin.clear();
+    h->warm_begin.clear();
+    h->graph_kernels_begin.clear();
     h->cap_B = 0;
 }
 
@@ -985,6 +992,7 @@ int score_create(const ScoreConfig* cfg, int device, ScoreHandle* out) {
         cudaEventCreateWithFlags(&h->ev_tgt, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_q, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_prep, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_keys, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         h->err = "stream/event creation failed";
         return die(SCORE_ERR_CUDA);
@@ -1019,6 +1027,7 @@ int score_destroy(ScoreHandle h) {
     if (h->err_host) cudaFreeHost(h->err_host);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_keys) cudaEventDestroy(h->ev_keys);
     if (h->ev_l2) cudaEventDestroy(h->ev_l2);
     if (h->ev_w) cudaEventDestroy(h->ev_w);
     if (h->ev_tgt) cudaEventDestroy(h->ev_tgt);
@@ -1458,20 +1467,86 @@ int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg
         if (rc) return rc;
     }
     h->last_mode = MODE_BEGIN;
-    cudaEventRecord(h->ev_fork, h->st);
-    if (batch) launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag);
-    if (staged_table) {
-        h->emb_fwd = staged_table; h->keys_fwd = staged_keys;
-    } else {
-        h->emb_fwd = h->emb; h->keys_fwd = h->keys;
-        if (h->cfg.adam_mode == SCORE_ADAM_LAZY)
-            launch_emb_catchup_rows(h->st, h->keys, dm.N, dm.V, h->emb, h->emb_m, h->emb_v, h->last_step, dm.d,
-                                    h->alpha_hist, h->hyper_dev, h->claim_list, h->claim_counter);
+    const bool with_keys = batch != nullptr;
+    auto enqueue_begin = [&]() {
+        cudaEventRecord(h->ev_fork, h->st);
+        if (with_keys) launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag);
+        if (staged_table) {
+            h->emb_fwd = staged_table; h->keys_fwd = staged_keys;
+        } else {
+            h->emb_fwd = h->emb; h->keys_fwd = h->keys;
+            if (h->cfg.adam_mode == SCORE_ADAM_LAZY)
+                launch_emb_catchup_rows(h->st, h->keys, dm.N, dm.V, h->emb, h->emb_m, h->emb_v, h->last_step, dm.d,
+                                        h->alpha_hist, h->hyper_dev, h->claim_list, h->claim_counter);
+        }
+        if (train && !staged_table) {   // sort of this rank's own keys under forward/backward (score_local_reduce)
+            cudaEventRecord(h->ev_keys, h->st);
+            cudaStreamWaitEvent(h->st2, h->ev_keys, 0);
+            h->sort_out = launch_sort_pairs(h->st2, h->sb, h->keys, dm.N, key_bits(dm.V));
+            launch_emb_runs(h->st2, h->sb.keys[h->sort_out], h->sb.vals[h->sort_out], dm.N, h->sb.runs, h->sb.runs_long, h->n_heads_dev);
+            cudaEventRecord(h->ev_join, h->st2);
+        }
+        enqueue_forward(h, train != 0);
+        if (train) enqueue_backward(h);
+        if (train && !staged_table) cudaStreamWaitEvent(h->st, h->ev_join, 0);   // joins the sort branch (capture needs it)
+    };
+    h->local_sorted = train && !staged_table;
+    // the data-parallel training half-step is the same launch sequence every step: replay it as a CUDA graph
+    bool launched = false;
+    if (h->cfg.use_graph && train && !staged_table && with_keys) {
+        const int B = dm.B;
+        auto it = h->graphs_begin.find(B);
+        if (it != h->graphs_begin.end()) {
+            CK(cudaGraphLaunch(it->second, h->st));
+            g_launch_count += h->graph_kernels_begin[B];
+            h->emb_fwd = h->emb; h->keys_fwd = h->keys;
+            launched = true;
+        } else if (h->warm_begin[B] >= 1) {
+            cudaGraph_t graph = nullptr;
+            h->capturing = true;
+            const int64_t before = g_launch_count;
+            CK(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+            enqueue_begin();
+            h->graph_kernels_begin[B] = g_launch_count - before;
+            cudaError_t ce = cudaStreamEndCapture(h->st, &graph);
+            h->capturing = false;
+            if (ce != cudaSuccess) { h->err = std::string("graph capture failed: ") + cudaGetErrorString(ce); return SCORE_ERR_CUDA; }
+            cudaGraphExec_t exec = nullptr;
+            CK(cudaGraphInstantiate(&exec, graph, 0));
+            cudaGraphDestroy(graph);
+            h->graphs_begin[B] = exec;
+            CK(cudaGraphLaunch(exec, h->st));
+            launched = true;
+        }
+        h->warm_begin[B]++;
     }
-    enqueue_forward(h, train != 0);
-    if (train) enqueue_backward(h);
+    if (!launched) enqueue_begin();
     h->begun = train != 0;
     h->begun_lr = lr;
+    CK(cudaGetLastError());
+    return SCORE_OK;
+}
+
+// Data-parallel, replicated table: reduce this rank's per-position gradient rows to ONE row per unique id before the
+// exchange (deterministic segment reduce of scatter.cu, export mode), so the all-gather carries unique rows instead
+// of positions.  Outputs are device pointers owned by the handle: keys [N] int32 (slots past *count hold 0),
+// rows [N, d] float, count = number of unique non-zero ids.  Call between score_step_begin and score_step_finish.
+int score_local_reduce(ScoreHandle h, void** keys_dev, void** rows_dev, void** count_dev) {
+    if (!h || !keys_dev || !rows_dev || !count_dev) return SCORE_ERR_ARG;
+    if (!h->begun || !h->local_sorted) return fail(h, SCORE_ERR_ARG, "score_local_reduce needs a training score_step_begin on the handle's own table");
+    CK(cudaSetDevice(h->device));
+    const Dims& dm = h->dm;
+    int rc = ensure_seg(h, dm.N);
+    if (rc) return rc;
+    // the sort branch has already been joined into the main stream by score_step_begin
+    cudaMemsetAsync(h->seg_heads, 0, sizeof(int32_t) * dm.N, h->st);
+    EmbUpdateArgs ea{};
+    ea.skeys = h->sb.keys[h->sort_out]; ea.spos = h->sb.vals[h->sort_out]; ea.n = dm.N;
+    ea.runs = h->sb.runs; ea.runs_long = h->sb.runs_long; ea.long_cap = emb_runs_long_cap(dm.N); ea.counters = h->n_heads_dev;
+    ea.grad_rows = h->grad_rows; ea.d = dm.d; ea.hp = h->hyper_dev; ea.mode = 2;
+    ea.out_rows = h->seg_rows; ea.out_heads = h->seg_heads;
+    launch_emb_update(h->st, ea);
+    *keys_dev = h->seg_heads; *rows_dev = h->seg_rows; *count_dev = h->n_heads_dev + 3;
     CK(cudaGetLastError());
     return SCORE_OK;
 }
@@ -1536,6 +1611,9 @@ int score_enable_probes(ScoreHandle h, int on) {
     for (auto& kv : h->graphs_train) cudaGraphExecDestroy(kv.second);
     h->graphs_train.clear();
     h->graph_kernels.clear();
+    for (auto& kv : h->graphs_begin) cudaGraphExecDestroy(kv.second);
+    h->graphs_begin.clear();
+    h->graph_kernels_begin.clear();
     return SCORE_OK;
 }
 

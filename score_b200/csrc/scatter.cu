@@ -332,13 +332,15 @@ void launch_emb_runs(cudaStream_t st, const int32_t* skeys, const int32_t* spos,
 __device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
 // optimizer step of one row by one group of LPR lanes (all of them active here, identical control flow)
-template <bool EXPORT, int LPR>
-__device__ __forceinline__ void emb_apply_row(const EmbUpdateArgs& a, int32_t key, int32_t start, const float4& acc,
+// EXPORT: 0 = apply Adam; 1 = write the run's gradient sum at the run's first sorted index; 2 = at the run's slot in
+// the descriptor lists (compact: slots 0 .. number of runs - 1)
+template <int EXPORT, int LPR>
+__device__ __forceinline__ void emb_apply_row(const EmbUpdateArgs& a, int32_t key, int64_t out_idx, const float4& acc,
                                               float4 var, float4 m, float4 v, int last, int sub, float alpha, int step) {
     constexpr int D = LPR * 4;
     if (EXPORT) {
-        *reinterpret_cast<float4*>(a.out_rows + (int64_t)start * D + sub * 4) = acc;
-        if (sub == 0) a.out_heads[start] = key;
+        *reinterpret_cast<float4*>(a.out_rows + out_idx * D + sub * 4) = acc;
+        if (sub == 0) a.out_heads[out_idx] = key;
         return;
     }
     const int64_t off = (int64_t)key * D + sub * 4;
@@ -397,7 +399,7 @@ __device__ __forceinline__ float4 emb_team_combine(const float4& part, int lane)
     return tot;
 }
 
-template <bool EXPORT, int LPR>
+template <int EXPORT, int LPR>
 __global__ void __launch_bounds__(256) emb_update_kernel(EmbUpdateArgs a) {
     constexpr int D = LPR * 4;
     constexpr int G = 32 / LPR;          // groups per warp
@@ -432,7 +434,8 @@ __global__ void __launch_bounds__(256) emb_update_kernel(EmbUpdateArgs a) {
             float4 acc = red[0][sub];
 #pragma unroll
             for (int w = 1; w < 8; ++w) add4(acc, red[w][sub]);
-            emb_apply_row<EXPORT, LPR>(a, key, start, acc, var, m, v, last, sub, alpha, step);
+            emb_apply_row<EXPORT, LPR>(a, key, EXPORT == 2 ? (int64_t)nS + nM + r : (int64_t)start, acc, var, m, v, last, sub,
+                                       alpha, step);
         }
         __syncthreads();
     }
@@ -460,7 +463,9 @@ __global__ void __launch_bounds__(256) emb_update_kernel(EmbUpdateArgs a) {
             const float4 part = emb_strided_sum<LPR>(a, start, cnt, tl / LPR, TL / LPR, sub);
             __syncwarp();
             const float4 acc = emb_team_combine<LPR, TL>(part, lane);
-            if (owner) emb_apply_row<EXPORT, LPR>(a, key, start, acc, var, m, v, last, sub, alpha, step);
+            if (owner)
+                emb_apply_row<EXPORT, LPR>(a, key, EXPORT == 2 ? (int64_t)nS + r : (int64_t)start, acc, var, m, v, last, sub,
+                                           alpha, step);
             __syncwarp();
         }
     }
@@ -493,13 +498,14 @@ __global__ void __launch_bounds__(256) emb_update_kernel(EmbUpdateArgs a) {
 #pragma unroll
         for (int u = 1; u < 4; ++u)
             if (u < n4) add4(acc, g[u]);
-        emb_apply_row<EXPORT, LPR>(a, key, start, acc, var, m, v, last, sub, alpha, step);
+        emb_apply_row<EXPORT, LPR>(a, key, EXPORT == 2 ? (int64_t)h : (int64_t)start, acc, var, m, v, last, sub, alpha, step);
     }
 }
 template <int LPR>
 static void emb_update_launch(cudaStream_t st, const EmbUpdateArgs& a, unsigned grid) {
-    if (a.mode == 1) emb_update_kernel<true, LPR><<<grid, 256, 0, st>>>(a);
-    else emb_update_kernel<false, LPR><<<grid, 256, 0, st>>>(a);
+    if (a.mode == 1) emb_update_kernel<1, LPR><<<grid, 256, 0, st>>>(a);
+    else if (a.mode == 2) emb_update_kernel<2, LPR><<<grid, 256, 0, st>>>(a);
+    else emb_update_kernel<0, LPR><<<grid, 256, 0, st>>>(a);
 }
 void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a) {
     static int sms = 0;

@@ -6,9 +6,10 @@ The reference is single-device; both schemes keep SCOREB
 
 * ``DataParallelTrainer`` - replicated table (Tmall / Taobao / CCMR sizes).  Samples are independent (BN runs in
   inference mode, the loss is a batch mean), so each rank runs forward/backward on its shard with 1/global_B
-  scaling; dense gradients are summed with ONE all-reduce of one flat buffer; the per-position embedding
-  gradient rows and their keys are all-gathered and every replica applies the SAME deterministic
-  sort + segment-reduce + Adam, so replicas stay bit-identical without ever broadcasting the table.
+  scaling; dense gradients are summed with ONE all-reduce of one flat buffer; each rank reduces its embedding
+  gradient to one row per unique id (deterministic segment reduce), those (key, row) lists are all-gathered and
+  every replica applies the SAME deterministic sort + segment-reduce (rank order) + Adam, so replicas stay
+  bit-identical without ever broadcasting the table.
 
 * ``ShardedEmbeddingTrainer`` - row-sharded table (large-vocab config): owner(id) = id % world, local row
   = id // world + 1 (local row 0 is the dummy).  Forward: bucket ids by owner -> all-to-all ids -> owners gather
@@ -126,11 +127,21 @@ class DataParallelTrainer(_Base):
             self._keep_batch = b   # host id arrays stay alive until their H2D copies have run
             g = self._dev("dense_grad", torch.float32)
             dist.all_reduce(g, group=self.group)
-            keys = self._dev("keys", torch.int32)
-            rows = self._dev("grad_rows", torch.float32)
-            if getattr(self, "_all_keys", None) is None or self._all_keys.numel() != self.world * keys.numel():
-                self._all_keys = torch.empty(self.world * keys.numel(), dtype=torch.int32, device=self.device)
-                self._all_rows = torch.empty(self.world * rows.numel(), dtype=torch.float32, device=self.device)
+            # one gradient row per unique id of this rank (deterministic segment reduce on the device), then the
+            # all-gather carries unique rows, not positions
+            kp, rp, cp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            self.m._check(self.lib.score_local_reduce(self.h, C.byref(kp), C.byref(rp), C.byref(cp)))
+            d = self.m.cfg["eb_dim"]
+            cnt = torch.as_tensor(_DevView(cp.value, (1,), "<i4"), device=self.device).clone()
+            dist.all_reduce(cnt, op=dist.ReduceOp.MAX, group=self.group)
+            cap = (int(cnt.item()) + 1023) // 1024 * 1024      # host sync: the size of the exchange
+            n_pos = self._dev("keys", torch.int32).numel()
+            cap = max(min(cap, n_pos), 1)
+            keys = torch.as_tensor(_DevView(kp.value, (cap,), "<i4"), device=self.device)
+            rows = torch.as_tensor(_DevView(rp.value, (cap * d,), "<f4"), device=self.device)
+            if getattr(self, "_all_keys", None) is None or self._all_keys.numel() != self.world * cap:
+                self._all_keys = torch.empty(self.world * cap, dtype=torch.int32, device=self.device)
+                self._all_rows = torch.empty(self.world * cap * d, dtype=torch.float32, device=self.device)
             all_keys, all_rows = self._all_keys, self._all_rows
             dist.all_gather_into_tensor(all_keys, keys, group=self.group)
             dist.all_gather_into_tensor(all_rows, rows, group=self.group)
