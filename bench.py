@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="taobao")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's own, BASELINE.json)")
     ap.add_argument("--adam-mode", default="lazy", choices=["dense", "lazy", "sparse"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--zipf", type=float, default=0.0)
@@ -187,6 +188,9 @@ def main():
 
     from score_b200.synth import SHAPES, make_batch
     shape = SHAPES[args.workload]
+    if args.batch > 0:
+        import dataclasses
+        shape = dataclasses.replace(shape, batch=args.batch)
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
 
     if args.impl == "reference":
