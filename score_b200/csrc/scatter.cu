@@ -11,6 +11,8 @@
 // kernel so that no FMA contraction changes a bit:
 //     alpha = lr * sqrt(1 - beta2^t) / (1 - beta1^t)          (host, fp32)
 //     m += (g - m) * (1 - beta1);  v += (g*g - v) * (1 - beta2);  var -= (m * alpha) / (sqrt(v) + eps)
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace score {
@@ -126,19 +128,22 @@ size_t sort_hist_elems(int64_t n) {
     return total + (total + 1023) / 1024 + 1;   // histogram + one total per 1024-entry scan chunk
 }
 
+// The tile kernels are grid-stride over the tiles so the grid can be capped (sort_grid_cap).
 __global__ void sort_hist_kernel(const int32_t* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ hist,
                                  int nblocks) {
     __shared__ uint32_t cnt[256];
-    cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+    for (int tile = blockIdx.x; tile < nblocks; tile += gridDim.x) {
+        cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const int64_t base = (int64_t)tile * SORT_TILE;
 #pragma unroll
-    for (int r = 0; r < SORT_ITEMS; ++r) {
-        int64_t i = base + r * SORT_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&cnt[((uint32_t)keys[i] >> shift) & 255u], 1u);
+        for (int r = 0; r < SORT_ITEMS; ++r) {
+            int64_t i = base + r * SORT_THREADS + threadIdx.x;
+            if (i < n) atomicAdd(&cnt[((uint32_t)keys[i] >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        hist[(int64_t)threadIdx.x * nblocks + tile] = cnt[threadIdx.x];
     }
-    __syncthreads();
-    hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
 }
 
 // Exclusive scan of the (digit-major, tile-minor) histogram in two fully parallel kernels:
@@ -179,9 +184,11 @@ sort_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restri
     __shared__ uint32_t whist[WARPS][256];
     __shared__ uint32_t gbase[256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int tile = blockIdx.x; tile < nblocks; tile += gridDim.x) {
+    __syncthreads();   // the previous tile's readers of whist / gbase are done
     for (int i = threadIdx.x; i < WARPS * 256; i += SORT_THREADS) (&whist[0][0])[i] = 0;
     __syncthreads();
-    const int64_t wbase = (int64_t)blockIdx.x * SORT_TILE + warp * (32 * SORT_ITEMS);
+    const int64_t wbase = (int64_t)tile * SORT_TILE + warp * (32 * SORT_ITEMS);
     int32_t k[SORT_ITEMS];
     uint32_t lrank[SORT_ITEMS];
 #pragma unroll
@@ -205,7 +212,7 @@ sort_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restri
         uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) { uint32_t c = whist[w][dgt]; whist[w][dgt] = run; run += c; }
-        const int64_t hidx = (int64_t)dgt * nblocks + blockIdx.x;
+        const int64_t hidx = (int64_t)dgt * nblocks + tile;
         uint32_t pre = 0;
         const int chunk = (int)(hidx >> 10);
         for (int c = 0; c < chunk; ++c) pre += chunk_sums[c];   // prefix of the 1024-entry chunk totals
@@ -222,22 +229,35 @@ sort_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restri
             vals_out[pos] = vals_in ? vals_in[i] : (int32_t)i;
         }
     }
+    }   // tiles
 }
 
+// CTAs of the tile kernels: SCORE_SORT_CTAS caps them (profiling knob; measured on B200: capping the grid makes the
+// gather a little faster but stretches the sort into the dense backward - the step is fastest uncapped).
+static int sort_grid_cap() {
+    static int cap = 0;
+    if (!cap) {
+        const char* e = getenv("SCORE_SORT_CTAS");
+        cap = e ? atoi(e) : 0;
+        if (cap <= 0) cap = 1 << 30;
+    }
+    return cap;
+}
 int launch_sort_pairs(cudaStream_t st, SortBufs& sb, const int32_t* keys_in, int64_t n, int key_bits) {
     int passes = (key_bits + 7) / 8;
     if (passes < 1) passes = 1;
     const int nblocks = (int)((n + SORT_TILE - 1) / SORT_TILE);
+    const int grid = nblocks < sort_grid_cap() ? nblocks : sort_grid_cap();
     const int32_t* kin = keys_in;
     const int32_t* vin = nullptr;
     int out = 0;
     for (int p = 0; p < passes; ++p) {
         out = p & 1;
-        sort_hist_kernel<<<nblocks, SORT_THREADS, 0, st>>>(kin, n, 8 * p, sb.hist, nblocks);
+        sort_hist_kernel<<<grid, SORT_THREADS, 0, st>>>(kin, n, 8 * p, sb.hist, nblocks);
         const int total = 256 * nblocks, nchunks = (total + 1023) / 1024;
         uint32_t* chunk_sums = sb.hist + total;   // tail of the histogram allocation
         sort_scan_local_kernel<<<nchunks, 1024, 0, st>>>(sb.hist, total, chunk_sums);
-        sort_scatter_kernel<<<nblocks, SORT_THREADS, 0, st>>>(kin, vin, sb.keys[out], sb.vals[out], n, 8 * p, sb.hist,
+        sort_scatter_kernel<<<grid, SORT_THREADS, 0, st>>>(kin, vin, sb.keys[out], sb.vals[out], n, 8 * p, sb.hist,
                                                              nblocks, chunk_sums);
         g_launch_count += 3;
         kin = sb.keys[out];
