@@ -698,7 +698,7 @@ __global__ void target_bwd_kernel(Dims dm, TargetBwdArgs a) {
     }
 }
 
-int target_bwd_num_ctas() { return num_sms(); }
+int target_bwd_num_ctas() { return 2 * num_sms(); }   // one sample per warp at B = 1024
 
 void launch_target_bwd(cudaStream_t st, const Dims& dm, const TargetBwdArgs& a) {
     const int warps = 4;
@@ -708,16 +708,16 @@ void launch_target_bwd(cudaStream_t st, const Dims& dm, const TargetBwdArgs& a) 
 }
 
 // ------------------------------------------------------------------------------------------
-// co-attention kernel gradient [Wt | W1 | W2] + bias, for both co-attentions: one warp per output element,
-// lanes stride over the per-CTA partial rows, fixed-shape butterfly at the end (deterministic).
-__global__ void coatt_grad_reduce_kernel(Dims dm, const float* __restrict__ cp, int n_coatt,
-                                         const float* __restrict__ tp, int n_target,
-                                         float* g_w_item, float* g_b_item, float* g_w_user, float* g_b_user) {
+// co-attention kernel gradient [Wt | W1 | W2] + bias, for both co-attentions: one CTA of 128 threads per output
+// element, every thread adds its rows of the per-CTA partials in index order (independent loads), then a fixed-shape
+// tree over the CTA (deterministic).
+__global__ void __launch_bounds__(128) coatt_grad_reduce_kernel(Dims dm, const float* __restrict__ cp, int n_coatt,
+                                                                const float* __restrict__ tp, int n_target,
+                                                                float* g_w_item, float* g_b_item, float* g_w_user, float* g_b_user) {
+    __shared__ float red[128];
     const int nacc_c = 2 * dm.Di + 2 * dm.Du;
     const int nacc_t = dm.Di + 1 + dm.Du + 1;
-    const int total = 3 * dm.Di + 1 + 3 * dm.Du + 1;
-    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (e >= total) return;
+    const int e = blockIdx.x;
     // map e -> (source buffer, column, destination)
     const float* src; int col, n, stride; float* dst;
     if (e < 3 * dm.Di) {
@@ -735,17 +735,22 @@ __global__ void coatt_grad_reduce_kernel(Dims dm, const float* __restrict__ cp, 
         src = tp; col = dm.Di + 1 + dm.Du; n = n_target; stride = nacc_t; dst = g_b_user;
     }
     float s = 0.f;
-    for (int i = lane; i < n; i += 32) s += src[(int64_t)i * stride + col];
-    s = warp_sum(s);
-    if (lane == 0) *dst = s;
+    for (int i = threadIdx.x; i < n; i += 128) s += src[(int64_t)i * stride + col];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *dst = red[0];
 }
 
 void launch_coatt_grad_reduce(cudaStream_t st, const Dims& dm, const float* coatt_partials, int n_coatt,
                               const float* target_partials, int n_target,
                               float* g_w_item, float* g_b_item, float* g_w_user, float* g_b_user) {
     int total = 3 * dm.Di + 1 + 3 * dm.Du + 1;
-    coatt_grad_reduce_kernel<<<(total * 32 + 127) / 128, 128, 0, st>>>(dm, coatt_partials, n_coatt, target_partials,
-                                                                       n_target, g_w_item, g_b_item, g_w_user, g_b_user);
+    coatt_grad_reduce_kernel<<<total, 128, 0, st>>>(dm, coatt_partials, n_coatt, target_partials, n_target, g_w_item,
+                                                    g_b_item, g_w_user, g_b_user);
     ++g_launch_count;
 }
 

@@ -239,8 +239,11 @@ constexpr int L2_PARTS = 32;
 void launch_l2_sum(cudaStream_t st, const float* params, const uint8_t* flags, int n, float* out);
 // G[i] = sum_s partial[s][i]
 // optional derived range afterwards: g[dst + i] = g[a + i] - g[b + i], i < count  (dWc = dWa - dWb of the attention's first layer)
+// optional fused dense Adam step on element i (same arithmetic as launch_dense_adam)
+struct DenseAdamArgs { float* p; float* m; float* v; const uint8_t* flags; const Hyper* hp; float* alpha_hist; };
 void launch_reduce_partials(cudaStream_t st, const float* partials, int splits, int n, float* g,
-                            int64_t derive_dst = -1, int64_t derive_a = 0, int64_t derive_b = 0, int derive_count = 0);
+                            int64_t derive_dst = -1, int64_t derive_a = 0, int64_t derive_b = 0, int derive_count = 0,
+                            const DenseAdamArgs* adam = nullptr);
 void launch_add_l2(cudaStream_t st, float* g, const float* p, const uint8_t* flags, int n, const Hyper* hp);
 // dense Adam on the flat parameter buffer: g = G + reg*p (flags bit0), skip non-trainables (flags bit1 clear)
 void launch_dense_adam(cudaStream_t st, float* p, float* m, float* v, const float* g, const uint8_t* flags,

@@ -12,6 +12,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -111,7 +113,7 @@ struct ScoreModel {
     SortBufs sb_ext{}; int64_t sb_ext_cap = 0;
     bool local_sorted = false;   // score_step_begin sorted this rank's own keys (side stream)
     std::map<int, cudaGraphExec_t> graphs_begin; std::map<int, int64_t> graph_kernels_begin; std::map<int, int> warm_begin;
-    cudaEvent_t ev_keys = nullptr;
+    cudaEvent_t ev_keys = nullptr, ev_fc = nullptr;
     bool begun = false; float begun_lr = 0.f;
     const int32_t* last_sorted = nullptr; int64_t last_sorted_n = 0;   // sorted key list of the last optimizer step
 
@@ -626,12 +628,22 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
     fa.w3 = pp(h, "fc3/kernel"); fa.b3 = pp(h, "fc3/bias"); fa.label = h->label; fa.hp = h->hyper_dev;
     fa.z0 = h->z0; fa.g1 = h->g1; fa.g2 = h->g2; fa.y = h->y; fa.loss_b = h->loss_b; fa.dlogit = h->dlogit;
     launch_fc_fwd(h->st, fa);
-    cudaStreamWaitEvent(h->st, h->ev_l2, 0);
-    launch_loss_final(h->st, B, h->loss_b, h->l2sum, h->hyper_dev, h->loss_dev);
     probe_end(h, PR_FWD_DENSE, h->st);
+    // the loss scalar only leaves the device at the end of the step: reduce it on the side stream (behind l2_sum, same
+    // stream) instead of between the forward and the backward chain
+    cudaEventRecord(h->ev_fc, h->st);
+    cudaStreamWaitEvent(h->st_w, h->ev_fc, 0);
+    launch_loss_final(h->st_w, B, h->loss_b, h->l2sum, h->hyper_dev, h->loss_dev);
+    if (!will_bwd) {   // no backward: nothing else joins the side stream
+        cudaEventRecord(h->ev_w, h->st_w);
+        cudaStreamWaitEvent(h->st, h->ev_w, 0);
+    }
 }
 
-void enqueue_backward(ScoreModel* h) {
+// fused_adam: the dense Adam step rides on the final gradient reduce (single-GPU training step)
+void enqueue_backward(ScoreModel* h, bool fused_adam = false) {
+    DenseAdamArgs adam_args{h->P, h->M1, h->V1, h->flags, h->hyper_dev, h->alpha_hist};
+    const DenseAdamArgs* adam = fused_adam ? &adam_args : nullptr;
     const Dims& dm = h->dm;
     const int B = dm.B, T = dm.T, H = dm.H, Ds = dm.Ds, Dk = dm.Dk, Dfc = dm.Dfc, ldx = dm.ldx;
     const int M = B * T;
@@ -738,9 +750,9 @@ void enqueue_backward(ScoreModel* h) {
     cudaStreamWaitEvent(h->st, h->ev_w, 0);
     if (has_att) {   // dWc = dWa - dWb (attn.cu header)
         const int64_t w1 = po(h, (nm.att1 + "/kernel").c_str()), blk = (int64_t)Dk * 80;
-        launch_reduce_partials(h->st, h->PG, kSplits, (int)h->n_dense, h->G, w1 + 2 * blk, w1, w1 + blk, (int)blk);
+        launch_reduce_partials(h->st, h->PG, kSplits, (int)h->n_dense, h->G, w1 + 2 * blk, w1, w1 + blk, (int)blk, adam);
     } else {
-        launch_reduce_partials(h->st, h->PG, kSplits, (int)h->n_dense, h->G);
+        launch_reduce_partials(h->st, h->PG, kSplits, (int)h->n_dense, h->G, -1, 0, 0, 0, adam);
     }
 }
 
@@ -787,7 +799,7 @@ void enqueue_step(ScoreModel* h, int mode) {
     }
     enqueue_forward(h, need_bwd);
     if (need_bwd) {
-        enqueue_backward(h);
+        enqueue_backward(h, train);
         cudaStreamWaitEvent(h->st, h->ev_join, 0);
     }
     if (mode == MODE_FWDBWD) {
@@ -800,8 +812,7 @@ void enqueue_step(ScoreModel* h, int mode) {
         ea.out_rows = h->seg_rows; ea.out_heads = h->seg_heads;
         launch_emb_update(h->st, ea);
     }
-    if (train) {
-        launch_dense_adam(h->st, h->P, h->M1, h->V1, h->G, h->flags, (int)h->n_dense, h->hyper_dev, h->alpha_hist);
+    if (train) {   // the dense Adam step was fused into the gradient reduce (enqueue_backward)
         EmbUpdateArgs ea{};
         ea.skeys = h->sb.keys[h->sort_out]; ea.spos = h->sb.vals[h->sort_out]; ea.n = dm.N;
         ea.runs = h->sb.runs; ea.runs_long = h->sb.runs_long; ea.long_cap = emb_runs_long_cap(dm.N); ea.counters = h->n_heads_dev;
@@ -980,6 +991,13 @@ int score_create(const ScoreConfig* cfg, int device, ScoreHandle* out) {
         h->err = "this build contains sm_100a kernels only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
         return die(SCORE_ERR_CUDA);
     }
+    if (const char* e = getenv("SCORE_L2_FETCH")) {   // profiling knob: L2 fetch granularity hint (32 / 64 / 128 bytes)
+        const int gran = atoi(e);
+        if (gran > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "score_b200: cudaLimitMaxL2FetchGranularity = %zu\n", got);
+    }
     // the main stream carries the critical path; the sort / weight-gradient branches only fill idle SMs
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -993,6 +1011,7 @@ int score_create(const ScoreConfig* cfg, int device, ScoreHandle* out) {
         cudaEventCreateWithFlags(&h->ev_q, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_prep, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_keys, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fc, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         h->err = "stream/event creation failed";
         return die(SCORE_ERR_CUDA);
@@ -1028,6 +1047,7 @@ int score_destroy(ScoreHandle h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_keys) cudaEventDestroy(h->ev_keys);
+    if (h->ev_fc) cudaEventDestroy(h->ev_fc);
     if (h->ev_l2) cudaEventDestroy(h->ev_l2);
     if (h->ev_w) cudaEventDestroy(h->ev_w);
     if (h->ev_tgt) cudaEventDestroy(h->ev_tgt);

@@ -52,9 +52,12 @@ void launch_l2_sum(cudaStream_t st, const float* params, const uint8_t* flags, i
     ++g_launch_count;
 }
 
+// G[i] = fixed-order sum of the partial planes (+ derived range); with `ad` set the dense Adam step of element i follows
+// in the same thread (training path: one launch instead of two on the critical path)
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int splits, int n, float* __restrict__ g,
-                                       int64_t d_dst, int64_t d_a, int64_t d_b, int d_count) {
+                                       int64_t d_dst, int64_t d_a, int64_t d_b, int d_count, DenseAdamArgs ad) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && ad.p && ad.alpha_hist) ad.alpha_hist[ad.hp->step] = ad.hp->alpha;
     if (i >= n) return;
     // fixed-order sum over the planes, eight independent loads in flight
     auto plane_sum = [&](int64_t col) {
@@ -70,17 +73,28 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int s
         for (; k < splits; ++k) s += partials[(int64_t)k * n + col];
         return s;
     };
+    float gi;
     if (d_dst >= 0 && i >= d_dst && i < d_dst + d_count) {
         // derived range: the same fixed-order sums its two source elements get, then their difference
-        g[i] = plane_sum(d_a + (i - d_dst)) - plane_sum(d_b + (i - d_dst));
-        return;
+        gi = plane_sum(d_a + (i - d_dst)) - plane_sum(d_b + (i - d_dst));
+    } else {
+        gi = plane_sum(i);
     }
-    g[i] = plane_sum(i);
+    g[i] = gi;
+    if (!ad.p) return;
+    const uint8_t f = ad.flags[i];
+    if (!(f & 2)) return;   // non-trainable (bn moving statistics)
+    float var = ad.p[i], mm = ad.m[i], vv = ad.v[i];
+    if (f & 1) gi = __fadd_rn(gi, __fmul_rn(ad.hp->reg_lambda, var));   // d/dv of reg_lambda * l2_loss(v)
+    adam_elem(var, mm, vv, gi, ad.hp->alpha);
+    ad.p[i] = var; ad.m[i] = mm; ad.v[i] = vv;
 }
 void launch_reduce_partials(cudaStream_t st, const float* partials, int splits, int n, float* g, int64_t derive_dst,
-                            int64_t derive_a, int64_t derive_b, int derive_count) {
+                            int64_t derive_a, int64_t derive_b, int derive_count, const DenseAdamArgs* adam) {
+    DenseAdamArgs ad{};
+    if (adam) ad = *adam;
     reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(partials, splits, n, g, derive_dst, derive_a, derive_b,
-                                                            derive_count);
+                                                            derive_count, ad);
     ++g_launch_count;
 }
 
@@ -538,7 +552,13 @@ void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a) {
     const int lpr = a.d >> 2;
     // the run counts live on the device: size the grid for one group per sorted index, capped at a few resident waves
     // (groups past the run count exit at once; the grid-stride loops cover the rest)
-    int64_t want = (a.n * lpr + 255) / 256, cap = (int64_t)sms * 16;
+    static int per_sm = 0;
+    if (!per_sm) {
+        const char* e = getenv("SCORE_UPD_CTAS_PER_SM");
+        per_sm = e ? atoi(e) : 0;
+        if (per_sm <= 0) per_sm = 16;
+    }
+    int64_t want = (a.n * lpr + 255) / 256, cap = (int64_t)sms * per_sm;
     unsigned grid = (unsigned)(want < cap ? want : cap);
     if (grid == 0) grid = 1;
     switch (lpr) {

@@ -33,20 +33,21 @@ class _Batch:
         B = None
         shapes = [(T, K, fi), (T, K, fu), (T, K, fu), (T, K, fi), (fu,), (fi,), (), ()]
         for x, tail in zip(batch_data, shapes):
-            if on_device:
-                import torch
-                if x.dtype != torch.int32 or not x.is_contiguous():
+            if hasattr(x, "data_ptr") and (on_device or not x.is_cuda):
+                # torch tensor (CUDA, or CPU incl. pinned): take the pointer, no NumPy round trip
+                if str(x.dtype) != "torch.int32" or not x.is_contiguous():
+                    import torch
                     x = x.to(torch.int32).contiguous()
                 shape = tuple(x.shape)
                 ptr = x.data_ptr()
             else:
-                if hasattr(x, "numpy") and hasattr(x, "is_cuda"):   # CPU torch tensor (e.g. pinned)
-                    x = x.numpy()
-                a = np.asarray(x)
+                if hasattr(x, "is_cuda") and x.is_cuda:      # mixed host / device tuple: stage through the host
+                    x = x.cpu().numpy()
+                a = x if isinstance(x, np.ndarray) else np.asarray(x)
                 if a.dtype != np.int32:
                     # nested lists mix ints with the loader's float dummy rows (graph_loader.py:90-91)
                     a = a.astype(np.int32)
-                x = np.ascontiguousarray(a)
+                x = a if a.flags.c_contiguous else np.ascontiguousarray(a)
                 shape = x.shape
                 ptr = x.ctypes.data
             if B is None:

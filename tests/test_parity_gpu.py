@@ -253,6 +253,41 @@ def test_save_restore_roundtrip(tmp_path, capsys):
     m2.close()
 
 
+def test_npz_checkpoint_interop_and_log_files(tmp_path):
+    """section 8f-3: TF-name-keyed npz checkpoint incl. Adam slots continues training bit-identically; the log /
+    result files have train_score.py's names and line formats (train_score.py:86-92, 260-275)"""
+    import pickle
+    from score_b200 import logs
+    shape = SHAPES["tiny"]
+    cfg, params, m = pu.make_models(shape, adam_mode="dense")
+    bs = [make_batch(shape, seed=90 + i) for i in range(3)]
+    for b in bs[:2]:
+        m.train(None, b, 5e-4, 1e-4, keep_prob=1.0)
+    names = logs.export_npz(m, str(tmp_path / "ckpt.npz"))
+    assert "emb_mtx/Adam_1" in names and "beta2_power" in names and "bn1/moving_mean" in names
+    assert "bn1/moving_mean/Adam" not in names
+    want = m.train(None, bs[2], 5e-4, 1e-4, keep_prob=1.0)
+    after = m.get_tensor("fc1/kernel")
+    m.close()
+    m2 = sb.SCORE(*shape.ctor_args(), adam_mode="dense", init_weights=False, use_graph=False)
+    logs.import_npz(m2, str(tmp_path / "ckpt.npz"))
+    assert m2.train(None, bs[2], 5e-4, 1e-4, keep_prob=1.0) == want
+    assert np.array_equal(m2.get_tensor("fc1/kernel"), after)
+    m2.close()
+    name = logs.model_name("SCORE", 100, 5e-4, 1e-4)
+    assert name == "SCORE_100_0.0005_0.0001"
+    assert logs.save_path("tmall", name, root=str(tmp_path)).endswith("save_model_tmall/SCORE_100_0.0005_0.0001/ckpt")
+    best = logs.write_train_log("tmall", name, [0.7, 0.6], [0.9, 0.8, 0.7], [0.1, 0.2, 0.15], [0.2, 0.3, 0.25],
+                                [0.0, 0.1, 0.0], [0.1, 0.2, 0.1], [0.2, 0.3, 0.2], [0.05, 0.09, 0.07], root=str(tmp_path))
+    assert best == 0.09
+    with open(tmp_path / "logs_tmall" / (name + ".pkl"), "rb") as f:
+        assert len(pickle.load(f)) == 8
+    lines = open(tmp_path / "logs_tmall" / (name + ".result")).read().splitlines()
+    assert lines[0] == "Result Validation NDCG@5: 0.2" and lines[-1] == "Result Validation MRR: 0.09"
+    logs.write_test_result("tmall", name, 10, 0.1, 0.2, 0.0, 0.1, 0.2, 0.05, root=str(tmp_path))
+    assert open(tmp_path / "logs_tmall" / (name + "_10.test.result")).read().splitlines()[5] == "Result Test MRR: 0.05"
+
+
 def test_device_resident_batch_equals_host_batch():
     shape = SHAPES["tiny"]
     cfg, params, m = pu.make_models(shape)
