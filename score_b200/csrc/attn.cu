@@ -122,6 +122,7 @@ static AttPlan att_fwd_plan(int Dk, int T, int G) {
 }
 
 __global__ void __launch_bounds__(TL_CT) att_fwd2_kernel(AttFwd2Args a, int rows_pad) {
+    pdl_enter();
     constexpr int RT = 32;
     extern __shared__ __align__(16) float sm[];
     const int Dk = a.Dk, T = a.T, G = a.G, H = a.H, tid = threadIdx.x;
@@ -254,7 +255,7 @@ void launch_att_fwd2(cudaStream_t st, AttFwd2Args a) {
         cudaFuncSetAttribute(att_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.bytes);
         attr_set = p.bytes;
     }
-    att_fwd2_kernel<<<(a.B + a.G - 1) / a.G, TL_CT, p.bytes, st>>>(a, p.rows_pad);
+    launch_chain(att_fwd2_kernel, dim3((a.B + a.G - 1) / a.G), dim3(TL_CT), p.bytes, st, a, p.rows_pad);
     ++g_launch_count;
 }
 
@@ -272,6 +273,7 @@ static AttBwdPlan att_bwd_plan(int Dk, int T, int G, int H) {
 }
 
 __global__ void __launch_bounds__(TL_CT) att_bwd2_kernel(AttBwd2Args a, AttBwdPlan pl) {
+    pdl_enter();
     constexpr int RT = 32;
     using GE = TileGeom<RT>;
     extern __shared__ __align__(16) float sm[];
@@ -446,12 +448,13 @@ void launch_att_bwd2(cudaStream_t st, AttBwd2Args a) {
         cudaFuncSetAttribute(att_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.bytes);
         attr_set = p.bytes;
     }
-    att_bwd2_kernel<<<(a.B + a.G - 1) / a.G, TL_CT, p.bytes, st>>>(a, p);
+    launch_chain(att_bwd2_kernel, dim3((a.B + a.G - 1) / a.G), dim3(TL_CT), p.bytes, st, a, p);
     ++g_launch_count;
 }
 
 // ------------------------------------------------------------------------------------------ per-sample query side, backward
 __global__ void __launch_bounds__(TL_CT) att_qb_kernel(AttQbArgs a) {
+    pdl_enter();
     constexpr int RT = 16;
     using G = TileGeom<RT>;
     extern __shared__ __align__(16) float sm[];
@@ -513,7 +516,7 @@ void launch_att_qb(cudaStream_t st, const AttQbArgs& a) {
         cudaFuncSetAttribute(att_qb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = smem;
     }
-    att_qb_kernel<<<(a.B + RT - 1) / RT, TL_CT, smem, st>>>(a);
+    launch_chain(att_qb_kernel, dim3((a.B + RT - 1) / RT), dim3(TL_CT), smem, st, a);
     ++g_launch_count;
 }
 
@@ -526,6 +529,7 @@ void launch_att_qb(cudaStream_t st, const AttQbArgs& a) {
 namespace score {
 
 __global__ void __launch_bounds__(TL_CT) rowgemm_kernel(RowGemmBatch batch) {
+    pdl_enter();
     constexpr int RT = 32;
     using G = TileGeom<RT>;
     extern __shared__ __align__(16) float sm[];
@@ -575,7 +579,7 @@ void launch_rowgemm(cudaStream_t st, const RowGemmArgs* list, int n) {
         cudaFuncSetAttribute(rowgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = smem;
     }
-    rowgemm_kernel<<<dim3((maxM + 31) / 32, n), TL_CT, smem, st>>>(b);
+    launch_chain(rowgemm_kernel, dim3((maxM + 31) / 32, n), dim3(TL_CT), smem, st, b);
     ++g_launch_count;
 }
 

@@ -18,6 +18,7 @@ __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_ca
 
 // ------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(TL_CT) fc_fwd_kernel(FcArgs a) {
+    pdl_enter();
     extern __shared__ __align__(16) float sm[];
     const int F = a.F, tid = threadIdx.x;
     float* X0 = sm;                 // [F][R]   bn1 output
@@ -120,13 +121,14 @@ void launch_fc_fwd(cudaStream_t st, const FcArgs& a) {
         cudaFuncSetAttribute(fc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = smem;
     }
-    fc_fwd_kernel<<<(a.B + R - 1) / R, TL_CT, smem, st>>>(a);
+    launch_chain(fc_fwd_kernel, dim3((a.B + R - 1) / R), dim3(TL_CT), smem, st, a);
     ++g_launch_count;
 }
 
 // ------------------------------------------------------------------------------------------ backward
 // dg2 = dlogit w3^T (*) mask(g2);  dg1 = (dg2 W2^T) (*) mask(g1);  dz0 = dg1 W1^T;  dfc_in = dz0 * gamma/sqrt(var+eps)
 __global__ void __launch_bounds__(TL_CT) fc_bwd_kernel(FcBwdArgs a) {
+    pdl_enter();
     using G = TileGeom<R>;
     extern __shared__ __align__(16) float sm[];
     const int F = a.F, tid = threadIdx.x;
@@ -204,7 +206,7 @@ void launch_fc_bwd(cudaStream_t st, const FcBwdArgs& a) {
         cudaFuncSetAttribute(fc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = smem;
     }
-    fc_bwd_kernel<<<(a.B + R - 1) / R, TL_CT, smem, st>>>(a);
+    launch_chain(fc_bwd_kernel, dim3((a.B + R - 1) / R), dim3(TL_CT), smem, st, a);
     ++g_launch_count;
 }
 

@@ -20,7 +20,8 @@ struct Hyper {
     int32_t step;         // 1-based optimizer step this launch performs
     int32_t batch;        // B of this launch
     int32_t train;        // 1: training step (dropout active when keep_prob < 1)
-    int32_t pad0, pad1;
+    int32_t seq;          // launch sequence number (every upload): selects the ping-pong claim counter
+    int32_t pad1;
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -43,6 +44,16 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Programmatic dependent launch (sm_90+), an opt-in experiment (SCORE_PDL=1, kernels.h: launch_chain): the kernels of
+// the step's critical chain can be launched with cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel's CTAs
+// are scheduled while its predecessor drains; pdl_enter() - the first statement of every such kernel - lets the
+// successor be scheduled in turn and then waits until the predecessor grid has completed and its writes are visible.
+// Launched without the attribute (the default) both instructions are no-ops.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 

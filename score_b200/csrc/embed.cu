@@ -35,6 +35,7 @@ namespace score {
 __global__ void build_keys_kernel(Dims dm, const BatchPtrs* __restrict__ bpp, int32_t* __restrict__ keys,
                                   int32_t* __restrict__ label_out, int32_t* __restrict__ length_out,
                                   int32_t* __restrict__ err_flag, ClaimArgs ca) {
+    pdl_enter();
     const BatchPtrs bp = *bpp;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gtid < dm.B) {
@@ -71,6 +72,12 @@ __global__ void build_keys_kernel(Dims dm, const BatchPtrs* __restrict__ bpp, in
         for (int u = 0; u < 4; ++u) if (p0 + u < dm.N) keys[p0 + u] = id[u];
     }
     if (!ca.last_step) return;   // uniform
+    int32_t* counter = ca.counter;
+    if (ca.pingpong) {
+        const int sel = ca.hp->seq & 1;
+        counter += sel;
+        if (gtid == 0) ca.counter[sel ^ 1] = 0;   // the next launch's counter (idle now: its reader finished a launch ago)
+    }
     const int upto = ca.hp->step - 1;
     int seen[4], old[4];
 #pragma unroll
@@ -92,7 +99,7 @@ __global__ void build_keys_kernel(Dims dm, const BatchPtrs* __restrict__ bpp, in
     const int total = __shfl_sync(FULL_MASK, incl, 31);
     if (total == 0) return;
     int base = 0;
-    if (lane == 31) base = atomicAdd(ca.counter, total);
+    if (lane == 31) base = atomicAdd(counter, total);
     base = __shfl_sync(FULL_MASK, base, 31);
     int idx = base + incl - nwin;
 #pragma unroll
@@ -103,12 +110,15 @@ __global__ void build_keys_kernel(Dims dm, const BatchPtrs* __restrict__ bpp, in
 void launch_build_keys(cudaStream_t st, const Dims& dm, const BatchPtrs* bp_dev, int32_t* keys, int32_t* label_out,
                        int32_t* length_out, int32_t* err_flag, const ClaimArgs* claim) {
     ClaimArgs ca{};
-    if (claim) { ca = *claim; cudaMemsetAsync(ca.counter, 0, sizeof(int32_t), st); }
+    if (claim) {
+        ca = *claim;
+        if (!ca.pingpong) cudaMemsetAsync(ca.counter, 0, sizeof(int32_t), st);
+    }
     const int threads = 256;
     int64_t work = (dm.N + 3) / 4;
     if (work < dm.B) work = dm.B;
     const int64_t blocks = (work + threads - 1) / threads;
-    build_keys_kernel<<<(unsigned)blocks, threads, 0, st>>>(dm, bp_dev, keys, label_out, length_out, err_flag, ca);
+    launch_chain(build_keys_kernel, dim3((unsigned)blocks), dim3(threads), 0, st, dm, bp_dev, keys, label_out, length_out, err_flag, ca);
     ++g_launch_count;
 }
 
@@ -130,6 +140,7 @@ __device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__
 // ------------------------------------------------------------------------------------------
 // target rows: one warp per sample b
 __global__ void target_fwd_kernel(Dims dm, TargetArgs a) {
+    pdl_enter();
     extern __shared__ float sm[];
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* buf = sm + warp * dm.Ds;   // [tu (Du) | ti (Di)]
@@ -161,7 +172,7 @@ __global__ void target_fwd_kernel(Dims dm, TargetArgs a) {
 void launch_target_fwd(cudaStream_t st, const Dims& dm, const TargetArgs& a) {
     const int warps = 4;
     size_t smem = (size_t)warps * dm.Ds * sizeof(float);
-    target_fwd_kernel<<<(dm.B + warps - 1) / warps, warps * 32, smem, st>>>(dm, a);
+    launch_chain(target_fwd_kernel, dim3((dm.B + warps - 1) / warps), dim3(warps * 32), smem, st, dm, a);
     ++g_launch_count;
 }
 
@@ -277,6 +288,7 @@ __device__ __forceinline__ float half_max(float v) {
 
 template <class G>
 __global__ void __launch_bounds__(128) coatt_fwd_kernel(Dims dm, CoattArgs a, CoattSmem sp) {
+    pdl_enter();
     extern __shared__ __align__(16) float sm[];
     const G g(dm);
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -435,7 +447,7 @@ static void coatt_fwd_launch(cudaStream_t st, const Dims& dm, const CoattArgs& a
     int64_t want = (M + warps - 1) / warps;
     int64_t cap = (int64_t)num_sms() * 32;
     int grid = (int)(want < cap ? want : cap);
-    coatt_fwd_kernel<G><<<grid, warps * 32, smem, st>>>(dm, a, sp);
+    launch_chain(coatt_fwd_kernel<G>, dim3(grid), dim3(warps * 32), smem, st, dm, a, sp);
 }
 
 // geometries of the reference's data sets (train_score.py:23-54) + the large-vocab config; anything else: run-time
@@ -462,6 +474,7 @@ void launch_coatt_fwd(cudaStream_t st, const Dims& dm, const CoattArgs& a) {
 //   dW1 += sum_i dz_i seq1[i]                 dW2 += sum_i dz_i seq2[i]           sdz = sum_i dz_i
 template <class G>
 __global__ void __launch_bounds__(128) coatt_bwd_kernel(Dims dm, CoattBwdArgs a, CoattSmem sp) {
+    pdl_enter();
     extern __shared__ __align__(16) float sm[];
     const G g(dm);
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -645,7 +658,7 @@ static void coatt_bwd_launch(cudaStream_t st, const Dims& dm, const CoattBwdArgs
         cudaFuncSetAttribute(coatt_bwd_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = smem;
     }
-    coatt_bwd_kernel<G><<<a.n_partials, warps * 32, smem, st>>>(dm, a, sp);
+    launch_chain(coatt_bwd_kernel<G>, dim3(a.n_partials), dim3(warps * 32), smem, st, dm, a, sp);
 }
 
 void launch_coatt_bwd(cudaStream_t st, const Dims& dm, const CoattBwdArgs& a) {
@@ -656,6 +669,7 @@ void launch_coatt_bwd(cudaStream_t st, const Dims& dm, const CoattBwdArgs& a) {
 // ------------------------------------------------------------------------------------------
 // target rows backward: one warp per sample, grid-stride, per-CTA partials for dWt / dbias.
 __global__ void target_bwd_kernel(Dims dm, TargetBwdArgs a) {
+    pdl_enter();
     extern __shared__ float sm[];
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nacc = dm.Di + 1 + dm.Du + 1;
@@ -703,7 +717,7 @@ int target_bwd_num_ctas() { return 2 * num_sms(); }   // one sample per warp at 
 void launch_target_bwd(cudaStream_t st, const Dims& dm, const TargetBwdArgs& a) {
     const int warps = 4;
     size_t smem = (size_t)warps * (dm.Di + dm.Du + 2) * sizeof(float);
-    target_bwd_kernel<<<a.n_partials, warps * 32, smem, st>>>(dm, a);
+    launch_chain(target_bwd_kernel, dim3(a.n_partials), dim3(warps * 32), smem, st, dm, a);
     ++g_launch_count;
 }
 
@@ -714,6 +728,7 @@ void launch_target_bwd(cudaStream_t st, const Dims& dm, const TargetBwdArgs& a) 
 __global__ void __launch_bounds__(128) coatt_grad_reduce_kernel(Dims dm, const float* __restrict__ cp, int n_coatt,
                                                                 const float* __restrict__ tp, int n_target,
                                                                 float* g_w_item, float* g_b_item, float* g_w_user, float* g_b_user) {
+    pdl_enter();
     __shared__ float red[128];
     const int nacc_c = 2 * dm.Di + 2 * dm.Du;
     const int nacc_t = dm.Di + 1 + dm.Du + 1;
@@ -749,7 +764,7 @@ void launch_coatt_grad_reduce(cudaStream_t st, const Dims& dm, const float* coat
                               const float* target_partials, int n_target,
                               float* g_w_item, float* g_b_item, float* g_w_user, float* g_b_user) {
     int total = 3 * dm.Di + 1 + 3 * dm.Du + 1;
-    coatt_grad_reduce_kernel<<<total, 128, 0, st>>>(dm, coatt_partials, n_coatt, target_partials, n_target, g_w_item,
+    launch_chain(coatt_grad_reduce_kernel, dim3(total), dim3(128), 0, st, dm, coatt_partials, n_coatt, target_partials, n_target, g_w_item,
                                                     g_b_item, g_w_user, g_b_user);
     ++g_launch_count;
 }

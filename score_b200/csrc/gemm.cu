@@ -14,11 +14,18 @@
 // is 16-byte aligned, 4-byte copies otherwise); each operand is kept in shared memory in the
 // orientation of its contiguous global dimension so the copies never transpose.
 // Split partials are reduced in a fixed order by reduce_partials -> deterministic gradients.
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace score {
 
 int64_t g_launch_count = 0;
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("SCORE_PDL"); on = (e && atoi(e) != 0) ? 1 : 0; }
+    return on == 1;
+}
 
 namespace {
 

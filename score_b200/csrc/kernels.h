@@ -9,6 +9,22 @@ namespace score {
 // Every launcher bumps this (bench.py reports it as gpu_launches).
 extern int64_t g_launch_count;
 
+// Launch of a kernel of the step's critical chain, optionally with programmatic stream serialization (common.cuh:
+// pdl_enter).  Measured on B200 (profiles/README.md): with every chain kernel releasing its successor at entry the
+// Taobao step got 5 % SLOWER (0.430 vs 0.410 ms) - the early CTAs of the successor hold SM slots the side streams
+// would have used - so plain stream order is the default and SCORE_PDL=1 turns the experiment on.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---------------------------------------------------------------- dense layers (gemm.cu)
 enum GemmEpi {
     EPI_STORE = 0,        // C = acc
@@ -57,12 +73,14 @@ struct BatchPtrs {
 };
 
 // LAZY optimizer mode: claim the stale rows among the keys while they are built (see scatter.cu: emb_replay_kernel)
-struct ClaimArgs { int32_t* last_step; const Hyper* hp; int32_t* list; int32_t* counter; };
+// counter: two int32; pingpong != 0: this launch appends through counter[hp->seq & 1] and zeroes the other one (no
+// memset node on the critical path); pingpong == 0: counter[0], zeroed by the launcher
+struct ClaimArgs { int32_t* last_step; const Hyper* hp; int32_t* list; int32_t* counter; int pingpong; };
 void launch_build_keys(cudaStream_t st, const Dims& dm, const BatchPtrs* bp_dev, int32_t* keys, int32_t* label_out,
                        int32_t* length_out, int32_t* err_flag, const ClaimArgs* claim = nullptr);
 // replay the rows of a claim list (2 int32 per entry: row, last step); *counter entries
 void launch_emb_replay(cudaStream_t st, const int32_t* claim_list, const int32_t* claim_counter, int64_t max_rows, float* emb,
-                       float* m, float* v, int d, const float* alpha_hist, const Hyper* hp);
+                       float* m, float* v, int d, const float* alpha_hist, const Hyper* hp, int pingpong = 0);
 
 struct TargetArgs {
     const float* emb; const int32_t* keys;

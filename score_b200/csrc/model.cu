@@ -102,6 +102,7 @@ struct ScoreModel {
     static constexpr int kHyperSlots = 32;
     StepParams* hyper_ring = nullptr; cudaEvent_t hyper_ev[kHyperSlots] = {nullptr}; bool hyper_used[kHyperSlots] = {false};
     int hyper_next = 0;
+    int32_t hyper_seq = 0;
     Hyper* hyper_host = nullptr;
     float* loss_host = nullptr;
     int32_t* err_host = nullptr;
@@ -281,7 +282,8 @@ int alloc_params(ScoreModel* h) {
         if (!t.is_emb)
             for (int64_t i = 0; i < t.rows * t.cols; ++i) fl[t.off + i] = t.flags;
     CK(cudaMemcpy(h->flags, fl.data(), n, cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&h->claim_counter, sizeof(int32_t)));
+    CK(cudaMalloc(&h->claim_counter, 2 * sizeof(int32_t)));   // ping-pong pair (build_keys / emb_replay)
+    CK(cudaMemsetAsync(h->claim_counter, 0, 2 * sizeof(int32_t), h->st));
     CK(cudaMalloc(&h->n_heads_dev, 4 * sizeof(int32_t)));
     CK(cudaMemsetAsync(h->n_heads_dev, 0, 4 * sizeof(int32_t), h->st));
     CK(cudaMalloc(&h->l2sum, sizeof(float) * L2_PARTS));
@@ -780,10 +782,10 @@ void enqueue_step(ScoreModel* h, int mode) {
     probe_begin(h, PR_STEP, h->st);
     if (h->cfg.adam_mode == SCORE_ADAM_LAZY) {
         probe_begin(h, PR_CATCHUP, h->st);
-        ClaimArgs ca{h->last_step, h->hyper_dev, h->claim_list, h->claim_counter};
+        ClaimArgs ca{h->last_step, h->hyper_dev, h->claim_list, h->claim_counter, 1};
         launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag, &ca);
         launch_emb_replay(h->st, h->claim_list, h->claim_counter, dm.N, h->emb, h->emb_m, h->emb_v, dm.d, h->alpha_hist,
-                          h->hyper_dev);
+                          h->hyper_dev, 1);
         probe_end(h, PR_CATCHUP, h->st);
     } else {
         launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag);
@@ -848,7 +850,7 @@ void fill_hyper(ScoreModel* h, int B, float lr, float reg_lambda, float keep_pro
     hp.alpha = lr * sqrtf(one - h->beta2_power) / (one - h->beta1_power);
     hp.inv_batch = 1.0f / (float)(global_batch > 0 ? global_batch : B);
     hp.seed_lo = (uint32_t)h->cfg.seed; hp.seed_hi = (uint32_t)(h->cfg.seed >> 32);
-    hp.step = h->step + 1; hp.batch = B; hp.train = train; hp.pad0 = hp.pad1 = 0;
+    hp.step = h->step + 1; hp.batch = B; hp.train = train; hp.seq = h->hyper_seq++; hp.pad1 = 0;
 }
 
 // fill the next ring slot and enqueue its H2D copy

@@ -56,6 +56,7 @@ void launch_l2_sum(cudaStream_t st, const float* params, const uint8_t* flags, i
 // in the same thread (training path: one launch instead of two on the critical path)
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int splits, int n, float* __restrict__ g,
                                        int64_t d_dst, int64_t d_a, int64_t d_b, int d_count, DenseAdamArgs ad) {
+    pdl_enter();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && ad.p && ad.alpha_hist) ad.alpha_hist[ad.hp->step] = ad.hp->alpha;
     if (i >= n) return;
@@ -93,7 +94,7 @@ void launch_reduce_partials(cudaStream_t st, const float* partials, int splits, 
                             int64_t derive_a, int64_t derive_b, int derive_count, const DenseAdamArgs* adam) {
     DenseAdamArgs ad{};
     if (adam) ad = *adam;
-    reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(partials, splits, n, g, derive_dst, derive_a, derive_b,
+    launch_chain(reduce_partials_kernel, dim3((n + 255) / 256), dim3(256), 0, st, partials, splits, n, g, derive_dst, derive_a, derive_b,
                                                             derive_count, ad);
     ++g_launch_count;
 }
@@ -435,6 +436,7 @@ __device__ __forceinline__ float4 emb_team_combine(const float4& part, int lane)
 
 template <int EXPORT, int LPR>
 __global__ void __launch_bounds__(256) emb_update_kernel(EmbUpdateArgs a) {
+    pdl_enter();
     constexpr int D = LPR * 4;
     constexpr int G = 32 / LPR;          // groups per warp
     constexpr int NGC = 256 / LPR;       // groups per CTA
@@ -537,9 +539,9 @@ __global__ void __launch_bounds__(256) emb_update_kernel(EmbUpdateArgs a) {
 }
 template <int LPR>
 static void emb_update_launch(cudaStream_t st, const EmbUpdateArgs& a, unsigned grid) {
-    if (a.mode == 1) emb_update_kernel<1, LPR><<<grid, 256, 0, st>>>(a);
-    else if (a.mode == 2) emb_update_kernel<2, LPR><<<grid, 256, 0, st>>>(a);
-    else emb_update_kernel<0, LPR><<<grid, 256, 0, st>>>(a);
+    if (a.mode == 1) launch_chain(emb_update_kernel<1, LPR>, dim3(grid), dim3(256), 0, st, a);
+    else if (a.mode == 2) launch_chain(emb_update_kernel<2, LPR>, dim3(grid), dim3(256), 0, st, a);
+    else launch_chain(emb_update_kernel<0, LPR>, dim3(grid), dim3(256), 0, st, a);
 }
 void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a) {
     static int sms = 0;
@@ -633,9 +635,10 @@ __global__ void emb_claim_kernel(const int32_t* __restrict__ keys, int64_t n, in
 }
 __global__ void __launch_bounds__(256) emb_replay_kernel(const int32_t* __restrict__ list, const int32_t* __restrict__ counter,
                                                          float* __restrict__ emb, float* __restrict__ m, float* __restrict__ v,
-                                                         int d, const float* __restrict__ alpha_hist, const Hyper* hp) {
+                                                         int d, const float* __restrict__ alpha_hist, const Hyper* hp, int pingpong) {
+    pdl_enter();
     const int upto = hp->step - 1;
-    const int64_t total = (int64_t)(*counter) * d;
+    const int64_t total = (int64_t)(counter[pingpong ? (hp->seq & 1) : 0]) * d;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = e / d;
         const int c = (int)(e - r * d);
@@ -659,10 +662,10 @@ static int num_sms_cached() {
     return sms;
 }
 void launch_emb_replay(cudaStream_t st, const int32_t* claim_list, const int32_t* claim_counter, int64_t max_rows, float* emb,
-                       float* m, float* v, int d, const float* alpha_hist, const Hyper* hp) {
+                       float* m, float* v, int d, const float* alpha_hist, const Hyper* hp, int pingpong) {
     int64_t want = (max_rows * d + 255) / 256, cap = (int64_t)num_sms_cached() * 8;
     if (want < 1) want = 1;
-    emb_replay_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(claim_list, claim_counter, emb, m, v, d, alpha_hist, hp);
+    launch_chain(emb_replay_kernel, dim3((unsigned)(want < cap ? want : cap)), dim3(256), 0, st, claim_list, claim_counter, emb, m, v, d, alpha_hist, hp, pingpong);
     ++g_launch_count;
 }
 void launch_emb_catchup_rows(cudaStream_t st, const int32_t* keys, int64_t n, int64_t V, float* emb, float* m, float* v,
@@ -672,6 +675,7 @@ void launch_emb_catchup_rows(cudaStream_t st, const int32_t* keys, int64_t n, in
     emb_claim_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, n, V, last_step, hp, claim_list, claim_counter);
     ++g_launch_count;
     launch_emb_replay(st, claim_list, claim_counter, n, emb, m, v, d, alpha_hist, hp);
+    cudaMemsetAsync(claim_counter, 0, 2 * sizeof(int32_t), st);   // leave the ping-pong pair of the fused path clean
 }
 __global__ void emb_catchup_all_kernel(float* __restrict__ emb, float* __restrict__ m, float* __restrict__ v,
                                        int32_t* __restrict__ last_step, int64_t V, int d,

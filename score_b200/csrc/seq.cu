@@ -15,6 +15,7 @@ namespace score {
 // steps), so the only global loads inside it - the hoisted input projections px - are prefetched one step ahead, and
 // the loop stops at the longest length of the CTA's rows (later steps only store the zero outputs).
 __global__ void gru_fwd_kernel(Dims dm, GruArgs a, int RB) {
+    pdl_enter();
     extern __shared__ float sm[];
     __shared__ int s_tmax;
     const int H = dm.H, H2 = 2 * dm.H, T = dm.T;
@@ -109,7 +110,7 @@ void launch_gru_fwd(cudaStream_t st, const Dims& dm, const GruArgs& a) {
         attr_set = smem;
     }
     dim3 block(2 * dm.H, RB), grid((dm.B + RB - 1) / RB, 2);
-    gru_fwd_kernel<<<grid, block, smem, st>>>(dm, a, RB);
+    launch_chain(gru_fwd_kernel, dim3(grid), dim3(block), smem, st, dm, a, RB);
     ++g_launch_count;
 }
 
@@ -118,6 +119,7 @@ void launch_gru_fwd(cudaStream_t st, const Dims& dm, const GruArgs& a) {
 // Same latency structure as the forward pass: the saved activations of step t-1 are prefetched while step t runs, and
 // steps beyond the longest length of the CTA's rows only store their zero gradients.
 __global__ void gru_bwd_kernel(Dims dm, GruBwdArgs a, int RB) {
+    pdl_enter();
     extern __shared__ float sm[];
     __shared__ int s_tmax;
     const int H = dm.H, H2 = 2 * dm.H, T = dm.T;
@@ -225,7 +227,7 @@ void launch_gru_bwd(cudaStream_t st, const Dims& dm, const GruBwdArgs& a) {
         attr_set = smem;
     }
     dim3 block(2 * dm.H, RB), grid((dm.B + RB - 1) / RB, 2);
-    gru_bwd_kernel<<<grid, block, smem, st>>>(dm, a, RB);
+    launch_chain(gru_bwd_kernel, dim3(grid), dim3(block), smem, st, dm, a, RB);
     ++g_launch_count;
 }
 
