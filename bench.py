@@ -161,7 +161,8 @@ def workload_config(shape, args, global_batch):
             "ids": "uniform" if not args.zipf else "zipf %.2f" % args.zipf,
             "adam": args.adam_mode, "cuda_graph": not args.no_graph,
             "parallelism": {"single": "single GPU",
-                            "dp": "dp%d: replicated table, dense all-reduce + embedding-gradient all-gather" % args.gpus,
+                            "dp": "dp%d: replicated table, ONE all-gather per step of packed blocks (dense gradient + one embedding-"
+                                  "gradient row per unique id), rank-ordered deterministic reduce on every replica" % args.gpus,
                             "sharded": "dp%d dense + embedding rows sharded by id %% %d, all-to-all of ids / rows / gradient rows"
                                        % (args.gpus, args.gpus)}[getattr(args, "par", "single")],
             "l2_policy": "inputs larger than L2: %.2f GB of embedding state (var+m+v), uniform-random rows, %d rotating "

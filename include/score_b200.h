@@ -138,9 +138,10 @@ int score_eval_metrics(ScoreHandle h, const float* preds, const int32_t* target_
 /* Multi-GPU split step (one process per GPU; the collectives themselves are issued by the host side with
  * torch.distributed / NCCL on score_stream(), between these calls).  There is no reference counterpart: the
  * reference is single-device; the split keeps SCOREBASE.train's arithmetic.
- *   data-parallel, replicated table:  score_step_begin -> all-reduce "dense_grad" -> score_local_reduce (one
- *       gradient row per unique id) -> all-gather of those keys / rows -> score_step_finish(gathered keys, gathered
- *       rows)  (identical deterministic update on every replica)
+ *   data-parallel, replicated table:  score_step_begin -> score_dp_local_count (early, from the sort branch) ->
+ *       counts exchanged -> score_dp_pack(cap) -> ONE all-gather of the packed blocks (dense gradient + one embedding-
+ *       gradient row per unique id, ascending) -> score_dp_finish  (rank-ordered sums, merge instead of sort; the
+ *       identical deterministic update on every replica)
  *   row-sharded table (owner = id % world):  score_prepare_batch -> all-to-all ids -> score_gather_rows on the
  *       owners -> all-to-all rows -> score_step_begin(staged table) -> all-reduce "dense_grad", all-to-all
  *       "grad_rows" to the owners -> score_step_finish(owned keys, owned rows).                              */
@@ -149,9 +150,15 @@ int score_device_buffer(ScoreHandle h, const char* name, void** dev_ptr, size_t*
 int score_gather_rows(ScoreHandle h, const int32_t* idx_dev, int64_t n, float* out_dev);
 int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg_lambda, float keep_prob,
                      int32_t global_batch, int32_t train, const float* staged_table, const int32_t* staged_keys);
-/* data-parallel only: this rank's gradient rows reduced to one row per unique id (device pointers owned by the
- * handle: keys int32 [N] with zeros past *count, rows float [N, d], count int32) - what the all-gather carries. */
-int score_local_reduce(ScoreHandle h, void** keys_dev, void** rows_dev, void** count_dev);
+/* data-parallel only (see above).  A block of one rank is score_dp_block_words(cap) 4-byte words:
+ *   [0,128) header {unique-row count, step sequence number, loss, L2 part}; [128, +n_dense) dense gradient;
+ *   then cap ids (int32, ascending, zero-padded) and cap rows of eb_dim floats.  cap: multiple of 1024, the same on
+ *   every rank, >= every rank's count.  score_dp_finish: loss_out == NULL enqueues only; otherwise *loss_out = the
+ *   global loss (sum of the ranks' data terms, each scaled by 1/global_batch, + the L2 term). */
+int score_dp_local_count(ScoreHandle h, int32_t* count_out);
+int64_t score_dp_block_words(ScoreHandle h, int64_t cap);
+int score_dp_pack(ScoreHandle h, int64_t cap, void** block_dev, int64_t* block_words);
+int score_dp_finish(ScoreHandle h, const void* gathered_blocks_dev, int32_t world, int64_t cap, double* loss_out);
 /* loss2 == NULL: enqueue only (no host synchronisation); otherwise loss2[0] = this rank's loss incl. the L2 term
  * (data term scaled by 1/global_batch), loss2[1] = the L2 term alone. */
 int score_step_finish(ScoreHandle h, const int32_t* ext_keys, const float* ext_rows, int64_t n_ext, float* loss2);

@@ -57,7 +57,10 @@ SYMBOLS = {
     "score_device_buffer": (C.c_int, [_H, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "score_gather_rows": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p]),
     "score_step_begin": (C.c_int, [_H, C.POINTER(ScoreBatch), _F, _F, _F, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
-    "score_local_reduce": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "score_dp_local_count": (C.c_int, [_H, C.POINTER(C.c_int32)]),
+    "score_dp_block_words": (C.c_int64, [_H, C.c_int64]),
+    "score_dp_pack": (C.c_int, [_H, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "score_dp_finish": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_double)]),
     "score_step_finish": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "score_stream": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "score_launch_count": (C.c_int64, [_H]),

@@ -9,7 +9,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libscore_b200.so")
+# SCORE_B200_LIB: load / build another library file (compile-time variants for A/B runs, tools/build_variants.py)
+LIB = os.environ.get("SCORE_B200_LIB") or os.path.join(HERE, "libscore_b200.so")
 SOURCES = ["gemm.cu", "embed.cu", "seq.cu", "chain.cu", "attn.cu", "scatter.cu", "metrics.cu", "sampler.cu", "model.cu"]
 HEADERS = ["common.cuh", "tile.cuh", "kernels.h", os.path.join("..", "..", "include", "score_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -31,18 +32,19 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu into one shared library; returns its path."""
-    if not force and not is_stale():
+def build_library(force: bool = False, verbose: bool = False, defines=(), variant_path: str = "") -> str:
+    """Compile every .cu into one shared library; returns its path.  defines / out: a compile-time variant."""
+    if not force and not is_stale() and not variant_path:
         return LIB
     nvcc = _nvcc()
     objs = []
-    build_dir = os.path.join(HERE, "build")
+    build_dir = os.path.join(HERE, "build" + ("_" + os.path.basename(variant_path)[:-3] if variant_path else ""))
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False
@@ -53,9 +55,10 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-cudart", "static"]
+    target = variant_path or LIB
+    cmd = [nvcc, "-shared", "-o", target] + objs + ["-cudart", "static"]
     subprocess.run(cmd, check=True)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

@@ -295,10 +295,31 @@ struct EmbUpdateArgs {
     const float* alpha_hist;       // LAZY: rows that are not current through step-1 are replayed first (may be null)
     const Hyper* hp;
     int mode;                      // 0: apply Adam; 1 / 2: export the run sums to out_rows / out_heads at the run's first sorted
-                                   // index / at its compact slot (0 .. runs-1), no update
+                                   // index / at head_slot[first sorted index] (compact, ascending by key), no update
     float* out_rows; int32_t* out_heads;
+    const int32_t* head_slot; int64_t out_cap;   // mode 2 (launch_head_slots); out_cap = capacity of the compact list
 };
 void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a);
+
+// ---- data-parallel exchange (replicated table): every rank contributes ONE packed block of int32 / float words
+//   [0,128)                      header: unique-row count, step sequence number, loss (total, L2 part) as float bits
+//   [dense_off, +n_dense)        this rank's dense gradient (flat buffer, 1/global_batch scaling applied)
+//   [keys_off, +cap)             unique row ids, ascending, zeros past the count
+//   [keys_off+cap, +cap*d)       one gradient row per id
+// blocks of all ranks lie `stride` words apart in the gathered buffer `base`; every offset is a multiple of 128 words,
+// so a gradient row is addressable as row (word offset / d) of the buffer viewed as [*, d] floats.
+struct DpLayout { const int32_t* base; int world; int d; int64_t stride, dense_off, keys_off, cap; };
+int64_t head_slot_tiles(int64_t n);
+// head_slot[i] = number of run heads before sorted index i, written at run heads only; tile_counts: head_slot_tiles(n) ints
+void launch_head_slots(cudaStream_t st, const int32_t* skeys, int64_t n, int32_t* tile_counts, int32_t* head_slot);
+void launch_dp_count(cudaStream_t st, const int32_t* counters, const Hyper* hp, int32_t* slot);
+void launch_dp_header(cudaStream_t st, int32_t* block, const int32_t* counters, const Hyper* hp, const float* loss_dev);
+// (key, rank)-ordered merge of the ranks' ascending key lists: skeys / spos [world*cap] like a stable sort's output
+void launch_dp_merge(cudaStream_t st, const DpLayout& L, int32_t* skeys, int32_t* spos, int32_t* err_flag);
+// rank-ordered sum of the gathered dense gradients + dense Adam; loss_out[0] = global loss (double)
+void launch_dp_dense_adam(cudaStream_t st, const DpLayout& L, float* p, float* m, float* v, float* g_out,
+                          const uint8_t* flags, int n, const Hyper* hp, float* alpha_hist, double* loss_out);
+
 // DENSE mode: zero-gradient Adam step for every row whose last_step != hp->step
 void launch_emb_dense_sweep(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d,
                             const Hyper* hp);

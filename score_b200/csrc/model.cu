@@ -114,9 +114,18 @@ struct ScoreModel {
     SortBufs sb_ext{}; int64_t sb_ext_cap = 0;
     bool local_sorted = false;   // score_step_begin sorted this rank's own keys (side stream)
     std::map<int, cudaGraphExec_t> graphs_begin; std::map<int, int64_t> graph_kernels_begin; std::map<int, int> warm_begin;
-    cudaEvent_t ev_keys = nullptr, ev_fc = nullptr;
+    cudaEvent_t ev_keys = nullptr, ev_fc = nullptr, ev_att = nullptr, ev_qb = nullptr;
+    bool sort_deferred = false;   // enqueue_forward forks the sort branch right after the gather kernel
     bool begun = false; float begun_lr = 0.f;
     const int32_t* last_sorted = nullptr; int64_t last_sorted_n = 0;   // sorted key list of the last optimizer step
+    // data-parallel packed exchange (score_dp_*): rank of every run head (compact sorted export), the early unique-row
+    // count for the host (its own stream + event, so reading it never drains the main stream), this rank's block
+    int32_t *head_slot = nullptr, *hs_tiles = nullptr;          // workspace (per capacity)
+    int32_t *cnt_slot = nullptr, *cnt_host = nullptr;           // {count, step sequence number}: device / pinned host
+    cudaStream_t st_cnt = nullptr; cudaEvent_t ev_counts = nullptr;
+    int32_t begin_seq = -1; bool warned_stale = false;
+    int32_t* dp_block = nullptr; int64_t dp_block_words = 0;
+    double *loss_glob = nullptr, *loss_glob_host = nullptr;
 
     // graphs
     std::map<int, cudaGraphExec_t> graphs_train;
@@ -418,6 +427,8 @@ int ensure_workspace(ScoreModel* h, int B) {
         if (rc) return rc;
         h->sb.hist = hist;
     }
+    WSI(h->head_slot, N, nullptr);
+    WSI(h->hs_tiles, head_slot_tiles(N) + 1, nullptr);
     h->seg_rows = nullptr; h->seg_heads = nullptr; h->seg_cap = 0;
     h->cap_B = cap;
     CK(cudaStreamSynchronize(h->st));
@@ -547,6 +558,18 @@ void probe_end(ScoreModel* h, int p, cudaStream_t s) {
 
 enum StepMode { MODE_TRAIN = 0, MODE_EVAL = 1, MODE_FWDBWD = 2, MODE_BEGIN = 3 };
 
+int key_bits(int64_t V);
+// radix sort of the batch's (key, position) pairs + run descriptors on the sort stream, forked at `after`
+void enqueue_sort_branch(ScoreModel* h, cudaEvent_t after) {
+    const Dims& dm = h->dm;
+    cudaStreamWaitEvent(h->st2, after, 0);
+    probe_begin(h, PR_SORT, h->st2);
+    h->sort_out = launch_sort_pairs(h->st2, h->sb, h->keys, dm.N, key_bits(dm.V));
+    launch_emb_runs(h->st2, h->sb.keys[h->sort_out], h->sb.vals[h->sort_out], dm.N, h->sb.runs, h->sb.runs_long, h->n_heads_dev);
+    probe_end(h, PR_SORT, h->st2);
+    cudaEventRecord(h->ev_join, h->st2);
+}
+
 // forward graph of class SCORE (score.py:188-224); everything enqueued on h->st
 void enqueue_forward(ScoreModel* h, bool will_bwd) {
     const Dims& dm = h->dm;
@@ -592,6 +615,11 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
     probe_begin(h, PR_COATT_FWD, h->st);
     launch_coatt_fwd(h->st, dm, ca);
     probe_end(h, PR_COATT_FWD, h->st);
+    if (h->sort_deferred) {
+        cudaEventRecord(h->ev_keys, h->st);
+        enqueue_sort_branch(h, h->ev_keys);
+        h->sort_deferred = false;
+    }
 
     probe_begin(h, PR_FWD_DENSE, h->st);
     const char* sides[2] = {"gru_user_side", "gru_item_side"};
@@ -643,7 +671,17 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
 }
 
 // fused_adam: the dense Adam step rides on the final gradient reduce (single-GPU training step)
-void enqueue_backward(ScoreModel* h, bool fused_adam = false) {
+// scheduling knobs (measured on B200, profiles/README.md); SCORE_SCHED=0 restores the serial order
+static int sched_flags() {
+    static int f = -1;
+    if (f < 0) { const char* e = getenv("SCORE_SCHED"); f = e ? atoi(e) : 7; }
+    return f;
+}
+static bool side_qb() { return (sched_flags() & 1) != 0; }        // att_qb on the side stream
+static bool side_reduce() { return (sched_flags() & 2) != 0; }    // final dense reduce + Adam next to the embedding update
+static bool sort_after_gather() { return (sched_flags() & 4) != 0; }   // sort branch forks after the gather kernel
+
+void enqueue_backward(ScoreModel* h, bool fused_adam = false, bool defer_join = false) {
     DenseAdamArgs adam_args{h->P, h->M1, h->V1, h->flags, h->hyper_dev, h->alpha_hist};
     const DenseAdamArgs* adam = fused_adam ? &adam_args : nullptr;
     const Dims& dm = h->dm;
@@ -689,11 +727,19 @@ void enqueue_backward(ScoreModel* h, bool fused_adam = false) {
         w1l[1] = gemm_bwd_weight_args(h, h->qk, Dk, h->df1, 80, Wo(nm.att1) + 3 * blk, -1, M, Dk, 80);   // dWd = (q*key)^T df1
         w1l[2] = gemm_bwd_weight_args(h, h->f1, 80, h->df2, 40, Wo(nm.att2), Bo(nm.att2), M, 80, 40);
         w1l[3] = gemm_bwd_weight_args(h, h->f2, 40, h->ds, 1, Wo(nm.att3), Bo(nm.att3), M, 40, 1);
-        gemm_bwd_weight_batch(h, w1l, 4);
+        // query side of the attention backward (per sample): only target_bwd and two weight gradients consume it, so it
+        // leaves the critical path (the GRU backward does not wait for it) and runs first on the side stream
         AttQbArgs qb{};
         qb.B = B; qb.Ds = Ds; qb.Dk = Dk; qb.sdf1 = h->sdf1; qb.dqD = h->dqD; qb.WacT = h->Dv + h->dv_WacT;
         qb.WqT = h->Dv + h->dv_WqT; qb.dq = h->dq; qb.dq0 = h->dq0;
-        launch_att_qb(h->st, qb);
+        if (side_qb()) {
+            cudaEventRecord(h->ev_att, h->st);
+            cudaStreamWaitEvent(h->st_w, h->ev_att, 0);
+            launch_att_qb(h->st_w, qb);
+            cudaEventRecord(h->ev_qb, h->st_w);
+        }
+        gemm_bwd_weight_batch(h, w1l, 4);
+        if (!side_qb()) launch_att_qb(h->st, qb);
         GemmArgs wql[2];
         wql[0] = gemm_bwd_weight_args(h, h->q, Dk, h->sdf1, 80, Wo(nm.att1), Bo(nm.att1), B, Dk, 80);    // dWa = q^T sum_t df1
         wql[1] = gemm_bwd_weight_args(h, h->q0, Ds, h->dq, Dk, Wo(nm.att_q), Bo(nm.att_q), B, Ds, Dk);
@@ -743,20 +789,34 @@ void enqueue_backward(ScoreModel* h, bool fused_adam = false) {
     tb.q0 = h->q0; tb.dq0 = has_att ? h->dq0 : nullptr;
     tb.dfc_in = h->dfc_in; tb.fc_off = Dfc - Ds; tb.ldfc = Dfc; tb.sdz = h->sdz; tb.grad_rows = h->grad_rows;
     tb.partials = h->target_part; tb.n_partials = h->n_target_part;
+    if (has_att && side_qb()) cudaStreamWaitEvent(h->st, h->ev_qb, 0);
     launch_target_bwd(h->st, dm, tb);
+    // Final reduce of the dense gradients (+ fused dense Adam).  defer_join: it runs on the side stream, next to the
+    // embedding update that follows on the main stream (neither reads what the other writes); the caller joins with
+    // join_dense() afterwards.
+    cudaStream_t rs = h->st;
+    if (defer_join) {
+        cudaEventRecord(h->ev_att, h->st);
+        cudaStreamWaitEvent(h->st_w, h->ev_att, 0);
+        rs = h->st_w;
+    }
     if (has_coatt)
-        launch_coatt_grad_reduce(h->st, dm, h->coatt_part, h->n_coatt_part, h->target_part, h->n_target_part,
+        launch_coatt_grad_reduce(rs, dm, h->coatt_part, h->n_coatt_part, h->target_part, h->n_target_part,
                                  h->PG + Wo(nm.co_item), h->PG + Bo(nm.co_item), h->PG + Wo(nm.co_user),
                                  h->PG + Bo(nm.co_user));
-    cudaEventRecord(h->ev_w, h->st_w);
-    cudaStreamWaitEvent(h->st, h->ev_w, 0);
+    if (!defer_join) {
+        cudaEventRecord(h->ev_w, h->st_w);
+        cudaStreamWaitEvent(h->st, h->ev_w, 0);
+    }
     if (has_att) {   // dWc = dWa - dWb (attn.cu header)
         const int64_t w1 = po(h, (nm.att1 + "/kernel").c_str()), blk = (int64_t)Dk * 80;
-        launch_reduce_partials(h->st, h->PG, kSplits, (int)h->n_dense, h->G, w1 + 2 * blk, w1, w1 + blk, (int)blk, adam);
+        launch_reduce_partials(rs, h->PG, kSplits, (int)h->n_dense, h->G, w1 + 2 * blk, w1, w1 + blk, (int)blk, adam);
     } else {
-        launch_reduce_partials(h->st, h->PG, kSplits, (int)h->n_dense, h->G, -1, 0, 0, 0, adam);
+        launch_reduce_partials(rs, h->PG, kSplits, (int)h->n_dense, h->G, -1, 0, 0, 0, adam);
     }
+    if (defer_join) cudaEventRecord(h->ev_w, h->st_w);
 }
+void join_dense(ScoreModel* h) { cudaStreamWaitEvent(h->st, h->ev_w, 0); }
 
 int key_bits(int64_t V) {
     int bits = 1;
@@ -791,17 +851,14 @@ void enqueue_step(ScoreModel* h, int mode) {
         launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag);
     }
     cudaEventRecord(h->ev_fork, h->st);
-    if (need_bwd) {   // the sort depends on ids only: run it on the side stream under forward/backward
-        cudaStreamWaitEvent(h->st2, h->ev_fork, 0);
-        probe_begin(h, PR_SORT, h->st2);
-        h->sort_out = launch_sort_pairs(h->st2, h->sb, h->keys, dm.N, key_bits(dm.V));
-        launch_emb_runs(h->st2, h->sb.keys[h->sort_out], h->sb.vals[h->sort_out], dm.N, h->sb.runs, h->sb.runs_long, h->n_heads_dev);
-        probe_end(h, PR_SORT, h->st2);
-        cudaEventRecord(h->ev_join, h->st2);
-    }
+    // the sort depends on ids only: it runs on the side stream under forward/backward - forked after the gather kernel
+    // (the one bandwidth-bound kernel of the forward pass does not share the SMs with it) or right here
+    h->sort_deferred = need_bwd && sort_after_gather();
+    if (need_bwd && !h->sort_deferred) enqueue_sort_branch(h, h->ev_fork);
     enqueue_forward(h, need_bwd);
+    const bool defer = train && side_reduce();
     if (need_bwd) {
-        enqueue_backward(h, train);
+        enqueue_backward(h, train, defer);
         cudaStreamWaitEvent(h->st, h->ev_join, 0);
     }
     if (mode == MODE_FWDBWD) {
@@ -829,6 +886,7 @@ void enqueue_step(ScoreModel* h, int mode) {
         if (h->cfg.adam_mode == SCORE_ADAM_DENSE)
             launch_emb_dense_sweep(h->st, h->emb, h->emb_m, h->emb_v, h->last_step, dm.V, dm.d, h->hyper_dev);
     }
+    if (defer) join_dense(h);
     probe_end(h, PR_STEP, h->st);
 }
 
@@ -888,7 +946,9 @@ int finish_sync(ScoreModel* h, float* loss_out) {
     }
     if (loss_out) *loss_out = *h->loss_host;
     if (*h->err_host) {
+        const int32_t code = *h->err_host;
         cudaMemsetAsync(h->err_flag, 0, sizeof(int32_t), h->st);
+        if (code == 2) return fail(h, SCORE_ERR_ARG, "data-parallel exchange: a rank's unique-row count exceeds the block capacity");
         return fail(h, SCORE_ERR_ID_RANGE, "an id in the batch is outside [0, feature_size)");
     }
     return SCORE_OK;
@@ -1014,6 +1074,8 @@ int score_create(const ScoreConfig* cfg, int device, ScoreHandle* out) {
         cudaEventCreateWithFlags(&h->ev_prep, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_keys, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fc, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_att, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_qb, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         h->err = "stream/event creation failed";
         return die(SCORE_ERR_CUDA);
@@ -1050,6 +1112,8 @@ int score_destroy(ScoreHandle h) {
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_keys) cudaEventDestroy(h->ev_keys);
     if (h->ev_fc) cudaEventDestroy(h->ev_fc);
+    if (h->ev_att) cudaEventDestroy(h->ev_att);
+    if (h->ev_qb) cudaEventDestroy(h->ev_qb);
     if (h->ev_l2) cudaEventDestroy(h->ev_l2);
     if (h->ev_w) cudaEventDestroy(h->ev_w);
     if (h->ev_tgt) cudaEventDestroy(h->ev_tgt);
@@ -1062,6 +1126,13 @@ int score_destroy(ScoreHandle h) {
         cudaStreamDestroy(h->st);
     }
     if (h->st2) cudaStreamDestroy(h->st2);
+    if (h->st_cnt) cudaStreamDestroy(h->st_cnt);
+    if (h->ev_counts) cudaEventDestroy(h->ev_counts);
+    if (h->cnt_slot) cudaFree(h->cnt_slot);
+    if (h->cnt_host) cudaFreeHost(h->cnt_host);
+    if (h->dp_block) cudaFree(h->dp_block);
+    if (h->loss_glob) cudaFree(h->loss_glob);
+    if (h->loss_glob_host) cudaFreeHost(h->loss_glob_host);
     delete h;
     return SCORE_OK;
 }
@@ -1396,6 +1467,29 @@ int ensure_ext_sort(ScoreModel* h, int64_t n) {
     return SCORE_OK;
 }
 
+// streams / scalars of the packed data-parallel exchange (created on first use)
+int ensure_dp(ScoreModel* h) {
+    if (h->st_cnt) return SCORE_OK;
+    CK(cudaStreamCreateWithFlags(&h->st_cnt, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_counts, cudaEventDisableTiming));
+    CK(cudaMalloc(&h->cnt_slot, 2 * sizeof(int32_t)));
+    CK(cudaMemset(h->cnt_slot, 0xff, 2 * sizeof(int32_t)));
+    CK(cudaMallocHost(&h->cnt_host, 2 * sizeof(int32_t)));
+    CK(cudaMalloc(&h->loss_glob, sizeof(double)));
+    CK(cudaMemset(h->loss_glob, 0, sizeof(double)));
+    CK(cudaMallocHost(&h->loss_glob_host, sizeof(double)));
+    return SCORE_OK;
+}
+
+DpLayout dp_layout(const ScoreModel* h, const void* base, int world, int64_t cap) {
+    DpLayout L{};
+    L.base = static_cast<const int32_t*>(base); L.world = world; L.d = h->dm.d; L.cap = cap;
+    L.dense_off = 128;
+    L.keys_off = L.dense_off + (h->n_dense + 127) / 128 * 128;
+    L.stride = L.keys_off + cap + cap * h->dm.d;
+    return L;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1489,6 +1583,8 @@ int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg
         if (rc) return rc;
     }
     h->last_mode = MODE_BEGIN;
+    h->begin_seq = h->hyper_host->seq;
+    if (train && !staged_table) { int rc = ensure_dp(h); if (rc) return rc; }
     const bool with_keys = batch != nullptr;
     auto enqueue_begin = [&]() {
         cudaEventRecord(h->ev_fork, h->st);
@@ -1506,6 +1602,10 @@ int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg
             cudaStreamWaitEvent(h->st2, h->ev_keys, 0);
             h->sort_out = launch_sort_pairs(h->st2, h->sb, h->keys, dm.N, key_bits(dm.V));
             launch_emb_runs(h->st2, h->sb.keys[h->sort_out], h->sb.vals[h->sort_out], dm.N, h->sb.runs, h->sb.runs_long, h->n_heads_dev);
+            // the host sizes the exchange from the unique-row count: publish it as soon as it exists (score_dp_local_count)
+            launch_dp_count(h->st2, h->n_heads_dev, h->hyper_dev, h->cnt_slot);
+            cudaEventRecordWithFlags(h->ev_counts, h->st2, h->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+            launch_head_slots(h->st2, h->sb.keys[h->sort_out], dm.N, h->hs_tiles, h->head_slot);
             cudaEventRecord(h->ev_join, h->st2);
         }
         enqueue_forward(h, train != 0);
@@ -1549,28 +1649,111 @@ int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg
     return SCORE_OK;
 }
 
-// Data-parallel, replicated table: reduce this rank's per-position gradient rows to ONE row per unique id before the
-// exchange (deterministic segment reduce of scatter.cu, export mode), so the all-gather carries unique rows instead
-// of positions.  Outputs are device pointers owned by the handle: keys [N] int32 (slots past *count hold 0),
-// rows [N, d] float, count = number of unique non-zero ids.  Call between score_step_begin and score_step_finish.
-int score_local_reduce(ScoreHandle h, void** keys_dev, void** rows_dev, void** count_dev) {
-    if (!h || !keys_dev || !rows_dev || !count_dev) return SCORE_ERR_ARG;
-    if (!h->begun || !h->local_sorted) return fail(h, SCORE_ERR_ARG, "score_local_reduce needs a training score_step_begin on the handle's own table");
+// ---- data-parallel, replicated table: the packed exchange (kernels.h: DpLayout) --------------------------------
+// Number of unique non-zero ids of the batch score_step_begin was given.  The count comes from the sort branch, which
+// finishes long before forward/backward: the host waits for THAT (own stream + event), not for the main stream, so the
+// device never idles while the exchange is being sized.
+int score_dp_local_count(ScoreHandle h, int32_t* count_out) {
+    if (!h || !count_out) return SCORE_ERR_ARG;
+    if (!h->begun || !h->local_sorted) return fail(h, SCORE_ERR_ARG, "score_dp_local_count needs a training score_step_begin on the handle's own table");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamWaitEvent(h->st_cnt, h->ev_counts, 0));
+    CK(cudaMemcpyAsync(h->cnt_host, h->cnt_slot, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st_cnt));
+    CK(cudaStreamSynchronize(h->st_cnt));
+    if (h->cnt_host[1] != h->begin_seq) {
+        // the event did not cover this step's launch (should not happen): fall back to draining the main stream
+        if (!h->warned_stale) { fprintf(stderr, "score_b200: early count not ready (seq %d != %d), synchronising the step\n", h->cnt_host[1], h->begin_seq); h->warned_stale = true; }
+        CK(cudaStreamSynchronize(h->st));
+        CK(cudaMemcpy(h->cnt_host, h->cnt_slot, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (h->cnt_host[1] != h->begin_seq) return fail(h, SCORE_ERR_CUDA, "unique-row count of the step is missing");
+    }
+    *count_out = h->cnt_host[0];
+    return SCORE_OK;
+}
+
+// words (4 bytes each) of one rank's block for a list capacity of `cap` rows
+int64_t score_dp_block_words(ScoreHandle h, int64_t cap) {
+    if (!h || cap <= 0) return 0;
+    return dp_layout(h, nullptr, 1, cap).stride;
+}
+
+// Assemble this rank's block (device memory owned by the handle, valid until the next call): header, dense gradient,
+// and its embedding gradient reduced to ONE row per unique id (deterministic segment reduce of scatter.cu in export
+// mode), ascending by id.  cap: capacity of the id / row lists, a multiple of 1024 and >= every rank's count (all ranks
+// must use the same value).  Call between score_step_begin and score_dp_finish; the all-gather of the blocks is the
+// caller's (NCCL on score_stream()).
+int score_dp_pack(ScoreHandle h, int64_t cap, void** block_dev, int64_t* block_words) {
+    if (!h || !block_dev || !block_words) return SCORE_ERR_ARG;
+    if (!h->begun || !h->local_sorted) return fail(h, SCORE_ERR_ARG, "score_dp_pack needs a training score_step_begin on the handle's own table");
+    if (cap <= 0 || cap % 1024) return fail(h, SCORE_ERR_ARG, "cap must be a positive multiple of 1024");
     CK(cudaSetDevice(h->device));
     const Dims& dm = h->dm;
-    int rc = ensure_seg(h, dm.N);
-    if (rc) return rc;
-    // the sort branch has already been joined into the main stream by score_step_begin
-    cudaMemsetAsync(h->seg_heads, 0, sizeof(int32_t) * dm.N, h->st);
+    const DpLayout L = dp_layout(h, nullptr, 1, cap);
+    if (L.stride > h->dp_block_words) {
+        CK(cudaStreamSynchronize(h->st));
+        if (h->dp_block) cudaFree(h->dp_block);
+        h->dp_block = nullptr; h->dp_block_words = 0;
+        const int64_t words = L.stride + L.stride / 4;
+        CK(cudaMalloc(&h->dp_block, sizeof(int32_t) * words));
+        CK(cudaMemsetAsync(h->dp_block, 0, sizeof(int32_t) * words, h->st));
+        h->dp_block_words = words;
+    }
+    int32_t* blk = h->dp_block;
+    // the sort branch and the loss branch have been joined into the main stream by score_step_begin
+    launch_dp_header(h->st, blk, h->n_heads_dev, h->hyper_dev, h->loss_dev);
+    CK(cudaMemcpyAsync(blk + L.dense_off, h->G, sizeof(float) * h->n_dense, cudaMemcpyDeviceToDevice, h->st));
+    CK(cudaMemsetAsync(blk + L.keys_off, 0, sizeof(int32_t) * cap, h->st));
     EmbUpdateArgs ea{};
     ea.skeys = h->sb.keys[h->sort_out]; ea.spos = h->sb.vals[h->sort_out]; ea.n = dm.N;
     ea.runs = h->sb.runs; ea.runs_long = h->sb.runs_long; ea.long_cap = emb_runs_long_cap(dm.N); ea.counters = h->n_heads_dev;
     ea.grad_rows = h->grad_rows; ea.d = dm.d; ea.hp = h->hyper_dev; ea.mode = 2;
-    ea.out_rows = h->seg_rows; ea.out_heads = h->seg_heads;
+    ea.out_heads = blk + L.keys_off; ea.out_rows = reinterpret_cast<float*>(blk + L.keys_off + cap);
+    ea.head_slot = h->head_slot; ea.out_cap = cap;
     launch_emb_update(h->st, ea);
-    *keys_dev = h->seg_heads; *rows_dev = h->seg_rows; *count_dev = h->n_heads_dev + 3;
+    *block_dev = blk; *block_words = L.stride;
     CK(cudaGetLastError());
     return SCORE_OK;
+}
+
+// Optimizer half of the data-parallel step on the gathered blocks of all ranks (`gathered`: world blocks of
+// score_dp_block_words(cap) words, rank order, device memory): dense gradients summed in rank order + dense Adam; the
+// ranks' id lists merged into (id, rank) order (no sort: every list is already ascending), rows of one id added in
+// rank order, fused row Adam - the same update on every replica, bit for bit.
+// loss_out == NULL: enqueue only; otherwise *loss_out = the GLOBAL loss (sum of the ranks' data terms + the L2 term).
+int score_dp_finish(ScoreHandle h, const void* gathered, int32_t world, int64_t cap, double* loss_out) {
+    if (!h || !gathered || world < 1) return SCORE_ERR_ARG;
+    if (!h->begun) return fail(h, SCORE_ERR_ARG, "score_dp_finish needs score_step_begin");
+    if (cap <= 0 || cap % 1024) return fail(h, SCORE_ERR_ARG, "cap must be a positive multiple of 1024");
+    CK(cudaSetDevice(h->device));
+    const DpLayout L = dp_layout(h, gathered, world, cap);
+    const int64_t n_ext = (int64_t)world * cap;
+    if (n_ext >= ((int64_t)1 << 31) || (int64_t)world * L.stride / L.d >= ((int64_t)1 << 31))
+        return fail(h, SCORE_ERR_ARG, "gathered lists too large for int32 positions");
+    launch_dp_dense_adam(h->st, L, h->P, h->M1, h->V1, h->G, h->flags, (int)h->n_dense, h->hyper_dev, h->alpha_hist, h->loss_glob);
+    int rc = ensure_ext_sort(h, n_ext);
+    if (rc) return rc;
+    launch_dp_merge(h->st, L, h->sb_ext.keys[0], h->sb_ext.vals[0], h->err_flag);
+    launch_emb_runs(h->st, h->sb_ext.keys[0], h->sb_ext.vals[0], n_ext, h->sb_ext.runs, h->sb_ext.runs_long, h->n_heads_dev);
+    EmbUpdateArgs ea{};
+    ea.skeys = h->sb_ext.keys[0]; ea.spos = h->sb_ext.vals[0]; ea.n = n_ext;
+    ea.runs = h->sb_ext.runs; ea.runs_long = h->sb_ext.runs_long; ea.long_cap = emb_runs_long_cap(n_ext); ea.counters = h->n_heads_dev;
+    ea.grad_rows = static_cast<const float*>(gathered); ea.d = h->dm.d;
+    ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.last_step = h->last_step;
+    ea.alpha_hist = h->alpha_hist; ea.hp = h->hyper_dev; ea.mode = 0;
+    h->last_sorted = ea.skeys; h->last_sorted_n = ea.n;
+    launch_emb_update(h->st, ea);
+    if (h->cfg.adam_mode == SCORE_ADAM_DENSE)
+        launch_emb_dense_sweep(h->st, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.V, h->dm.d, h->hyper_dev);
+    h->step += 1;
+    h->beta1_power = h->beta1_power * 0.9f;
+    h->beta2_power = h->beta2_power * 0.999f;
+    h->begun = false;
+    CK(cudaGetLastError());
+    if (!loss_out) return SCORE_OK;   // asynchronous: the caller collects errors later with score_wait()
+    CK(cudaMemcpyAsync(h->loss_glob_host, h->loss_glob, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    rc = finish_sync(h, nullptr);
+    *loss_out = *h->loss_glob_host;
+    return rc;
 }
 
 // Optimizer half of the split step: dense Adam on the (all-reduced) "dense_grad" buffer and the deterministic

@@ -364,16 +364,210 @@ void launch_emb_runs(cudaStream_t st, const int32_t* skeys, const int32_t* spos,
     ++g_launch_count;
 }
 
+
+// ------------------------------------------------------------------------------------------ data-parallel exchange helpers
+// Rank of every run head among the run heads of the sorted key list (exclusive count of heads before it): the slot of
+// the run in a compact list that is still ascending by key.  Two kernels on the sort stream, off the critical path:
+// per-tile head counts, then (prefix of the tile counts) + (rank inside the tile).
+constexpr int HS_THREADS = 256;
+constexpr int HS_ITEMS = 8;
+constexpr int HS_TILE = HS_THREADS * HS_ITEMS;
+
+__device__ __forceinline__ bool is_run_head(const int32_t* __restrict__ skeys, int64_t i, int64_t n) {
+    if (i >= n) return false;
+    const int32_t key = skeys[i];
+    return key != 0 && (i == 0 || skeys[i - 1] != key);
+}
+__global__ void __launch_bounds__(HS_THREADS) head_count_kernel(const int32_t* __restrict__ skeys, int64_t n,
+                                                                int32_t* __restrict__ tile_counts) {
+    __shared__ int wcnt[HS_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * HS_TILE;
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < HS_ITEMS; ++r) c += is_run_head(skeys, base + r * HS_THREADS + threadIdx.x, n) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL_MASK, c, o);
+    if ((threadIdx.x & 31) == 0) wcnt[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < HS_THREADS / 32; ++w) t += wcnt[w];
+        tile_counts[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(HS_THREADS) head_slot_kernel(const int32_t* __restrict__ skeys, int64_t n,
+                                                               const int32_t* __restrict__ tile_counts,
+                                                               int32_t* __restrict__ head_slot) {
+    constexpr int WARPS = HS_THREADS / 32;
+    __shared__ int red[WARPS];
+    __shared__ int cnt[HS_ITEMS][WARPS];
+    __shared__ int tile_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // heads in the tiles before this one
+    int pre = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += HS_THREADS) pre += tile_counts[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(FULL_MASK, pre, o);
+    if (lane == 0) red[warp] = pre;
+    const int64_t base = (int64_t)blockIdx.x * HS_TILE;
+    bool head[HS_ITEMS];
+    unsigned bal[HS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < HS_ITEMS; ++r) {
+        head[r] = is_run_head(skeys, base + r * HS_THREADS + threadIdx.x, n);
+        bal[r] = __ballot_sync(FULL_MASK, head[r]);
+        if (lane == 0) cnt[r][warp] = __popc(bal[r]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) t += red[w];
+        tile_base = t;
+        int run = 0;   // exclusive prefix in (item, warp) order = ascending sorted index
+        for (int r = 0; r < HS_ITEMS; ++r)
+            for (int w = 0; w < WARPS; ++w) { const int c = cnt[r][w]; cnt[r][w] = run; run += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < HS_ITEMS; ++r)
+        if (head[r]) head_slot[base + r * HS_THREADS + threadIdx.x] = tile_base + cnt[r][warp] + __popc(bal[r] & ((1u << lane) - 1u));
+}
+int64_t head_slot_tiles(int64_t n) { return (n + HS_TILE - 1) / HS_TILE; }
+void launch_head_slots(cudaStream_t st, const int32_t* skeys, int64_t n, int32_t* tile_counts, int32_t* head_slot) {
+    const unsigned tiles = (unsigned)head_slot_tiles(n);
+    if (!tiles) return;
+    head_count_kernel<<<tiles, HS_THREADS, 0, st>>>(skeys, n, tile_counts);
+    head_slot_kernel<<<tiles, HS_THREADS, 0, st>>>(skeys, n, tile_counts, head_slot);
+    g_launch_count += 2;
+}
+
+// {number of unique rows, sequence number of the step} for the host, which sizes the exchange from it while the
+// forward / backward kernels are still running
+__global__ void dp_count_kernel(const int32_t* __restrict__ counters, const Hyper* hp, int32_t* __restrict__ slot) {
+    slot[0] = counters[3];
+    slot[1] = hp->seq;
+}
+void launch_dp_count(cudaStream_t st, const int32_t* counters, const Hyper* hp, int32_t* slot) {
+    dp_count_kernel<<<1, 1, 0, st>>>(counters, hp, slot);
+    ++g_launch_count;
+}
+// header of this rank's packed block: unique-row count, step sequence number, loss (total, L2 part)
+__global__ void dp_header_kernel(int32_t* __restrict__ block, const int32_t* __restrict__ counters, const Hyper* hp,
+                                 const float* __restrict__ loss_dev) {
+    block[0] = counters[3];
+    block[1] = hp->seq;
+    block[2] = __float_as_int(loss_dev[0]);
+    block[3] = __float_as_int(loss_dev[1]);
+}
+void launch_dp_header(cudaStream_t st, int32_t* block, const int32_t* counters, const Hyper* hp, const float* loss_dev) {
+    dp_header_kernel<<<1, 1, 0, st>>>(block, counters, hp, loss_dev);
+    ++g_launch_count;
+}
+
+// Merge of the ranks' key lists (each ascending, one entry per unique row of that rank) into ONE list sorted by
+// (key, rank) - the order a stable sort of their concatenation would produce - without sorting: the final index of
+// entry i of rank r is i + sum over the other ranks of the number of their keys that sort before it (binary searches,
+// the lists are L2-resident; the searches of the up-to-eight other ranks advance together, so their loads overlap).
+// spos = index of the entry's gradient row in the gathered buffer viewed as rows of d floats.
+__global__ void __launch_bounds__(256) dp_merge_kernel(DpLayout L, int iters, int32_t* __restrict__ skeys,
+                                                        int32_t* __restrict__ spos, int32_t* __restrict__ err_flag) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (int)(idx / L.cap);
+    const int64_t i = idx - (int64_t)r * L.cap;
+    if (r >= L.world) return;
+    const int32_t* __restrict__ mine = L.base + (int64_t)r * L.stride;
+    int32_t cnt = mine[0];
+    if (cnt > L.cap || cnt < 0) { if (i == 0) atomicExch(err_flag, 2); cnt = cnt < 0 ? 0 : (int32_t)L.cap; }
+    if (i >= cnt) return;
+    const int32_t key = mine[L.keys_off + i];
+    int64_t pos = i;
+    for (int r0 = 0; r0 < L.world; r0 += 8) {
+        const int32_t* kp[8];
+        int lo[8], hi[8];
+        int32_t tgt[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int rr = r0 + u;
+            const bool valid = rr < L.world && rr != r;
+            const int32_t* blk = L.base + (int64_t)(valid ? rr : r) * L.stride;
+            kp[u] = blk + L.keys_off;
+            int c = valid ? blk[0] : 0;
+            c = c < 0 ? 0 : (c > L.cap ? (int)L.cap : c);
+            lo[u] = 0; hi[u] = c;
+            tgt[u] = key + (rr < r ? 1 : 0);   // earlier ranks: their equal key goes first (count keys <= key)
+        }
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (lo[u] < hi[u]) {
+                    const int mid = (lo[u] + hi[u]) >> 1;
+                    if (kp[u][mid] < tgt[u]) lo[u] = mid + 1; else hi[u] = mid;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) pos += lo[u];
+    }
+    skeys[pos] = key;
+    spos[pos] = (int32_t)(((int64_t)r * L.stride + L.keys_off + L.cap) / L.d + i);
+}
+void launch_dp_merge(cudaStream_t st, const DpLayout& L, int32_t* skeys, int32_t* spos, int32_t* err_flag) {
+    const int64_t n = (int64_t)L.world * L.cap;
+    cudaMemsetAsync(skeys, 0, sizeof(int32_t) * n, st);   // slots past the total count: key 0 = no row
+    int iters = 1;
+    while (((int64_t)1 << iters) <= L.cap) ++iters;
+    dp_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, iters, skeys, spos, err_flag);
+    ++g_launch_count;
+}
+
+// Dense half of the data-parallel finish: G[i] = sum over ranks (rank order: every replica adds in the same order, so
+// the replicas stay bit-identical whatever the collective does) of the gathered dense gradients, then TF-form Adam.
+// Thread 0 also composes the global loss: sum of the ranks' data terms (each already scaled by 1/global_batch) + L2 once.
+__global__ void dp_dense_adam_kernel(DpLayout L, float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                     float* __restrict__ g_out, const uint8_t* __restrict__ flags, int n, const Hyper* hp,
+                                     float* alpha_hist, double* __restrict__ loss_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        if (alpha_hist) alpha_hist[hp->step] = hp->alpha;
+        double s = 0.0;
+        for (int r = 0; r < L.world; ++r) {
+            const int32_t* blk = L.base + (int64_t)r * L.stride;
+            s += (double)__int_as_float(blk[2]) - (double)__int_as_float(blk[3]);
+        }
+        loss_out[0] = s + (double)__int_as_float(L.base[3]);
+    }
+    if (i >= n) return;
+    float gi = 0.f;
+    for (int r = 0; r < L.world; ++r)
+        gi = __fadd_rn(gi, reinterpret_cast<const float*>(L.base + (int64_t)r * L.stride + L.dense_off)[i]);
+    g_out[i] = gi;
+    const uint8_t f = flags[i];
+    if (!(f & 2)) return;
+    float var = p[i], mm = m[i], vv = v[i];
+    if (f & 1) gi = __fadd_rn(gi, __fmul_rn(hp->reg_lambda, var));
+    adam_elem(var, mm, vv, gi, hp->alpha);
+    p[i] = var; m[i] = mm; v[i] = vv;
+}
+void launch_dp_dense_adam(cudaStream_t st, const DpLayout& L, float* p, float* m, float* v, float* g_out,
+                          const uint8_t* flags, int n, const Hyper* hp, float* alpha_hist, double* loss_out) {
+    dp_dense_adam_kernel<<<(n + 255) / 256, 256, 0, st>>>(L, p, m, v, g_out, flags, n, hp, alpha_hist, loss_out);
+    ++g_launch_count;
+}
+
 __device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
 // optimizer step of one row by one group of LPR lanes (all of them active here, identical control flow)
-// EXPORT: 0 = apply Adam; 1 = write the run's gradient sum at the run's first sorted index; 2 = at the run's slot in
-// the descriptor lists (compact: slots 0 .. number of runs - 1)
+// EXPORT: 0 = apply Adam; 1 = write the run's gradient sum at the run's first sorted index; 2 = at the run's rank among
+// the runs of the sorted list (a.head_slot, launch_head_slots): compact AND ascending by key, which is what lets the
+// data-parallel finish merge the ranks' lists instead of sorting their concatenation
 template <int EXPORT, int LPR>
 __device__ __forceinline__ void emb_apply_row(const EmbUpdateArgs& a, int32_t key, int64_t out_idx, const float4& acc,
                                               float4 var, float4 m, float4 v, int last, int sub, float alpha, int step) {
     constexpr int D = LPR * 4;
     if (EXPORT) {
+        if (EXPORT == 2 && out_idx >= a.out_cap) return;   // the caller sized the list from the run count: never taken
         *reinterpret_cast<float4*>(a.out_rows + out_idx * D + sub * 4) = acc;
         if (sub == 0) a.out_heads[out_idx] = key;
         return;
@@ -470,7 +664,7 @@ __global__ void __launch_bounds__(256) emb_update_kernel(EmbUpdateArgs a) {
             float4 acc = red[0][sub];
 #pragma unroll
             for (int w = 1; w < 8; ++w) add4(acc, red[w][sub]);
-            emb_apply_row<EXPORT, LPR>(a, key, EXPORT == 2 ? (int64_t)nS + nM + r : (int64_t)start, acc, var, m, v, last, sub,
+            emb_apply_row<EXPORT, LPR>(a, key, EXPORT == 2 ? (int64_t)a.head_slot[start] : (int64_t)start, acc, var, m, v, last, sub,
                                        alpha, step);
         }
         __syncthreads();
@@ -500,7 +694,7 @@ __global__ void __launch_bounds__(256) emb_update_kernel(EmbUpdateArgs a) {
             __syncwarp();
             const float4 acc = emb_team_combine<LPR, TL>(part, lane);
             if (owner)
-                emb_apply_row<EXPORT, LPR>(a, key, EXPORT == 2 ? (int64_t)nS + r : (int64_t)start, acc, var, m, v, last, sub,
+                emb_apply_row<EXPORT, LPR>(a, key, EXPORT == 2 ? (int64_t)a.head_slot[start] : (int64_t)start, acc, var, m, v, last, sub,
                                            alpha, step);
             __syncwarp();
         }
@@ -534,7 +728,7 @@ __global__ void __launch_bounds__(256) emb_update_kernel(EmbUpdateArgs a) {
 #pragma unroll
         for (int u = 1; u < 4; ++u)
             if (u < n4) add4(acc, g[u]);
-        emb_apply_row<EXPORT, LPR>(a, key, EXPORT == 2 ? (int64_t)h : (int64_t)start, acc, var, m, v, last, sub, alpha, step);
+        emb_apply_row<EXPORT, LPR>(a, key, EXPORT == 2 ? (int64_t)a.head_slot[start] : (int64_t)start, acc, var, m, v, last, sub, alpha, step);
     }
 }
 template <int LPR>

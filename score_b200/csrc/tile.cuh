@@ -12,8 +12,15 @@
 namespace score {
 
 constexpr int TL_CT = 256;    // threads per CTA (8 warps)
-constexpr int TL_KC = 16;     // weight rows per pipeline stage
-constexpr int TL_NST = 4;     // cp.async ring depth
+// compile-time tuning points (tools/build_variants.py builds the alternatives for an A/B on the GPU box)
+#ifndef SCORE_TL_KC
+#define SCORE_TL_KC 16
+#endif
+#ifndef SCORE_TL_NST
+#define SCORE_TL_NST 4
+#endif
+constexpr int TL_KC = SCORE_TL_KC;      // weight rows per pipeline stage
+constexpr int TL_NST = SCORE_TL_NST;    // cp.async ring depth
 
 template <int RT>
 struct TileGeom {

@@ -116,39 +116,78 @@ class _Base:
         return float(t.item()) + float(loss2[1])
 
 
-class DataParallelTrainer(_Base):
-    """Dense data-parallel training with a replicated embedding table (BASELINE.json config 4)."""
+def exchange_capacity(counts) -> int:
+    """list capacity of the packed exchange: the largest rank count rounded up to a multiple of 1024 (same on all ranks)."""
+    return max(1024, (int(max(counts)) + 1023) // 1024 * 1024)
 
-    def train(self, sess, batch_data, lr, reg_lambda, keep_prob=TRAIN_KEEP_PROB, want_loss=True):
+
+class DataParallelTrainer(_Base):
+    """Dense data-parallel training with a replicated embedding table (BASELINE.json config 4).
+
+    One step = score_step_begin (forward/backward on the local shard, CUDA graph) -> ONE all-gather of one packed block
+    per rank (dense gradient + one embedding-gradient row per unique id, ascending) -> score_dp_finish (rank-ordered
+    sums, merge of the sorted lists, row Adam).  The list capacity comes from the unique-row counts, which the sort
+    branch publishes long before forward/backward ends: they are exchanged on a side stream while the main stream keeps
+    running, so the host never drains the device inside a step.  The phases are separate methods so a single-process
+    test can drive several handles through them (tests/test_parity_gpu.py)."""
+
+    def __init__(self, model, world, rank, group=None):
+        super().__init__(model, world, rank, group)
+        self.side = torch.cuda.Stream(device=self.device)
+        self._gathered = None
+
+    # ---- phases
+    def begin(self, batch_data, lr, reg_lambda, keep_prob=TRAIN_KEEP_PROB, global_batch=None):
         b = _Batch(batch_data, self.m.cfg)
-        gb = b.B * self.world
+        gb = global_batch if global_batch else b.B * self.world
         with torch.cuda.stream(self.stream):
             self.m._check(self.lib.score_step_begin(self.h, C.byref(b.struct), lr, reg_lambda, keep_prob, gb, 1, None, None))
-            self._keep_batch = b   # host id arrays stay alive until their H2D copies have run
-            g = self._dev("dense_grad", torch.float32)
-            dist.all_reduce(g, group=self.group)
-            # one gradient row per unique id of this rank (deterministic segment reduce on the device), then the
-            # all-gather carries unique rows, not positions
-            kp, rp, cp = C.c_void_p(), C.c_void_p(), C.c_void_p()
-            self.m._check(self.lib.score_local_reduce(self.h, C.byref(kp), C.byref(rp), C.byref(cp)))
-            d = self.m.cfg["eb_dim"]
-            cnt = torch.as_tensor(_DevView(cp.value, (1,), "<i4"), device=self.device).clone()
-            dist.all_reduce(cnt, op=dist.ReduceOp.MAX, group=self.group)
-            cap = (int(cnt.item()) + 1023) // 1024 * 1024      # host sync: the size of the exchange
-            n_pos = self._dev("keys", torch.int32).numel()
-            cap = max(min(cap, n_pos), 1)
-            keys = torch.as_tensor(_DevView(kp.value, (cap,), "<i4"), device=self.device)
-            rows = torch.as_tensor(_DevView(rp.value, (cap * d,), "<f4"), device=self.device)
-            if getattr(self, "_all_keys", None) is None or self._all_keys.numel() != self.world * cap:
-                self._all_keys = torch.empty(self.world * cap, dtype=torch.int32, device=self.device)
-                self._all_rows = torch.empty(self.world * cap * d, dtype=torch.float32, device=self.device)
-            all_keys, all_rows = self._all_keys, self._all_rows
-            dist.all_gather_into_tensor(all_keys, keys, group=self.group)
-            dist.all_gather_into_tensor(all_rows, rows, group=self.group)
-            loss2 = (C.c_float * 2)() if want_loss else None
-            self.m._check(self.lib.score_step_finish(self.h, all_keys.data_ptr(), all_rows.data_ptr(),
-                                                     all_keys.numel(), loss2))
-            return self._global_loss(loss2) if want_loss else None
+        self._keep_batch = b   # host id arrays stay alive until their H2D copies have run
+        return b
+
+    def local_count(self) -> int:
+        c = C.c_int32()
+        self.m._check(self.lib.score_dp_local_count(self.h, C.byref(c)))
+        return int(c.value)
+
+    def exchange_counts(self, count):
+        """all ranks' unique-row counts (NCCL on a side stream: the main stream is neither waited for nor blocked)."""
+        with torch.cuda.stream(self.side):
+            mine = torch.tensor([count], dtype=torch.int32, device=self.device)
+            out = torch.empty(self.world, dtype=torch.int32, device=self.device)
+            dist.all_gather_into_tensor(out, mine, group=self.group)
+            return out.tolist()
+
+    def pack(self, cap):
+        """-> this rank's packed block as an int32 tensor view (device memory owned by the handle)."""
+        ptr, words = C.c_void_p(), C.c_int64()
+        with torch.cuda.stream(self.stream):
+            self.m._check(self.lib.score_dp_pack(self.h, cap, C.byref(ptr), C.byref(words)))
+        return torch.as_tensor(_DevView(ptr.value, (words.value,), "<i4"), device=self.device)
+
+    def finish(self, gathered, cap, want_loss=True):
+        loss = C.c_double() if want_loss else None
+        with torch.cuda.stream(self.stream):
+            self.m._check(self.lib.score_dp_finish(self.h, gathered.data_ptr(), self.world, cap,
+                                                   C.byref(loss) if want_loss else None))
+        return float(loss.value) if want_loss else None
+
+    # ---- the step
+    def train(self, sess, batch_data, lr, reg_lambda, keep_prob=TRAIN_KEEP_PROB, want_loss=True):
+        self.begin(batch_data, lr, reg_lambda, keep_prob)
+        return self._rest(want_loss)
+
+    def _rest(self, want_loss):
+        cap = exchange_capacity(self.exchange_counts(self.local_count()))
+        block = self.pack(cap)
+        n = block.numel() * self.world
+        with torch.cuda.stream(self.stream):
+            if self._gathered is None or self._gathered.numel() < n:
+                self.stream.synchronize()          # the previous step's update may still be reading the old buffer
+                self._gathered = torch.empty(n + n // 4, dtype=torch.int32, device=self.device)
+            gathered = self._gathered[:n]
+            dist.all_gather_into_tensor(gathered, block, group=self.group)
+        return self.finish(gathered, cap, want_loss)
 
     def train_async(self, batch_data, lr, reg_lambda, keep_prob=TRAIN_KEEP_PROB):
         self.train(None, batch_data, lr, reg_lambda, keep_prob, want_loss=False)

@@ -358,3 +358,85 @@ def test_eval_metrics_match_train_score_arithmetic():
     for g, w in zip(got[2:], want[2:]):
         assert g == pytest.approx(w, rel=1e-12, abs=1e-15)
     m.close()
+
+
+# ---------------------------------------------------------------------------------- data-parallel packed exchange
+def _dp_layout(n_dense, d, cap):
+    dense_off = 128
+    keys_off = dense_off + (n_dense + 127) // 128 * 128
+    return dense_off, keys_off, keys_off + cap + cap * d
+
+
+def test_dp_pack_exports_sorted_unique_rows():
+    """score_dp_pack: header count, ids ascending, one row per id = the sum of that id's per-position gradient rows."""
+    from score_b200 import parallel
+    shape = SHAPES["tiny_tb"]
+    cfg, params, m = pu.make_models(shape, adam_mode="lazy")
+    dp = parallel.DataParallelTrainer(m, 1, 0)
+    dp.begin(make_batch(shape, seed=61), 1e-3, 1e-4, keep_prob=1.0)
+    cnt = dp.local_count()
+    cap = parallel.exchange_capacity([cnt])
+    block = dp.pack(cap)
+    torch.cuda.synchronize()
+    blk = block.cpu().numpy()
+    keys = m.get_buffer("keys")
+    d = shape.eb_dim
+    grad_rows = m.get_buffer("grad_rows").reshape(-1, d)
+    uniq = np.unique(keys[keys != 0])
+    g_flat = dp._dev("dense_grad", torch.float32).cpu().numpy().copy()   # the flat dense-gradient buffer (aligned offsets)
+    n_dense = g_flat.size
+    dense_off, keys_off, words = _dp_layout(n_dense, d, cap)
+    assert blk.size == words and cnt == len(uniq) and blk[0] == cnt
+    got_keys = blk[keys_off:keys_off + cap]
+    assert np.array_equal(got_keys[:cnt], uniq.astype(np.int32)) and not got_keys[cnt:].any()
+    rows = blk[keys_off + cap:keys_off + cap + cap * d].view(np.float32).reshape(cap, d)[:cnt]
+    want = np.zeros((len(uniq), d), np.float64)
+    np.add.at(want, np.searchsorted(uniq, keys[keys != 0]), grad_rows[keys != 0].astype(np.float64))
+    assert pu.rel_err(rows, want) <= 1e-6
+    assert np.array_equal(blk[dense_off:dense_off + n_dense].view(np.float32), g_flat)
+    # finishing the step on the single block equals a plain single-GPU step, bit for bit
+    loss = dp.finish(block, cap)
+    cfg2, params2, m2 = pu.make_models(shape, adam_mode="lazy")
+    loss2 = m2.train(None, make_batch(shape, seed=61), 1e-3, 1e-4, keep_prob=1.0)
+    assert abs(loss - loss2) <= 1e-6 * abs(loss2)
+    for name in ("emb_mtx", "emb_mtx/Adam", "emb_mtx/Adam_1", "fc1/kernel", "dense_3/kernel"):
+        assert np.array_equal(m.get_tensor(name), m2.get_tensor(name)), name
+    m.close(); m2.close()
+
+
+@pytest.mark.parametrize("world,mode,graph", [(2, "lazy", True), (3, "dense", False), (8, "lazy", False)])
+def test_dp_packed_exchange_emulated_ranks(world, mode, graph):
+    """`world` handles on one GPU driven through the phases of DataParallelTrainer (the all-gather is a torch.cat):
+    every replica must end bit-identical, and equal to one model stepping on the concatenated batch."""
+    from score_b200 import parallel
+    shape = SHAPES["tiny_tb"]
+    steps, lr, lam = 4, 1e-3, 1e-4
+    per = [[make_batch(shape, seed=700 + 10 * s + r) for r in range(world)] for s in range(steps)]
+    glob = [tuple(np.concatenate([b[i] for b in bs], 0) for i in range(8)) for bs in per]
+    cfg, params, m1 = pu.make_models(shape, adam_mode=mode)
+    l1 = [m1.train(None, g, lr, lam, keep_prob=1.0) for g in glob]
+    ms = [pu.make_models(shape, adam_mode=mode, use_graph=graph)[2] for _ in range(world)]
+    dps = [parallel.DataParallelTrainer(m, world, r) for r, m in enumerate(ms)]
+    l2 = []
+    for bs in per:
+        for dp, b in zip(dps, bs):
+            dp.begin(b, lr, lam, keep_prob=1.0)
+        cap = parallel.exchange_capacity([dp.local_count() for dp in dps])
+        blocks = [dp.pack(cap) for dp in dps]
+        torch.cuda.synchronize()
+        gathered = torch.cat(blocks)
+        torch.cuda.synchronize()
+        losses = [dp.finish(gathered, cap) for dp in dps]
+        assert all(x == losses[0] for x in losses)
+        l2.append(losses[0])
+    assert pu.rel_err(l2, l1) <= 2e-6
+    names = ("emb_mtx", "emb_mtx/Adam", "emb_mtx/Adam_1", "fc1/kernel", "dense_3/kernel", "gru_user_side/gru_cell/gates/kernel")
+    ref_t = {n: ms[0].get_tensor(n) for n in names}
+    for m in ms[1:]:
+        for n in names:
+            assert np.array_equal(m.get_tensor(n), ref_t[n]), "replicas diverged: " + n
+    assert pu.rel_err(ref_t["emb_mtx"], m1.get_tensor("emb_mtx")) <= 2e-4
+    assert pu.rel_err(ref_t["emb_mtx/Adam"], m1.get_tensor("emb_mtx/Adam")) <= 2e-4
+    assert pu.rel_err(ref_t["emb_mtx/Adam_1"], m1.get_tensor("emb_mtx/Adam_1")) <= 2e-4
+    for m in ms + [m1]:
+        m.close()
