@@ -278,6 +278,9 @@ size_t sort_hist_elems(int64_t n);
 // stable LSD radix sort of (key, position) pairs; keys_in is left untouched, values start as 0..n-1;
 // returns the index (0/1) of the ping-pong buffer that holds the result
 int launch_sort_pairs(cudaStream_t st, SortBufs& sb, const int32_t* keys_in, int64_t n, int key_bits);
+// the same sort in two instalments (the step runs the first pass before the gather kernel and the rest after it)
+int sort_num_passes(int key_bits);
+int launch_sort_passes(cudaStream_t st, SortBufs& sb, const int32_t* keys_in, int64_t n, int p_begin, int p_end);
 
 // Run descriptors of the sorted (key, position) list, three tiers by run length (scatter.cu):
 //   runs       8 int32 per run of <= 4 entries: {key, start, n, pos0, pos1, pos2, pos3, 0}           (capacity n runs)

@@ -559,12 +559,15 @@ void probe_end(ScoreModel* h, int p, cudaStream_t s) {
 enum StepMode { MODE_TRAIN = 0, MODE_EVAL = 1, MODE_FWDBWD = 2, MODE_BEGIN = 3 };
 
 int key_bits(int64_t V);
-// radix sort of the batch's (key, position) pairs + run descriptors on the sort stream, forked at `after`
-void enqueue_sort_branch(ScoreModel* h, cudaEvent_t after) {
+// radix sort of the batch's (key, position) pairs + run descriptors on the sort stream, forked at `after`.
+// part 0: everything; part 1: the first pass only (before the gather kernel); part 2: the remaining passes + descriptors
+void enqueue_sort_branch(ScoreModel* h, cudaEvent_t after, int part = 0) {
     const Dims& dm = h->dm;
+    const int np = sort_num_passes(key_bits(dm.V));
     cudaStreamWaitEvent(h->st2, after, 0);
-    probe_begin(h, PR_SORT, h->st2);
-    h->sort_out = launch_sort_pairs(h->st2, h->sb, h->keys, dm.N, key_bits(dm.V));
+    if (part != 2) probe_begin(h, PR_SORT, h->st2);
+    if (part == 1) { h->sort_out = launch_sort_passes(h->st2, h->sb, h->keys, dm.N, 0, 1); return; }
+    h->sort_out = launch_sort_passes(h->st2, h->sb, h->keys, dm.N, part == 2 ? 1 : 0, np);
     launch_emb_runs(h->st2, h->sb.keys[h->sort_out], h->sb.vals[h->sort_out], dm.N, h->sb.runs, h->sb.runs_long, h->n_heads_dev);
     probe_end(h, PR_SORT, h->st2);
     cudaEventRecord(h->ev_join, h->st2);
@@ -615,9 +618,9 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
     probe_begin(h, PR_COATT_FWD, h->st);
     launch_coatt_fwd(h->st, dm, ca);
     probe_end(h, PR_COATT_FWD, h->st);
-    if (h->sort_deferred) {
+    if (h->sort_deferred) {   // remaining passes of the sort: after the gather (enqueue_step)
         cudaEventRecord(h->ev_keys, h->st);
-        enqueue_sort_branch(h, h->ev_keys);
+        enqueue_sort_branch(h, h->ev_keys, 2);
         h->sort_deferred = false;
     }
 
@@ -840,20 +843,23 @@ void enqueue_step(ScoreModel* h, int mode) {
     const bool need_bwd = (mode != MODE_EVAL);
     h->emb_fwd = h->emb; h->keys_fwd = h->keys;
     probe_begin(h, PR_STEP, h->st);
+    // The sort depends on ids only and runs on the side stream under forward/backward.  With sort_after_gather() it
+    // pauses while the gather kernel - the one bandwidth-bound kernel of the forward pass - has the SMs to itself: the
+    // first pass runs next to the (instruction-bound) lazy replay, the other passes are forked after the gather.
+    h->sort_deferred = need_bwd && sort_after_gather();
     if (h->cfg.adam_mode == SCORE_ADAM_LAZY) {
         probe_begin(h, PR_CATCHUP, h->st);
         ClaimArgs ca{h->last_step, h->hyper_dev, h->claim_list, h->claim_counter, 1};
         launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag, &ca);
+        if (h->sort_deferred) { cudaEventRecord(h->ev_keys, h->st); enqueue_sort_branch(h, h->ev_keys, 1); }
         launch_emb_replay(h->st, h->claim_list, h->claim_counter, dm.N, h->emb, h->emb_m, h->emb_v, dm.d, h->alpha_hist,
                           h->hyper_dev, 1);
         probe_end(h, PR_CATCHUP, h->st);
     } else {
         launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag);
+        if (h->sort_deferred) { cudaEventRecord(h->ev_keys, h->st); enqueue_sort_branch(h, h->ev_keys, 1); }
     }
     cudaEventRecord(h->ev_fork, h->st);
-    // the sort depends on ids only: it runs on the side stream under forward/backward - forked after the gather kernel
-    // (the one bandwidth-bound kernel of the forward pass does not share the SMs with it) or right here
-    h->sort_deferred = need_bwd && sort_after_gather();
     if (need_bwd && !h->sort_deferred) enqueue_sort_branch(h, h->ev_fork);
     enqueue_forward(h, need_bwd);
     const bool defer = train && side_reduce();
@@ -1587,6 +1593,7 @@ int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg
     if (train && !staged_table) { int rc = ensure_dp(h); if (rc) return rc; }
     const bool with_keys = batch != nullptr;
     auto enqueue_begin = [&]() {
+        h->sort_deferred = false;
         cudaEventRecord(h->ev_fork, h->st);
         if (with_keys) launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag);
         if (staged_table) {

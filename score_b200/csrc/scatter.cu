@@ -258,15 +258,18 @@ static int sort_grid_cap() {
     }
     return cap;
 }
-int launch_sort_pairs(cudaStream_t st, SortBufs& sb, const int32_t* keys_in, int64_t n, int key_bits) {
-    int passes = (key_bits + 7) / 8;
-    if (passes < 1) passes = 1;
+int sort_num_passes(int key_bits) {
+    const int passes = (key_bits + 7) / 8;
+    return passes < 1 ? 1 : passes;
+}
+// passes [p_begin, p_end) of the sort; pass 0 reads keys_in, pass p > 0 the output of pass p-1 (ping-pong p & 1)
+int launch_sort_passes(cudaStream_t st, SortBufs& sb, const int32_t* keys_in, int64_t n, int p_begin, int p_end) {
     const int nblocks = (int)((n + SORT_TILE - 1) / SORT_TILE);
     const int grid = nblocks < sort_grid_cap() ? nblocks : sort_grid_cap();
-    const int32_t* kin = keys_in;
-    const int32_t* vin = nullptr;
-    int out = 0;
-    for (int p = 0; p < passes; ++p) {
+    int out = (p_begin > 0) ? ((p_begin - 1) & 1) : 0;
+    for (int p = p_begin; p < p_end; ++p) {
+        const int32_t* kin = p == 0 ? keys_in : sb.keys[(p - 1) & 1];
+        const int32_t* vin = p == 0 ? nullptr : sb.vals[(p - 1) & 1];
         out = p & 1;
         sort_hist_kernel<<<grid, SORT_THREADS, 0, st>>>(kin, n, 8 * p, sb.hist, nblocks);
         const int total = 256 * nblocks, nchunks = (total + 1023) / 1024;
@@ -275,10 +278,11 @@ int launch_sort_pairs(cudaStream_t st, SortBufs& sb, const int32_t* keys_in, int
         sort_scatter_kernel<<<grid, SORT_THREADS, 0, st>>>(kin, vin, sb.keys[out], sb.vals[out], n, 8 * p, sb.hist,
                                                              nblocks, chunk_sums);
         g_launch_count += 3;
-        kin = sb.keys[out];
-        vin = sb.vals[out];
     }
     return out;
+}
+int launch_sort_pairs(cudaStream_t st, SortBufs& sb, const int32_t* keys_in, int64_t n, int key_bits) {
+    return launch_sort_passes(st, sb, keys_in, n, 0, sort_num_passes(key_bits));
 }
 
 // LAZY mode: replay the zero-gradient steps (from, upto] of one row chunk, same op sequence as the sweep.
