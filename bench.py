@@ -138,7 +138,7 @@ def cpu_baseline(shape, batch_size, budget_s=20.0, max_steps=8):
                       "installed offline" % (len(times), batch_size, med)}, med
 
 
-def run_reference(args, shape, rank, world):
+def run_reference(args, shape, rank, world, emit):
     if rank != 0:
         return
     cb, med = cpu_baseline(shape, shape.batch, budget_s=max(10.0, 3.0 * (args.steps + args.warmup)),
@@ -150,7 +150,7 @@ def run_reference(args, shape, rank, world):
             "cpu_baseline": dict(cb),
             "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(shape, args, global_batch):
@@ -187,6 +187,12 @@ def main():
                     help="N>1: dp = replicated table + gradient all-gather, sharded = row-sharded table + all-to-all")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner) go to stderr instead
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     from score_b200.synth import SHAPES, make_batch
     shape = SHAPES[args.workload]
@@ -196,7 +202,7 @@ def main():
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
 
     if args.impl == "reference":
-        run_reference(args, shape, rank, world)
+        run_reference(args, shape, rank, world, emit)
         return
 
     import torch
@@ -361,7 +367,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_baseline(shape, B)
             line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+        emit(line)
     m.close()
     if world > 1:
         dist.destroy_process_group()

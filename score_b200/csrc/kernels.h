@@ -309,16 +309,19 @@ void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a);
 //   [dense_off, +n_dense)        this rank's dense gradient (flat buffer, 1/global_batch scaling applied)
 //   [keys_off, +cap)             unique row ids, ascending, zeros past the count
 //   [keys_off+cap, +cap*d)       one gradient row per id
-// blocks of all ranks lie `stride` words apart in the gathered buffer `base`; every offset is a multiple of 128 words,
-// so a gradient row is addressable as row (word offset / d) of the buffer viewed as [*, d] floats.
+// blocks of all ranks lie `stride` words apart in the gathered buffer `base`; every offset is a multiple of 128 words
+// (rows are 16-byte aligned for any d).
 struct DpLayout { const int32_t* base; int world; int d; int64_t stride, dense_off, keys_off, cap; };
 int64_t head_slot_tiles(int64_t n);
 // head_slot[i] = number of run heads before sorted index i, written at run heads only; tile_counts: head_slot_tiles(n) ints
 void launch_head_slots(cudaStream_t st, const int32_t* skeys, int64_t n, int32_t* tile_counts, int32_t* head_slot);
 void launch_dp_count(cudaStream_t st, const int32_t* counters, const Hyper* hp, int32_t* slot);
-void launch_dp_header(cudaStream_t st, int32_t* block, const int32_t* counters, const Hyper* hp, const float* loss_dev);
-// (key, rank)-ordered merge of the ranks' ascending key lists: skeys / spos [world*cap] like a stable sort's output
-void launch_dp_merge(cudaStream_t st, const DpLayout& L, int32_t* skeys, int32_t* spos, int32_t* err_flag);
+// header + dense gradient + zero padding of the id list of this rank's block (the rows come from launch_emb_update, mode 2)
+void launch_dp_pack_misc(cudaStream_t st, int32_t* block, const DpLayout& L, const int32_t* counters, const Hyper* hp,
+                         const float* loss_dev, const float* g, int n_dense);
+// embedding half of the data-parallel finish over the gathered blocks, one kernel: per id, the ranks' rows added in
+// rank order + the row's Adam step (a: emb / m / v / last_step / alpha_hist / hp / d as for launch_emb_update)
+void launch_dp_apply(cudaStream_t st, const DpLayout& L, const EmbUpdateArgs& a, int32_t* err_flag);
 // rank-ordered sum of the gathered dense gradients + dense Adam; loss_out[0] = global loss (double)
 void launch_dp_dense_adam(cudaStream_t st, const DpLayout& L, float* p, float* m, float* v, float* g_out,
                           const uint8_t* flags, int n, const Hyper* hp, float* alpha_hist, double* loss_out);

@@ -116,6 +116,7 @@ struct ScoreModel {
     std::map<int, cudaGraphExec_t> graphs_begin; std::map<int, int64_t> graph_kernels_begin; std::map<int, int> warm_begin;
     cudaEvent_t ev_keys = nullptr, ev_fc = nullptr, ev_att = nullptr, ev_qb = nullptr;
     bool sort_deferred = false;   // enqueue_forward forks the sort branch right after the gather kernel
+    bool sort_dp = false;         // the sort branch also publishes the unique-row count and the run ranks (data-parallel)
     bool begun = false; float begun_lr = 0.f;
     const int32_t* last_sorted = nullptr; int64_t last_sorted_n = 0;   // sorted key list of the last optimizer step
     // data-parallel packed exchange (score_dp_*): rank of every run head (compact sorted export), the early unique-row
@@ -570,6 +571,13 @@ void enqueue_sort_branch(ScoreModel* h, cudaEvent_t after, int part = 0) {
     h->sort_out = launch_sort_passes(h->st2, h->sb, h->keys, dm.N, part == 2 ? 1 : 0, np);
     launch_emb_runs(h->st2, h->sb.keys[h->sort_out], h->sb.vals[h->sort_out], dm.N, h->sb.runs, h->sb.runs_long, h->n_heads_dev);
     probe_end(h, PR_SORT, h->st2);
+    if (h->sort_dp) {
+        // data-parallel half-step: the host sizes the exchange from the unique-row count - publish it as soon as it
+        // exists (score_dp_local_count) - and the export needs every run's rank among the runs (compact sorted list)
+        launch_dp_count(h->st2, h->n_heads_dev, h->hyper_dev, h->cnt_slot);
+        cudaEventRecordWithFlags(h->ev_counts, h->st2, h->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+        launch_head_slots(h->st2, h->sb.keys[h->sort_out], dm.N, h->hs_tiles, h->head_slot);
+    }
     cudaEventRecord(h->ev_join, h->st2);
 }
 
@@ -847,6 +855,7 @@ void enqueue_step(ScoreModel* h, int mode) {
     // pauses while the gather kernel - the one bandwidth-bound kernel of the forward pass - has the SMs to itself: the
     // first pass runs next to the (instruction-bound) lazy replay, the other passes are forked after the gather.
     h->sort_deferred = need_bwd && sort_after_gather();
+    h->sort_dp = false;
     if (h->cfg.adam_mode == SCORE_ADAM_LAZY) {
         probe_begin(h, PR_CATCHUP, h->st);
         ClaimArgs ca{h->last_step, h->hyper_dev, h->claim_list, h->claim_counter, 1};
@@ -1593,27 +1602,30 @@ int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg
     if (train && !staged_table) { int rc = ensure_dp(h); if (rc) return rc; }
     const bool with_keys = batch != nullptr;
     auto enqueue_begin = [&]() {
-        h->sort_deferred = false;
+        const bool own_sort = train && !staged_table;   // sort of this rank's own keys under forward/backward (score_dp_pack)
+        h->sort_dp = own_sort;
+        h->sort_deferred = own_sort && sort_after_gather();
         cudaEventRecord(h->ev_fork, h->st);
-        if (with_keys) launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag);
+        const bool lazy = h->cfg.adam_mode == SCORE_ADAM_LAZY;
+        const bool fused_claim = with_keys && !staged_table && lazy;   // claim of the stale rows rides on build_keys
+        if (with_keys) {
+            ClaimArgs ca{h->last_step, h->hyper_dev, h->claim_list, h->claim_counter, 1};
+            launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag, fused_claim ? &ca : nullptr);
+        }
+        if (own_sort) {
+            cudaEventRecord(h->ev_keys, h->st);
+            enqueue_sort_branch(h, h->ev_keys, h->sort_deferred ? 1 : 0);
+        }
         if (staged_table) {
             h->emb_fwd = staged_table; h->keys_fwd = staged_keys;
         } else {
             h->emb_fwd = h->emb; h->keys_fwd = h->keys;
-            if (h->cfg.adam_mode == SCORE_ADAM_LAZY)
+            if (fused_claim)
+                launch_emb_replay(h->st, h->claim_list, h->claim_counter, dm.N, h->emb, h->emb_m, h->emb_v, dm.d, h->alpha_hist,
+                                  h->hyper_dev, 1);
+            else if (lazy)
                 launch_emb_catchup_rows(h->st, h->keys, dm.N, dm.V, h->emb, h->emb_m, h->emb_v, h->last_step, dm.d,
                                         h->alpha_hist, h->hyper_dev, h->claim_list, h->claim_counter);
-        }
-        if (train && !staged_table) {   // sort of this rank's own keys under forward/backward (score_local_reduce)
-            cudaEventRecord(h->ev_keys, h->st);
-            cudaStreamWaitEvent(h->st2, h->ev_keys, 0);
-            h->sort_out = launch_sort_pairs(h->st2, h->sb, h->keys, dm.N, key_bits(dm.V));
-            launch_emb_runs(h->st2, h->sb.keys[h->sort_out], h->sb.vals[h->sort_out], dm.N, h->sb.runs, h->sb.runs_long, h->n_heads_dev);
-            // the host sizes the exchange from the unique-row count: publish it as soon as it exists (score_dp_local_count)
-            launch_dp_count(h->st2, h->n_heads_dev, h->hyper_dev, h->cnt_slot);
-            cudaEventRecordWithFlags(h->ev_counts, h->st2, h->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
-            launch_head_slots(h->st2, h->sb.keys[h->sort_out], dm.N, h->hs_tiles, h->head_slot);
-            cudaEventRecord(h->ev_join, h->st2);
         }
         enqueue_forward(h, train != 0);
         if (train) enqueue_backward(h);
@@ -1707,9 +1719,7 @@ int score_dp_pack(ScoreHandle h, int64_t cap, void** block_dev, int64_t* block_w
     }
     int32_t* blk = h->dp_block;
     // the sort branch and the loss branch have been joined into the main stream by score_step_begin
-    launch_dp_header(h->st, blk, h->n_heads_dev, h->hyper_dev, h->loss_dev);
-    CK(cudaMemcpyAsync(blk + L.dense_off, h->G, sizeof(float) * h->n_dense, cudaMemcpyDeviceToDevice, h->st));
-    CK(cudaMemsetAsync(blk + L.keys_off, 0, sizeof(int32_t) * cap, h->st));
+    launch_dp_pack_misc(h->st, blk, L, h->n_heads_dev, h->hyper_dev, h->loss_dev, h->G, (int)h->n_dense);
     EmbUpdateArgs ea{};
     ea.skeys = h->sb.keys[h->sort_out]; ea.spos = h->sb.vals[h->sort_out]; ea.n = dm.N;
     ea.runs = h->sb.runs; ea.runs_long = h->sb.runs_long; ea.long_cap = emb_runs_long_cap(dm.N); ea.counters = h->n_heads_dev;
@@ -1733,22 +1743,14 @@ int score_dp_finish(ScoreHandle h, const void* gathered, int32_t world, int64_t 
     if (cap <= 0 || cap % 1024) return fail(h, SCORE_ERR_ARG, "cap must be a positive multiple of 1024");
     CK(cudaSetDevice(h->device));
     const DpLayout L = dp_layout(h, gathered, world, cap);
-    const int64_t n_ext = (int64_t)world * cap;
-    if (n_ext >= ((int64_t)1 << 31) || (int64_t)world * L.stride / L.d >= ((int64_t)1 << 31))
-        return fail(h, SCORE_ERR_ARG, "gathered lists too large for int32 positions");
+    if ((int64_t)world * cap * (h->dm.d >> 2) >= ((int64_t)1 << 40)) return fail(h, SCORE_ERR_ARG, "gathered lists too large");
     launch_dp_dense_adam(h->st, L, h->P, h->M1, h->V1, h->G, h->flags, (int)h->n_dense, h->hyper_dev, h->alpha_hist, h->loss_glob);
-    int rc = ensure_ext_sort(h, n_ext);
-    if (rc) return rc;
-    launch_dp_merge(h->st, L, h->sb_ext.keys[0], h->sb_ext.vals[0], h->err_flag);
-    launch_emb_runs(h->st, h->sb_ext.keys[0], h->sb_ext.vals[0], n_ext, h->sb_ext.runs, h->sb_ext.runs_long, h->n_heads_dev);
     EmbUpdateArgs ea{};
-    ea.skeys = h->sb_ext.keys[0]; ea.spos = h->sb_ext.vals[0]; ea.n = n_ext;
-    ea.runs = h->sb_ext.runs; ea.runs_long = h->sb_ext.runs_long; ea.long_cap = emb_runs_long_cap(n_ext); ea.counters = h->n_heads_dev;
-    ea.grad_rows = static_cast<const float*>(gathered); ea.d = h->dm.d;
+    ea.d = h->dm.d;
     ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.last_step = h->last_step;
     ea.alpha_hist = h->alpha_hist; ea.hp = h->hyper_dev; ea.mode = 0;
-    h->last_sorted = ea.skeys; h->last_sorted_n = ea.n;
-    launch_emb_update(h->st, ea);
+    launch_dp_apply(h->st, L, ea, h->err_flag);
+    if (h->local_sorted) { h->last_sorted = h->sb.keys[h->sort_out]; h->last_sorted_n = h->dm.N; }   // this rank's share (stats)
     if (h->cfg.adam_mode == SCORE_ADAM_DENSE)
         launch_emb_dense_sweep(h->st, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.V, h->dm.d, h->hyper_dev);
     h->step += 1;
@@ -1758,7 +1760,7 @@ int score_dp_finish(ScoreHandle h, const void* gathered, int32_t world, int64_t 
     CK(cudaGetLastError());
     if (!loss_out) return SCORE_OK;   // asynchronous: the caller collects errors later with score_wait()
     CK(cudaMemcpyAsync(h->loss_glob_host, h->loss_glob, sizeof(double), cudaMemcpyDeviceToHost, h->st));
-    rc = finish_sync(h, nullptr);
+    const int rc = finish_sync(h, nullptr);
     *loss_out = *h->loss_glob_host;
     return rc;
 }

@@ -457,72 +457,25 @@ void launch_dp_count(cudaStream_t st, const int32_t* counters, const Hyper* hp, 
     dp_count_kernel<<<1, 1, 0, st>>>(counters, hp, slot);
     ++g_launch_count;
 }
-// header of this rank's packed block: unique-row count, step sequence number, loss (total, L2 part)
-__global__ void dp_header_kernel(int32_t* __restrict__ block, const int32_t* __restrict__ counters, const Hyper* hp,
-                                 const float* __restrict__ loss_dev) {
-    block[0] = counters[3];
-    block[1] = hp->seq;
-    block[2] = __float_as_int(loss_dev[0]);
-    block[3] = __float_as_int(loss_dev[1]);
-}
-void launch_dp_header(cudaStream_t st, int32_t* block, const int32_t* counters, const Hyper* hp, const float* loss_dev) {
-    dp_header_kernel<<<1, 1, 0, st>>>(block, counters, hp, loss_dev);
-    ++g_launch_count;
-}
-
-// Merge of the ranks' key lists (each ascending, one entry per unique row of that rank) into ONE list sorted by
-// (key, rank) - the order a stable sort of their concatenation would produce - without sorting: the final index of
-// entry i of rank r is i + sum over the other ranks of the number of their keys that sort before it (binary searches,
-// the lists are L2-resident; the searches of the up-to-eight other ranks advance together, so their loads overlap).
-// spos = index of the entry's gradient row in the gathered buffer viewed as rows of d floats.
-__global__ void __launch_bounds__(256) dp_merge_kernel(DpLayout L, int iters, int32_t* __restrict__ skeys,
-                                                        int32_t* __restrict__ spos, int32_t* __restrict__ err_flag) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = (int)(idx / L.cap);
-    const int64_t i = idx - (int64_t)r * L.cap;
-    if (r >= L.world) return;
-    const int32_t* __restrict__ mine = L.base + (int64_t)r * L.stride;
-    int32_t cnt = mine[0];
-    if (cnt > L.cap || cnt < 0) { if (i == 0) atomicExch(err_flag, 2); cnt = cnt < 0 ? 0 : (int32_t)L.cap; }
-    if (i >= cnt) return;
-    const int32_t key = mine[L.keys_off + i];
-    int64_t pos = i;
-    for (int r0 = 0; r0 < L.world; r0 += 8) {
-        const int32_t* kp[8];
-        int lo[8], hi[8];
-        int32_t tgt[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int rr = r0 + u;
-            const bool valid = rr < L.world && rr != r;
-            const int32_t* blk = L.base + (int64_t)(valid ? rr : r) * L.stride;
-            kp[u] = blk + L.keys_off;
-            int c = valid ? blk[0] : 0;
-            c = c < 0 ? 0 : (c > L.cap ? (int)L.cap : c);
-            lo[u] = 0; hi[u] = c;
-            tgt[u] = key + (rr < r ? 1 : 0);   // earlier ranks: their equal key goes first (count keys <= key)
-        }
-        for (int it = 0; it < iters; ++it) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (lo[u] < hi[u]) {
-                    const int mid = (lo[u] + hi[u]) >> 1;
-                    if (kp[u][mid] < tgt[u]) lo[u] = mid + 1; else hi[u] = mid;
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) pos += lo[u];
+// Everything of this rank's packed block except the exported rows, in one launch: header (unique-row count, step
+// sequence number, loss total / L2 part), the dense gradient, zeros in the id slots past the count
+__global__ void dp_pack_misc_kernel(int32_t* __restrict__ block, DpLayout L, const int32_t* __restrict__ counters,
+                                    const Hyper* hp, const float* __restrict__ loss_dev, const float* __restrict__ g, int n_dense) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t cnt = counters[3];
+    if (i == 0) {
+        block[0] = cnt;
+        block[1] = hp->seq;
+        block[2] = __float_as_int(loss_dev[0]);
+        block[3] = __float_as_int(loss_dev[1]);
     }
-    skeys[pos] = key;
-    spos[pos] = (int32_t)(((int64_t)r * L.stride + L.keys_off + L.cap) / L.d + i);
+    if (i < n_dense) reinterpret_cast<float*>(block + L.dense_off)[i] = g[i];
+    if (i >= cnt && i < L.cap) block[L.keys_off + i] = 0;
 }
-void launch_dp_merge(cudaStream_t st, const DpLayout& L, int32_t* skeys, int32_t* spos, int32_t* err_flag) {
-    const int64_t n = (int64_t)L.world * L.cap;
-    cudaMemsetAsync(skeys, 0, sizeof(int32_t) * n, st);   // slots past the total count: key 0 = no row
-    int iters = 1;
-    while (((int64_t)1 << iters) <= L.cap) ++iters;
-    dp_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, iters, skeys, spos, err_flag);
+void launch_dp_pack_misc(cudaStream_t st, int32_t* block, const DpLayout& L, const int32_t* counters, const Hyper* hp,
+                         const float* loss_dev, const float* g, int n_dense) {
+    const int64_t n = L.cap > n_dense ? L.cap : n_dense;
+    dp_pack_misc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(block, L, counters, hp, loss_dev, g, n_dense);
     ++g_launch_count;
 }
 
@@ -769,6 +722,85 @@ void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a) {
         case 16: emb_update_launch<16>(st, a, grid); break;
         case 32: emb_update_launch<32>(st, a, grid); break;
         default: break;   // score_create rejects other widths
+    }
+    ++g_launch_count;
+}
+
+// ------------------------------------------------------------------------------------------ data-parallel update
+// Embedding half of the data-parallel finish, ONE kernel over the gathered blocks of all ranks: every rank's id list is
+// ascending with one entry per unique row, so no sort and no merged list is needed.  One group of LPR lanes per entry
+// (rank r, index i): the lanes split the other ranks among themselves and look the entry's id up in their lists (binary
+// searches over L2-resident lists, one per lane, side by side); the entry of the LOWEST rank that holds the id owns the
+// row: it adds the gradient rows of the higher ranks in rank order (fixed order: every replica computes the same bits)
+// and applies the row's Adam step, the other entries retire.  The optimizer state of the row is fetched before the
+// searches - most entries own their row - so the two latencies overlap.
+template <int LPR>
+__global__ void __launch_bounds__(256) dp_apply_kernel(DpLayout L, int iters, EmbUpdateArgs a, int32_t* __restrict__ err_flag) {
+    constexpr int D = LPR * 4;
+    const int lane = threadIdx.x & 31;
+    const int sub = threadIdx.x % LPR;
+    const unsigned gmask = (LPR >= 32) ? FULL_MASK : (((1u << LPR) - 1u) << (lane & ~(LPR - 1)));
+    const int glane0 = lane & ~(LPR - 1);
+    const int64_t gidx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+    const int r = (int)(gidx / L.cap);
+    const int64_t i = gidx - (int64_t)r * L.cap;
+    if (r >= L.world) return;
+    const int32_t* __restrict__ mine = L.base + (int64_t)r * L.stride;
+    int32_t cnt = mine[0];
+    if (cnt > L.cap || cnt < 0) { if (i == 0 && sub == 0) atomicExch(err_flag, 2); cnt = cnt < 0 ? 0 : (int32_t)L.cap; }
+    if (i >= cnt) return;                                   // uniform over the group
+    const int32_t key = mine[L.keys_off + i];
+    const int64_t off = (int64_t)key * D + sub * 4;
+    float4 var = *reinterpret_cast<const float4*>(a.emb + off);
+    float4 m = *reinterpret_cast<const float4*>(a.m + off);
+    float4 v = *reinterpret_cast<const float4*>(a.v + off);
+    const int last = a.alpha_hist ? a.last_step[key] : 0;
+    float4 acc = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(mine + L.keys_off + L.cap) + i * D + sub * 4);
+    for (int r0 = 0; r0 < L.world; r0 += LPR) {
+        // lane `sub` looks the id up in the list of rank r0 + sub
+        const int rr = r0 + sub;
+        int found = -1;
+        if (rr < L.world && rr != r) {
+            const int32_t* blk = L.base + (int64_t)rr * L.stride;
+            const int32_t* kp = blk + L.keys_off;
+            int c = blk[0];
+            c = c < 0 ? 0 : (c > L.cap ? (int)L.cap : c);
+            int lo = 0, hi = c;
+            for (int it = 0; it < iters; ++it) {
+                if (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (kp[mid] < key) lo = mid + 1; else hi = mid;
+                }
+            }
+            if (lo < c && kp[lo] == key) found = lo;
+        }
+#pragma unroll
+        for (int q = 0; q < LPR; ++q) {
+            const int fq = __shfl_sync(gmask, found, glane0 + q);
+            const int rq = r0 + q;
+            if (fq < 0) continue;
+            if (rq < r) return;                             // a lower rank owns the row (uniform over the group)
+            const float* rows_q = reinterpret_cast<const float*>(L.base + (int64_t)rq * L.stride + L.keys_off + L.cap);
+            const float4 g = *reinterpret_cast<const float4*>(rows_q + (int64_t)fq * D + sub * 4);
+            acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+        }
+    }
+    emb_apply_row<0, LPR>(a, key, 0, acc, var, m, v, last, sub, a.hp->alpha, a.hp->step);
+}
+void launch_dp_apply(cudaStream_t st, const DpLayout& L, const EmbUpdateArgs& a, int32_t* err_flag) {
+    const int lpr = a.d >> 2;
+    const int64_t threads = (int64_t)L.world * L.cap * lpr;
+    const unsigned grid = (unsigned)((threads + 255) / 256);
+    int iters = 1;
+    while (((int64_t)1 << iters) <= L.cap) ++iters;
+    switch (lpr) {
+        case 1: dp_apply_kernel<1><<<grid, 256, 0, st>>>(L, iters, a, err_flag); break;
+        case 2: dp_apply_kernel<2><<<grid, 256, 0, st>>>(L, iters, a, err_flag); break;
+        case 4: dp_apply_kernel<4><<<grid, 256, 0, st>>>(L, iters, a, err_flag); break;
+        case 8: dp_apply_kernel<8><<<grid, 256, 0, st>>>(L, iters, a, err_flag); break;
+        case 16: dp_apply_kernel<16><<<grid, 256, 0, st>>>(L, iters, a, err_flag); break;
+        case 32: dp_apply_kernel<32><<<grid, 256, 0, st>>>(L, iters, a, err_flag); break;
+        default: break;
     }
     ++g_launch_count;
 }
