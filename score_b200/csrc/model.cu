@@ -127,6 +127,13 @@ struct ScoreModel {
     int32_t begin_seq = -1; bool warned_stale = false;
     int32_t* dp_block = nullptr; int64_t dp_block_words = 0;
     double *loss_glob = nullptr, *loss_glob_host = nullptr;
+    // Synchronous train step without draining the device: the loss (+ error flag) leaves the device right after the
+    // forward pass (result packet, own event); backward and update keep running while the caller prepares the next
+    // batch.  Host batches are staged through two buffers on a copy stream, so the next step's H2D overlaps them.
+    float *early_dev = nullptr, *early_host = nullptr; cudaEvent_t ev_loss = nullptr; bool early_on = false;
+    int32_t *ids_stage[2] = {nullptr, nullptr}, *lab_stage[2] = {nullptr, nullptr}, *len_stage[2] = {nullptr, nullptr};
+    cudaStream_t st_h2d = nullptr; cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_stage_free[2] = {nullptr, nullptr};
+    bool stage_busy[2] = {false, false}; int stage_idx = 0; int stage_last = -1;
 
     // graphs
     std::map<int, cudaGraphExec_t> graphs_train;
@@ -298,6 +305,9 @@ int alloc_params(ScoreModel* h) {
     CK(cudaMemsetAsync(h->n_heads_dev, 0, 4 * sizeof(int32_t), h->st));
     CK(cudaMalloc(&h->l2sum, sizeof(float) * L2_PARTS));
     CK(cudaMalloc(&h->loss_dev, 2 * sizeof(float)));
+    CK(cudaMalloc(&h->early_dev, 4 * sizeof(float)));
+    CK(cudaMemset(h->early_dev, 0xff, 4 * sizeof(float)));
+    CK(cudaMallocHost(&h->early_host, 4 * sizeof(float)));
     CK(cudaMalloc(&h->err_flag, sizeof(int32_t)));
     CK(cudaMemsetAsync(h->err_flag, 0, sizeof(int32_t), h->st));
     CK(cudaMalloc(&h->step_dev, sizeof(ScoreModel::StepParams)));
@@ -428,6 +438,11 @@ int ensure_workspace(ScoreModel* h, int B) {
         if (rc) return rc;
         h->sb.hist = hist;
     }
+    // host batches are staged through two buffer sets (upload_batch): set 0 is `ids`
+    h->ids_stage[0] = h->ids;
+    WSI(h->ids_stage[1], N, nullptr);
+    for (int i = 0; i < 2; ++i) { WSI(h->lab_stage[i], cap, nullptr); WSI(h->len_stage[i], cap, nullptr); }
+    h->stage_busy[0] = h->stage_busy[1] = false; h->stage_last = -1;
     WSI(h->head_slot, N, nullptr);
     WSI(h->hs_tiles, head_slot_tiles(N) + 1, nullptr);
     h->seg_rows = nullptr; h->seg_heads = nullptr; h->seg_cap = 0;
@@ -454,25 +469,43 @@ int upload_batch(ScoreModel* h, const ScoreBatch* b) {
     const int64_t M = (int64_t)B * dm.T;
     BatchPtrs& bp = h->bp_cur;
     if (b->on_device) {
+        h->stage_last = -1;
         bp.u1 = b->user_1hop; bp.u2 = b->user_2hop; bp.i1 = b->item_1hop; bp.i2 = b->item_2hop;
         bp.tu = b->target_user; bp.ti = b->target_item; bp.label = b->label; bp.length = b->length;
         return SCORE_OK;
     }
+    // Host batch: copied into one of two staging sets on the copy stream, so the copy of the NEXT batch can run while the
+    // previous step is still in its backward pass (its build_keys - the only reader of a staging set - ran long ago; the
+    // event guards the asynchronous callers that run several steps ahead).
     const size_t s_i = sizeof(int32_t);
     const int64_t n_i = M * dm.K * dm.fi, n_u = M * dm.K * dm.fu;
-    int32_t* st_u1 = h->ids; int32_t* st_u2 = st_u1 + n_i; int32_t* st_i1 = st_u2 + n_u; int32_t* st_i2 = st_i1 + n_u;
+    const int sidx = h->stage_idx ^= 1;
+    cudaStream_t cs = h->st_h2d;
+    if (h->stage_busy[sidx]) CK(cudaStreamWaitEvent(cs, h->ev_stage_free[sidx], 0));
+    int32_t* st_u1 = h->ids_stage[sidx]; int32_t* st_u2 = st_u1 + n_i; int32_t* st_i1 = st_u2 + n_u; int32_t* st_i2 = st_i1 + n_u;
     int32_t* st_tu = st_i2 + n_i; int32_t* st_ti = st_tu + (int64_t)B * dm.fu;
-    CK(cudaMemcpyAsync(st_u1, b->user_1hop, s_i * n_i, cudaMemcpyHostToDevice, h->st));
-    CK(cudaMemcpyAsync(st_u2, b->user_2hop, s_i * n_u, cudaMemcpyHostToDevice, h->st));
-    CK(cudaMemcpyAsync(st_i1, b->item_1hop, s_i * n_u, cudaMemcpyHostToDevice, h->st));
-    CK(cudaMemcpyAsync(st_i2, b->item_2hop, s_i * n_i, cudaMemcpyHostToDevice, h->st));
-    CK(cudaMemcpyAsync(st_tu, b->target_user, s_i * B * dm.fu, cudaMemcpyHostToDevice, h->st));
-    CK(cudaMemcpyAsync(st_ti, b->target_item, s_i * B * dm.fi, cudaMemcpyHostToDevice, h->st));
-    CK(cudaMemcpyAsync(h->label, b->label, s_i * B, cudaMemcpyHostToDevice, h->st));
-    CK(cudaMemcpyAsync(h->length, b->length, s_i * B, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(st_u1, b->user_1hop, s_i * n_i, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(st_u2, b->user_2hop, s_i * n_u, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(st_i1, b->item_1hop, s_i * n_u, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(st_i2, b->item_2hop, s_i * n_i, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(st_tu, b->target_user, s_i * B * dm.fu, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(st_ti, b->target_item, s_i * B * dm.fi, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(h->lab_stage[sidx], b->label, s_i * B, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(h->len_stage[sidx], b->length, s_i * B, cudaMemcpyHostToDevice, cs));
+    CK(cudaEventRecord(h->ev_h2d[sidx], cs));
+    CK(cudaStreamWaitEvent(h->st, h->ev_h2d[sidx], 0));
+    h->stage_last = sidx;
     bp.u1 = st_u1; bp.u2 = st_u2; bp.i1 = st_i1; bp.i2 = st_i2; bp.tu = st_tu; bp.ti = st_ti;
-    bp.label = h->label; bp.length = h->length;
+    bp.label = h->lab_stage[sidx]; bp.length = h->len_stage[sidx];
     return SCORE_OK;
+}
+
+// after the kernels that read the current batch have been enqueued: the staging set may be refilled behind them
+void stage_release(ScoreModel* h) {
+    if (h->stage_last < 0) return;
+    cudaEventRecord(h->ev_stage_free[h->stage_last], h->st);
+    h->stage_busy[h->stage_last] = true;
+    h->stage_last = -1;
 }
 
 // ------------------------------------------------------------------------------------------ GEMM helpers
@@ -674,7 +707,11 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
     // stream) instead of between the forward and the backward chain
     cudaEventRecord(h->ev_fc, h->st);
     cudaStreamWaitEvent(h->st_w, h->ev_fc, 0);
-    launch_loss_final(h->st_w, B, h->loss_b, h->l2sum, h->hyper_dev, h->loss_dev);
+    launch_loss_final(h->st_w, B, h->loss_b, h->l2sum, h->hyper_dev, h->loss_dev, h->err_flag, h->early_on ? h->early_dev : nullptr);
+    if (h->early_on) {   // the step's result leaves the device now; the host waits for this event only (finish_early)
+        cudaMemcpyAsync(h->early_host, h->early_dev, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->st_w);
+        cudaEventRecordWithFlags(h->ev_loss, h->st_w, h->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+    }
     if (!will_bwd) {   // no backward: nothing else joins the side stream
         cudaEventRecord(h->ev_w, h->st_w);
         cudaStreamWaitEvent(h->st, h->ev_w, 0);
@@ -685,12 +722,13 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
 // scheduling knobs (measured on B200, profiles/README.md); SCORE_SCHED=0 restores the serial order
 static int sched_flags() {
     static int f = -1;
-    if (f < 0) { const char* e = getenv("SCORE_SCHED"); f = e ? atoi(e) : 7; }
+    if (f < 0) { const char* e = getenv("SCORE_SCHED"); f = e ? atoi(e) : 15; }
     return f;
 }
 static bool side_qb() { return (sched_flags() & 1) != 0; }        // att_qb on the side stream
 static bool side_reduce() { return (sched_flags() & 2) != 0; }    // final dense reduce + Adam next to the embedding update
 static bool sort_after_gather() { return (sched_flags() & 4) != 0; }   // sort branch forks after the gather kernel
+static bool early_return() { return (sched_flags() & 8) != 0; }        // synchronous train returns when the loss is ready
 
 void enqueue_backward(ScoreModel* h, bool fused_adam = false, bool defer_join = false) {
     DenseAdamArgs adam_args{h->P, h->M1, h->V1, h->flags, h->hyper_dev, h->alpha_hist};
@@ -856,6 +894,7 @@ void enqueue_step(ScoreModel* h, int mode) {
     // first pass runs next to the (instruction-bound) lazy replay, the other passes are forked after the gather.
     h->sort_deferred = need_bwd && sort_after_gather();
     h->sort_dp = false;
+    h->early_on = train;
     if (h->cfg.adam_mode == SCORE_ADAM_LAZY) {
         probe_begin(h, PR_CATCHUP, h->st);
         ClaimArgs ca{h->last_step, h->hyper_dev, h->claim_list, h->claim_counter, 1};
@@ -969,6 +1008,23 @@ int finish_sync(ScoreModel* h, float* loss_out) {
     return SCORE_OK;
 }
 
+// Result of a training step without waiting for its backward pass and update: wait for the result packet only.  Every
+// later call on the handle is ordered behind the step by the stream, so nothing can observe the pre-update state.
+int finish_early(ScoreModel* h, float* loss_out) {
+    CK(cudaEventSynchronize(h->ev_loss));
+    int32_t seq, err;
+    memcpy(&seq, &h->early_host[3], sizeof seq);
+    memcpy(&err, &h->early_host[2], sizeof err);
+    if (seq != h->hyper_host->seq) return finish_sync(h, loss_out);   // packet of another step (should not happen)
+    if (loss_out) *loss_out = h->early_host[0];
+    h->loss_host[0] = h->early_host[0]; h->loss_host[1] = h->early_host[1];
+    if (err) {
+        cudaMemsetAsync(h->err_flag, 0, sizeof(int32_t), h->st);
+        return fail(h, SCORE_ERR_ID_RANGE, "an id in the batch is outside [0, feature_size)");
+    }
+    return SCORE_OK;
+}
+
 int run_step(ScoreModel* h, const ScoreBatch* b, int mode, float lr, float reg_lambda, float keep_prob,
              int global_batch, bool sync, float* loss_out) {
     int rc = check_batch(h, b);
@@ -1022,8 +1078,10 @@ int run_step(ScoreModel* h, const ScoreBatch* b, int mode, float lr, float reg_l
         h->beta1_power = h->beta1_power * 0.9f;
         h->beta2_power = h->beta2_power * 0.999f;
     }
+    stage_release(h);
     h->pending_step = true;
     if (sync) {
+        if (train && !h->probes_on && early_return()) return finish_early(h, loss_out);
         h->pending_step = false;
         return finish_sync(h, loss_out);
     }
@@ -1090,6 +1148,12 @@ int score_create(const ScoreConfig* cfg, int device, ScoreHandle* out) {
         cudaEventCreateWithFlags(&h->ev_keys, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fc, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_att, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_loss, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_h2d[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_h2d[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_stage_free[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_stage_free[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_qb, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         h->err = "stream/event creation failed";
@@ -1141,6 +1205,11 @@ int score_destroy(ScoreHandle h) {
         cudaStreamDestroy(h->st);
     }
     if (h->st2) cudaStreamDestroy(h->st2);
+    if (h->st_h2d) cudaStreamDestroy(h->st_h2d);
+    if (h->ev_loss) cudaEventDestroy(h->ev_loss);
+    for (int i = 0; i < 2; ++i) { if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]); if (h->ev_stage_free[i]) cudaEventDestroy(h->ev_stage_free[i]); }
+    if (h->early_dev) cudaFree(h->early_dev);
+    if (h->early_host) cudaFreeHost(h->early_host);
     if (h->st_cnt) cudaStreamDestroy(h->st_cnt);
     if (h->ev_counts) cudaEventDestroy(h->ev_counts);
     if (h->cnt_slot) cudaFree(h->cnt_slot);
@@ -1528,6 +1597,7 @@ int score_prepare_batch(ScoreHandle h, const ScoreBatch* batch) {
     rc = upload_hyper(h, B, 0.f, 0.f, 1.f, 0, 0);   // carries the batch's pointer table
     if (rc) return rc;
     launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag);
+    stage_release(h);
     return SCORE_OK;
 }
 
@@ -1604,6 +1674,7 @@ int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg
     auto enqueue_begin = [&]() {
         const bool own_sort = train && !staged_table;   // sort of this rank's own keys under forward/backward (score_dp_pack)
         h->sort_dp = own_sort;
+        h->early_on = false;
         h->sort_deferred = own_sort && sort_after_gather();
         cudaEventRecord(h->ev_fork, h->st);
         const bool lazy = h->cfg.adam_mode == SCORE_ADAM_LAZY;
@@ -1662,6 +1733,7 @@ int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg
         h->warm_begin[B]++;
     }
     if (!launched) enqueue_begin();
+    stage_release(h);
     h->begun = train != 0;
     h->begun_lr = lr;
     CK(cudaGetLastError());

@@ -345,7 +345,8 @@ void launch_head(cudaStream_t st, int B, int F, const float* g2, const float* w3
 
 // loss = (sum_b loss_b) * inv_batch + reg_lambda * l2sum ; single block, fixed-shape tree
 __global__ void loss_final_kernel(int B, const float* __restrict__ loss_b, const float* __restrict__ l2sum,
-                                  const Hyper* hp, float* __restrict__ loss) {
+                                  const Hyper* hp, float* __restrict__ loss, const int32_t* __restrict__ err_flag,
+                                  float* __restrict__ early) {
     __shared__ float red[256];
     float s = 0.f;
     for (int i = threadIdx.x; i < B; i += 256) s += loss_b[i];
@@ -361,10 +362,16 @@ __global__ void loss_final_kernel(int B, const float* __restrict__ loss_b, const
         const float reg = hp->reg_lambda * l2;
         loss[0] = red[0] * hp->inv_batch + reg;
         loss[1] = reg;
+        if (early) {   // the step's result packet for the host: loss, L2 part, id-range error flag, step sequence number
+            early[0] = loss[0]; early[1] = reg;
+            early[2] = __int_as_float(err_flag ? *err_flag : 0);
+            early[3] = __int_as_float(hp->seq);
+        }
     }
 }
-void launch_loss_final(cudaStream_t st, int B, const float* loss_b, const float* l2sum, const Hyper* hp, float* loss) {
-    loss_final_kernel<<<1, 256, 0, st>>>(B, loss_b, l2sum, hp, loss);
+void launch_loss_final(cudaStream_t st, int B, const float* loss_b, const float* l2sum, const Hyper* hp, float* loss,
+                       const int32_t* err_flag, float* early) {
+    loss_final_kernel<<<1, 256, 0, st>>>(B, loss_b, l2sum, hp, loss, err_flag, early);
     ++g_launch_count;
 }
 
