@@ -190,8 +190,9 @@ void launch_bn_param_grads(cudaStream_t st, int B, int F, const float* x, const 
 void launch_head(cudaStream_t st, int B, int F, const float* g2, const float* w3, const float* b3,
                  const int32_t* label, const Hyper* hp, float* y, float* loss_b, float* dlogit);
 // loss = sum_b loss_b * inv_batch + reg_lambda * l2sum    (fixed-order reduction)
-// early (may be null): 4 floats {loss, L2 part, *err_flag as bits, hp->seq as bits} - the result packet the host can
-// read as soon as the forward pass is done
+// early (may be null; device-visible pinned HOST memory): 4 floats {loss, L2 part, *err_flag as bits, hp->seq as bits},
+// the sequence number last and behind a system fence - the result packet the host polls for, available as soon as the
+// forward pass is done
 void launch_loss_final(cudaStream_t st, int B, const float* loss_b, const float* l2sum, const Hyper* hp, float* loss,
                        const int32_t* err_flag = nullptr, float* early = nullptr);
 

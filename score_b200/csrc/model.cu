@@ -128,9 +128,9 @@ struct ScoreModel {
     int32_t* dp_block = nullptr; int64_t dp_block_words = 0;
     double *loss_glob = nullptr, *loss_glob_host = nullptr;
     // Synchronous train step without draining the device: the loss (+ error flag) leaves the device right after the
-    // forward pass (result packet, own event); backward and update keep running while the caller prepares the next
-    // batch.  Host batches are staged through two buffers on a copy stream, so the next step's H2D overlaps them.
-    float *early_dev = nullptr, *early_host = nullptr; cudaEvent_t ev_loss = nullptr; bool early_on = false;
+    // forward pass (result packet written by loss_final into pinned host memory, which the host polls); backward and
+    // update keep running while the caller prepares the next batch.  Host batches are staged through two buffers on a copy stream, so the next step's H2D overlaps them.
+    float* early_host = nullptr; bool early_on = false;
     int32_t *ids_stage[2] = {nullptr, nullptr}, *lab_stage[2] = {nullptr, nullptr}, *len_stage[2] = {nullptr, nullptr};
     cudaStream_t st_h2d = nullptr; cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_stage_free[2] = {nullptr, nullptr};
     bool stage_busy[2] = {false, false}; int stage_idx = 0; int stage_last = -1;
@@ -305,9 +305,8 @@ int alloc_params(ScoreModel* h) {
     CK(cudaMemsetAsync(h->n_heads_dev, 0, 4 * sizeof(int32_t), h->st));
     CK(cudaMalloc(&h->l2sum, sizeof(float) * L2_PARTS));
     CK(cudaMalloc(&h->loss_dev, 2 * sizeof(float)));
-    CK(cudaMalloc(&h->early_dev, 4 * sizeof(float)));
-    CK(cudaMemset(h->early_dev, 0xff, 4 * sizeof(float)));
-    CK(cudaMallocHost(&h->early_host, 4 * sizeof(float)));
+    CK(cudaMallocHost(&h->early_host, 4 * sizeof(float)));   // page-locked: the device writes the result packet into it
+    memset(h->early_host, 0xff, 4 * sizeof(float));
     CK(cudaMalloc(&h->err_flag, sizeof(int32_t)));
     CK(cudaMemsetAsync(h->err_flag, 0, sizeof(int32_t), h->st));
     CK(cudaMalloc(&h->step_dev, sizeof(ScoreModel::StepParams)));
@@ -707,11 +706,7 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
     // stream) instead of between the forward and the backward chain
     cudaEventRecord(h->ev_fc, h->st);
     cudaStreamWaitEvent(h->st_w, h->ev_fc, 0);
-    launch_loss_final(h->st_w, B, h->loss_b, h->l2sum, h->hyper_dev, h->loss_dev, h->err_flag, h->early_on ? h->early_dev : nullptr);
-    if (h->early_on) {   // the step's result leaves the device now; the host waits for this event only (finish_early)
-        cudaMemcpyAsync(h->early_host, h->early_dev, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->st_w);
-        cudaEventRecordWithFlags(h->ev_loss, h->st_w, h->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
-    }
+    launch_loss_final(h->st_w, B, h->loss_b, h->l2sum, h->hyper_dev, h->loss_dev, h->err_flag, h->early_on ? h->early_host : nullptr);
     if (!will_bwd) {   // no backward: nothing else joins the side stream
         cudaEventRecord(h->ev_w, h->st_w);
         cudaStreamWaitEvent(h->st, h->ev_w, 0);
@@ -1011,13 +1006,25 @@ int finish_sync(ScoreModel* h, float* loss_out) {
 // Result of a training step without waiting for its backward pass and update: wait for the result packet only.  Every
 // later call on the handle is ordered behind the step by the stream, so nothing can observe the pre-update state.
 int finish_early(ScoreModel* h, float* loss_out) {
-    CK(cudaEventSynchronize(h->ev_loss));
-    int32_t seq, err;
-    memcpy(&seq, &h->early_host[3], sizeof seq);
-    memcpy(&err, &h->early_host[2], sizeof err);
-    if (seq != h->hyper_host->seq) return finish_sync(h, loss_out);   // packet of another step (should not happen)
-    if (loss_out) *loss_out = h->early_host[0];
-    h->loss_host[0] = h->early_host[0]; h->loss_host[1] = h->early_host[1];
+    volatile int32_t* pk = reinterpret_cast<volatile int32_t*>(h->early_host);
+    const int32_t want = h->hyper_host->seq;
+    bool got = false;
+    for (int64_t spin = 0; !got; ++spin) {
+        got = pk[3] == want;
+        if (got || (spin & 0xfff) != 0xfff) continue;
+        // every few thousand polls: has the whole step finished (or failed) without delivering the packet?
+        const cudaError_t q = cudaStreamQuery(h->st);
+        if (q == cudaErrorNotReady) continue;
+        got = pk[3] == want;
+        if (!got) return finish_sync(h, loss_out);
+    }
+    __sync_synchronize();
+    int32_t err = pk[2];
+    float lv[2];
+    int32_t bits0 = pk[0], bits1 = pk[1];
+    memcpy(&lv[0], &bits0, 4); memcpy(&lv[1], &bits1, 4);
+    if (loss_out) *loss_out = lv[0];
+    h->loss_host[0] = lv[0]; h->loss_host[1] = lv[1];
     if (err) {
         cudaMemsetAsync(h->err_flag, 0, sizeof(int32_t), h->st);
         return fail(h, SCORE_ERR_ID_RANGE, "an id in the batch is outside [0, feature_size)");
@@ -1149,7 +1156,6 @@ int score_create(const ScoreConfig* cfg, int device, ScoreHandle* out) {
         cudaEventCreateWithFlags(&h->ev_fc, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_att, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_loss, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_h2d[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_h2d[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_stage_free[0], cudaEventDisableTiming) != cudaSuccess ||
@@ -1206,9 +1212,7 @@ int score_destroy(ScoreHandle h) {
     }
     if (h->st2) cudaStreamDestroy(h->st2);
     if (h->st_h2d) cudaStreamDestroy(h->st_h2d);
-    if (h->ev_loss) cudaEventDestroy(h->ev_loss);
     for (int i = 0; i < 2; ++i) { if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]); if (h->ev_stage_free[i]) cudaEventDestroy(h->ev_stage_free[i]); }
-    if (h->early_dev) cudaFree(h->early_dev);
     if (h->early_host) cudaFreeHost(h->early_host);
     if (h->st_cnt) cudaStreamDestroy(h->st_cnt);
     if (h->ev_counts) cudaEventDestroy(h->ev_counts);

@@ -362,10 +362,14 @@ __global__ void loss_final_kernel(int B, const float* __restrict__ loss_b, const
         const float reg = hp->reg_lambda * l2;
         loss[0] = red[0] * hp->inv_batch + reg;
         loss[1] = reg;
-        if (early) {   // the step's result packet for the host: loss, L2 part, id-range error flag, step sequence number
-            early[0] = loss[0]; early[1] = reg;
-            early[2] = __int_as_float(err_flag ? *err_flag : 0);
-            early[3] = __int_as_float(hp->seq);
+        if (early) {
+            // the step's result packet, written straight into pinned host memory: loss, L2 part, id-range error flag,
+            // then (after a system-wide fence) the step sequence number the host is polling for
+            volatile float* e = early;
+            e[0] = loss[0]; e[1] = reg;
+            e[2] = __int_as_float(err_flag ? *err_flag : 0);
+            __threadfence_system();
+            e[3] = __int_as_float(hp->seq);
         }
     }
 }
