@@ -10,8 +10,9 @@ K=10, batch 1024), the config the >=100x target is quoted on.
 Prints ONE JSON line (rank 0).  `value` = whole-job samples/s with the id tensors already resident in
 HBM; `e2e` = the same metric through the reference-facing call model.train(sess, batch, lr, reg) with
 pinned HOST buffers (H2D of the ids and D2H of the loss inside the timed region).  `roofline` is the
-embedding gather kernel (coatt_fwd) timed with CUDA events on its own stream inside the timed steps;
-`roofline_scatter` the sort-free part of the scatter (segment-reduce + row Adam).  `cpu_baseline` is the
+dominant HBM-bound kernel of the step - the scatter's segment-reduce + fused row Adam (emb_update) - timed with
+CUDA events on its own stream inside the timed steps; `roofline_gather` is the fused embedding gather +
+co-attention kernel (coatt_fwd) measured the same way.  `cpu_baseline` is the
 literal CPU restatement of score.py (oracle/, "port": TF 1.x cannot be installed offline) timed on the
 box's host cores on a bounded sample of the same workload.
 """
@@ -349,7 +350,9 @@ def main():
         roof_s = {"bound": "hbm", "kernel": "emb_update_kernel (segment-reduce + fused row Adam)",
                   "achieved": scatter_bytes / (t_s * 1e-3) / 1e9 if t_s else None, "peak": peak, "unit": "GB/s",
                   "frac": scatter_bytes / (t_s * 1e-3) / 1e9 / peak if t_s else None, "traffic": tr_s,
-                  "traffic_source": src_s,
+                  "traffic_source": src_s, "peak_source": peak_src,
+                  "timing": "CUDA events around the kernel on its own stream inside every step of a second timed region "
+                            "of the same K steps (ms_per_step_probed; the event nodes add ~3 us to each bracketed kernel)",
                   "bytes_per_launch": scatter_bytes, "ms_per_launch": t_s, "unique_rows": uniq,
                   "bytes_rule": "live ids x (4 + 4d) + unique rows x 6 x 4d"}
         line = {"metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
@@ -360,7 +363,10 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                         "steps": e2e_steps, "api": "SCORE.train(sess, batch_data, lr, reg_lambda) -> float, pinned host ids"},
                 "gpu_launches": int(launches),
-                "roofline": roof, "roofline_scatter": roof_s,
+                # `roofline` = the dominant HBM-bound kernel of the step (most DRAM traffic, longest of the HBM-side
+                # kernels): the scatter + row Adam; the gather kernel is reported beside it (BASELINE.json's metric
+                # names both)
+                "roofline": roof_s, "roofline_gather": roof, "roofline_scatter": roof_s,
                 "kernel_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in probes.items()},
                 "ms_per_step_probed": ms_probed,
                 "final_loss": loss}

@@ -325,7 +325,9 @@ void launch_dp_pack_misc(cudaStream_t st, int32_t* block, const DpLayout& L, con
                          const float* loss_dev, const float* g, int n_dense);
 // embedding half of the data-parallel finish over the gathered blocks, one kernel: per id, the ranks' rows added in
 // rank order + the row's Adam step (a: emb / m / v / last_step / alpha_hist / hp / d as for launch_emb_update)
-void launch_dp_apply(cudaStream_t st, const DpLayout& L, const EmbUpdateArgs& a, int32_t* err_flag);
+// sample: dp_sample_count(world, cap) ints of scratch (sampled copies of the id lists, built by the same call)
+int64_t dp_sample_count(int world, int64_t cap);
+void launch_dp_apply(cudaStream_t st, const DpLayout& L, const EmbUpdateArgs& a, int32_t* sample, int32_t* err_flag);
 // rank-ordered sum of the gathered dense gradients + dense Adam; loss_out[0] = global loss (double)
 void launch_dp_dense_adam(cudaStream_t st, const DpLayout& L, float* p, float* m, float* v, float* g_out,
                           const uint8_t* flags, int n, const Hyper* hp, float* alpha_hist, double* loss_out);

@@ -126,6 +126,7 @@ struct ScoreModel {
     cudaStream_t st_cnt = nullptr; cudaEvent_t ev_counts = nullptr;
     int32_t begin_seq = -1; bool warned_stale = false;
     int32_t* dp_block = nullptr; int64_t dp_block_words = 0;
+    int32_t* dp_sample = nullptr; int64_t dp_sample_cap = 0;   // sampled id lists of the gathered blocks (launch_dp_apply)
     double *loss_glob = nullptr, *loss_glob_host = nullptr;
     // Synchronous train step without draining the device: the loss (+ error flag) leaves the device right after the
     // forward pass (result packet written by loss_final into pinned host memory, which the host polls); backward and
@@ -1219,6 +1220,7 @@ int score_destroy(ScoreHandle h) {
     if (h->cnt_slot) cudaFree(h->cnt_slot);
     if (h->cnt_host) cudaFreeHost(h->cnt_host);
     if (h->dp_block) cudaFree(h->dp_block);
+    if (h->dp_sample) cudaFree(h->dp_sample);
     if (h->loss_glob) cudaFree(h->loss_glob);
     if (h->loss_glob_host) cudaFreeHost(h->loss_glob_host);
     delete h;
@@ -1787,6 +1789,7 @@ int score_dp_pack(ScoreHandle h, int64_t cap, void** block_dev, int64_t* block_w
     if (L.stride > h->dp_block_words) {
         CK(cudaStreamSynchronize(h->st));
         if (h->dp_block) cudaFree(h->dp_block);
+    if (h->dp_sample) cudaFree(h->dp_sample);
         h->dp_block = nullptr; h->dp_block_words = 0;
         const int64_t words = L.stride + L.stride / 4;
         CK(cudaMalloc(&h->dp_block, sizeof(int32_t) * words));
@@ -1825,7 +1828,15 @@ int score_dp_finish(ScoreHandle h, const void* gathered, int32_t world, int64_t 
     ea.d = h->dm.d;
     ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.last_step = h->last_step;
     ea.alpha_hist = h->alpha_hist; ea.hp = h->hyper_dev; ea.mode = 0;
-    launch_dp_apply(h->st, L, ea, h->err_flag);
+    if (dp_sample_count(world, cap) > h->dp_sample_cap) {
+        CK(cudaStreamSynchronize(h->st));
+        if (h->dp_sample) cudaFree(h->dp_sample);
+        h->dp_sample = nullptr; h->dp_sample_cap = 0;
+        const int64_t want = 2 * dp_sample_count(world, cap);
+        CK(cudaMalloc(&h->dp_sample, sizeof(int32_t) * want));
+        h->dp_sample_cap = want;
+    }
+    launch_dp_apply(h->st, L, ea, h->dp_sample, h->err_flag);
     if (h->local_sorted) { h->last_sorted = h->sb.keys[h->sort_out]; h->last_sorted_n = h->dm.N; }   // this rank's share (stats)
     if (h->cfg.adam_mode == SCORE_ADAM_DENSE)
         launch_emb_dense_sweep(h->st, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.V, h->dm.d, h->hyper_dev);

@@ -729,13 +729,30 @@ void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a) {
 // ------------------------------------------------------------------------------------------ data-parallel update
 // Embedding half of the data-parallel finish, ONE kernel over the gathered blocks of all ranks: every rank's id list is
 // ascending with one entry per unique row, so no sort and no merged list is needed.  One group of LPR lanes per entry
-// (rank r, index i): the lanes split the other ranks among themselves and look the entry's id up in their lists (binary
-// searches over L2-resident lists, one per lane, side by side); the entry of the LOWEST rank that holds the id owns the
-// row: it adds the gradient rows of the higher ranks in rank order (fixed order: every replica computes the same bits)
-// and applies the row's Adam step, the other entries retire.  The optimizer state of the row is fetched before the
-// searches - most entries own their row - so the two latencies overlap.
-template <int LPR>
-__global__ void __launch_bounds__(256) dp_apply_kernel(DpLayout L, int iters, EmbUpdateArgs a, int32_t* __restrict__ err_flag) {
+// (rank r, index i): the lanes split the other ranks among themselves and look the entry's id up in their lists; the
+// entry of the LOWEST rank that holds the id owns the row: it adds the gradient rows of the higher ranks in rank order
+// (fixed order: every replica computes the same bits) and applies the row's Adam step, the other entries retire.  The
+// optimizer state of the row is fetched before the lookups - most entries own their row - so the latencies overlap.
+// A lookup is two short binary searches: first in a sampled copy of the list (every DP_SAMPLE-th id; all ranks' samples
+// together are a few tens of KB and stay in L1), then inside the one DP_SAMPLE-id block of the full list it points at -
+// two or three L2 round trips instead of seventeen; the up-to-DP_J lookups of a lane advance side by side (DP_J = 1 when
+// the world is small enough for one lookup per lane, 4 otherwise).
+constexpr int DP_SAMPLE = 64;
+
+__global__ void dp_sample_kernel(DpLayout L, int ns, int32_t* __restrict__ sample) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)L.world * ns) return;
+    const int r = (int)(idx / ns), j = (int)(idx - (int64_t)r * ns);
+    const int32_t* blk = L.base + (int64_t)r * L.stride;
+    int c = blk[0];
+    c = c < 0 ? 0 : (c > L.cap ? (int)L.cap : c);
+    const int pos = j * DP_SAMPLE;
+    sample[idx] = pos < c ? blk[L.keys_off + pos] : 0x7fffffff;
+}
+
+template <int LPR, int DP_J>
+__global__ void __launch_bounds__(256) dp_apply_kernel(DpLayout L, int ns, int it1, const int32_t* __restrict__ sample,
+                                                        EmbUpdateArgs a, int32_t* __restrict__ err_flag) {
     constexpr int D = LPR * 4;
     const int lane = threadIdx.x & 31;
     const int sub = threadIdx.x % LPR;
@@ -756,53 +773,90 @@ __global__ void __launch_bounds__(256) dp_apply_kernel(DpLayout L, int iters, Em
     float4 v = *reinterpret_cast<const float4*>(a.v + off);
     const int last = a.alpha_hist ? a.last_step[key] : 0;
     float4 acc = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(mine + L.keys_off + L.cap) + i * D + sub * 4);
-    for (int r0 = 0; r0 < L.world; r0 += LPR) {
-        // lane `sub` looks the id up in the list of rank r0 + sub
-        const int rr = r0 + sub;
-        int found = -1;
-        if (rr < L.world && rr != r) {
-            const int32_t* blk = L.base + (int64_t)rr * L.stride;
-            const int32_t* kp = blk + L.keys_off;
-            int c = blk[0];
-            c = c < 0 ? 0 : (c > L.cap ? (int)L.cap : c);
-            int lo = 0, hi = c;
-            for (int it = 0; it < iters; ++it) {
-                if (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (kp[mid] < key) lo = mid + 1; else hi = mid;
+    for (int r0 = 0; r0 < L.world; r0 += LPR * DP_J) {
+        // lane `sub` looks the id up in the lists of ranks r0 + sub, r0 + LPR + sub, ... (DP_J lookups side by side)
+        const int32_t* kp[DP_J];
+        const int32_t* sp[DP_J];
+        int lo[DP_J], hi[DP_J], c[DP_J], found[DP_J];
+#pragma unroll
+        for (int j = 0; j < DP_J; ++j) {
+            const int rr = r0 + j * LPR + sub;
+            const bool valid = rr < L.world && rr != r;
+            const int32_t* blk = L.base + (int64_t)(valid ? rr : r) * L.stride;
+            kp[j] = blk + L.keys_off;
+            sp[j] = sample + (int64_t)(valid ? rr : r) * ns;
+            int cc = valid ? blk[0] : 0;
+            c[j] = cc < 0 ? 0 : (cc > L.cap ? (int)L.cap : cc);
+            lo[j] = 0; hi[j] = c[j] > 0 ? ns : 0;           // phase 1: first sample > key (samples past the count are INT_MAX)
+            found[j] = -1;
+        }
+        for (int it = 0; it < it1; ++it) {
+#pragma unroll
+            for (int j = 0; j < DP_J; ++j)
+                if (lo[j] < hi[j]) {
+                    const int mid = (lo[j] + hi[j]) >> 1;
+                    if (__ldg(sp[j] + mid) <= key) lo[j] = mid + 1; else hi[j] = mid;
                 }
-            }
-            if (lo < c && kp[lo] == key) found = lo;
         }
 #pragma unroll
-        for (int q = 0; q < LPR; ++q) {
-            const int fq = __shfl_sync(gmask, found, glane0 + q);
-            const int rq = r0 + q;
-            if (fq < 0) continue;
-            if (rq < r) return;                             // a lower rank owns the row (uniform over the group)
-            const float* rows_q = reinterpret_cast<const float*>(L.base + (int64_t)rq * L.stride + L.keys_off + L.cap);
-            const float4 g = *reinterpret_cast<const float4*>(rows_q + (int64_t)fq * D + sub * 4);
-            acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+        for (int j = 0; j < DP_J; ++j) {                    // phase 2: lower bound inside block lo-1 of the full list
+            const int blk0 = (lo[j] - 1) * DP_SAMPLE;
+            const bool any = c[j] > 0 && lo[j] > 0;
+            const int end = blk0 + DP_SAMPLE < c[j] ? blk0 + DP_SAMPLE : c[j];
+            lo[j] = any ? blk0 : 0; hi[j] = any ? end : 0;
+        }
+#pragma unroll
+        for (int it = 0; it < 7; ++it) {                    // 2^6 = DP_SAMPLE ids: at most 7 halvings
+#pragma unroll
+            for (int j = 0; j < DP_J; ++j)
+                if (lo[j] < hi[j]) {
+                    const int mid = (lo[j] + hi[j]) >> 1;
+                    if (kp[j][mid] < key) lo[j] = mid + 1; else hi[j] = mid;
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < DP_J; ++j)
+            if (lo[j] < c[j] && c[j] > 0 && kp[j][lo[j]] == key) found[j] = lo[j];
+#pragma unroll
+        for (int j = 0; j < DP_J; ++j) {
+#pragma unroll
+            for (int q = 0; q < LPR; ++q) {
+                const int rq = r0 + j * LPR + q;
+                if (rq >= L.world) continue;                // uniform
+                const int fq = __shfl_sync(gmask, found[j], glane0 + q);
+                if (fq < 0) continue;
+                if (rq < r) return;                         // a lower rank owns the row (uniform over the group)
+                const float* rows_q = reinterpret_cast<const float*>(L.base + (int64_t)rq * L.stride + L.keys_off + L.cap);
+                const float4 g = *reinterpret_cast<const float4*>(rows_q + (int64_t)fq * D + sub * 4);
+                acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+            }
         }
     }
     emb_apply_row<0, LPR>(a, key, 0, acc, var, m, v, last, sub, a.hp->alpha, a.hp->step);
 }
-void launch_dp_apply(cudaStream_t st, const DpLayout& L, const EmbUpdateArgs& a, int32_t* err_flag) {
+int64_t dp_sample_count(int world, int64_t cap) { return (int64_t)world * (cap / DP_SAMPLE); }
+void launch_dp_apply(cudaStream_t st, const DpLayout& L, const EmbUpdateArgs& a, int32_t* sample, int32_t* err_flag) {
     const int lpr = a.d >> 2;
+    const int ns = (int)(L.cap / DP_SAMPLE);                // cap is a multiple of 1024
+    dp_sample_kernel<<<(unsigned)(((int64_t)L.world * ns + 255) / 256), 256, 0, st>>>(L, ns, sample);
     const int64_t threads = (int64_t)L.world * L.cap * lpr;
     const unsigned grid = (unsigned)((threads + 255) / 256);
-    int iters = 1;
-    while (((int64_t)1 << iters) <= L.cap) ++iters;
+    int it1 = 1;
+    while ((1 << it1) <= ns) ++it1;
+#define DP_APPLY(LPR_)                                                                                          \
+    if (L.world <= (LPR_) + 1) dp_apply_kernel<LPR_, 1><<<grid, 256, 0, st>>>(L, ns, it1, sample, a, err_flag);   \
+    else dp_apply_kernel<LPR_, 4><<<grid, 256, 0, st>>>(L, ns, it1, sample, a, err_flag)
     switch (lpr) {
-        case 1: dp_apply_kernel<1><<<grid, 256, 0, st>>>(L, iters, a, err_flag); break;
-        case 2: dp_apply_kernel<2><<<grid, 256, 0, st>>>(L, iters, a, err_flag); break;
-        case 4: dp_apply_kernel<4><<<grid, 256, 0, st>>>(L, iters, a, err_flag); break;
-        case 8: dp_apply_kernel<8><<<grid, 256, 0, st>>>(L, iters, a, err_flag); break;
-        case 16: dp_apply_kernel<16><<<grid, 256, 0, st>>>(L, iters, a, err_flag); break;
-        case 32: dp_apply_kernel<32><<<grid, 256, 0, st>>>(L, iters, a, err_flag); break;
+        case 1: DP_APPLY(1); break;
+        case 2: DP_APPLY(2); break;
+        case 4: DP_APPLY(4); break;
+        case 8: DP_APPLY(8); break;
+        case 16: DP_APPLY(16); break;
+        case 32: DP_APPLY(32); break;
         default: break;
     }
-    ++g_launch_count;
+#undef DP_APPLY
+    g_launch_count += 2;
 }
 
 // DENSE mode: the zero-gradient Adam step of every row the batch did not touch (row 0 included:
