@@ -249,6 +249,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput
+    # clocks / throttle reasons are sampled from here to the end of the timed regions (nvidia-smi needs ~100 ms to
+    # deliver its first line, the default timed region is shorter than that): warm-up and timed steps are the same load
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         step_dev(i)
     m.wait()
@@ -274,11 +279,7 @@ def main():
 
     # (1) the throughput region: no instrumentation inside the step
     launches0 = m.launch_count()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ms, loss = timed_region(args.steps)
-    clocks = sampler.stop() if rank == 0 else None
     launches = m.launch_count() - launches0
     ms_per_step = ms / args.steps
     value = B * world / (ms_per_step * 1e-3)
@@ -294,6 +295,13 @@ def main():
         ms_p, _ = timed_region(args.steps)
         ms_probed = ms_p / args.steps
         probes = m.probe_times()
+    if rank == 0 and len(sampler.rows) < 3:      # very short runs: keep the load up until a few samples exist
+        t_end = time.perf_counter() + 1.0
+        while len(sampler.rows) < 3 and time.perf_counter() < t_end:
+            for i in range(20):
+                step_dev(i)
+            m.wait()
+    clocks = sampler.stop() if rank == 0 else None
     stats = m.last_step_stats()
 
     # ---------------- end to end through the reference-facing API, host buffers
@@ -360,8 +368,12 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(shape, args, B * world),
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-                        "steps": e2e_steps, "api": "SCORE.train(sess, batch_data, lr, reg_lambda) -> float, pinned host ids"},
+                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 16 if world == 1 else 20,
+                        "steps": e2e_steps,
+                        "api": "SCORE.train(sess, batch_data, lr, reg_lambda) -> float, pinned host ids; the call returns "
+                               "when the step's result packet (loss, error flag) has reached the host, the region ends "
+                               "with a device synchronize"},
                 "gpu_launches": int(launches),
                 # `roofline` = the dominant HBM-bound kernel of the step (most DRAM traffic, longest of the HBM-side
                 # kernels): the scatter + row Adam; the gather kernel is reported beside it (BASELINE.json's metric
