@@ -125,14 +125,14 @@ void launch_build_keys(cudaStream_t st, const Dims& dm, const BatchPtrs* bp_dev,
 // ------------------------------------------------------------------------------------------
 // stage `nrows` table rows (ids at key_ptr[0..nrows)) into smem dst[nrows][d]; whole warp cooperates, consecutive
 // lanes fetch consecutive 16-byte chunks (a d=16 row is 4 lanes, 64 B contiguous).
-__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ emb, const int32_t* key_ptr,
+__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ emb, int es, const int32_t* key_ptr,
                                            int nrows, int d, int lane) {
     const int cpr = d >> 2;   // 16-byte chunks per row
     const int total = nrows * cpr;
     for (int q = lane; q < total; q += 32) {
         int r = q / cpr, c = q - r * cpr;
         int32_t id = key_ptr[r];
-        const float* src = emb + (int64_t)id * d + c * 4;
+        const float* src = emb + (int64_t)id * es + c * 4;
         cp_async16(dst + r * d + c * 4, id != 0 ? src : emb, id != 0 ? 16 : 0);
     }
 }
@@ -146,8 +146,8 @@ __global__ void target_fwd_kernel(Dims dm, TargetArgs a) {
     float* buf = sm + warp * dm.Ds;   // [tu (Du) | ti (Di)]
     int b = blockIdx.x * warps + warp;
     if (b >= dm.B) return;
-    stage_rows(buf, a.emb, a.keys + dm.off_tu + (int64_t)b * dm.fu, dm.fu, dm.d, lane);
-    stage_rows(buf + dm.Du, a.emb, a.keys + dm.off_ti + (int64_t)b * dm.fi, dm.fi, dm.d, lane);
+    stage_rows(buf, a.emb, a.es, a.keys + dm.off_tu + (int64_t)b * dm.fu, dm.fu, dm.d, lane);
+    stage_rows(buf + dm.Du, a.emb, a.es, a.keys + dm.off_ti + (int64_t)b * dm.fi, dm.fi, dm.d, lane);
     cp_async_commit();
     cp_async_wait<0>();
     __syncwarp();
@@ -236,17 +236,16 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) { return
 // Gather one (b,t) slice: every lane fetches its 16-byte chunks with cp.async; the id of a row is read by the lanes
 // that need it (one broadcast load per row, all of them independent), never staged first.
 template <class G>
-__device__ __forceinline__ void stage_slice(const G& g, float* rows, const float* __restrict__ emb,
+__device__ __forceinline__ void stage_slice(const G& g, float* rows, const float* __restrict__ emb, int es,
                                             const int32_t* __restrict__ ks, int nrows, int lane) {
     const int total = nrows << g.logcpr();
-    const int D = g.D();
 #pragma unroll
     for (int q0 = 0; q0 < total; q0 += 32) {
         const int q = q0 + lane;
         if (q < total) {
             const int r = q >> g.logcpr(), c4 = q & (g.cpr() - 1);
             const int32_t id = __ldg(ks + r);
-            const float* src = emb + (int64_t)id * D + c4 * 4;
+            const float* src = emb + (int64_t)id * es + c4 * 4;
             cp_async16(rows + q * 4, id != 0 ? src : emb, id != 0 ? 16 : 0);
         }
     }
@@ -318,7 +317,7 @@ __global__ void __launch_bounds__(128) coatt_fwd_kernel(Dims dm, CoattArgs a, Co
             if (!sum_pool) for (int c = lane; c < 4 * K; c += 32) info[c] = 0.f;
             continue;
         }
-        stage_slice(g, rows, a.emb, a.keys + (int64_t)slice * nrows, nrows, lane);
+        stage_slice(g, rows, a.emb, a.es, a.keys + (int64_t)slice * nrows, nrows, lane);
         const float cz1 = sum_pool ? 0.f : a.c_item[b], cz2 = sum_pool ? 0.f : a.c_user[b];
         cp_async_wait<0>();
         __syncwarp();
@@ -501,7 +500,7 @@ __global__ void __launch_bounds__(128) coatt_bwd_kernel(Dims dm, CoattBwdArgs a,
             if (lane == 0) { a.sdz[(int64_t)slice * 2] = 0.f; a.sdz[(int64_t)slice * 2 + 1] = 0.f; }
             continue;   // positions of dead slices carry key 0: their gradient rows are never read
         }
-        stage_slice(g, rows, a.emb, a.keys + (int64_t)slice * nrows, nrows, lane);
+        stage_slice(g, rows, a.emb, a.es, a.keys + (int64_t)slice * nrows, nrows, lane);
         {   // incoming gradients of this slice (overlaps the row gather)
             const float4* dxu = reinterpret_cast<const float4*>(a.dxu + (int64_t)slice * Ds);
             const float4* dxi = reinterpret_cast<const float4*>(a.dxi + (int64_t)slice * Ds);

@@ -80,10 +80,12 @@ void launch_build_keys(cudaStream_t st, const Dims& dm, const BatchPtrs* bp_dev,
                        int32_t* length_out, int32_t* err_flag, const ClaimArgs* claim = nullptr);
 // replay the rows of a claim list (2 int32 per entry: row, last step); *counter entries
 void launch_emb_replay(cudaStream_t st, const int32_t* claim_list, const int32_t* claim_counter, int64_t max_rows, float* emb,
-                       float* m, float* v, int d, const float* alpha_hist, const Hyper* hp, int pingpong = 0);
+                       float* m, float* v, int d, int es, const float* alpha_hist, const Hyper* hp, int pingpong = 0);
 
+// `es` in the argument structs below: floats between consecutive rows of the table `emb` points into - 3*d for the
+// handle's own table (one record var | m | v per row, model.cu), d for a staged mini-table of a row-sharded step
 struct TargetArgs {
-    const float* emb; const int32_t* keys;
+    const float* emb; int es; const int32_t* keys;
     const float* w_item; const float* b_item;   // co-attention #1 kernel [3*Di] (rows: target|seq1|seq2), bias
     const float* w_user; const float* b_user;   // co-attention #2 kernel [3*Du]
     float* q0;      // [B, Ds]  = [target_user || target_item]      (score.py:210)
@@ -93,7 +95,7 @@ struct TargetArgs {
 void launch_target_fwd(cudaStream_t st, const Dims& dm, const TargetArgs& a);
 
 struct CoattArgs {
-    const float* emb; const int32_t* keys; const int32_t* length;
+    const float* emb; int es; const int32_t* keys; const int32_t* length;
     const float* w_item; const float* w_user;
     const float* c_item; const float* c_user;
     float* xhg_u; float* xhc_u; float* xhg_i; float* xhc_i;   // [M, ldx], x part written here
@@ -104,7 +106,7 @@ struct CoattArgs {
 void launch_coatt_fwd(cudaStream_t st, const Dims& dm, const CoattArgs& a);
 
 struct CoattBwdArgs {
-    const float* emb; const int32_t* keys; const int32_t* length;
+    const float* emb; int es; const int32_t* keys; const int32_t* length;
     const float* w_item; const float* w_user;
     const float* save_r; const float* save_w;
     const float* dxu; const float* dxi;        // [M, Ds]
@@ -298,7 +300,7 @@ struct EmbUpdateArgs {
     const int32_t* skeys; const int32_t* spos; int64_t n;
     const int32_t* runs; const int32_t* runs_long; int64_t long_cap; const int32_t* counters;   // from launch_emb_runs
     const float* grad_rows; int d;
-    float* emb; float* m; float* v; int32_t* last_step;
+    float* emb; float* m; float* v; int es; int32_t* last_step;   // es: floats between consecutive rows of emb / m / v
     const float* alpha_hist;       // LAZY: rows that are not current through step-1 are replayed first (may be null)
     const Hyper* hp;
     int mode;                      // 0: apply Adam; 1 / 2: export the run sums to out_rows / out_heads at the run's first sorted
@@ -333,24 +335,26 @@ void launch_dp_dense_adam(cudaStream_t st, const DpLayout& L, float* p, float* m
                           const uint8_t* flags, int n, const Hyper* hp, float* alpha_hist, double* loss_out);
 
 // DENSE mode: zero-gradient Adam step for every row whose last_step != hp->step
-void launch_emb_dense_sweep(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d,
+void launch_emb_dense_sweep(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d, int es,
                             const Hyper* hp);
 // LAZY mode: replay skipped zero-gradient steps of the rows about to be gathered (keys in position order;
 // duplicates are resolved by an atomic claim on last_step, the replay result does not depend on the winner).
 // claim_list: 2*n int32 of scratch, claim_counter: one int32.
 void launch_emb_catchup_rows(cudaStream_t st, const int32_t* keys, int64_t n, int64_t V, float* emb, float* m, float* v,
-                             int32_t* last_step, int d, const float* alpha_hist, const Hyper* hp, int32_t* claim_list,
+                             int32_t* last_step, int d, int es, const float* alpha_hist, const Hyper* hp, int32_t* claim_list,
                              int32_t* claim_counter);
 // LAZY mode: bring the whole table up to `upto_step` (before read-back / save / eval of everything)
-void launch_emb_catchup_all(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d,
+void launch_emb_catchup_all(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d, int es,
                             const float* alpha_hist, int upto_step);
 
 // out[i] = table[idx[i]] (idx 0 -> zeros; out-of-range -> zeros + error flag): owner side of a sharded gather
-void launch_gather_rows(cudaStream_t st, const float* table, const int32_t* idx, int64_t n, int d, int64_t V, float* out,
+void launch_gather_rows(cudaStream_t st, const float* table, int es, const int32_t* idx, int64_t n, int d, int64_t V, float* out,
                         int32_t* err_flag);
 
 // device-side TF-default initialisers
-void launch_init_trunc_normal(cudaStream_t st, float* p, int64_t n, uint64_t seed, uint32_t stream_id);
+// row_len / row_stride: element i goes to p[(i / row_len) * row_stride + i % row_len] (0: contiguous)
+void launch_init_trunc_normal(cudaStream_t st, float* p, int64_t n, uint64_t seed, uint32_t stream_id, int row_len = 0,
+                              int row_stride = 0);
 void launch_init_uniform(cudaStream_t st, float* p, int64_t n, float limit, uint64_t seed, uint32_t stream_id);
 void launch_fill(cudaStream_t st, float* p, int64_t n, float v);
 void launch_fill_i32(cudaStream_t st, int32_t* p, int64_t n, int32_t v);

@@ -56,7 +56,11 @@ struct ScoreModel {
     std::vector<Tensor> tensors;
     std::map<std::string, int> tindex;
     int64_t n_dense = 0;
-    float *emb = nullptr, *emb_m = nullptr, *emb_v = nullptr;
+    // Embedding state: ONE buffer of V records [var | m | v] (3*d floats each), so the optimizer kernels touch one
+    // contiguous 12*d-byte run per row instead of three rows in three arrays (a d=16 row is half a 128-byte DRAM
+    // access: profiles/README.md).  emb / emb_m / emb_v point at the three fields of record 0; `es` = 3*d is the row stride.
+    float *emb_tab = nullptr, *emb = nullptr, *emb_m = nullptr, *emb_v = nullptr; int es = 0;
+    int es_fwd = 0;   // row stride of emb_fwd (es, or d for a staged mini-table)
     int32_t* last_step = nullptr;   // per-row step at which the row is current (DENSE / LAZY)
     float *P = nullptr, *G = nullptr, *M1 = nullptr, *V1 = nullptr, *PG = nullptr;
     uint8_t* flags = nullptr;
@@ -272,12 +276,10 @@ void build_registry(ScoreModel* h) {
 
 int alloc_params(ScoreModel* h) {
     const int64_t V = h->cfg.feature_size, d = h->cfg.eb_dim;
-    CK(cudaMalloc(&h->emb, sizeof(float) * V * d));
-    CK(cudaMalloc(&h->emb_m, sizeof(float) * V * d));
-    CK(cudaMalloc(&h->emb_v, sizeof(float) * V * d));
-    CK(cudaMemsetAsync(h->emb_m, 0, sizeof(float) * V * d, h->st));
-    CK(cudaMemsetAsync(h->emb_v, 0, sizeof(float) * V * d, h->st));
-    CK(cudaMemsetAsync(h->emb, 0, sizeof(float) * V * d, h->st));
+    h->es = 3 * d;
+    CK(cudaMalloc(&h->emb_tab, sizeof(float) * V * h->es));
+    CK(cudaMemsetAsync(h->emb_tab, 0, sizeof(float) * V * h->es, h->st));
+    h->emb = h->emb_tab; h->emb_m = h->emb_tab + d; h->emb_v = h->emb_tab + 2 * d;
     if (h->cfg.adam_mode != SCORE_ADAM_SPARSE) {
         CK(cudaMalloc(&h->last_step, sizeof(int32_t) * V));
         CK(cudaMemsetAsync(h->last_step, 0, sizeof(int32_t) * V, h->st));
@@ -330,7 +332,7 @@ int alloc_params(ScoreModel* h) {
 // GRUCell gate bias 1.0; batch_normalization gamma 1, beta 0, moving_mean 0, moving_variance 1)
 int init_weights(ScoreModel* h) {
     const uint64_t seed = h->cfg.seed;
-    launch_init_trunc_normal(h->st, h->emb, h->cfg.feature_size * h->cfg.eb_dim, seed, 1000u);
+    launch_init_trunc_normal(h->st, h->emb, h->cfg.feature_size * h->cfg.eb_dim, seed, 1000u, h->cfg.eb_dim, h->es);
     uint32_t sid = 1;
     for (const Tensor& t : h->tensors) {
         if (t.is_emb) continue;
@@ -635,7 +637,7 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
     const bool has_coatt = mt != SCORE_MODEL_RCA;   // RCA sums the neighbors (score.py:266-269)
     const bool has_att = mt != SCORE_MODEL_RIA;     // RIA feeds the final GRU states to the MLP (score.py:244-249)
     TargetArgs ta{};
-    ta.emb = h->emb_fwd; ta.keys = h->keys_fwd;
+    ta.emb = h->emb_fwd; ta.es = h->es_fwd; ta.keys = h->keys_fwd;
     if (has_coatt) { ta.w_item = W(nm.co_item); ta.b_item = Bi(nm.co_item); ta.w_user = W(nm.co_user); ta.b_user = Bi(nm.co_user); }
     ta.q0 = h->q0; ta.fc_in = h->fc_in; ta.fc_off = Dfc - Ds; ta.c_item = h->c_item; ta.c_user = h->c_user;
     launch_target_fwd(h->st, dm, ta);
@@ -650,7 +652,7 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
     }
 
     CoattArgs ca{};
-    ca.emb = h->emb_fwd; ca.keys = h->keys_fwd; ca.length = h->length;
+    ca.emb = h->emb_fwd; ca.es = h->es_fwd; ca.keys = h->keys_fwd; ca.length = h->length;
     if (has_coatt) { ca.w_item = W(nm.co_item); ca.w_user = W(nm.co_user); }
     ca.sum_pool = has_coatt ? 0 : 1;
     ca.c_item = h->c_item; ca.c_user = h->c_user;
@@ -817,7 +819,7 @@ void enqueue_backward(ScoreModel* h, bool fused_adam = false, bool defer_join = 
     probe_end(h, PR_BWD_DENSE, h->st);
     // co-attention + gather backward: per-position embedding gradient rows
     CoattBwdArgs cb{};
-    cb.emb = h->emb_fwd; cb.keys = h->keys_fwd; cb.length = h->length;
+    cb.emb = h->emb_fwd; cb.es = h->es_fwd; cb.keys = h->keys_fwd; cb.length = h->length;
     if (has_coatt) { cb.w_item = W(nm.co_item); cb.w_user = W(nm.co_user); }
     cb.sum_pool = has_coatt ? 0 : 1;
     cb.save_r = h->save_r; cb.save_w = h->save_w;
@@ -883,7 +885,7 @@ void enqueue_step(ScoreModel* h, int mode) {
     const Dims& dm = h->dm;
     const bool train = (mode == MODE_TRAIN);
     const bool need_bwd = (mode != MODE_EVAL);
-    h->emb_fwd = h->emb; h->keys_fwd = h->keys;
+    h->emb_fwd = h->emb; h->es_fwd = h->es; h->keys_fwd = h->keys;
     probe_begin(h, PR_STEP, h->st);
     // The sort depends on ids only and runs on the side stream under forward/backward.  With sort_after_gather() it
     // pauses while the gather kernel - the one bandwidth-bound kernel of the forward pass - has the SMs to itself: the
@@ -896,7 +898,7 @@ void enqueue_step(ScoreModel* h, int mode) {
         ClaimArgs ca{h->last_step, h->hyper_dev, h->claim_list, h->claim_counter, 1};
         launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag, &ca);
         if (h->sort_deferred) { cudaEventRecord(h->ev_keys, h->st); enqueue_sort_branch(h, h->ev_keys, 1); }
-        launch_emb_replay(h->st, h->claim_list, h->claim_counter, dm.N, h->emb, h->emb_m, h->emb_v, dm.d, h->alpha_hist,
+        launch_emb_replay(h->st, h->claim_list, h->claim_counter, dm.N, h->emb, h->emb_m, h->emb_v, dm.d, h->es, h->alpha_hist,
                           h->hyper_dev, 1);
         probe_end(h, PR_CATCHUP, h->st);
     } else {
@@ -926,7 +928,7 @@ void enqueue_step(ScoreModel* h, int mode) {
         ea.skeys = h->sb.keys[h->sort_out]; ea.spos = h->sb.vals[h->sort_out]; ea.n = dm.N;
         ea.runs = h->sb.runs; ea.runs_long = h->sb.runs_long; ea.long_cap = emb_runs_long_cap(dm.N); ea.counters = h->n_heads_dev;
         ea.grad_rows = h->grad_rows; ea.d = dm.d;
-        ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.last_step = h->last_step;
+        ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.es = h->es; ea.last_step = h->last_step;
         ea.alpha_hist = h->alpha_hist;
         ea.hp = h->hyper_dev; ea.mode = 0;
         h->last_sorted = ea.skeys; h->last_sorted_n = ea.n;
@@ -934,7 +936,7 @@ void enqueue_step(ScoreModel* h, int mode) {
         launch_emb_update(h->st, ea);
         probe_end(h, PR_EMB_UPDATE, h->st);
         if (h->cfg.adam_mode == SCORE_ADAM_DENSE)
-            launch_emb_dense_sweep(h->st, h->emb, h->emb_m, h->emb_v, h->last_step, dm.V, dm.d, h->hyper_dev);
+            launch_emb_dense_sweep(h->st, h->emb, h->emb_m, h->emb_v, h->last_step, dm.V, dm.d, h->es, h->hyper_dev);
     }
     if (defer) join_dense(h);
     probe_end(h, PR_STEP, h->st);
@@ -976,7 +978,7 @@ int upload_hyper(ScoreModel* h, int B, float lr, float reg_lambda, float keep_pr
 
 int flush_lazy(ScoreModel* h) {
     if (h->cfg.adam_mode == SCORE_ADAM_LAZY && h->step > 0) {
-        launch_emb_catchup_all(h->st, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.V, h->dm.d, h->alpha_hist, h->step);
+        launch_emb_catchup_all(h->st, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.V, h->dm.d, h->es, h->alpha_hist, h->step);
         CK(cudaStreamSynchronize(h->st));
     }
     return SCORE_OK;
@@ -1186,7 +1188,7 @@ int score_destroy(ScoreHandle h) {
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
     free_workspace(h);
-    for (void* p : {(void*)h->emb, (void*)h->emb_m, (void*)h->emb_v, (void*)h->last_step, (void*)h->P, (void*)h->G,
+    for (void* p : {(void*)h->emb_tab, (void*)h->last_step, (void*)h->P, (void*)h->G,
                     (void*)h->M1, (void*)h->V1, (void*)h->PG, (void*)h->flags, (void*)h->Dv, (void*)h->n_heads_dev, (void*)h->claim_counter, (void*)h->claim_ext, (void*)h->alpha_hist, (void*)h->l2sum,
                     (void*)h->loss_dev, (void*)h->err_flag, (void*)h->step_dev, (void*)h->seg_rows, (void*)h->seg_heads})
         if (p) cudaFree(p);
@@ -1309,6 +1311,21 @@ int score_tensor_info(ScoreHandle h, int index, char* name, size_t name_cap, int
 namespace {
 
 // resolve "<var>", "<var>/Adam", "<var>/Adam_1" to a device pointer + element count
+// rows [row0, row0 + nrows) of one field (var / m / v) of the embedding records <-> contiguous host memory [nrows, d]
+int emb_copy(ScoreModel* h, float* field, int64_t row0, int64_t nrows, float* host, bool to_host) {
+    const size_t w = sizeof(float) * h->dm.d, pitch = sizeof(float) * h->es;
+    const int64_t step = (int64_t)1 << 20;
+    for (int64_t r = 0; r < nrows; r += step) {
+        const int64_t n = nrows - r < step ? nrows - r : step;
+        float* dev = field + (row0 + r) * h->es;
+        float* hp = host + r * h->dm.d;
+        if (to_host) CK(cudaMemcpy2DAsync(hp, w, dev, pitch, w, (size_t)n, cudaMemcpyDeviceToHost, h->st));
+        else CK(cudaMemcpy2DAsync(dev, pitch, hp, w, w, (size_t)n, cudaMemcpyHostToDevice, h->st));
+    }
+    CK(cudaStreamSynchronize(h->st));
+    return SCORE_OK;
+}
+
 int resolve(ScoreModel* h, const std::string& name, float** ptr, size_t* count, bool* is_emb) {
     std::string base = name;
     int slot = 0;
@@ -1345,7 +1362,11 @@ int score_get_tensor(ScoreHandle h, const char* name, float* data, size_t count)
     int rc = resolve(h, n, &p, &cnt, &is_emb);
     if (rc) return rc;
     if (count != cnt) return fail(h, SCORE_ERR_ARG, "element count mismatch for " + n);
-    if (is_emb) { rc = flush_lazy(h); if (rc) return rc; }
+    if (is_emb) {
+        rc = flush_lazy(h);
+        if (rc) return rc;
+        return emb_copy(h, p, 0, h->dm.V, data, true);
+    }
     CK(cudaMemcpyAsync(data, p, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     return SCORE_OK;
@@ -1368,7 +1389,11 @@ int score_set_tensor(ScoreHandle h, const char* name, const float* data, size_t 
     int rc = resolve(h, n, &p, &cnt, &is_emb);
     if (rc) return rc;
     if (count != cnt) return fail(h, SCORE_ERR_ARG, "element count mismatch for " + n);
-    if (is_emb) { rc = flush_lazy(h); if (rc) return rc; }
+    if (is_emb) {
+        rc = flush_lazy(h);
+        if (rc) return rc;
+        return emb_copy(h, p, 0, h->dm.V, const_cast<float*>(data), false);
+    }
     CK(cudaMemcpyAsync(p, data, cnt * sizeof(float), cudaMemcpyHostToDevice, h->st));
     CK(cudaStreamSynchronize(h->st));
     return SCORE_OK;
@@ -1384,9 +1409,7 @@ int score_get_rows(ScoreHandle h, const char* name, int64_t row0, int64_t nrows,
     if (row0 < 0 || nrows < 0 || row0 + nrows > h->dm.V) return fail(h, SCORE_ERR_ARG, "row range out of bounds");
     rc = flush_lazy(h);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(data, p + row0 * h->dm.d, sizeof(float) * nrows * h->dm.d, cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
-    return SCORE_OK;
+    return emb_copy(h, p, row0, nrows, data, true);
 }
 
 int score_set_rows(ScoreHandle h, const char* name, int64_t row0, int64_t nrows, const float* data) {
@@ -1399,9 +1422,7 @@ int score_set_rows(ScoreHandle h, const char* name, int64_t row0, int64_t nrows,
     if (row0 < 0 || nrows < 0 || row0 + nrows > h->dm.V) return fail(h, SCORE_ERR_ARG, "row range out of bounds");
     rc = flush_lazy(h);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(p + row0 * h->dm.d, data, sizeof(float) * nrows * h->dm.d, cudaMemcpyHostToDevice, h->st));
-    CK(cudaStreamSynchronize(h->st));
-    return SCORE_OK;
+    return emb_copy(h, p, row0, nrows, const_cast<float*>(data), false);
 }
 
 // Checkpoint: "SCB2CKPT" | version | n tensors | per tensor {name, rows, cols, var, [Adam, Adam_1]} | beta powers.
@@ -1428,8 +1449,11 @@ int score_save(ScoreHandle h, const char* path) {
             const float* src = t.is_emb ? (s == 0 ? h->emb : s == 1 ? h->emb_m : h->emb_v)
                                         : (s == 0 ? h->P : s == 1 ? h->M1 : h->V1) + t.off;
             for (size_t o = 0; o < cnt && ok; o += chunk) {
-                size_t n = cnt - o < chunk ? cnt - o : chunk;
-                if (cudaMemcpy(host.data(), src + o, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
+                size_t n = cnt - o < chunk ? cnt - o : chunk;   // chunk is a multiple of every supported row width
+                const bool read_ok = t.is_emb
+                    ? emb_copy(h, const_cast<float*>(src), (int64_t)(o / h->dm.d), (int64_t)(n / h->dm.d), host.data(), true) == SCORE_OK
+                    : cudaMemcpy(host.data(), src + o, n * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess;
+                if (!read_ok) {
                     fclose(f);
                     return fail(h, SCORE_ERR_CUDA, "device read failed during save");
                 }
@@ -1469,7 +1493,10 @@ int score_restore(ScoreHandle h, const char* path) {
             for (size_t o = 0; o < cnt; o += chunk) {
                 size_t n = cnt - o < chunk ? cnt - o : chunk;
                 if (fread(host.data(), sizeof(float), n, f) != n) { fclose(f); return fail(h, SCORE_ERR_IO, "truncated checkpoint"); }
-                if (cudaMemcpy(dst + o, host.data(), n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+                const bool write_ok = t->is_emb
+                    ? emb_copy(h, dst, (int64_t)(o / h->dm.d), (int64_t)(n / h->dm.d), host.data(), false) == SCORE_OK
+                    : cudaMemcpy(dst + o, host.data(), n * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+                if (!write_ok) {
                     fclose(f);
                     return fail(h, SCORE_ERR_CUDA, "device write failed during restore");
                 }
@@ -1638,10 +1665,10 @@ int score_gather_rows(ScoreHandle h, const int32_t* idx_dev, int64_t n, float* o
             CK(cudaMalloc(&h->claim_ext, sizeof(int32_t) * 2 * (n + n / 4)));
             h->claim_ext_cap = n + n / 4;
         }
-        launch_emb_catchup_rows(h->st, idx_dev, n, h->dm.V, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.d, h->alpha_hist,
+        launch_emb_catchup_rows(h->st, idx_dev, n, h->dm.V, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.d, h->es, h->alpha_hist,
                                 h->hyper_dev, h->claim_ext, h->claim_counter);
     }
-    launch_gather_rows(h->st, h->emb, idx_dev, n, h->dm.d, h->dm.V, out_dev, h->err_flag);
+    launch_gather_rows(h->st, h->emb, h->es, idx_dev, n, h->dm.d, h->dm.V, out_dev, h->err_flag);
     return SCORE_OK;
 }
 
@@ -1694,14 +1721,14 @@ int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg
             enqueue_sort_branch(h, h->ev_keys, h->sort_deferred ? 1 : 0);
         }
         if (staged_table) {
-            h->emb_fwd = staged_table; h->keys_fwd = staged_keys;
+            h->emb_fwd = staged_table; h->es_fwd = h->dm.d; h->keys_fwd = staged_keys;
         } else {
-            h->emb_fwd = h->emb; h->keys_fwd = h->keys;
+            h->emb_fwd = h->emb; h->es_fwd = h->es; h->keys_fwd = h->keys;
             if (fused_claim)
-                launch_emb_replay(h->st, h->claim_list, h->claim_counter, dm.N, h->emb, h->emb_m, h->emb_v, dm.d, h->alpha_hist,
+                launch_emb_replay(h->st, h->claim_list, h->claim_counter, dm.N, h->emb, h->emb_m, h->emb_v, dm.d, h->es, h->alpha_hist,
                                   h->hyper_dev, 1);
             else if (lazy)
-                launch_emb_catchup_rows(h->st, h->keys, dm.N, dm.V, h->emb, h->emb_m, h->emb_v, h->last_step, dm.d,
+                launch_emb_catchup_rows(h->st, h->keys, dm.N, dm.V, h->emb, h->emb_m, h->emb_v, h->last_step, dm.d, h->es,
                                         h->alpha_hist, h->hyper_dev, h->claim_list, h->claim_counter);
         }
         enqueue_forward(h, train != 0);
@@ -1717,7 +1744,7 @@ int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg
         if (it != h->graphs_begin.end()) {
             CK(cudaGraphLaunch(it->second, h->st));
             g_launch_count += h->graph_kernels_begin[B];
-            h->emb_fwd = h->emb; h->keys_fwd = h->keys;
+            h->emb_fwd = h->emb; h->es_fwd = h->es; h->keys_fwd = h->keys;
             launched = true;
         } else if (h->warm_begin[B] >= 1) {
             cudaGraph_t graph = nullptr;
@@ -1826,7 +1853,7 @@ int score_dp_finish(ScoreHandle h, const void* gathered, int32_t world, int64_t 
     launch_dp_dense_adam(h->st, L, h->P, h->M1, h->V1, h->G, h->flags, (int)h->n_dense, h->hyper_dev, h->alpha_hist, h->loss_glob);
     EmbUpdateArgs ea{};
     ea.d = h->dm.d;
-    ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.last_step = h->last_step;
+    ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.es = h->es; ea.last_step = h->last_step;
     ea.alpha_hist = h->alpha_hist; ea.hp = h->hyper_dev; ea.mode = 0;
     if (dp_sample_count(world, cap) > h->dp_sample_cap) {
         CK(cudaStreamSynchronize(h->st));
@@ -1839,7 +1866,7 @@ int score_dp_finish(ScoreHandle h, const void* gathered, int32_t world, int64_t 
     launch_dp_apply(h->st, L, ea, h->dp_sample, h->err_flag);
     if (h->local_sorted) { h->last_sorted = h->sb.keys[h->sort_out]; h->last_sorted_n = h->dm.N; }   // this rank's share (stats)
     if (h->cfg.adam_mode == SCORE_ADAM_DENSE)
-        launch_emb_dense_sweep(h->st, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.V, h->dm.d, h->hyper_dev);
+        launch_emb_dense_sweep(h->st, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.V, h->dm.d, h->es, h->hyper_dev);
     h->step += 1;
     h->beta1_power = h->beta1_power * 0.9f;
     h->beta2_power = h->beta2_power * 0.999f;
@@ -1871,13 +1898,13 @@ int score_step_finish(ScoreHandle h, const int32_t* ext_keys, const float* ext_r
             ea.skeys = h->sb_ext.keys[out]; ea.spos = h->sb_ext.vals[out]; ea.n = n_ext;
             ea.runs = h->sb_ext.runs; ea.runs_long = h->sb_ext.runs_long; ea.long_cap = emb_runs_long_cap(n_ext); ea.counters = h->n_heads_dev;
             ea.grad_rows = ext_rows; ea.d = h->dm.d;
-            ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.last_step = h->last_step;
+            ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.es = h->es; ea.last_step = h->last_step;
             ea.alpha_hist = h->alpha_hist; ea.hp = h->hyper_dev; ea.mode = 0;
             h->last_sorted = ea.skeys; h->last_sorted_n = ea.n;
             launch_emb_update(h->st, ea);
         }
         if (h->cfg.adam_mode == SCORE_ADAM_DENSE)
-            launch_emb_dense_sweep(h->st, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.V, h->dm.d, h->hyper_dev);
+            launch_emb_dense_sweep(h->st, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.V, h->dm.d, h->es, h->hyper_dev);
         h->step += 1;
         h->beta1_power = h->beta1_power * 0.9f;
         h->beta2_power = h->beta2_power * 0.999f;

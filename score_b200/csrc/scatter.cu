@@ -529,7 +529,7 @@ __device__ __forceinline__ void emb_apply_row(const EmbUpdateArgs& a, int32_t ke
         if (sub == 0) a.out_heads[out_idx] = key;
         return;
     }
-    const int64_t off = (int64_t)key * D + sub * 4;
+    const int64_t off = (int64_t)key * a.es + sub * 4;
     if (a.alpha_hist) {   // LAZY: a row another rank gathered may not be current here yet
         const int upto = step - 1;
         if (last < upto && !(all_zero(m) && all_zero(v))) replay4(var, m, v, last, upto, a.alpha_hist);
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(256) emb_update_kernel(EmbUpdateArgs a) {
         const bool owner = threadIdx.x < LPR;
         float4 var = z4, m = z4, v = z4; int last = 0;
         if (owner && !EXPORT) {
-            const int64_t off = (int64_t)key * D + sub * 4;
+            const int64_t off = (int64_t)key * a.es + sub * 4;
             var = *reinterpret_cast<const float4*>(a.emb + off);
             m = *reinterpret_cast<const float4*>(a.m + off);
             v = *reinterpret_cast<const float4*>(a.v + off);
@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(256) emb_update_kernel(EmbUpdateArgs a) {
             const bool owner = valid && tl < LPR;
             float4 var = z4, m = z4, v = z4; int last = 0;
             if (owner && !EXPORT) {
-                const int64_t off = (int64_t)key * D + sub * 4;
+                const int64_t off = (int64_t)key * a.es + sub * 4;
                 var = *reinterpret_cast<const float4*>(a.emb + off);
                 m = *reinterpret_cast<const float4*>(a.m + off);
                 v = *reinterpret_cast<const float4*>(a.v + off);
@@ -671,7 +671,7 @@ __global__ void __launch_bounds__(256) emb_update_kernel(EmbUpdateArgs a) {
         }
         float4 var = z4, m = z4, v = z4; int last = 0;
         if (!EXPORT) {
-            const int64_t off = (int64_t)key * D + sub * 4;
+            const int64_t off = (int64_t)key * a.es + sub * 4;
             var = *reinterpret_cast<const float4*>(a.emb + off);
             m = *reinterpret_cast<const float4*>(a.m + off);
             v = *reinterpret_cast<const float4*>(a.v + off);
@@ -735,8 +735,8 @@ void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a) {
 // optimizer state of the row is fetched before the lookups - most entries own their row - so the latencies overlap.
 // A lookup is two short binary searches: first in a sampled copy of the list (every DP_SAMPLE-th id; all ranks' samples
 // together are a few tens of KB and stay in L1), then inside the one DP_SAMPLE-id block of the full list it points at -
-// two or three L2 round trips instead of seventeen; the up-to-DP_J lookups of a lane advance side by side (DP_J = 1 when
-// the world is small enough for one lookup per lane, 4 otherwise).
+// two or three L2 round trips instead of seventeen; the up-to-DP_J lookups of a lane advance side by side (DP_J = 1, 2 or 4
+// lookups per lane, the smallest that covers the world in one round).
 constexpr int DP_SAMPLE = 64;
 
 __global__ void dp_sample_kernel(DpLayout L, int ns, int32_t* __restrict__ sample) {
@@ -767,7 +767,7 @@ __global__ void __launch_bounds__(256) dp_apply_kernel(DpLayout L, int ns, int i
     if (cnt > L.cap || cnt < 0) { if (i == 0 && sub == 0) atomicExch(err_flag, 2); cnt = cnt < 0 ? 0 : (int32_t)L.cap; }
     if (i >= cnt) return;                                   // uniform over the group
     const int32_t key = mine[L.keys_off + i];
-    const int64_t off = (int64_t)key * D + sub * 4;
+    const int64_t off = (int64_t)key * a.es + sub * 4;
     float4 var = *reinterpret_cast<const float4*>(a.emb + off);
     float4 m = *reinterpret_cast<const float4*>(a.m + off);
     float4 v = *reinterpret_cast<const float4*>(a.v + off);
@@ -843,8 +843,9 @@ void launch_dp_apply(cudaStream_t st, const DpLayout& L, const EmbUpdateArgs& a,
     const unsigned grid = (unsigned)((threads + 255) / 256);
     int it1 = 1;
     while ((1 << it1) <= ns) ++it1;
-#define DP_APPLY(LPR_)                                                                                          \
-    if (L.world <= (LPR_) + 1) dp_apply_kernel<LPR_, 1><<<grid, 256, 0, st>>>(L, ns, it1, sample, a, err_flag);   \
+#define DP_APPLY(LPR_)                                                                                              \
+    if (L.world <= (LPR_) + 1) dp_apply_kernel<LPR_, 1><<<grid, 256, 0, st>>>(L, ns, it1, sample, a, err_flag);       \
+    else if (L.world <= 2 * (LPR_)) dp_apply_kernel<LPR_, 2><<<grid, 256, 0, st>>>(L, ns, it1, sample, a, err_flag);  \
     else dp_apply_kernel<LPR_, 4><<<grid, 256, 0, st>>>(L, ns, it1, sample, a, err_flag)
     switch (lpr) {
         case 1: DP_APPLY(1); break;
@@ -862,25 +863,26 @@ void launch_dp_apply(cudaStream_t st, const DpLayout& L, const EmbUpdateArgs& a,
 // DENSE mode: the zero-gradient Adam step of every row the batch did not touch (row 0 included:
 // its gradient is always zero, so its slots stay zero and it never moves).
 __global__ void emb_dense_sweep_kernel(float* __restrict__ emb, float* __restrict__ m, float* __restrict__ v,
-                                       const int32_t* __restrict__ last_step, int64_t V, int d, const Hyper* hp) {
+                                       const int32_t* __restrict__ last_step, int64_t V, int d, int es, const Hyper* hp) {
     const int lpr = d >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= V * lpr) return;
     const int64_t row = idx / lpr;
+    const int64_t off = row * es + (idx - row * lpr) * 4;
     if (last_step[row] == hp->step) return;
-    float4 mm = reinterpret_cast<float4*>(m)[idx];
-    float4 vv = reinterpret_cast<float4*>(v)[idx];
+    float4 mm = *reinterpret_cast<float4*>(m + off);
+    float4 vv = *reinterpret_cast<float4*>(v + off);
     if (all_zero(mm) && all_zero(vv)) return;   // never touched: the update is exactly a no-op
-    float4 var = reinterpret_cast<float4*>(emb)[idx];
+    float4 var = *reinterpret_cast<float4*>(emb + off);
     adam4(var, mm, vv, make_float4(0.f, 0.f, 0.f, 0.f), hp->alpha);
-    reinterpret_cast<float4*>(emb)[idx] = var;
-    reinterpret_cast<float4*>(m)[idx] = mm;
-    reinterpret_cast<float4*>(v)[idx] = vv;
+    *reinterpret_cast<float4*>(emb + off) = var;
+    *reinterpret_cast<float4*>(m + off) = mm;
+    *reinterpret_cast<float4*>(v + off) = vv;
 }
-void launch_emb_dense_sweep(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d,
+void launch_emb_dense_sweep(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d, int es,
                             const Hyper* hp) {
     int64_t n = V * (d >> 2);
-    emb_dense_sweep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(emb, m, v, last_step, V, d, hp);
+    emb_dense_sweep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(emb, m, v, last_step, V, d, es, hp);
     ++g_launch_count;
 }
 
@@ -919,7 +921,7 @@ __global__ void emb_claim_kernel(const int32_t* __restrict__ keys, int64_t n, in
 }
 __global__ void __launch_bounds__(256) emb_replay_kernel(const int32_t* __restrict__ list, const int32_t* __restrict__ counter,
                                                          float* __restrict__ emb, float* __restrict__ m, float* __restrict__ v,
-                                                         int d, const float* __restrict__ alpha_hist, const Hyper* hp, int pingpong) {
+                                                         int d, int es, const float* __restrict__ alpha_hist, const Hyper* hp, int pingpong) {
     pdl_enter();
     const int upto = hp->step - 1;
     const int64_t total = (int64_t)(counter[pingpong ? (hp->seq & 1) : 0]) * d;
@@ -927,7 +929,7 @@ __global__ void __launch_bounds__(256) emb_replay_kernel(const int32_t* __restri
         const int64_t r = e / d;
         const int c = (int)(e - r * d);
         const int32_t key = list[2 * r], old = list[2 * r + 1];
-        const int64_t off = (int64_t)key * d + c;
+        const int64_t off = (int64_t)key * es + c;
         float mm = m[off], vv = v[off];
         if (mm == 0.f && vv == 0.f) continue;   // never touched: every replayed step is exactly a no-op
         float var = emb[off];
@@ -946,23 +948,23 @@ static int num_sms_cached() {
     return sms;
 }
 void launch_emb_replay(cudaStream_t st, const int32_t* claim_list, const int32_t* claim_counter, int64_t max_rows, float* emb,
-                       float* m, float* v, int d, const float* alpha_hist, const Hyper* hp, int pingpong) {
+                       float* m, float* v, int d, int es, const float* alpha_hist, const Hyper* hp, int pingpong) {
     int64_t want = (max_rows * d + 255) / 256, cap = (int64_t)num_sms_cached() * 8;
     if (want < 1) want = 1;
-    launch_chain(emb_replay_kernel, dim3((unsigned)(want < cap ? want : cap)), dim3(256), 0, st, claim_list, claim_counter, emb, m, v, d, alpha_hist, hp, pingpong);
+    launch_chain(emb_replay_kernel, dim3((unsigned)(want < cap ? want : cap)), dim3(256), 0, st, claim_list, claim_counter, emb, m, v, d, es, alpha_hist, hp, pingpong);
     ++g_launch_count;
 }
 void launch_emb_catchup_rows(cudaStream_t st, const int32_t* keys, int64_t n, int64_t V, float* emb, float* m, float* v,
-                             int32_t* last_step, int d, const float* alpha_hist, const Hyper* hp, int32_t* claim_list,
+                             int32_t* last_step, int d, int es, const float* alpha_hist, const Hyper* hp, int32_t* claim_list,
                              int32_t* claim_counter) {
     cudaMemsetAsync(claim_counter, 0, sizeof(int32_t), st);
     emb_claim_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, n, V, last_step, hp, claim_list, claim_counter);
     ++g_launch_count;
-    launch_emb_replay(st, claim_list, claim_counter, n, emb, m, v, d, alpha_hist, hp);
+    launch_emb_replay(st, claim_list, claim_counter, n, emb, m, v, d, es, alpha_hist, hp);
     cudaMemsetAsync(claim_counter, 0, 2 * sizeof(int32_t), st);   // leave the ping-pong pair of the fused path clean
 }
 __global__ void emb_catchup_all_kernel(float* __restrict__ emb, float* __restrict__ m, float* __restrict__ v,
-                                       int32_t* __restrict__ last_step, int64_t V, int d,
+                                       int32_t* __restrict__ last_step, int64_t V, int d, int es,
                                        const float* __restrict__ alpha_hist, int upto) {
     const int lpr = d >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -972,30 +974,31 @@ __global__ void emb_catchup_all_kernel(float* __restrict__ emb, float* __restric
     // every lane of a row must read last_step before lane 0 overwrites it
     __syncwarp();
     if (!ok || old >= upto) return;
-    float4 mm = reinterpret_cast<float4*>(m)[idx];
-    float4 vv = reinterpret_cast<float4*>(v)[idx];
+    const int64_t off = row * es + (idx - row * lpr) * 4;
+    float4 mm = *reinterpret_cast<float4*>(m + off);
+    float4 vv = *reinterpret_cast<float4*>(v + off);
     if (!(all_zero(mm) && all_zero(vv))) {
-        float4 var = reinterpret_cast<float4*>(emb)[idx];
+        float4 var = *reinterpret_cast<float4*>(emb + off);
         replay4(var, mm, vv, old, upto, alpha_hist);
-        reinterpret_cast<float4*>(emb)[idx] = var;
-        reinterpret_cast<float4*>(m)[idx] = mm;
-        reinterpret_cast<float4*>(v)[idx] = vv;
+        *reinterpret_cast<float4*>(emb + off) = var;
+        *reinterpret_cast<float4*>(m + off) = mm;
+        *reinterpret_cast<float4*>(v + off) = vv;
     }
 }
 __global__ void set_last_step_kernel(int32_t* last_step, int64_t V, int upto) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < V && last_step[i] < upto) last_step[i] = upto;
 }
-void launch_emb_catchup_all(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d,
+void launch_emb_catchup_all(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d, int es,
                             const float* alpha_hist, int upto) {
     int64_t n = V * (d >> 2);
-    emb_catchup_all_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(emb, m, v, last_step, V, d, alpha_hist, upto);
+    emb_catchup_all_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(emb, m, v, last_step, V, d, es, alpha_hist, upto);
     set_last_step_kernel<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(last_step, V, upto);
     g_launch_count += 2;
 }
 
 // ------------------------------------------------------------------------------------------ plain row gather
-__global__ void gather_rows_kernel(const float* __restrict__ table, const int32_t* __restrict__ idx, int64_t n, int d,
+__global__ void gather_rows_kernel(const float* __restrict__ table, int es, const int32_t* __restrict__ idx, int64_t n, int d,
                                    int64_t V, float* __restrict__ out, int32_t* __restrict__ err_flag) {
     const int lpr = d >> 2;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1005,18 +1008,19 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, const int32_
     int32_t id = idx[i];
     if (id < 0 || id >= V) { atomicExch(err_flag, 1); id = 0; }
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (id != 0) v = *reinterpret_cast<const float4*>(table + (int64_t)id * d + sub * 4);
+    if (id != 0) v = *reinterpret_cast<const float4*>(table + (int64_t)id * es + sub * 4);
     *reinterpret_cast<float4*>(out + i * d + sub * 4) = v;
 }
-void launch_gather_rows(cudaStream_t st, const float* table, const int32_t* idx, int64_t n, int d, int64_t V, float* out,
+void launch_gather_rows(cudaStream_t st, const float* table, int es, const int32_t* idx, int64_t n, int d, int64_t V, float* out,
                         int32_t* err_flag) {
     const int64_t threads = n * (d >> 2);
-    gather_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(table, idx, n, d, V, out, err_flag);
+    gather_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(table, es, idx, n, d, V, out, err_flag);
     ++g_launch_count;
 }
 
 // ------------------------------------------------------------------------------------------ initialisers
-__global__ void init_trunc_normal_kernel(float* __restrict__ p, int64_t n, uint32_t lo, uint32_t hi, uint32_t stream_id) {
+__global__ void init_trunc_normal_kernel(float* __restrict__ p, int64_t n, uint32_t lo, uint32_t hi, uint32_t stream_id,
+                                         int row_len, int row_stride) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float z = 0.f;
@@ -1028,11 +1032,14 @@ __global__ void init_trunc_normal_kernel(float* __restrict__ p, int64_t n, uint3
         if (fabsf(z) <= 2.0f) break;
         z = 0.f;
     }
-    p[i] = z;
+    // the random stream is keyed by the LOGICAL element index, so the values do not depend on the row layout
+    const int64_t at = row_len > 0 ? (i / row_len) * row_stride + i % row_len : i;
+    p[at] = z;
 }
-void launch_init_trunc_normal(cudaStream_t st, float* p, int64_t n, uint64_t seed, uint32_t stream_id) {
+void launch_init_trunc_normal(cudaStream_t st, float* p, int64_t n, uint64_t seed, uint32_t stream_id, int row_len,
+                              int row_stride) {
     init_trunc_normal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, (uint32_t)seed, (uint32_t)(seed >> 32),
-                                                                          stream_id);
+                                                                          stream_id, row_len, row_stride);
     ++g_launch_count;
 }
 __global__ void init_uniform_kernel(float* __restrict__ p, int64_t n, float limit, uint32_t lo, uint32_t hi,

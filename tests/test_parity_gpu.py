@@ -404,7 +404,7 @@ def test_dp_pack_exports_sorted_unique_rows():
     m.close(); m2.close()
 
 
-@pytest.mark.parametrize("world,mode,graph", [(2, "lazy", True), (3, "dense", False), (8, "lazy", False)])
+@pytest.mark.parametrize("world,mode,graph", [(2, "lazy", True), (3, "dense", False), (8, "lazy", False), (9, "lazy", False)])
 def test_dp_packed_exchange_emulated_ranks(world, mode, graph):
     """`world` handles on one GPU driven through the phases of DataParallelTrainer (the all-gather is a torch.cat):
     every replica must end bit-identical, and equal to one model stepping on the concatenated batch."""
