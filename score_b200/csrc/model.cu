@@ -511,44 +511,6 @@ void stage_release(ScoreModel* h) {
 }
 
 // ------------------------------------------------------------------------------------------ GEMM helpers
-GemmArgs gemm_fwd_args(ScoreModel* h, const float* A, int lda, const float* W, int ldw, const float* bias, float* C,
-                       int ldc, int M, int N, int K, int epi, uint32_t rng_stream = 0) {
-    GemmArgs g{};
-    g.A = A; g.a_rs = lda; g.a_cs = 1;
-    g.B = W; g.b_rs = ldw; g.b_cs = 1;
-    g.C = C; g.c_rs = ldc; g.M = M; g.N = N; g.K = K; g.epi = epi; g.bias = bias;
-    g.splits = 1; g.hp = h->hyper_dev; g.rng_stream = rng_stream;
-    return g;
-}
-void gemm_fwd(ScoreModel* h, const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
-              int M, int N, int K, int epi, uint32_t rng_stream = 0) {
-    GemmArgs g{};
-    g.A = A; g.a_rs = lda; g.a_cs = 1;
-    g.B = W; g.b_rs = ldw; g.b_cs = 1;
-    g.C = C; g.c_rs = ldc; g.M = M; g.N = N; g.K = K; g.epi = epi; g.bias = bias;
-    g.splits = 1; g.hp = h->hyper_dev; g.rng_stream = rng_stream;
-    launch_gemm(h->st, g);
-}
-// dA[M, Kl] = dC[M, Nl] W[Kl, Nl]^T, optionally masked by the saved activation
-GemmArgs gemm_bwd_data_args(ScoreModel* h, const float* dC, int lddc, const float* W, int ldw, float* dA, int ldda, int M,
-                            int Kl, int Nl, int epi) {
-    GemmArgs g{};
-    g.A = dC; g.a_rs = lddc; g.a_cs = 1;
-    g.B = W; g.b_rs = 1; g.b_cs = ldw;
-    g.C = dA; g.c_rs = ldda; g.M = M; g.N = Kl; g.K = Nl; g.epi = epi;
-    g.splits = 1; g.hp = h->hyper_dev;
-    return g;
-}
-void gemm_bwd_data(ScoreModel* h, const float* dC, int lddc, const float* W, int ldw, float* dA, int ldda, int M,
-                   int Kl, int Nl, int epi, const float* aux = nullptr, int aux_rs = 0, int mask_dropout = 0) {
-    GemmArgs g{};
-    g.A = dC; g.a_rs = lddc; g.a_cs = 1;
-    g.B = W; g.b_rs = 1; g.b_cs = ldw;
-    g.C = dA; g.c_rs = ldda; g.M = M; g.N = Kl; g.K = Nl; g.epi = epi;
-    g.aux = aux; g.aux_rs = aux_rs; g.mask_dropout = mask_dropout;
-    g.splits = 1; g.hp = h->hyper_dev;
-    launch_gemm(h->st, g);
-}
 // dW[Kl, Nl] (+ db[Nl]) = A[M, Kl]^T dC[M, Nl], into the kSplits partial planes of PG
 GemmArgs gemm_bwd_weight_args(ScoreModel* h, const float* A, int lda, const float* dC, int lddc, int64_t w_off,
                               int64_t b_off, int M, int Kl, int Nl) {
@@ -561,30 +523,14 @@ GemmArgs gemm_bwd_weight_args(ScoreModel* h, const float* A, int lda, const floa
     g.hp = h->hyper_dev;
     return g;
 }
-// several weight-gradient problems in one side-stream launch
+// several weight-gradient problems in one side-stream launch: weight gradients are off the critical path (they only
+// feed the final reduce), ordered after the producer of dC by an event
 void gemm_bwd_weight_batch(ScoreModel* h, const GemmArgs* list, int n) {
     cudaEvent_t e = h->ev_pool[h->ev_next++ & 15];
     cudaEventRecord(e, h->st);
     cudaStreamWaitEvent(h->st_w, e, 0);
     launch_gemm_batch(h->st_w, list, n);
 }
-void gemm_bwd_weight(ScoreModel* h, const float* A, int lda, const float* dC, int lddc, int64_t w_off, int64_t b_off,
-                     int M, int Kl, int Nl) {
-    GemmArgs g{};
-    g.A = A; g.a_rs = 1; g.a_cs = lda;
-    g.B = dC; g.b_rs = lddc; g.b_cs = 1;
-    g.C = h->PG + w_off; g.c_rs = Nl; g.M = Kl; g.N = Nl; g.K = M; g.epi = EPI_SPLIT;
-    g.splits = kSplits; g.c_split_stride = h->n_dense;
-    g.colsum = (b_off >= 0) ? h->PG + b_off : nullptr; g.colsum_split_stride = h->n_dense;
-    g.hp = h->hyper_dev;
-    // weight gradients are off the critical path: they only feed the final reduce, so they run on the
-    // side stream, ordered after the producer of dC by an event
-    cudaEvent_t e = h->ev_pool[h->ev_next++ & 15];
-    cudaEventRecord(e, h->st);
-    cudaStreamWaitEvent(h->st_w, e, 0);
-    launch_gemm(h->st_w, g);
-}
-
 void probe_begin(ScoreModel* h, int p, cudaStream_t s) {
     if (h->probes_on) cudaEventRecordWithFlags(h->pr_beg[p], s, h->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
 }
