@@ -290,7 +290,7 @@ int launch_sort_passes(cudaStream_t st, SortBufs& sb, const int32_t* keys_in, in
 
 // Run descriptors of the sorted (key, position) list, three tiers by run length (scatter.cu):
 //   runs       8 int32 per run of <= 4 entries: {key, start, n, pos0, pos1, pos2, pos3, 0}           (capacity n runs)
-//   runs_long  4 int32 per longer run {key, start, count, 0}: runs of <= 512 entries from the front, longer ones from
+//   runs_long  4 int32 per longer run {key, start, count, 0}: runs of up to RUN_M (32, scatter.cu) entries from the front, longer ones from
 //              the back of a buffer of emb_runs_long_cap(n) descriptors
 //   counters   4 int32: number of short / medium / long runs, and of all runs (= unique rows)
 int64_t emb_runs_long_cap(int64_t n);

@@ -298,18 +298,33 @@ __device__ __forceinline__ void replay4(float4& var, float4& m, float4& v, int f
 // runs of the sorted list are split into three tiers by length and every tier has its own fixed summation tree:
 //   S  (<= 4 entries)     one group of d/4 lanes per run; the 32-byte descriptor holds the run's positions, so the
 //                         optimizer state and all gradient rows are ONE batch of independent 16-byte loads;
-//   M  (5 .. 512)         one team of 16 lanes (d <= 32) or one warp per run: group g of the team adds entries g, g+G,
+//   M  (5 .. 32)          one team of 16 lanes (d <= 32) or one warp per run: group g of the team adds entries g, g+G,
 //                         g+2G ... in ascending order, the G partial sums are added in group order (shuffles);
-//   L  (> 512)            one CTA per run: the same with 256/LPR groups, the warps' sums added in warp order (smem).
+//   L  (> 32)             one CTA per run: the same with 256/LPR groups, the warps' sums added in warp order (smem).
 // No float atomics anywhere; the tree of a run depends only on its length, so results are reproducible.
 // emb_runs_kernel (on the sort stream, off the critical path) builds the three descriptor lists; the order inside a
 // list comes from atomics and only decides which threads serve which run.
 constexpr int RUN_S_MAX = 4;
-constexpr int RUN_M_MAX = 512;
+// Upper length of tier M.  A team of 16 lanes needs ceil(n/16) dependent load rounds for a run of n entries, a CTA one
+// round for up to 256, so the break-even is around 32 entries.  Measured on B200 (Taobao shape, uniform ids, longest
+// run 207): 32 and 512 give the same 30 us inside the step - the hot runs are not what bounds the kernel there - so
+// the smaller value is kept for skewed id distributions, where the hot runs are longer.
+// SCORE_RUN_M_MAX overrides (A/B knob); RUN_M_FLOOR sizes the descriptor lists for the smallest allowed value.
+constexpr int RUN_M_DEFAULT = 32;
+constexpr int RUN_M_FLOOR = 16;
+static int run_m_max() {
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("SCORE_RUN_M_MAX");
+        v = e ? atoi(e) : RUN_M_DEFAULT;
+        if (v < RUN_M_FLOOR) v = RUN_M_FLOOR;
+    }
+    return v;
+}
 
 __global__ void emb_runs_kernel(const int32_t* __restrict__ skeys, const int32_t* __restrict__ spos, int64_t n,
                                 int4* __restrict__ runs, int4* __restrict__ runs_long, int64_t long_cap,
-                                int32_t* __restrict__ counters) {
+                                int32_t* __restrict__ counters, int m_max) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int32_t key = 0, prev = -1;
@@ -350,7 +365,7 @@ __global__ void emb_runs_kernel(const int32_t* __restrict__ skeys, const int32_t
         if (skeys[mid] == key) lo = mid; else hi = mid;
     }
     const int32_t cnt = (int32_t)(hi - i);
-    if (cnt <= RUN_M_MAX) {
+    if (cnt <= m_max) {
         const int slot = atomicAdd(counters + 1, 1);
         runs_long[slot] = make_int4(key, (int32_t)i, cnt, 0);              // M list grows from the front
     } else {
@@ -358,13 +373,13 @@ __global__ void emb_runs_kernel(const int32_t* __restrict__ skeys, const int32_t
         runs_long[long_cap - 1 - slot] = make_int4(key, (int32_t)i, cnt, 0);   // L list grows from the back
     }
 }
-int64_t emb_runs_long_cap(int64_t n) { return n / (RUN_S_MAX + 1) + n / (RUN_M_MAX + 1) + 8; }
+int64_t emb_runs_long_cap(int64_t n) { return n / (RUN_S_MAX + 1) + n / (RUN_M_FLOOR + 1) + 8; }
 void launch_emb_runs(cudaStream_t st, const int32_t* skeys, const int32_t* spos, int64_t n, int32_t* runs,
                      int32_t* runs_long, int32_t* counters) {
     cudaMemsetAsync(counters, 0, 4 * sizeof(int32_t), st);
     emb_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(skeys, spos, n, reinterpret_cast<int4*>(runs),
                                                                  reinterpret_cast<int4*>(runs_long), emb_runs_long_cap(n),
-                                                                 counters);
+                                                                 counters, run_m_max());
     ++g_launch_count;
 }
 
