@@ -85,3 +85,14 @@ def test_shard_layout_roundtrip():
             seen[v] = True
         assert float(loc[0].abs().sum()) == 0.0
     assert bool(seen.all())
+
+
+def test_exchange_capacity_is_a_common_multiple_of_1024():
+    # the list capacity of the packed data-parallel exchange: >= every rank's count, multiple of 1024, never 0
+    assert parallel.exchange_capacity([0, 0]) == 1024
+    assert parallel.exchange_capacity([1, 1024]) == 1024
+    assert parallel.exchange_capacity([1025, 7]) == 2048
+    assert parallel.exchange_capacity([129259, 129022, 128870]) == 130048
+    for counts in ([5], [1023, 1024, 1025], [10 ** 6]):
+        cap = parallel.exchange_capacity(counts)
+        assert cap % 1024 == 0 and cap >= max(counts) and cap - max(counts) < 1024 + (max(counts) == 0) * 1024
