@@ -159,6 +159,10 @@ int score_dp_local_count(ScoreHandle h, int32_t* count_out);
 int64_t score_dp_block_words(ScoreHandle h, int64_t cap);
 int score_dp_pack(ScoreHandle h, int64_t cap, void** block_dev, int64_t* block_words);
 int score_dp_finish(ScoreHandle h, const void* gathered_blocks_dev, int32_t world, int64_t cap, double* loss_out);
+/* opt-in peer-memory exchange instead of the all-gather: store the packed block at word offset dst_off_words of every
+ * replica's gathered buffer (peer_bases[r]: that buffer's address as mapped into this process); the caller runs a
+ * barrier across the replicas on score_stream() before score_dp_finish. */
+int score_dp_push(ScoreHandle h, int64_t cap, const uint64_t* peer_bases, int32_t world, int64_t dst_off_words);
 /* loss2 == NULL: enqueue only (no host synchronisation); otherwise loss2[0] = this rank's loss incl. the L2 term
  * (data term scaled by 1/global_batch), loss2[1] = the L2 term alone. */
 int score_step_finish(ScoreHandle h, const int32_t* ext_keys, const float* ext_rows, int64_t n_ext, float* loss2);

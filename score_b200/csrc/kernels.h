@@ -318,6 +318,10 @@ void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a);
 // blocks of all ranks lie `stride` words apart in the gathered buffer `base`; every offset is a multiple of 128 words
 // (rows are 16-byte aligned for any d).
 struct DpLayout { const int32_t* base; int world; int d; int64_t stride, dense_off, keys_off, cap; };
+// destinations of a peer-memory push: where this rank's block goes in every replica's gathered buffer
+constexpr int DP_MAX_WORLD = 16;
+struct DpPeers { int32_t* dst[DP_MAX_WORLD]; int world; };
+void launch_dp_push(cudaStream_t st, const int32_t* block, int64_t words, const DpPeers& peers);
 int64_t head_slot_tiles(int64_t n);
 // head_slot[i] = number of run heads before sorted index i, written at run heads only; tile_counts: head_slot_tiles(n) ints
 void launch_head_slots(cudaStream_t st, const int32_t* skeys, int64_t n, int32_t* tile_counts, int32_t* head_slot);

@@ -1784,6 +1784,24 @@ int score_dp_pack(ScoreHandle h, int64_t cap, void** block_dev, int64_t* block_w
     return SCORE_OK;
 }
 
+// Opt-in peer-memory exchange: store the block score_dp_pack assembled into every replica's gathered buffer.
+// peer_bases[r] = device address (mapped into this process, e.g. by torch's symmetric memory) of replica r's buffer;
+// the block lands at word offset dst_off_words in each of them.  The caller orders the stores against the readers
+// (a barrier across the replicas on score_stream()) before score_dp_finish runs on its own buffer.
+int score_dp_push(ScoreHandle h, int64_t cap, const uint64_t* peer_bases, int32_t world, int64_t dst_off_words) {
+    if (!h || !peer_bases || world < 1 || world > DP_MAX_WORLD) return SCORE_ERR_ARG;
+    if (!h->begun || !h->dp_block) return fail(h, SCORE_ERR_ARG, "score_dp_push needs score_dp_pack");
+    CK(cudaSetDevice(h->device));
+    const DpLayout L = dp_layout(h, nullptr, 1, cap);
+    if (L.stride > h->dp_block_words || dst_off_words < 0 || dst_off_words % 4) return fail(h, SCORE_ERR_ARG, "bad block / offset");
+    DpPeers peers{};
+    peers.world = world;
+    for (int r = 0; r < world; ++r) peers.dst[r] = reinterpret_cast<int32_t*>(peer_bases[r]) + dst_off_words;
+    launch_dp_push(h->st, h->dp_block, L.stride, peers);
+    CK(cudaGetLastError());
+    return SCORE_OK;
+}
+
 // Optimizer half of the data-parallel step on the gathered blocks of all ranks (`gathered`: world blocks of
 // score_dp_block_words(cap) words, rank order, device memory): dense gradients summed in rank order + dense Adam; the
 // ranks' id lists merged into (id, rank) order (no sort: every list is already ascending), rows of one id added in

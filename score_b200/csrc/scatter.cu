@@ -384,6 +384,7 @@ void launch_emb_runs(cudaStream_t st, const int32_t* skeys, const int32_t* spos,
 }
 
 
+static int num_sms_cached();
 // ------------------------------------------------------------------------------------------ data-parallel exchange helpers
 // Rank of every run head among the run heads of the sorted key list (exclusive count of heads before it): the slot of
 // the run in a compact list that is still ascending by key.  Two kernels on the sort stream, off the critical path:
@@ -491,6 +492,24 @@ void launch_dp_pack_misc(cudaStream_t st, int32_t* block, const DpLayout& L, con
                          const float* loss_dev, const float* g, int n_dense) {
     const int64_t n = L.cap > n_dense ? L.cap : n_dense;
     dp_pack_misc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(block, L, counters, hp, loss_dev, g, n_dense);
+    ++g_launch_count;
+}
+
+// Peer-memory variant of the exchange (opt-in, SCORE_DP_P2P=1 in parallel.py): this rank's block is stored straight
+// into every replica's gathered buffer over NVLink (16-byte stores, one grid-stride pass per destination) instead of
+// going through an all-gather; a device-side barrier of the symmetric-memory handle orders it against the readers.
+__global__ void __launch_bounds__(256) dp_push_kernel(const int4* __restrict__ src, int64_t n16, DpPeers peers) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const int4 v = src[i];
+#pragma unroll 4
+        for (int r = 0; r < peers.world; ++r) reinterpret_cast<int4*>(peers.dst[r])[i] = v;
+    }
+}
+void launch_dp_push(cudaStream_t st, const int32_t* block, int64_t words, const DpPeers& peers) {
+    const int64_t n16 = words / 4;   // a block is a multiple of 128 words
+    int64_t want = (n16 + 255) / 256, cap = (int64_t)num_sms_cached() * 8;
+    dp_push_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(reinterpret_cast<const int4*>(block), n16, peers);
     ++g_launch_count;
 }
 

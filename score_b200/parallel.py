@@ -21,6 +21,7 @@ The pure-torch exchange helpers below run on CPU tensors with the gloo backend t
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -131,10 +132,40 @@ class DataParallelTrainer(_Base):
     running, so the host never drains the device inside a step.  The phases are separate methods so a single-process
     test can drive several handles through them (tests/test_parity_gpu.py)."""
 
-    def __init__(self, model, world, rank, group=None):
+    def __init__(self, model, world, rank, group=None, p2p=None):
         super().__init__(model, world, rank, group)
         self.side = torch.cuda.Stream(device=self.device)
         self._gathered = None
+        # Opt-in (SCORE_DP_P2P=1): peer-memory exchange instead of the NCCL all-gather - every rank stores its block
+        # straight into all replicas' gathered buffers (torch symmetric memory supplies the peer mappings and the
+        # device-side barrier).  Experimental: not measured yet, the all-gather is the default.
+        self.p2p = (os.environ.get("SCORE_DP_P2P") == "1") if p2p is None else bool(p2p)
+        self._symm = None
+        self._step_no = 0
+
+    def _p2p_setup(self, words):
+        """two gathered buffers (alternating steps) of world blocks each in symmetric memory, mapped into every rank."""
+        import torch.distributed._symmetric_memory as symm_mem
+        n_pos = self._dev("keys", torch.int32).numel()
+        cap_max = exchange_capacity([n_pos])                       # every position a distinct row: the hard upper bound
+        self._max_words = int(self.lib.score_dp_block_words(self.h, cap_max))
+        self._symm = symm_mem.empty(2 * self.world * self._max_words, dtype=torch.int32, device=self.device)
+        grp = self.group if self.group is not None else dist.group.WORLD
+        self._symm_hdl = symm_mem.rendezvous(self._symm, grp)
+        self._peer_bases = (C.c_uint64 * self.world)(*[int(p) for p in self._symm_hdl.buffer_ptrs])
+
+    def _exchange_p2p(self, block, cap):
+        words = block.numel()
+        if self._symm is None:
+            self._p2p_setup(words)
+        if words > self._max_words:
+            raise RuntimeError("packed block larger than the symmetric buffer")
+        base = (self._step_no & 1) * self.world * self._max_words     # alternate buffers: a peer may still read the other
+        self._step_no += 1
+        with torch.cuda.stream(self.stream):
+            self.m._check(self.lib.score_dp_push(self.h, cap, self._peer_bases, self.world, base + self.rank * words))
+            self._symm_hdl.barrier(channel=0)                         # all blocks stored and visible; orders buffer reuse
+        return self._symm[base:base + self.world * words]
 
     # ---- phases
     def begin(self, batch_data, lr, reg_lambda, keep_prob=TRAIN_KEEP_PROB, global_batch=None):
@@ -180,6 +211,8 @@ class DataParallelTrainer(_Base):
     def _rest(self, want_loss):
         cap = exchange_capacity(self.exchange_counts(self.local_count()))
         block = self.pack(cap)
+        if self.p2p:
+            return self.finish(self._exchange_p2p(block, cap), cap, want_loss)
         n = block.numel() * self.world
         with torch.cuda.stream(self.stream):
             if self._gathered is None or self._gathered.numel() < n:

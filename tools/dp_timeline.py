@@ -34,11 +34,14 @@ def main():
         block = dp.pack(cap)
         ev[2].record(st)
         nw = block.numel() * world
-        with torch.cuda.stream(st):
-            if dp._gathered is None or dp._gathered.numel() < nw:
-                dp._gathered = torch.empty(nw + nw // 4, dtype=torch.int32, device=dp.device)
-            g = dp._gathered[:nw]
-            dist.all_gather_into_tensor(g, block)
+        if dp.p2p:
+            g = dp._exchange_p2p(block, cap)
+        else:
+            with torch.cuda.stream(st):
+                if dp._gathered is None or dp._gathered.numel() < nw:
+                    dp._gathered = torch.empty(nw + nw // 4, dtype=torch.int32, device=dp.device)
+                g = dp._gathered[:nw]
+                dist.all_gather_into_tensor(g, block)
         ev[3].record(st)
         dp.finish(g, cap, want_loss=False)
         ev[4].record(st)
