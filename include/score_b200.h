@@ -116,7 +116,10 @@ int score_get_buffer(ScoreHandle h, const char* name, void* data, size_t capacit
 
 /* Parameters and Adam slots by TF variable name ("emb_mtx", "dense/kernel", ...,
  * "<var>/Adam", "<var>/Adam_1", "beta1_power", "beta2_power").
- * Replaces reading / assigning tf variables; used for checkpoint interop and parity. */
+ * Replaces reading / assigning tf variables; used for checkpoint interop and parity.
+ * Setting a beta power also recovers the optimizer step from it (0.9^(step+1); 0.999^(step+1) once
+ * beta1_power has gone denormal); "step" (one float, not a TF variable) sets / reads it exactly.
+ * Either way the optimizer state present at that moment counts as current at that step. */
 int score_tensor_count(ScoreHandle h);
 int score_tensor_info(ScoreHandle h, int index, char* name, size_t name_cap, int64_t* rows, int64_t* cols);
 int score_get_tensor(ScoreHandle h, const char* name, float* data, size_t count);
@@ -166,6 +169,11 @@ int score_dp_push(ScoreHandle h, int64_t cap, const uint64_t* peer_bases, int32_
 /* loss2 == NULL: enqueue only (no host synchronisation); otherwise loss2[0] = this rank's loss incl. the L2 term
  * (data term scaled by 1/global_batch), loss2[1] = the L2 term alone. */
 int score_step_finish(ScoreHandle h, const int32_t* ext_keys, const float* ext_rows, int64_t n_ext, float* loss2);
+
+/* Global index of the first sample of the batches this handle steps on (a data-parallel rank: rank * per-rank batch;
+ * default 0).  It keys the dropout stream of tf.nn.dropout's stand-in (score.py:71-73), so N ranks draw the masks one
+ * process would draw on the concatenated batch instead of N copies of the same mask. */
+int score_set_sample_offset(ScoreHandle h, int32_t first_global_sample);
 
 /* The CUDA stream every call of this handle is ordered on (a cudaStream_t). */
 int score_stream(ScoreHandle h, void** cuda_stream);

@@ -63,6 +63,7 @@ SYMBOLS = {
     "score_dp_finish": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_double)]),
     "score_dp_push": (C.c_int, [_H, C.c_int64, C.POINTER(C.c_uint64), C.c_int32, C.c_int64]),
     "score_step_finish": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "score_set_sample_offset": (C.c_int, [_H, C.c_int32]),
     "score_stream": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "score_launch_count": (C.c_int64, [_H]),
     "score_enable_probes": (C.c_int, [_H, C.c_int]),

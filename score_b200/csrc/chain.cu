@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(TL_CT) fc_fwd_kernel(FcArgs a) {
     const float keep = a.hp->keep_prob;
     const bool drop = (a.hp->train != 0) && keep < 1.f;
     const uint32_t s_lo = a.hp->seed_lo, s_hi = a.hp->seed_hi, step = (uint32_t)a.hp->step;
+    const uint64_t sbase = (uint64_t)(uint32_t)a.hp->sample_base;   // dropout masks are keyed by the GLOBAL sample index
     int rg, cg;
     tile_coords<R>(tid, rg, cg);
     // batch norm in inference mode (score.py:69)
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(TL_CT) fc_fwd_kernel(FcArgs a) {
             for (int j = 0; j < 4; ++j) {
                 float v = fmaxf(acc[i][j] + bj[j], 0.f);
                 if (drop) {
-                    const float u = philox_uniform(s_lo, s_hi, 1u, step, (uint64_t)gm * F1 + 4 * cg + j);
+                    const float u = philox_uniform(s_lo, s_hi, 1u, step, (sbase + (uint64_t)gm) * F1 + 4 * cg + j);
                     v = (u < keep) ? v / keep : 0.f;
                 }
                 acc[i][j] = v;
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(TL_CT) fc_fwd_kernel(FcArgs a) {
             for (int j = 0; j < 4; ++j) {
                 float v = fmaxf(acc[i][j] + bj[j], 0.f);
                 if (drop) {
-                    const float u = philox_uniform(s_lo, s_hi, 2u, step, (uint64_t)gm * F2 + 4 * cg + j);
+                    const float u = philox_uniform(s_lo, s_hi, 2u, step, (sbase + (uint64_t)gm) * F2 + 4 * cg + j);
                     v = (u < keep) ? v / keep : 0.f;
                 }
                 acc[i][j] = v;

@@ -21,7 +21,7 @@ struct Hyper {
     int32_t batch;        // B of this launch
     int32_t train;        // 1: training step (dropout active when keep_prob < 1)
     int32_t seq;          // launch sequence number (every upload): selects the ping-pong claim counter
-    int32_t pad1;
+    int32_t sample_base;  // global index of this launch's sample 0 (data-parallel: rank * per-rank batch): keys the dropout stream
 };
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -68,11 +68,14 @@ struct ScoreModel {
     float* Dv = nullptr; int64_t n_derived = 0; PrepOps prep{};
     int64_t dv_W1e = 0, dv_Wac = 0, dv_W1eT = 0, dv_WacT = 0, dv_W2T = 0, dv_WqT = 0, dv_fc1T = 0, dv_fc2T = 0;
     int64_t dv_Wx[2] = {0, 0}, dv_WxT[2] = {0, 0};   // GRU input-side kernels [Wg_x | Wc_x] ([Ds,3H]) and their transpose
-    float* alpha_hist = nullptr; int64_t alpha_cap = 0;
-    std::vector<float> alpha_host;
+    // LAZY Adam: alpha of every step since the last re-base, indexed by the ABSOLUTE step through a shifted pointer
+    // (alpha_hist = alpha_buf - hist_base; valid for steps in (hist_base, hist_base + alpha_cap)).  When the window is
+    // nearly full every row is brought up to date and the window restarts at the current step (lazy_rebase).
+    float* alpha_hist = nullptr; float* alpha_buf = nullptr; int64_t alpha_cap = 0; int64_t hist_base = 0;
 
     // optimizer scalars (fp32 like the TF slot variables)
     int32_t step = 0;
+    int32_t sample_base = 0;   // score_set_sample_offset: global index of the local batch's first sample
     float beta1_power = 0.9f, beta2_power = 0.999f;
 
     // workspace
@@ -322,8 +325,13 @@ int alloc_params(ScoreModel* h) {
     CK(cudaMallocHost(&h->err_host, sizeof(int32_t)));
     if (h->cfg.adam_mode == SCORE_ADAM_LAZY) {
         h->alpha_cap = 1 << 20;
-        CK(cudaMalloc(&h->alpha_hist, sizeof(float) * h->alpha_cap));
-        CK(cudaMemsetAsync(h->alpha_hist, 0, sizeof(float) * h->alpha_cap, h->st));
+        if (const char* e = getenv("SCORE_ALPHA_CAP")) {   // test knob: a short window exercises the re-base
+            const long v = atol(e);
+            if (v >= 4) h->alpha_cap = v;
+        }
+        CK(cudaMalloc(&h->alpha_buf, sizeof(float) * h->alpha_cap));
+        CK(cudaMemsetAsync(h->alpha_buf, 0, sizeof(float) * h->alpha_cap, h->st));
+        h->alpha_hist = h->alpha_buf; h->hist_base = 0;
     }
     return SCORE_OK;
 }
@@ -365,6 +373,9 @@ void free_workspace(ScoreModel* h) {
     h->graphs_begin.clear();
     h->warm_begin.clear();
     h->graph_kernels_begin.clear();
+    if (h->seg_rows) cudaFree(h->seg_rows);
+    if (h->seg_heads) cudaFree(h->seg_heads);
+    h->seg_rows = nullptr; h->seg_heads = nullptr; h->seg_cap = 0;
     h->cap_B = 0;
 }
 
@@ -447,7 +458,6 @@ int ensure_workspace(ScoreModel* h, int B) {
     h->stage_busy[0] = h->stage_busy[1] = false; h->stage_last = -1;
     WSI(h->head_slot, N, nullptr);
     WSI(h->hs_tiles, head_slot_tiles(N) + 1, nullptr);
-    h->seg_rows = nullptr; h->seg_heads = nullptr; h->seg_cap = 0;
     h->cap_B = cap;
     CK(cudaStreamSynchronize(h->st));
     return SCORE_OK;
@@ -906,7 +916,7 @@ void fill_hyper(ScoreModel* h, int B, float lr, float reg_lambda, float keep_pro
     hp.alpha = lr * sqrtf(one - h->beta2_power) / (one - h->beta1_power);
     hp.inv_batch = 1.0f / (float)(global_batch > 0 ? global_batch : B);
     hp.seed_lo = (uint32_t)h->cfg.seed; hp.seed_hi = (uint32_t)(h->cfg.seed >> 32);
-    hp.step = h->step + 1; hp.batch = B; hp.train = train; hp.seq = h->hyper_seq++; hp.pad1 = 0;
+    hp.step = h->step + 1; hp.batch = B; hp.train = train; hp.seq = h->hyper_seq++; hp.sample_base = h->sample_base;
 }
 
 // fill the next ring slot and enqueue its H2D copy
@@ -928,6 +938,48 @@ int flush_lazy(ScoreModel* h) {
         CK(cudaStreamSynchronize(h->st));
     }
     return SCORE_OK;
+}
+
+void drop_graphs(ScoreModel* h) {
+    for (auto& kv : h->graphs_train) cudaGraphExecDestroy(kv.second);
+    h->graphs_train.clear(); h->graph_kernels.clear();
+    for (auto& kv : h->graphs_begin) cudaGraphExecDestroy(kv.second);
+    h->graphs_begin.clear(); h->graph_kernels_begin.clear();
+}
+
+// LAZY Adam: declare every row current at h->step and restart the alpha window there.  Callers have either just
+// replayed the whole table up to h->step (lazy_rollover) or replaced the optimizer state wholesale (restore / import).
+int lazy_rebase(ScoreModel* h) {
+    if (h->cfg.adam_mode != SCORE_ADAM_LAZY) return SCORE_OK;
+    CK(cudaStreamSynchronize(h->st));
+    launch_fill_i32(h->st, h->last_step, h->dm.V, h->step);
+    CK(cudaMemsetAsync(h->alpha_buf, 0, sizeof(float) * h->alpha_cap, h->st));
+    h->hist_base = h->step;
+    h->alpha_hist = h->alpha_buf - h->hist_base;
+    drop_graphs(h);   // the captured launches carry the old window pointer
+    CK(cudaStreamSynchronize(h->st));
+    return SCORE_OK;
+}
+// the window is nearly full: replay the skipped steps of every row, then restart the window (tf.train.AdamOptimizer has
+// no step limit; at 0.35 ms/step a window of 2^20 steps lasts ~6 minutes)
+int lazy_rollover_if_needed(ScoreModel* h) {
+    if (h->cfg.adam_mode != SCORE_ADAM_LAZY || (int64_t)h->step + 2 - h->hist_base < h->alpha_cap) return SCORE_OK;
+    int rc = flush_lazy(h);
+    if (rc) return rc;
+    return lazy_rebase(h);
+}
+
+// step counter from the Adam slot variables of a checkpoint (beta1_power = 0.9^(step+1), beta2_power = 0.999^(step+1)):
+// beta1_power while it is a normal float (it goes denormal near 830 steps), beta2_power after that
+void recover_step(ScoreModel* h) {
+    double s = 0.0;
+    const float b1 = h->beta1_power, b2 = h->beta2_power;
+    if (b1 > 1e-30f && b1 < 1.0f) s = log((double)b1) / log(0.9) - 1.0;
+    else if (b2 > 0.f && b2 < 1.0f) s = log((double)b2) / log(0.999) - 1.0;
+    else return;   // no usable slot value: keep the counter
+    if (!(s >= 0.0)) s = 0.0;
+    if (s > 2.0e9) s = 2.0e9;
+    h->step = (int32_t)llround(s);
 }
 
 int finish_sync(ScoreModel* h, float* loss_out) {
@@ -992,8 +1044,7 @@ int run_step(ScoreModel* h, const ScoreBatch* b, int mode, float lr, float reg_l
     set_batch_dims(h, B);
     if (mode == MODE_FWDBWD) { rc = ensure_seg(h, h->dm.N); if (rc) return rc; }
     const bool train = (mode == MODE_TRAIN);
-    if (train && h->cfg.adam_mode == SCORE_ADAM_LAZY && h->step + 2 >= h->alpha_cap)
-        return fail(h, SCORE_ERR_ARG, "lazy Adam step history exhausted");
+    if (train) { rc = lazy_rollover_if_needed(h); if (rc) return rc; }
     rc = upload_batch(h, b);
     if (rc) return rc;
     rc = upload_hyper(h, B, lr, reg_lambda, (mode == MODE_EVAL) ? 1.0f : keep_prob, mode != MODE_EVAL, global_batch);
@@ -1135,7 +1186,7 @@ int score_destroy(ScoreHandle h) {
     if (h->st) cudaStreamSynchronize(h->st);
     free_workspace(h);
     for (void* p : {(void*)h->emb_tab, (void*)h->last_step, (void*)h->P, (void*)h->G,
-                    (void*)h->M1, (void*)h->V1, (void*)h->PG, (void*)h->flags, (void*)h->Dv, (void*)h->n_heads_dev, (void*)h->claim_counter, (void*)h->claim_ext, (void*)h->alpha_hist, (void*)h->l2sum,
+                    (void*)h->M1, (void*)h->V1, (void*)h->PG, (void*)h->flags, (void*)h->Dv, (void*)h->n_heads_dev, (void*)h->claim_counter, (void*)h->claim_ext, (void*)h->alpha_buf, (void*)h->l2sum,
                     (void*)h->loss_dev, (void*)h->err_flag, (void*)h->step_dev, (void*)h->seg_rows, (void*)h->seg_heads})
         if (p) cudaFree(p);
     if (h->hyper_ring) cudaFreeHost(h->hyper_ring);
@@ -1304,6 +1355,11 @@ int score_get_tensor(ScoreHandle h, const char* name, float* data, size_t count)
         data[0] = n == "beta1_power" ? h->beta1_power : h->beta2_power;
         return SCORE_OK;
     }
+    if (n == "step") {
+        if (count < 1) return fail(h, SCORE_ERR_ARG, "count too small");
+        data[0] = (float)h->step;
+        return SCORE_OK;
+    }
     float* p; size_t cnt; bool is_emb;
     int rc = resolve(h, n, &p, &cnt, &is_emb);
     if (rc) return rc;
@@ -1325,11 +1381,13 @@ int score_set_tensor(ScoreHandle h, const char* name, const float* data, size_t 
     if (n == "beta1_power" || n == "beta2_power") {
         if (count < 1) return fail(h, SCORE_ERR_ARG, "count too small");
         (n == "beta1_power" ? h->beta1_power : h->beta2_power) = data[0];
-        if (n == "beta1_power") {   // recover the step counter from the slot variable (0.9^(step+1))
-            double s = log((double)data[0]) / log(0.9) - 1.0;
-            h->step = (int32_t)llround(s < 0 ? 0 : s);
-        }
-        return SCORE_OK;
+        recover_step(h);
+        return lazy_rebase(h);   // imported optimizer state is current at the imported step
+    }
+    if (n == "step") {   // explicit step counter (exact; the beta powers only approximate it after ~10^4 steps)
+        if (count < 1 || !(data[0] >= 0.f)) return fail(h, SCORE_ERR_ARG, "step must be a non-negative number");
+        h->step = (int32_t)llround((double)data[0]);
+        return lazy_rebase(h);
     }
     float* p; size_t cnt; bool is_emb;
     int rc = resolve(h, n, &p, &cnt, &is_emb);
@@ -1452,7 +1510,8 @@ int score_restore(ScoreHandle h, const char* path) {
     ok = fread(&h->beta1_power, 4, 1, f) == 1 && fread(&h->beta2_power, 4, 1, f) == 1 && fread(&h->step, 4, 1, f) == 1;
     fclose(f);
     if (!ok) return fail(h, SCORE_ERR_IO, "truncated checkpoint");
-    if (h->last_step) {   // every row of a restored table is current at the restored step
+    if (h->cfg.adam_mode == SCORE_ADAM_LAZY) return lazy_rebase(h);   // every row of a restored table is current at the restored step
+    if (h->last_step) {
         launch_fill_i32(h->st, h->last_step, h->dm.V, h->step);
         CK(cudaStreamSynchronize(h->st));
     }
@@ -1639,8 +1698,7 @@ int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg
     } else if (h->dm.B <= 0) {
         return fail(h, SCORE_ERR_ARG, "no prepared batch");
     }
-    if (train && h->cfg.adam_mode == SCORE_ADAM_LAZY && h->step + 2 >= h->alpha_cap)
-        return fail(h, SCORE_ERR_ARG, "lazy Adam step history exhausted");
+    if (train) { int rc = lazy_rollover_if_needed(h); if (rc) return rc; }
     const Dims& dm = h->dm;
     {
         int rc = upload_hyper(h, dm.B, lr, reg_lambda, train ? keep_prob : 1.0f, train, global_batch);
@@ -1762,7 +1820,6 @@ int score_dp_pack(ScoreHandle h, int64_t cap, void** block_dev, int64_t* block_w
     if (L.stride > h->dp_block_words) {
         CK(cudaStreamSynchronize(h->st));
         if (h->dp_block) cudaFree(h->dp_block);
-    if (h->dp_sample) cudaFree(h->dp_sample);
         h->dp_block = nullptr; h->dp_block_words = 0;
         const int64_t words = L.stride + L.stride / 4;
         CK(cudaMalloc(&h->dp_block, sizeof(int32_t) * words));
@@ -1884,6 +1941,12 @@ int score_step_finish(ScoreHandle h, const int32_t* ext_keys, const float* ext_r
 }  // extern "C"
 
 extern "C" {
+
+int score_set_sample_offset(ScoreHandle h, int32_t first_global_sample) {
+    if (!h || first_global_sample < 0) return SCORE_ERR_ARG;
+    h->sample_base = first_global_sample;
+    return SCORE_OK;
+}
 
 int score_stream(ScoreHandle h, void** cuda_stream) {
     if (!h || !cuda_stream) return SCORE_ERR_ARG;

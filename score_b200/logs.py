@@ -26,6 +26,7 @@ def export_npz(model, path):
             out[name + "/Adam_1"] = model.get_tensor(name + "/Adam_1")
     out["beta1_power"] = np.float32(model.get_tensor("beta1_power"))
     out["beta2_power"] = np.float32(model.get_tensor("beta2_power"))
+    out["step"] = np.int64(model.get_tensor("step"))   # not a TF variable: the exact optimizer step (see import_npz)
     np.savez(path, **out)
     return sorted(out)
 
@@ -43,9 +44,14 @@ def import_npz(model, path, strict=True):
         for suf in ("/Adam", "/Adam_1"):
             if name not in NON_TRAINABLE and name + suf in data.files:
                 model.set_tensor(name + suf, data[name + suf])
+    # The optimizer step is recovered from the slot variables (beta1_power = 0.9^(step+1); beta2_power once that has gone
+    # denormal) unless the file carries it explicitly; either way every imported row counts as current at that step
+    # (lazy Adam: nothing is replayed against the imported state).
     for p in ("beta1_power", "beta2_power"):
         if p in data.files:
             model.set_tensor(p, np.asarray([data[p]], np.float32))
+    if "step" in data.files:
+        model.set_tensor("step", np.asarray([data["step"]], np.float32))
 
 
 def model_name(model_type, train_batch_size, lr, reg_lambda):

@@ -159,7 +159,7 @@ class SCOREBASE(object):
         return out
 
     def get_tensor(self, name):
-        if name in ("beta1_power", "beta2_power"):
+        if name in ("beta1_power", "beta2_power", "step"):
             out = np.empty(1, np.float32)
             self._check(self._lib.score_get_tensor(self._h, name.encode(), out.ctypes.data, 1))
             return out[0]

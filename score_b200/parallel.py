@@ -171,6 +171,7 @@ class DataParallelTrainer(_Base):
     def begin(self, batch_data, lr, reg_lambda, keep_prob=TRAIN_KEEP_PROB, global_batch=None):
         b = _Batch(batch_data, self.m.cfg)
         gb = global_batch if global_batch else b.B * self.world
+        self.m._check(self.lib.score_set_sample_offset(self.h, self.rank * b.B))   # dropout masks of the global batch
         with torch.cuda.stream(self.stream):
             self.m._check(self.lib.score_step_begin(self.h, C.byref(b.struct), lr, reg_lambda, keep_prob, gb, 1, None, None))
         self._keep_batch = b   # host id arrays stay alive until their H2D copies have run
@@ -249,6 +250,7 @@ class ShardedEmbeddingTrainer(_Base):
         b = _Batch(batch_data, self.m.cfg)
         gb = b.B * self.world
         d = self.m.cfg["eb_dim"]
+        self.m._check(self.lib.score_set_sample_offset(self.h, self.rank * b.B))   # dropout masks of the global batch
         with torch.cuda.stream(self.stream):
             plan, want, staged = self._fetch(b)
             self._keep_batch = b

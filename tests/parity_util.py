@@ -30,6 +30,34 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / scale)
 
 
+# Elementwise bar beside the normwise one: |a - b| <= REL_TOL * |b| + ABS_FRAC * max|b| for EVERY entry.  The absolute
+# part is the rounding floor of an fp32 sum whose terms are of the tensor's scale (an entry that is the cancelled sum
+# of O(100) such terms cannot be reproduced to 1e-5 of ITSELF by any summation order); it is two orders below the
+# normwise bar, so entries far below the tensor maximum are checked too.
+ABS_FRAC = 1e-6
+
+
+def elem_excess(a, b, rtol=REL_TOL, abs_frac=ABS_FRAC):
+    """max over entries of |a-b| / (rtol*|b| + abs_frac*max|b|): <= 1 means every entry is inside the bar."""
+    a = np.asarray(a, np.float64).reshape(-1)
+    b = np.asarray(b, np.float64).reshape(-1)
+    if a.size == 0:
+        return 0.0
+    scale = max(float(np.abs(b).max()), 1e-30)
+    return float((np.abs(a - b) / (rtol * np.abs(b) + abs_frac * scale)).max())
+
+
+class Report(dict):
+    """{name: normwise relative error}; add() also records the elementwise excess under 'elem/<name>'."""
+
+    def add(self, name, a, b, scale_floor=None):
+        a = np.asarray(a, np.float64)
+        b = np.asarray(b, np.float64)
+        self[name] = rel_err(a, b)
+        self["elem/" + name] = elem_excess(a, b)
+        return self[name]
+
+
 def make_models(shape: Shape, seed=7, adam_mode="dense", model_type="SCORE", use_graph=False, dtype=torch.float32):
     cfg = ref.ScoreConfig(*shape.ctor_args(), model_type=model_type)
     params = ref.init_params(cfg, seed, torch.float32)
@@ -56,7 +84,7 @@ def forward_backward_report(shape: Shape, batch, seed=7, reg_lambda=1e-4, keep_p
         masks = (torch.from_numpy((g1 != 0).astype(np.float32)), torch.from_numpy((g2 != 0).astype(np.float32)))
     tb = ref.to_batch(batch)
     loss_o, y_o, g_o, inter = ref.loss_and_grads(params, tb, cfg, reg_lambda, keep_prob, masks)
-    rep = {}
+    rep = Report()
     live = (np.arange(T)[None, :] < np.asarray(batch[7])[:, None])   # [B,T]
     ldx = Ds + H
 
@@ -64,19 +92,19 @@ def forward_backward_report(shape: Shape, batch, seed=7, reg_lambda=1e-4, keep_p
         return x.reshape(B, T, width)[live]
 
     rep["loss"] = rel_err(loss_c, float(loss_o))
-    rep["y_pred"] = rel_err(m.get_buffer("y_pred"), y_o.numpy())
+    rep.add("y_pred", m.get_buffer("y_pred"), y_o.numpy())
     xu = m.get_buffer("xhg_user").reshape(B * T, ldx)[:, :Ds]
     xi = m.get_buffer("xhg_item").reshape(B * T, ldx)[:, :Ds]
-    rep["user_side"] = rel_err(live_rows(xu, Ds), inter["user_side"].numpy()[live])
-    rep["item_side"] = rel_err(live_rows(xi, Ds), inter["item_side"].numpy()[live])
+    rep.add("user_side", live_rows(xu, Ds), inter["user_side"].numpy()[live])
+    rep.add("item_side", live_rows(xi, Ds), inter["item_side"].numpy()[live])
     key = m.get_buffer("key").reshape(B * T, Dk)
-    rep["user_rep_t"] = rel_err(key[:, :H].reshape(B, T, H), inter["user_rep_t"].numpy())
-    rep["item_rep_t"] = rel_err(key[:, H:2 * H].reshape(B, T, H), inter["item_rep_t"].numpy())
+    rep.add("user_rep_t", key[:, :H].reshape(B, T, H), inter["user_rep_t"].numpy())
+    rep.add("item_rep_t", key[:, H:2 * H].reshape(B, T, H), inter["item_rep_t"].numpy())
     if inter.get("atten_info") is not None and model_type != "RIA":
-        rep["atten_info"] = rel_err(live_rows(key[:, 2 * H:], 4 * K), inter["atten_info"].numpy()[live])
+        rep.add("atten_info", live_rows(key[:, 2 * H:], 4 * K), inter["atten_info"].numpy()[live])
     if inter.get("score") is not None:
-        rep["att_score"] = rel_err(m.get_buffer("score").reshape(B, T), inter["score"].numpy().reshape(B, T))
-    rep["fc_in"] = rel_err(m.get_buffer("fc_in").reshape(B, -1), inter["fc_in"].numpy())
+        rep.add("att_score", m.get_buffer("score").reshape(B, T), inter["score"].numpy().reshape(B, T))
+    rep.add("fc_in", m.get_buffer("fc_in").reshape(B, -1), inter["fc_in"].numpy())
     for name, _ in m.tensor_names():
         if name == "emb_mtx" or name in ref.NON_TRAINABLE:
             continue
@@ -88,11 +116,12 @@ def forward_backward_report(shape: Shape, batch, seed=7, reg_lambda=1e-4, keep_p
             # its rounding error scales with those terms, not with the cancelled sum -> use the layer's scale
             scale = max(scale, float(g_o[name[:-5] + "/kernel"].abs().max()))
         rep["grad/" + name] = float(np.abs(a - b).max() / max(scale, 1e-30))
+        rep["elem/grad/" + name] = float((np.abs(a - b) / (REL_TOL * np.abs(b) + ABS_FRAC * max(scale, 1e-30))).max())
     rows_c, vals_c = m.embedding_row_grads()
     rows_o, vals_o = ref.embedding_row_grads(g_o["emb_mtx"])
     rep["emb_rows_exact"] = bool(np.array_equal(rows_c, rows_o.numpy()))
     if rep["emb_rows_exact"]:
-        rep["emb_row_grads"] = rel_err(vals_c, vals_o.numpy())
+        rep.add("emb_row_grads", vals_c, vals_o.numpy())
     else:
         common = np.intersect1d(rows_c, rows_o.numpy())
         rep["emb_rows_missing"] = int(len(rows_o) - len(common))
@@ -144,6 +173,8 @@ def print_report(title, rep, tol=REL_TOL):
             print("   %-48s %s" % (k, "exact" if v else "MISMATCH"))
         elif isinstance(v, int):
             print("   %-48s %d" % (k, v))
+        elif k.startswith("elem/"):
+            print("   %-48s %.3f of the elementwise bar%s" % (k, v, "" if v <= 1.0 else "   <-- OUTSIDE"))
         else:
             flag = "" if v <= tol else "   <-- above %.0e" % tol
             worst = max(worst, v)

@@ -25,36 +25,44 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     shape = SHAPES[sys.argv[1] if len(sys.argv) > 1 else "tiny_tb"]
-    steps, lr, lam = 3, 1e-3, 1e-4
+    # "plain": direct launches, keep_prob 1, one batch size.  "graph_dropout": the production configuration - CUDA-graph
+    # half-step, dropout (masks keyed by the GLOBAL sample index, so they equal the single-GPU run's), batch sizes that
+    # change from step to step (graph per size, exchange buffers regrow)
+    variant = sys.argv[2] if len(sys.argv) > 2 else "plain"
+    prod = variant == "graph_dropout"
+    lr, lam = 1e-3, 1e-4
+    kp = 0.8 if prod else 1.0
+    sizes = [shape.batch, shape.batch // 2, shape.batch, shape.batch, shape.batch // 4, shape.batch] if prod else [shape.batch] * 3
+    steps = len(sizes)
     cfg = ref.ScoreConfig(*shape.ctor_args())
     params = ref.init_params(cfg, 5)
-    per = [[make_batch(shape, seed=100 * s + r) for r in range(world)] for s in range(steps)]
+    per = [[make_batch(shape, seed=100 * s + r, batch=sizes[s]) for r in range(world)] for s in range(steps)]
     glob = [tuple(np.concatenate([b[i] for b in bs], 0) for i in range(8)) for bs in per]
     worst = 0.0
     for mode in ("dense", "lazy"):
         # single-GPU run on the global batch
         m1 = sb.SCORE(*shape.ctor_args(), device=local, adam_mode=mode, init_weights=False, use_graph=False)
         m1.load_params(params)
-        l1 = [m1.train(None, g, lr, lam, keep_prob=1.0) for g in glob]
+        l1 = [m1.train(None, g, lr, lam, keep_prob=kp) for g in glob]
         # data-parallel, replicated table
-        m2 = sb.SCORE(*shape.ctor_args(), device=local, adam_mode=mode, init_weights=False, use_graph=False)
+        m2 = sb.SCORE(*shape.ctor_args(), device=local, adam_mode=mode, init_weights=False, use_graph=prod)
         m2.load_params(params)
         dp = parallel.DataParallelTrainer(m2, world, rank)
-        l2 = [dp.train(None, bs[rank], lr, lam, keep_prob=1.0) for bs in per]
+        l2 = [dp.train(None, bs[rank], lr, lam, keep_prob=kp) for bs in per]
         # row-sharded table
         a = list(shape.ctor_args())
         a[0] = parallel.shard_rows(shape.feature_size, world)
-        m3 = sb.SCORE(*a, device=local, adam_mode=mode, init_weights=False, use_graph=False)
+        m3 = sb.SCORE(*a, device=local, adam_mode=mode, init_weights=False, use_graph=prod)
         for name, _ in m3.tensor_names():
             v = params[name]
             if name == "emb_mtx":
                 v = parallel.global_to_local_table(v, world, rank)
             m3.set_tensor(name, v.numpy())
         sh = parallel.ShardedEmbeddingTrainer(m3, world, rank)
-        l3 = [sh.train(None, bs[rank], lr, lam, keep_prob=1.0) for bs in per]
+        l3 = [sh.train(None, bs[rank], lr, lam, keep_prob=kp) for bs in per]
         p1, _, e1 = m1.eval(None, glob[0], lam)
         p3, _, e3 = sh.eval(None, per[0][rank], lam)
-        n = shape.batch
+        n = sizes[0]
         errs = {"loss dp": rel(l2, l1), "loss sharded": rel(l3, l1),
                 "eval preds sharded": rel(p3, p1[rank * n:(rank + 1) * n])}
         emb1 = m1.get_tensor("emb_mtx")
@@ -72,7 +80,7 @@ def main():
         dist.broadcast(t0, 0)
         errs["replica divergence (must be 0)"] = float((t != t0).sum().item())
         if rank == 0:
-            print("== adam=%s world=%d shape=%s" % (mode, world, shape.name))
+            print("== adam=%s world=%d shape=%s variant=%s" % (mode, world, shape.name, variant))
             for k, v in errs.items():
                 print("   %-52s %.3e" % (k, v))
         worst = max(worst, max(v for k, v in errs.items() if not k.endswith("kernel dp") and not k.endswith("kernel sharded")))
