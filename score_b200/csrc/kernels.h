@@ -60,6 +60,9 @@ struct Dims {
     int B, T, K, d, H, fu, fi;
     int Du, Di, Ds, Dk, Dfc;      // user/item node width, GRU input width, key width, fc input width
     int ldx;                       // Ds + H: leading dim of the [x || h] buffers
+    int Dx[2], ldxs[2];            // GRU input width / leading dim of [x || h] per side (user, item): Ds / ldx, except RRN
+                                   // (slice_model.py:155-173: user side = sum of user_1hop [Di], item side = sum of item_1hop [Du])
+    int hop1_only;                 // RRN: the 2-hop tensors are fed but never consumed - their positions carry key 0
     int nrows;                     // K * (2*fi + 2*fu): positions (ids) per (b,t) slice
     int64_t off_tu, off_ti, N;     // slice-major position space (embed.cu): B*T*nrows history positions, then the targets
     int model_type;
@@ -98,7 +101,7 @@ struct CoattArgs {
     const float* emb; int es; const int32_t* keys; const int32_t* length;
     const float* w_item; const float* w_user;
     const float* c_item; const float* c_user;
-    float* xhg_u; float* xhc_u; float* xhg_i; float* xhc_i;   // [M, ldx], x part written here
+    float* xhg_u; float* xhc_u; float* xhg_i; float* xhc_i;   // [M, ldxs[side]], x part written here
     float* key; int ldkey; int key_off;                       // atten_info -> key[:, key_off : key_off+4K]
     float* save_r; float* save_w;                             // [M, 2K]
     int sum_pool;   // RCA (score.py:266-269): plain sum over the K neighbors, no relatedness, no atten_info
@@ -109,7 +112,7 @@ struct CoattBwdArgs {
     const float* emb; int es; const int32_t* keys; const int32_t* length;
     const float* w_item; const float* w_user;
     const float* save_r; const float* save_w;
-    const float* dxu; const float* dxi;        // [M, Ds]
+    const float* dxu; const float* dxi;        // [M, Dx[0]], [M, Dx[1]]
     const float* dkey; int ldkey; int key_off; // d atten_info (NULL: atten_info has no consumer - RIA)
     int sum_pool;                              // RCA: backward of the plain neighbor sum
     float* grad_rows;                          // [N, d] per-position embedding gradient rows

@@ -728,118 +728,6 @@ static void emb_update_launch(cudaStream_t st, const EmbUpdateArgs& a, unsigned 
     else if (a.mode == 2) launch_chain(emb_update_kernel<2, LPR>, dim3(grid), dim3(256), 0, st, a);
     else launch_chain(emb_update_kernel<0, LPR>, dim3(grid), dim3(256), 0, st, a);
 }
-// Experimental split of the update (SCORE_KE_SPLIT=1, apply mode only; NOT measured yet - written after this round's GPU
-// budget was spent): ncu shows the one-kernel version latency-bound at 4 CTAs per SM (64 registers, the maximum over
-// its three tiers) with the tier-S groups - 97 % of the runs - waiting on the pair descriptor -> row.  Here tiers L/M
-// keep their code in a small launch and tier S gets a lean kernel of its own (no descriptor prefetch: a group handles
-// at most one run at these sizes) that fits five CTAs per SM.  Same summation trees, same arithmetic: results are
-// bit-identical to emb_update_kernel<0, LPR>.
-template <int LPR>
-__global__ void __launch_bounds__(256) emb_update_ml_kernel(EmbUpdateArgs a) {
-    __shared__ float4 red[8][LPR];
-    constexpr int D = LPR * 4;
-    constexpr int NGC = 256 / LPR;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub = threadIdx.x % LPR;
-    const int nM = a.counters[1], nL = a.counters[2];
-    const float alpha = a.hp->alpha;
-    const int step = a.hp->step;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int4* __restrict__ runs_long = reinterpret_cast<const int4*>(a.runs_long);
-    (void)D;
-    for (int r = blockIdx.x; r < nL; r += gridDim.x) {
-        const int4 dsc = runs_long[a.long_cap - 1 - r];
-        const int32_t key = dsc.x, start = dsc.y, cnt = dsc.z;
-        const bool owner = threadIdx.x < LPR;
-        float4 var = z4, m = z4, v = z4; int last = 0;
-        if (owner) {
-            const int64_t off = (int64_t)key * a.es + sub * 4;
-            var = *reinterpret_cast<const float4*>(a.emb + off);
-            m = *reinterpret_cast<const float4*>(a.m + off);
-            v = *reinterpret_cast<const float4*>(a.v + off);
-            if (a.alpha_hist) last = a.last_step[key];
-        }
-        const float4 part = emb_strided_sum<LPR>(a, start, cnt, threadIdx.x / LPR, NGC, sub);
-        const float4 wtot = emb_team_combine<LPR, 32>(part, lane);
-        if (lane < LPR) red[warp][lane] = wtot;
-        __syncthreads();
-        if (owner) {
-            float4 acc = red[0][sub];
-#pragma unroll
-            for (int w = 1; w < 8; ++w) add4(acc, red[w][sub]);
-            emb_apply_row<0, LPR>(a, key, (int64_t)start, acc, var, m, v, last, sub, alpha, step);
-        }
-        __syncthreads();
-    }
-    {
-        constexpr int TL = LPR <= 8 ? 16 : 32;
-        constexpr int TPW = 32 / TL;
-        const int tw = lane / TL, tl = lane % TL;
-        const int gwarp = blockIdx.x * 8 + warp, nwarps = gridDim.x * 8;
-        for (int r0 = gwarp * TPW; r0 < nM; r0 += nwarps * TPW) {
-            const int r = r0 + tw;
-            const bool valid = r < nM;
-            int4 dsc = make_int4(0, 0, 0, 0);
-            if (valid) dsc = runs_long[r];
-            const int32_t key = dsc.x, start = dsc.y, cnt = dsc.z;
-            const bool owner = valid && tl < LPR;
-            float4 var = z4, m = z4, v = z4; int last = 0;
-            if (owner) {
-                const int64_t off = (int64_t)key * a.es + sub * 4;
-                var = *reinterpret_cast<const float4*>(a.emb + off);
-                m = *reinterpret_cast<const float4*>(a.m + off);
-                v = *reinterpret_cast<const float4*>(a.v + off);
-                if (a.alpha_hist) last = a.last_step[key];
-            }
-            const float4 part = emb_strided_sum<LPR>(a, start, cnt, tl / LPR, TL / LPR, sub);
-            __syncwarp();
-            const float4 acc = emb_team_combine<LPR, TL>(part, lane);
-            if (owner) emb_apply_row<0, LPR>(a, key, (int64_t)start, acc, var, m, v, last, sub, alpha, step);
-            __syncwarp();
-        }
-    }
-}
-template <int LPR>
-__global__ void __launch_bounds__(256, 5) emb_update_s_kernel(EmbUpdateArgs a) {
-    constexpr int D = LPR * 4;
-    const int sub = threadIdx.x % LPR;
-    const int nS = a.counters[0];
-    const float alpha = a.hp->alpha;
-    const int step = a.hp->step;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int ngroups = (int)((gridDim.x * blockDim.x) / LPR);
-    const int4* __restrict__ runs = reinterpret_cast<const int4*>(a.runs);
-    for (int h = (int)((blockIdx.x * blockDim.x + threadIdx.x) / LPR); h < nS; h += ngroups) {
-        const int4 d0 = runs[2 * h], d1 = runs[2 * h + 1];
-        const int32_t key = d0.x, n4 = d0.z;
-        const int32_t pos[4] = {d0.w, d1.x, d1.y, d1.z};
-        const int64_t off = (int64_t)key * a.es + sub * 4;
-        float4 var = *reinterpret_cast<const float4*>(a.emb + off);
-        float4 m = *reinterpret_cast<const float4*>(a.m + off);
-        float4 v = *reinterpret_cast<const float4*>(a.v + off);
-        const int last = a.alpha_hist ? a.last_step[key] : 0;
-        float4 g[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            g[u] = (u < n4) ? *reinterpret_cast<const float4*>(a.grad_rows + (int64_t)pos[u] * D + sub * 4) : z4;
-        float4 acc = g[0];
-#pragma unroll
-        for (int u = 1; u < 4; ++u)
-            if (u < n4) add4(acc, g[u]);
-        emb_apply_row<0, LPR>(a, key, 0, acc, var, m, v, last, sub, alpha, step);
-    }
-}
-template <int LPR>
-static void emb_update_split_launch(cudaStream_t st, const EmbUpdateArgs& a, unsigned grid_ml, unsigned grid_s) {
-    emb_update_ml_kernel<LPR><<<grid_ml, 256, 0, st>>>(a);
-    emb_update_s_kernel<LPR><<<grid_s, 256, 0, st>>>(a);
-}
-static bool ke_split() {
-    static int f = -1;
-    if (f < 0) { const char* e = getenv("SCORE_KE_SPLIT"); f = e ? atoi(e) : 0; }
-    return f != 0;
-}
-
 void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a) {
     static int sms = 0;
     if (!sms) {
@@ -860,20 +748,6 @@ void launch_emb_update(cudaStream_t st, const EmbUpdateArgs& a) {
     int64_t want = (a.n * lpr + 255) / 256, cap = (int64_t)sms * per_sm;
     unsigned grid = (unsigned)(want < cap ? want : cap);
     if (grid == 0) grid = 1;
-    if (a.mode == 0 && ke_split()) {   // experimental: tiers L/M and tier S as two launches (see above)
-        const unsigned grid_ml = grid < (unsigned)(sms * 4) ? grid : (unsigned)(sms * 4);
-        switch (lpr) {
-            case 1: emb_update_split_launch<1>(st, a, grid_ml, grid); break;
-            case 2: emb_update_split_launch<2>(st, a, grid_ml, grid); break;
-            case 4: emb_update_split_launch<4>(st, a, grid_ml, grid); break;
-            case 8: emb_update_split_launch<8>(st, a, grid_ml, grid); break;
-            case 16: emb_update_split_launch<16>(st, a, grid_ml, grid); break;
-            case 32: emb_update_split_launch<32>(st, a, grid_ml, grid); break;
-            default: break;
-        }
-        g_launch_count += 2;
-        return;
-    }
     switch (lpr) {
         case 1: emb_update_launch<1>(st, a, grid); break;
         case 2: emb_update_launch<2>(st, a, grid); break;

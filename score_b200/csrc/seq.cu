@@ -28,8 +28,8 @@ __global__ void gru_fwd_kernel(Dims dm, GruArgs a, int RB) {
     float* hs = Wc + H * sc;                     // [RB][H]   current state
     float* rh = hs + RB * H;                     // [RB][H]   r * h
     float* us = rh + RB * H;                     // [RB][H]   update gate
-    const float* wg = a.wg[side] + (int64_t)dm.Ds * H2;
-    const float* wc = a.wc[side] + (int64_t)dm.Ds * H;
+    const float* wg = a.wg[side] + (int64_t)dm.Dx[side] * H2;
+    const float* wc = a.wc[side] + (int64_t)dm.Dx[side] * H;
     if (tid == 0) s_tmax = 0;
     for (int i = tid; i < H * H2; i += nthreads) Wg[(i / H2) * sg + (i % H2)] = wg[i];
     for (int i = tid; i < H * H; i += nthreads) Wc[(i / H) * sc + (i % H)] = wc[i];
@@ -77,8 +77,8 @@ __global__ void gru_fwd_kernel(Dims dm, GruArgs a, int RB) {
             hn = u * hold + (1.f - u) * c;
             const bool alive = t < len;
             a.c[side][m * H + j] = c;
-            a.xhg[side][m * dm.ldx + dm.Ds + j] = hold;            // h_{t-1}   (state input of the gates matmul)
-            a.xhc[side][m * dm.ldx + dm.Ds + j] = rh[r * H + j];   // r*h_{t-1} (state input of the candidate matmul)
+            a.xhg[side][m * dm.ldxs[side] + dm.Dx[side] + j] = hold;            // h_{t-1}   (state input of the gates matmul)
+            a.xhc[side][m * dm.ldxs[side] + dm.Dx[side] + j] = rh[r * H + j];   // r*h_{t-1} (state input of the candidate matmul)
             a.out[m * a.ldout + side * H + j] = alive ? hn : 0.f;
             hn = alive ? hn : hold;
         }
@@ -133,8 +133,8 @@ __global__ void gru_bwd_kernel(Dims dm, GruBwdArgs a, int RB) {
     float* dcp = dh + RB * H;                    // [RB][H]  d candidate pre-activation
     float* dg = dcp + RB * H;                    // [RB][2H] d gate pre-activations (r | u)
     float* dhd = dg + RB * H2;                   // [RB][H]  direct part of d h_{t-1}
-    const float* wg = a.wg[side] + (int64_t)dm.Ds * H2;
-    const float* wc = a.wc[side] + (int64_t)dm.Ds * H;
+    const float* wg = a.wg[side] + (int64_t)dm.Dx[side] * H2;
+    const float* wc = a.wc[side] + (int64_t)dm.Dx[side] * H;
     if (tid == 0) s_tmax = 0;
     for (int i = tid; i < H * H2; i += nthreads) Wg[(i / H2) * sg + (i % H2)] = wg[i];
     for (int i = tid; i < H * H; i += nthreads) Wc[(i / H) * sc + (i % H)] = wc[i];
@@ -160,7 +160,7 @@ __global__ void gru_bwd_kernel(Dims dm, GruBwdArgs a, int RB) {
             const int64_t m = (int64_t)b * T + t;
             f_do = a.dout ? a.dout[m * a.lddout + side * H + j] : 0.f;
             f_u = a.u[side][m * H + j]; f_c = a.c[side][m * H + j];
-            f_hp = a.xhg[side][m * dm.ldx + dm.Ds + j];
+            f_hp = a.xhg[side][m * dm.ldxs[side] + dm.Dx[side] + j];
             f_r = a.r[side][m * H + j];
         }
     };

@@ -558,8 +558,11 @@ def test_tf_known_answer_adam_update_numpy_on_the_cuda_path():
         for n in names:
             var[n], mm[n], vv[n] = adam_update_numpy(var[n], g[n], t, mm[n], vv[n])
             assert np.allclose(m.get_tensor(n), var[n], rtol=2e-6, atol=2e-7), (n, t)
-            assert np.allclose(m.get_tensor(n + "/Adam"), mm[n], rtol=1e-5, atol=1e-12), (n, t)
-            assert np.allclose(m.get_tensor(n + "/Adam_1"), vv[n], rtol=1e-5, atol=1e-15), (n, t)
+            # m mixes gradients of both signs: an entry that cancels carries the fp32 rounding of its terms
+            assert np.allclose(m.get_tensor(n + "/Adam"), mm[n], rtol=1e-5, atol=1e-6 * np.abs(mm[n]).max()), (n, t)
+            # ApplyAdam computes (1 - beta2) in the variable's type: 1 - 0.999f = 0.00099998713, 1.29e-5 below the fp64
+            # 0.001 of the NumPy reference (TF's own adam_test compares the variables only) -> 3e-5 on the v slot
+            assert np.allclose(m.get_tensor(n + "/Adam_1"), vv[n], rtol=3e-5, atol=1e-15), (n, t)
     assert float(m.get_tensor("beta1_power")) == pytest.approx(0.9 ** 4, rel=1e-6)
     assert float(m.get_tensor("beta2_power")) == pytest.approx(0.999 ** 4, rel=1e-6)
     m.close()
