@@ -170,6 +170,66 @@ def workload_config(shape, args, global_batch):
                          "batches; no explicit flush" % (3 * shape.feature_size * shape.eb_dim * 4 / 1e9, POOL)}
 
 
+def large_vocab_leg(args, world, rank, local, steps=30, warmup=5):
+    """N > 1 only: BASELINE.json config 5 (200 M-row table, d=64, row-sharded over the N GPUs, batch 1024 per GPU) and,
+    beside it, ONE GPU stepping on a 25 M-row shard of the same table (the per-GPU share at 8 GPUs) - the denominator of
+    the >= 6x target.  Same timing rules as the main line: barrier + synchronize on both sides, CUDA events on the
+    launching stream, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from score_b200 import model as sb
+    from score_b200 import parallel
+    from score_b200.synth import SHAPES, make_batch
+    out = {}
+    dev = torch.device("cuda", local)
+
+    def run(shape, sharded):
+        ctor = list(shape.ctor_args())
+        if sharded:
+            ctor[0] = parallel.shard_rows(shape.feature_size, world)
+        m = sb.SCORE(*ctor, device=local, adam_mode=args.adam_mode, use_graph=not args.no_graph, seed=1111, max_batch=shape.batch)
+        trainer = parallel.ShardedEmbeddingTrainer(m, world, rank) if sharded else None
+        stream = torch.cuda.ExternalStream(m.stream(), device=dev)
+        pool = [tuple(torch.from_numpy(x).cuda() for x in make_batch(shape, seed=7000 * (rank + 1) + i)) for i in range(8)]
+
+        def step(i):
+            (trainer or m).train_async(pool[i % 8], LR, REG)
+
+        for i in range(warmup):
+            step(i)
+        m.wait()
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for i in range(steps):
+                step(i)
+            e1.record(stream)
+        m.wait()
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        loss = (trainer.train(None, pool[0], LR, REG) if trainer else m.train(None, pool[0], LR, REG))
+        m.close()
+        del pool, m, trainer
+        torch.cuda.empty_cache()
+        return float(t.item()) / steps, loss
+
+    lv = SHAPES["large_vocab"]
+    ms, loss = run(lv, True)
+    out.update({"workload": "SCoRe large_vocab synthetic (V=%d rows, d=%d, H=%d), rows sharded by id %% %d over %d GPUs" % (
+                    lv.feature_size, lv.eb_dim, lv.hidden_size, world, world),
+                "value": lv.batch * world / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "per_gpu_batch": lv.batch,
+                "steps": steps, "warmup": warmup, "loss": loss})
+    one = SHAPES["large_vocab_shard"]
+    ms1, _ = run(one, False)     # every rank runs its own replica (no collective); the slowest one counts
+    v1 = one.batch / (ms1 * 1e-3)
+    out["one_gpu_shard"] = {"workload": "the same step on ONE GPU holding a %d-row shard (the per-GPU share at 8 GPUs), batch %d"
+                            % (one.feature_size, one.batch), "value": v1, "ms_per_step": ms1}
+    out["x_vs_1gpu_shard"] = out["value"] / v1
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -186,6 +246,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--parallel", default="auto", choices=["auto", "dp", "sharded"],
                     help="N>1: dp = replicated table + gradient all-gather, sharded = row-sharded table + all-to-all")
+    ap.add_argument("--no-large-vocab", action="store_true",
+                    help="N>1: skip the extra large_vocab leg (row-sharded 200 M-row table + the 1-GPU 25 M-row shard)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner) go to stderr instead
@@ -224,8 +286,9 @@ def main():
     ctor = list(shape.ctor_args())
     if world > 1 and par == "sharded":
         ctor[0] = parallel.shard_rows(shape.feature_size, world)
-    m = sb.SCORE(*ctor, device=local, adam_mode=args.adam_mode, use_graph=(not args.no_graph) and (world == 1 or par == "dp"),
-                 seed=1111 + (rank if par == "sharded" else 0), max_batch=B)
+    # every rank draws the same dense initial values (the dense part is data-parallel: replicas must start equal); a
+    # row-sharded table is drawn per rank from the same stream, which only makes the shards look alike - harmless here
+    m = sb.SCORE(*ctor, device=local, adam_mode=args.adam_mode, use_graph=not args.no_graph, seed=1111, max_batch=B)
     trainer = None
     if world > 1:
         trainer = (parallel.ShardedEmbeddingTrainer if par == "sharded" else parallel.DataParallelTrainer)(m, world, rank)
@@ -330,6 +393,14 @@ def main():
         e2e_ms = float(t.item())
     e2e_value = B * world / (e2e_ms / e2e_steps * 1e-3)
     h2d = int(sum(x.numel() * 4 for x in pin_pool[0]))
+    if trainer:
+        loss = loss_e2e      # the trainer's synchronous step returns the GLOBAL loss (m.wait() is this rank's share only)
+    m.close()
+    del dev_pool
+    torch.cuda.empty_cache()
+    lv_leg = None
+    if world > 1 and not args.no_large_vocab and args.workload == "taobao":
+        lv_leg = large_vocab_leg(args, world, rank, local)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -382,11 +453,12 @@ def main():
                 "kernel_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in probes.items()},
                 "ms_per_step_probed": ms_probed,
                 "final_loss": loss}
+        if lv_leg:
+            line["large_vocab"] = lv_leg
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_baseline(shape, B)
             line["cpu_baseline"] = cb
         emit(line)
-    m.close()
     if world > 1:
         dist.destroy_process_group()
 

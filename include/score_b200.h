@@ -40,9 +40,11 @@ enum {
     SCORE_ERR_NAME = 5      /* unknown tensor name                                                 */
 };
 
-/* model_type: which class of score.py the handle mirrors (train_score.py:170-182). */
+/* model_type: which class of score.py the handle mirrors (train_score.py:170-182); RRN is the slice baseline of
+ * code/slice_models/slice_model.py:155-173 (same constructor, batch and train / eval surface: 1-hop sum pooling,
+ * two GRUs on per-side widths item_fnum*d / user_fnum*d, final states into the prediction MLP). */
 enum { SCORE_MODEL_SCORE = 0, SCORE_MODEL_RIA = 1, SCORE_MODEL_RCA = 2,
-       SCORE_MODEL_SCORE_USER = 3, SCORE_MODEL_SCORE_ITEM = 4 };
+       SCORE_MODEL_SCORE_USER = 3, SCORE_MODEL_SCORE_ITEM = 4, SCORE_MODEL_RRN = 5 };
 
 /* Embedding optimizer mode.  The reference's emb_mtx gradient is dense (score.py:45-47 route the
  * lookup through a dense multiply), so tf.train.AdamOptimizer moves EVERY row EVERY step.
@@ -169,6 +171,24 @@ int score_dp_push(ScoreHandle h, int64_t cap, const uint64_t* peer_bases, int32_
 /* loss2 == NULL: enqueue only (no host synchronisation); otherwise loss2[0] = this rank's loss incl. the L2 term
  * (data term scaled by 1/global_batch), loss2[1] = the L2 term alone. */
 int score_step_finish(ScoreHandle h, const int32_t* ext_keys, const float* ext_rows, int64_t n_ext, float* loss2);
+
+/* Row-sharded table, device side of the exchange (no reference counterpart).  After
+ * score_prepare_batch: group this rank's positions by owner = id % world (position order inside a group, so the order in
+ * which an owner receives and adds gradient rows is fixed).  All pointers are DEVICE memory owned by the handle, valid
+ * until the next score_shard_plan; nothing is copied to the host (the caller all-gathers the count matrix):
+ *   counts     [world + 1]          positions per owner; the last entry counts the dummy positions (id 0)
+ *   send_rows  [n_valid]            owner-local row numbers (id / world + 1) in send order, n_valid = N - counts[world]
+ *   staged     [(1 + N) * eb_dim]   row 0 unused; the rows the owners return land at rows 1.. in send order
+ *   mini_keys  [N]                  position -> row of `staged` (0: dummy) - pass both to score_step_begin
+ *   grad_send  [N * eb_dim]         score_shard_pack_grads: this rank's gradient rows in send order
+ * score_shard_presort: sort the owner-side key list (the rows this rank serves, known before forward / backward) on the
+ * side stream; score_step_finish then takes the same pointer and skips its own sort. */
+typedef struct ScoreShardPlan {
+    int32_t* counts; int32_t* send_rows; float* staged; int32_t* mini_keys; float* grad_send; int64_t n_positions;
+} ScoreShardPlan;
+int score_shard_plan(ScoreHandle h, int32_t world, ScoreShardPlan* out);
+int score_shard_pack_grads(ScoreHandle h);
+int score_shard_presort(ScoreHandle h, const int32_t* ext_keys, int64_t n_ext);
 
 /* Global index of the first sample of the batches this handle steps on (a data-parallel rank: rank * per-rank batch;
  * default 0).  It keys the dropout stream of tf.nn.dropout's stand-in (score.py:71-73), so N ranks draw the masks one

@@ -42,7 +42,13 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
-MODEL_TYPES = ("SCORE", "RIA", "RCA", "SCORE_USER", "SCORE_ITEM")
+MODEL_TYPES = ("SCORE", "RIA", "RCA", "SCORE_USER", "SCORE_ITEM", "RRN")
+# RRN is the slice baseline of code/slice_models/slice_model.py:155-173: same constructor,
+# placeholders, embedding block (:41-64), build_fc_net (:66-74), build_logloss incl. the L2 term (:76-85), train / eval
+# (:111-143) as SCOREBASE; its graph is  user_side = reduce_sum(user_1hop, axis=2), item_side = reduce_sum(item_1hop,
+# axis=2) -> two GRUs -> final states -> [user_state || item_state || target_item || target_user] -> fc net.
+NO_COATT = ("RCA", "RRN")     # model types without the two co-attention dense layers
+NO_ATTENTION = ("RIA", "RRN")  # model types that never call attention()
 PAD_VALUE = float(-2 ** 32 + 1)  # score.py:180
 BN_EPS = 1e-3                    # tf.layers.batch_normalization default epsilon
 LOGLOSS_EPS = 1e-7               # tf.losses.log_loss default epsilon
@@ -75,9 +81,17 @@ class ScoreConfig:
         return self.d_user + self.d_item
 
     @property
+    def d_side_user(self):  # GRU input width of the user side (RRN: reduce_sum(user_1hop), slice_model.py:158)
+        return self.d_item if self.model_type == "RRN" else self.d_side
+
+    @property
+    def d_side_item(self):  # RRN: reduce_sum(item_1hop), slice_model.py:159
+        return self.d_user if self.model_type == "RRN" else self.d_side
+
+    @property
     def d_key(self):  # attention key width (score.py:211)
         H, K = self.hidden_size, self.obj_per_time_slice
-        if self.model_type == "RCA":
+        if self.model_type in NO_COATT:
             return 2 * H
         return 2 * H + 4 * K
 
@@ -103,13 +117,13 @@ def param_specs(cfg: ScoreConfig):
         return [(prefix + "/kernel", shape), (prefix + "/bias", (shape[1],))]
 
     out = [("emb_mtx", (cfg.feature_size, cfg.eb_dim))]
-    if cfg.model_type != "RCA":
+    if cfg.model_type not in NO_COATT:
         out += kb(roles["coatt_item"], (3 * cfg.d_item, 1))
         out += kb(roles["coatt_user"], (3 * cfg.d_user, 1))
-    for side in ("gru_user_side", "gru_item_side"):
-        out += kb(side + "/gru_cell/gates", (cfg.d_side + H, 2 * H))
-        out += kb(side + "/gru_cell/candidate", (cfg.d_side + H, H))
-    if cfg.model_type != "RIA":
+    for side, width in (("gru_user_side", cfg.d_side_user), ("gru_item_side", cfg.d_side_item)):
+        out += kb(side + "/gru_cell/gates", (width + H, 2 * H))
+        out += kb(side + "/gru_cell/candidate", (width + H, H))
+    if cfg.model_type not in NO_ATTENTION:
         out += kb(roles["att_q"], (cfg.d_side, cfg.d_key))
         out += kb(roles["att_fc1"], (4 * cfg.d_key, 80))
         out += kb(roles["att_fc2"], (80, 40))
@@ -125,11 +139,11 @@ def role_names(cfg: ScoreConfig):
     """Map logical layer roles to the TF variable prefix for this model type."""
     k = 0
     roles = {}
-    if cfg.model_type != "RCA":
+    if cfg.model_type not in NO_COATT:
         for r in ("coatt_item", "coatt_user"):
             roles[r] = "dense" if k == 0 else "dense_%d" % k
             k += 1
-    if cfg.model_type != "RIA":
+    if cfg.model_type not in NO_ATTENTION:
         for r in ("att_q", "att_fc1", "att_fc2", "att_fc3"):
             roles[r] = "dense" if k == 0 else "dense_%d" % k
             k += 1
@@ -242,7 +256,7 @@ def attention(key, query, mask, p, roles):
 
 def forward(params, batch, cfg: ScoreConfig, keep_prob: float = 1.0, dropout_masks=None,
             return_intermediates: bool = False):
-    """Forward graph of SCORE / RIA / RCA / SCORE_USER / SCORE_ITEM (score.py:12-369).
+    """Forward graph of SCORE / RIA / RCA / SCORE_USER / SCORE_ITEM (score.py:12-369) and RRN (slice_model.py:155-173).
 
     ``dropout_masks``: optional (mask1 [B,200], mask2 [B,80]) of 0/1 keep flags so a test can
     inject the masks the CUDA path drew; otherwise torch's RNG is used when keep_prob < 1.
@@ -270,6 +284,20 @@ def forward(params, batch, cfg: ScoreConfig, keep_prob: float = 1.0, dropout_mas
     target_item_t = target_item.unsqueeze(1).expand(B, T, cfg.d_item)
 
     inter = {}
+    if cfg.model_type == "RRN":
+        # slice_model.py:158-168: the 2-hop lookups exist in the graph (:52-59) but nothing consumes them
+        user_side = user_1hop.sum(2)
+        item_side = item_1hop.sum(2)
+        inter.update(user_side=user_side, item_side=item_side, atten_info=None)
+        user_rep_t, user_last = gru_dynamic_rnn(
+            user_side, length, p["gru_user_side/gru_cell/gates/kernel"], p["gru_user_side/gru_cell/gates/bias"],
+            p["gru_user_side/gru_cell/candidate/kernel"], p["gru_user_side/gru_cell/candidate/bias"], H)
+        item_rep_t, item_last = gru_dynamic_rnn(
+            item_side, length, p["gru_item_side/gru_cell/gates/kernel"], p["gru_item_side/gru_cell/gates/bias"],
+            p["gru_item_side/gru_cell/candidate/kernel"], p["gru_item_side/gru_cell/candidate/bias"], H)
+        inter.update(user_rep_t=user_rep_t, item_rep_t=item_rep_t)
+        inp = torch.cat([user_last, item_last, target_item, target_user], dim=1)
+        return _fc_head(p, inp, inter, keep_prob, dropout_masks, dtype, return_intermediates)
     if cfg.model_type == "RCA":
         user_1hop_seq, user_2hop_seq = user_1hop.sum(2), user_2hop.sum(2)
         item_1hop_seq, item_2hop_seq = item_1hop.sum(2), item_2hop.sum(2)
@@ -316,7 +344,11 @@ def forward(params, batch, cfg: ScoreConfig, keep_prob: float = 1.0, dropout_mas
         else:
             inp = torch.cat([user_final, item_final, target_item, target_user], dim=1)
 
-    # build_fc_net (score.py:68-76); BN always in inference mode
+    return _fc_head(p, inp, inter, keep_prob, dropout_masks, dtype, return_intermediates)
+
+
+def _fc_head(p, inp, inter, keep_prob, dropout_masks, dtype, return_intermediates):
+    """build_fc_net (score.py:68-76 = slice_model.py:66-74); BN always in inference mode"""
     inv = p["bn1/gamma"] / torch.sqrt(p["bn1/moving_variance"] + BN_EPS)
     bn1 = inp * inv + (p["bn1/beta"] - p["bn1/moving_mean"] * inv)
     fc1 = _dense(bn1, p["fc1/kernel"], p["fc1/bias"], "relu")

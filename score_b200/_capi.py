@@ -31,6 +31,11 @@ class ScoreGraphDesc(C.Structure):
                 ("hop2_ids", C.c_void_p), ("hop2_deg", C.c_void_p), ("user_feat", C.c_void_p), ("item_feat", C.c_void_p)]
 
 
+class ScoreShardPlan(C.Structure):
+    _fields_ = [("counts", C.c_void_p), ("send_rows", C.c_void_p), ("staged", C.c_void_p), ("mini_keys", C.c_void_p),
+                ("grad_send", C.c_void_p), ("n_positions", C.c_int64)]
+
+
 # every symbol include/score_b200.h declares: (restype, argtypes)
 _H = C.c_void_p
 _F = C.c_float
@@ -63,6 +68,9 @@ SYMBOLS = {
     "score_dp_finish": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_double)]),
     "score_dp_push": (C.c_int, [_H, C.c_int64, C.POINTER(C.c_uint64), C.c_int32, C.c_int64]),
     "score_step_finish": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "score_shard_plan": (C.c_int, [_H, C.c_int32, C.POINTER(ScoreShardPlan)]),
+    "score_shard_pack_grads": (C.c_int, [_H]),
+    "score_shard_presort": (C.c_int, [_H, C.c_void_p, C.c_int64]),
     "score_set_sample_offset": (C.c_int, [_H, C.c_int32]),
     "score_stream": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "score_launch_count": (C.c_int64, [_H]),

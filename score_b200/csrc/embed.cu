@@ -32,11 +32,45 @@ namespace score {
 // table in device memory, so a captured graph stays valid from batch to batch.  Four positions per thread.  In LAZY
 // optimizer mode the same pass claims the stale rows among the keys (atomic exchange on last_step, plain pre-check
 // first) and appends (row, last step) to the compact list emb_replay_kernel works through (scatter.cu).
+// Work list of the lean co-attention kernels: the live slices (t < length[b]) as (b << 8) | t in (b, t) order, their
+// number at live[B*T].  CTA `cta` of `ncta` covers 256 samples: the slices before its first sample are counted by the
+// whole CTA (<= B loads), its own 256 lengths are scanned, every thread writes its sample's entries.  No atomics: the
+// list order is fixed, so the per-warp accumulation order of the backward kernel is reproducible.
+__device__ void build_live_list(const Dims& dm, const int32_t* __restrict__ length, int32_t* __restrict__ live, int cta, int ncta) {
+    __shared__ int red[8], wtot[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b0 = cta * 256;
+    int s = 0;
+    for (int b = tid; b < b0; b += 256) s += min(max(length[b], 0), dm.T);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL_MASK, s, o);
+    const int b = b0 + tid;
+    const int len = b < dm.B ? min(max(length[b], 0), dm.T) : 0;
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(FULL_MASK, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 0) red[warp] = s;
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    int off = incl - len;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { off += red[w]; if (w < warp) off += wtot[w]; }
+    for (int t = 0; t < len; ++t) live[off + t] = (b << 8) | t;
+    if (cta == ncta - 1 && tid == 255) live[(int64_t)dm.B * dm.T] = off + len;
+}
+
 __global__ void build_keys_kernel(Dims dm, const BatchPtrs* __restrict__ bpp, int32_t* __restrict__ keys,
                                   int32_t* __restrict__ label_out, int32_t* __restrict__ length_out,
-                                  int32_t* __restrict__ err_flag, ClaimArgs ca) {
+                                  int32_t* __restrict__ err_flag, ClaimArgs ca, int32_t* __restrict__ live, int n_live_ctas) {
     pdl_enter();
     const BatchPtrs bp = *bpp;
+    if (blockIdx.x >= gridDim.x - n_live_ctas) {   // the last CTAs build the live-slice list (whole CTA, uniform)
+        build_live_list(dm, bp.length, live, blockIdx.x - (gridDim.x - n_live_ctas), n_live_ctas);
+        return;
+    }
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gtid < dm.B) {
         const int32_t lb = bp.label[gtid], ln = bp.length[gtid];
@@ -55,9 +89,10 @@ __global__ void build_keys_kernel(Dims dm, const BatchPtrs* __restrict__ bpp, in
             const uint32_t slice = (uint32_t)p / nrows, r = (uint32_t)p - slice * nrows;
             const uint32_t b = slice / (uint32_t)dm.T, t = slice - b * (uint32_t)dm.T;
             if ((int32_t)t < bp.length[b]) {
+                // hop1_only (RRN, slice_model.py:155-157): user_2hop / item_2hop are fed but have no consumer -> key 0
                 if (r < nfi) v = bp.u1[(int64_t)slice * nfi + r];
-                else if (r < 2 * nfi) v = bp.i2[(int64_t)slice * nfi + (r - nfi)];
-                else if (r < 2 * nfi + nfu) v = bp.u2[(int64_t)slice * nfu + (r - 2 * nfi)];
+                else if (r < 2 * nfi) v = dm.hop1_only ? 0 : bp.i2[(int64_t)slice * nfi + (r - nfi)];
+                else if (r < 2 * nfi + nfu) v = dm.hop1_only ? 0 : bp.u2[(int64_t)slice * nfu + (r - 2 * nfi)];
                 else v = bp.i1[(int64_t)slice * nfu + (r - 2 * nfi - nfu)];
             }
         } else if (p < dm.off_ti) v = bp.tu[p - dm.off_tu];
@@ -108,7 +143,7 @@ __global__ void build_keys_kernel(Dims dm, const BatchPtrs* __restrict__ bpp, in
 }
 
 void launch_build_keys(cudaStream_t st, const Dims& dm, const BatchPtrs* bp_dev, int32_t* keys, int32_t* label_out,
-                       int32_t* length_out, int32_t* err_flag, const ClaimArgs* claim) {
+                       int32_t* length_out, int32_t* err_flag, const ClaimArgs* claim, int32_t* live) {
     ClaimArgs ca{};
     if (claim) {
         ca = *claim;
@@ -118,7 +153,9 @@ void launch_build_keys(cudaStream_t st, const Dims& dm, const BatchPtrs* bp_dev,
     int64_t work = (dm.N + 3) / 4;
     if (work < dm.B) work = dm.B;
     const int64_t blocks = (work + threads - 1) / threads;
-    launch_chain(build_keys_kernel, dim3((unsigned)blocks), dim3(threads), 0, st, dm, bp_dev, keys, label_out, length_out, err_flag, ca);
+    const int n_live = (live && dm.T <= 255) ? (dm.B + 255) / 256 : 0;
+    launch_chain(build_keys_kernel, dim3((unsigned)(blocks + n_live)), dim3(threads), 0, st, dm, bp_dev, keys, label_out, length_out, err_flag, ca,
+                 live, n_live);
     ++g_launch_count;
 }
 
@@ -309,11 +346,12 @@ __global__ void __launch_bounds__(128) coatt_fwd_kernel(Dims dm, CoattArgs a, Co
     const int M = dm.B * dm.T;
     for (int slice = blockIdx.x * warps + warp; slice < M; slice += gridDim.x * warps) {
         const int b = slice / dm.T, t = slice - b * dm.T;
-        float* xu_g = a.xhg_u + (int64_t)slice * dm.ldx; float* xu_c = a.xhc_u + (int64_t)slice * dm.ldx;
-        float* xi_g = a.xhg_i + (int64_t)slice * dm.ldx; float* xi_c = a.xhc_i + (int64_t)slice * dm.ldx;
+        float* xu_g = a.xhg_u + (int64_t)slice * dm.ldxs[0]; float* xu_c = a.xhc_u + (int64_t)slice * dm.ldxs[0];
+        float* xi_g = a.xhg_i + (int64_t)slice * dm.ldxs[1]; float* xi_c = a.xhc_i + (int64_t)slice * dm.ldxs[1];
         float* info = a.key + (int64_t)slice * a.ldkey + a.key_off;
         if (t >= a.length[b]) {   // dead slice: nothing downstream reads it, keep buffers finite
-            for (int c = lane; c < Ds; c += 32) { xu_g[c] = 0.f; xu_c[c] = 0.f; xi_g[c] = 0.f; xi_c[c] = 0.f; }
+            for (int c = lane; c < dm.Dx[0]; c += 32) { xu_g[c] = 0.f; xu_c[c] = 0.f; }
+            for (int c = lane; c < dm.Dx[1]; c += 32) { xi_g[c] = 0.f; xi_c[c] = 0.f; }
             if (!sum_pool) for (int c = lane; c < 4 * K; c += 32) info[c] = 0.f;
             continue;
         }
@@ -385,6 +423,8 @@ __global__ void __launch_bounds__(128) coatt_fwd_kernel(Dims dm, CoattArgs a, Co
             const int e4 = e0 + lane;
             if (e4 < nchunk) {
                 const int e = e4 << 2;
+                // RRN: user side = sum of user_1hop, item side = sum of item_1hop; the 2-hop halves do not exist
+                if (dm.hop1_only && ((e >= Di && e < Ds) || e >= Ds + Du)) continue;
                 int row0, F, c, wsel; float* dst0; float* dst1;
                 if (e < Di) { row0 = 0; F = g.FI(); c = e; wsel = 0; dst0 = xu_g + e; dst1 = xu_c + e; }
                 else if (e < Ds) { row0 = 2 * nfi; F = g.FU(); c = e - Di; wsel = WS; dst0 = xu_g + e; dst1 = xu_c + e; }
@@ -461,8 +501,9 @@ static void coatt_fwd_launch(cudaStream_t st, const Dims& dm, const CoattArgs& a
     } while (0)
 
 void launch_coatt_fwd(cudaStream_t st, const Dims& dm, const CoattArgs& a) {
-    SCORE_GEOM_DISPATCH(coatt_fwd_launch, st, dm, a);
     ++g_launch_count;
+    if (try_coatt_fwd_lean(st, dm, a, a.live)) return;
+    SCORE_GEOM_DISPATCH(coatt_fwd_launch, st, dm, a);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -502,10 +543,14 @@ __global__ void __launch_bounds__(128) coatt_bwd_kernel(Dims dm, CoattBwdArgs a,
         }
         stage_slice(g, rows, a.emb, a.es, a.keys + (int64_t)slice * nrows, nrows, lane);
         {   // incoming gradients of this slice (overlaps the row gather)
-            const float4* dxu = reinterpret_cast<const float4*>(a.dxu + (int64_t)slice * Ds);
-            const float4* dxi = reinterpret_cast<const float4*>(a.dxi + (int64_t)slice * Ds);
+            const float4* dxu = reinterpret_cast<const float4*>(a.dxu + (int64_t)slice * dm.Dx[0]);
+            const float4* dxi = reinterpret_cast<const float4*>(a.dxi + (int64_t)slice * dm.Dx[1]);
             float4* d4 = reinterpret_cast<float4*>(dbuf);
-            for (int c = lane; c < (Ds >> 2); c += 32) { d4[c] = dxu[c]; d4[(Ds >> 2) + c] = dxi[c]; }
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);   // RRN: the 2-hop halves have no gradient
+            for (int c = lane; c < (Ds >> 2); c += 32) {
+                d4[c] = c < (dm.Dx[0] >> 2) ? dxu[c] : z4;
+                d4[(Ds >> 2) + c] = c < (dm.Dx[1] >> 2) ? dxi[c] : z4;
+            }
             if (a.dkey) {
                 const float* dinfo = a.dkey + (int64_t)slice * a.ldkey + a.key_off;
                 for (int c = lane; c < 4 * K; c += 32) dbuf[2 * Ds + c] = dinfo[c];
@@ -661,8 +706,9 @@ static void coatt_bwd_launch(cudaStream_t st, const Dims& dm, const CoattBwdArgs
 }
 
 void launch_coatt_bwd(cudaStream_t st, const Dims& dm, const CoattBwdArgs& a) {
-    SCORE_GEOM_DISPATCH(coatt_bwd_launch, st, dm, a);
     ++g_launch_count;
+    if (try_coatt_bwd_lean(st, dm, a, a.live)) return;
+    SCORE_GEOM_DISPATCH(coatt_bwd_launch, st, dm, a);
 }
 
 // ------------------------------------------------------------------------------------------

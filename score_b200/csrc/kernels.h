@@ -79,8 +79,10 @@ struct BatchPtrs {
 // counter: two int32; pingpong != 0: this launch appends through counter[hp->seq & 1] and zeroes the other one (no
 // memset node on the critical path); pingpong == 0: counter[0], zeroed by the launcher
 struct ClaimArgs { int32_t* last_step; const Hyper* hp; int32_t* list; int32_t* counter; int pingpong; };
+// live (may be null): B*T + 1 ints - the live slices (t < length[b]) of the batch as (b << 8) | t, in (b, t) order, and
+// their number at index B*T: the work list of the lean co-attention kernels (coatt.cu); needs T <= 255
 void launch_build_keys(cudaStream_t st, const Dims& dm, const BatchPtrs* bp_dev, int32_t* keys, int32_t* label_out,
-                       int32_t* length_out, int32_t* err_flag, const ClaimArgs* claim = nullptr);
+                       int32_t* length_out, int32_t* err_flag, const ClaimArgs* claim = nullptr, int32_t* live = nullptr);
 // replay the rows of a claim list (2 int32 per entry: row, last step); *counter entries
 void launch_emb_replay(cudaStream_t st, const int32_t* claim_list, const int32_t* claim_counter, int64_t max_rows, float* emb,
                        float* m, float* v, int d, int es, const float* alpha_hist, const Hyper* hp, int pingpong = 0);
@@ -105,6 +107,7 @@ struct CoattArgs {
     float* key; int ldkey; int key_off;                       // atten_info -> key[:, key_off : key_off+4K]
     float* save_r; float* save_w;                             // [M, 2K]
     int sum_pool;   // RCA (score.py:266-269): plain sum over the K neighbors, no relatedness, no atten_info
+    const int32_t* live;   // live-slice list of launch_build_keys (may be null: general kernel)
 };
 void launch_coatt_fwd(cudaStream_t st, const Dims& dm, const CoattArgs& a);
 
@@ -118,7 +121,11 @@ struct CoattBwdArgs {
     float* grad_rows;                          // [N, d] per-position embedding gradient rows
     float* sdz;                                // [M, 2]  sum_i d z_i per slice and co-attention
     float* partials; int n_partials;           // [n_partials, 2*Di + 2*Du] per-CTA dW1|dW2 (item), dW1|dW2 (user)
+    const int32_t* live;                       // live-slice list of launch_build_keys (may be null: general kernel)
 };
+// lean instances for the compiled-in geometries (coatt.cu); false: not applicable, launch the general kernel
+bool try_coatt_fwd_lean(cudaStream_t st, const Dims& dm, const CoattArgs& a, const int32_t* live);
+bool try_coatt_bwd_lean(cudaStream_t st, const Dims& dm, const CoattBwdArgs& a, const int32_t* live);
 int coatt_bwd_num_ctas();
 void launch_coatt_bwd(cudaStream_t st, const Dims& dm, const CoattBwdArgs& a);
 
@@ -353,6 +360,13 @@ void launch_emb_catchup_rows(cudaStream_t st, const int32_t* keys, int64_t n, in
 // LAZY mode: bring the whole table up to `upto_step` (before read-back / save / eval of everything)
 void launch_emb_catchup_all(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d, int es,
                             const float* alpha_hist, int upto_step);
+
+// ---- row-sharded table (shard.cu): positions grouped by owner = id % world (stable), see score_shard_plan
+//   owner [n] scratch; counts [world + 1] (last: dummy positions); send_rows / sel [n]; mini_keys [n]
+void launch_shard_plan(cudaStream_t st, SortBufs& sb, const int32_t* keys, int64_t n, int world, int32_t* owner,
+                       int32_t* counts, int32_t* send_rows, int32_t* sel, int32_t* mini_keys);
+void launch_shard_pack_grads(cudaStream_t st, const float* grad_rows, const int32_t* sel, const int32_t* counts, int world,
+                             int64_t n, int d, float* out);
 
 // out[i] = table[idx[i]] (idx 0 -> zeros; out-of-range -> zeros + error flag): owner side of a sharded gather
 void launch_gather_rows(cudaStream_t st, const float* table, int es, const int32_t* idx, int64_t n, int d, int64_t V, float* out,

@@ -83,6 +83,7 @@ struct ScoreModel {
     std::vector<void*> allocs;       // per-capacity allocations (freed on regrow)
     std::map<std::string, Buf> bufs;
     int32_t *ids = nullptr, *label = nullptr, *length = nullptr, *keys = nullptr;
+    int32_t* live = nullptr;   // live-slice work list of the lean co-attention kernels (launch_build_keys)
     float *q0, *c_item, *c_user, *xhg[2], *xhc[2], *key, *save_r, *save_w, *px[2], *gr[2], *gu[2], *gc[2];
     float *q, *attU, *qk, *f1, *f2, *score, *fc_in, *z0, *g1, *g2, *y, *loss_b, *dlogit;
     float *dg2, *dg1, *dz0, *dfc_in, *ds, *df2, *df1, *sdf1, *dqD, *dkey, *dq, *dq0, *dpx[2], *dx[2], *sdz, *grad_rows;
@@ -143,6 +144,12 @@ struct ScoreModel {
     cudaStream_t st_h2d = nullptr; cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_stage_free[2] = {nullptr, nullptr};
     bool stage_busy[2] = {false, false}; int stage_idx = 0; int stage_last = -1;
 
+    // row-sharded exchange plan (score_shard_plan): buffers sized for sh_cap positions
+    int64_t sh_cap = 0; int sh_world = 0;
+    int32_t *sh_owner = nullptr, *sh_counts = nullptr, *sh_send_rows = nullptr, *sh_sel = nullptr, *sh_mini = nullptr;
+    float *sh_staged = nullptr, *sh_grad_send = nullptr;
+    const int32_t* presorted_keys = nullptr; int64_t presorted_n = 0; int presorted_out = 0; cudaEvent_t ev_presort = nullptr;
+
     // graphs
     std::map<int, cudaGraphExec_t> graphs_train;
     std::map<int, int> warm_train;
@@ -192,8 +199,8 @@ Names role_names(int model_type) {
     Names n;
     int k = 0;
     auto next = [&]() { std::string s = k == 0 ? "dense" : "dense_" + std::to_string(k); ++k; return s; };
-    if (model_type != SCORE_MODEL_RCA) { n.co_item = next(); n.co_user = next(); }
-    if (model_type != SCORE_MODEL_RIA) { n.att_q = next(); n.att1 = next(); n.att2 = next(); n.att3 = next(); }
+    if (model_type != SCORE_MODEL_RCA && model_type != SCORE_MODEL_RRN) { n.co_item = next(); n.co_user = next(); }
+    if (model_type != SCORE_MODEL_RIA && model_type != SCORE_MODEL_RRN) { n.att_q = next(); n.att1 = next(); n.att2 = next(); n.att3 = next(); }
     return n;
 }
 
@@ -202,13 +209,18 @@ void build_registry(ScoreModel* h) {
     const int d = c.eb_dim, H = c.hidden_size, K = c.obj_per_time_slice;
     const int Du = c.user_fnum * d, Di = c.item_fnum * d, Ds = Du + Di;
     const int mt = c.model_type;
-    const int Dk = (mt == SCORE_MODEL_RCA) ? 2 * H : 2 * H + 4 * K;
+    const bool rrn = mt == SCORE_MODEL_RRN;
+    const bool has_coatt = mt != SCORE_MODEL_RCA && !rrn, has_att = mt != SCORE_MODEL_RIA && !rrn;
+    const int Dk = has_coatt ? 2 * H + 4 * K : 2 * H;
     const int nstate = (mt == SCORE_MODEL_SCORE_USER || mt == SCORE_MODEL_SCORE_ITEM) ? 1 : 2;
     const int Dfc = nstate * H + Du + Di;
     Dims& dm = h->dm;
     dm.V = c.feature_size; dm.T = c.max_time_len; dm.K = K; dm.d = d; dm.H = H;
     dm.fu = c.user_fnum; dm.fi = c.item_fnum; dm.Du = Du; dm.Di = Di; dm.Ds = Ds; dm.Dk = Dk; dm.Dfc = Dfc;
     dm.ldx = Ds + H; dm.model_type = mt; dm.B = 0;
+    // RRN (slice_model.py:158-159): user side = reduce_sum(user_1hop) [Di], item side = reduce_sum(item_1hop) [Du]
+    dm.Dx[0] = rrn ? Di : Ds; dm.Dx[1] = rrn ? Du : Ds;
+    dm.ldxs[0] = dm.Dx[0] + H; dm.ldxs[1] = dm.Dx[1] + H; dm.hop1_only = rrn ? 1 : 0;
 
     int64_t off = 0;
     auto add = [&](const std::string& name, int64_t r, int64_t cdim, uint8_t flags, bool emb = false) {
@@ -223,12 +235,15 @@ void build_registry(ScoreModel* h) {
     };
     Names nm = role_names(mt);
     add("emb_mtx", c.feature_size, d, 2, true);
-    if (mt != SCORE_MODEL_RCA) { kb(nm.co_item, 3 * Di, 1); kb(nm.co_user, 3 * Du, 1); }
-    for (const char* side : {"gru_user_side", "gru_item_side"}) {
-        kb(std::string(side) + "/gru_cell/gates", Ds + H, 2 * H);
-        kb(std::string(side) + "/gru_cell/candidate", Ds + H, H);
+    if (has_coatt) { kb(nm.co_item, 3 * Di, 1); kb(nm.co_user, 3 * Du, 1); }
+    {
+        const char* gsides[2] = {"gru_user_side", "gru_item_side"};
+        for (int sd = 0; sd < 2; ++sd) {
+            kb(std::string(gsides[sd]) + "/gru_cell/gates", dm.Dx[sd] + H, 2 * H);
+            kb(std::string(gsides[sd]) + "/gru_cell/candidate", dm.Dx[sd] + H, H);
+        }
     }
-    if (mt != SCORE_MODEL_RIA) { kb(nm.att_q, Ds, Dk); kb(nm.att1, 4 * Dk, 80); kb(nm.att2, 80, 40); kb(nm.att3, 40, 1); }
+    if (has_att) { kb(nm.att_q, Ds, Dk); kb(nm.att1, 4 * Dk, 80); kb(nm.att2, 80, 40); kb(nm.att3, 40, 1); }
     add("bn1/gamma", 1, Dfc, 3);
     add("bn1/beta", 1, Dfc, 3);
     add("bn1/moving_mean", 1, Dfc, 0);
@@ -246,7 +261,7 @@ void build_registry(ScoreModel* h) {
         o.dst_off = dst; o.ld_dst = ld; o.rows = rows; o.cols = cols; o.a_off = a; o.b_off = b; o.a_rs = a_rs; o.a_cs = a_cs; o.sign = sign;
     };
     auto toff = [&](const std::string& name) { return h->tensors[h->tindex[name]].off; };
-    if (mt != SCORE_MODEL_RIA) {
+    if (has_att) {
         const int64_t w1 = toff(nm.att1 + "/kernel"), blk = (int64_t)Dk * 80;   // row blocks Wa | Wb | Wc | Wd
         h->dv_W1e = reserve(2 * blk); h->dv_Wac = reserve(blk); h->dv_W1eT = reserve(2 * blk); h->dv_WacT = reserve(blk);
         h->dv_W2T = reserve(40 * 80); h->dv_WqT = reserve((int64_t)Dk * Ds);
@@ -264,11 +279,12 @@ void build_registry(ScoreModel* h) {
         for (int sd = 0; sd < 2; ++sd) {
             const int64_t wg = toff(std::string(sides[sd]) + "/gru_cell/gates/kernel");        // [Ds+H, 2H]
             const int64_t wc = toff(std::string(sides[sd]) + "/gru_cell/candidate/kernel");    // [Ds+H, H]
-            h->dv_Wx[sd] = reserve((int64_t)Ds * 3 * H); h->dv_WxT[sd] = reserve((int64_t)3 * H * Ds);
-            op(h->dv_Wx[sd], 3 * H, Ds, 2 * H, wg, -1, 2 * H, 1, 0);
-            op(h->dv_Wx[sd] + 2 * H, 3 * H, Ds, H, wc, -1, H, 1, 0);
-            op(h->dv_WxT[sd], Ds, 2 * H, Ds, wg, -1, 1, 2 * H, 0);
-            op(h->dv_WxT[sd] + (int64_t)2 * H * Ds, Ds, H, Ds, wc, -1, 1, H, 0);
+            const int Dx = dm.Dx[sd];
+            h->dv_Wx[sd] = reserve((int64_t)Dx * 3 * H); h->dv_WxT[sd] = reserve((int64_t)3 * H * Dx);
+            op(h->dv_Wx[sd], 3 * H, Dx, 2 * H, wg, -1, 2 * H, 1, 0);
+            op(h->dv_Wx[sd] + 2 * H, 3 * H, Dx, H, wc, -1, H, 1, 0);
+            op(h->dv_WxT[sd], Dx, 2 * H, Dx, wg, -1, 1, 2 * H, 0);
+            op(h->dv_WxT[sd] + (int64_t)2 * H * Dx, Dx, H, Dx, wc, -1, 1, H, 0);
         }
     }
     h->dv_fc1T = reserve((int64_t)200 * Dfc); h->dv_fc2T = reserve(80 * 200);
@@ -415,16 +431,17 @@ int ensure_workspace(ScoreModel* h, int B) {
     const int64_t M = (int64_t)cap * dm.T, N = (int64_t)cap * ids_per_sample(dm);
     const int H = dm.H, K = dm.K, Ds = dm.Ds, Dk = dm.Dk, Dfc = dm.Dfc, ldx = dm.ldx;
     WSI(h->ids, N, "ids"); WSI(h->label, cap, "label"); WSI(h->length, cap, "length"); WSI(h->keys, N, "keys");
+    WSI(h->live, M + 1, "live_slices");
     WS(h->q0, (int64_t)cap * Ds, "q0"); WS(h->c_item, cap, "c_item"); WS(h->c_user, cap, "c_user");
-    WS(h->xhg[0], M * ldx, "xhg_user"); WS(h->xhg[1], M * ldx, "xhg_item");
-    WS(h->xhc[0], M * ldx, "xhc_user"); WS(h->xhc[1], M * ldx, "xhc_item");
+    WS(h->xhg[0], M * dm.ldxs[0], "xhg_user"); WS(h->xhg[1], M * dm.ldxs[1], "xhg_item");
+    WS(h->xhc[0], M * dm.ldxs[0], "xhc_user"); WS(h->xhc[1], M * dm.ldxs[1], "xhc_item");
     WS(h->key, M * Dk, "key"); WS(h->save_r, M * 2 * K, "coatt_r"); WS(h->save_w, M * 2 * K, "coatt_w");
     for (int s = 0; s < 2; ++s) {
         const char* sn = s == 0 ? "user" : "item";
         std::string a = std::string("px_") + sn, b = std::string("gru_r_") + sn, c = std::string("gru_u_") + sn,
                     e = std::string("gru_c_") + sn, f = std::string("dpx_") + sn, g = std::string("dx_") + sn;
         WS(h->px[s], M * 3 * H, a.c_str()); WS(h->gr[s], M * H, b.c_str()); WS(h->gu[s], M * H, c.c_str());
-        WS(h->gc[s], M * H, e.c_str()); WS(h->dpx[s], M * 3 * H, f.c_str()); WS(h->dx[s], M * Ds, g.c_str());
+        WS(h->gc[s], M * H, e.c_str()); WS(h->dpx[s], M * 3 * H, f.c_str()); WS(h->dx[s], M * dm.Dx[s], g.c_str());
     }
     WS(h->q, (int64_t)cap * Dk, "q"); WS(h->attU, (int64_t)cap * 80, "att_u"); WS(h->qk, M * Dk, "att_qk"); WS(h->f1, M * 80, "att_fc1");
     WS(h->f2, M * 40, "att_fc2"); WS(h->score, M, "score"); WS(h->fc_in, (int64_t)cap * Dfc, "fc_in");
@@ -590,8 +607,10 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
     cudaEventRecord(h->ev_l2, h->st_w);
 
     const int mt = dm.model_type;
-    const bool has_coatt = mt != SCORE_MODEL_RCA;   // RCA sums the neighbors (score.py:266-269)
-    const bool has_att = mt != SCORE_MODEL_RIA;     // RIA feeds the final GRU states to the MLP (score.py:244-249)
+    // RCA sums the neighbors (score.py:266-269); RIA feeds the final GRU states to the MLP (score.py:244-249);
+    // RRN does both on the 1-hop tensors only (slice_model.py:158-168)
+    const bool has_coatt = mt != SCORE_MODEL_RCA && mt != SCORE_MODEL_RRN;
+    const bool has_att = mt != SCORE_MODEL_RIA && mt != SCORE_MODEL_RRN;
     TargetArgs ta{};
     ta.emb = h->emb_fwd; ta.es = h->es_fwd; ta.keys = h->keys_fwd;
     if (has_coatt) { ta.w_item = W(nm.co_item); ta.b_item = Bi(nm.co_item); ta.w_user = W(nm.co_user); ta.b_user = Bi(nm.co_user); }
@@ -611,6 +630,7 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
     ca.emb = h->emb_fwd; ca.es = h->es_fwd; ca.keys = h->keys_fwd; ca.length = h->length;
     if (has_coatt) { ca.w_item = W(nm.co_item); ca.w_user = W(nm.co_user); }
     ca.sum_pool = has_coatt ? 0 : 1;
+    ca.live = dm.T <= 255 ? h->live : nullptr;
     ca.c_item = h->c_item; ca.c_user = h->c_user;
     ca.xhg_u = h->xhg[0]; ca.xhc_u = h->xhc[0]; ca.xhg_i = h->xhg[1]; ca.xhc_i = h->xhc[1];
     ca.key = h->key; ca.ldkey = Dk; ca.key_off = 2 * H; ca.save_r = h->save_r; ca.save_w = h->save_w;
@@ -631,7 +651,7 @@ void enqueue_forward(ScoreModel* h, bool will_bwd) {
     for (int s = 0; s < 2; ++s) {
         std::string g = std::string(sides[s]) + "/gru_cell/gates", c = std::string(sides[s]) + "/gru_cell/candidate";
         // input part of both matmuls for all (b,t) rows at once: px = x [Wg_x | Wc_x]  (both sides, one launch)
-        pxl[s] = RowGemmArgs{h->xhg[s], ldx, h->Dv + h->dv_Wx[s], 3 * H, nullptr, h->px[s], 3 * H, M, Ds, 3 * H};
+        pxl[s] = RowGemmArgs{h->xhg[s], dm.ldxs[s], h->Dv + h->dv_Wx[s], 3 * H, nullptr, h->px[s], 3 * H, M, dm.Dx[s], 3 * H};
         ga.px[s] = h->px[s]; ga.wg[s] = W(g); ga.bg[s] = Bi(g); ga.wc[s] = W(c); ga.bc[s] = Bi(c);
         ga.xhg[s] = h->xhg[s]; ga.xhc[s] = h->xhc[s]; ga.r[s] = h->gr[s]; ga.u[s] = h->gu[s]; ga.c[s] = h->gc[s];
     }
@@ -716,7 +736,7 @@ void enqueue_backward(ScoreModel* h, bool fused_adam = false, bool defer_join = 
 
     // attention: pooling + softmax + MLP backward in one fused chain, then the per-sample query side
     const int mt = dm.model_type;
-    const bool has_coatt = mt != SCORE_MODEL_RCA, has_att = mt != SCORE_MODEL_RIA;
+    const bool has_coatt = mt != SCORE_MODEL_RCA && mt != SCORE_MODEL_RRN, has_att = mt != SCORE_MODEL_RIA && mt != SCORE_MODEL_RRN;
     const int64_t blk = (int64_t)Dk * 80;   // dense_3/kernel row blocks: Wa | Wb | Wc | Wd
     if (has_att) {
         AttBwd2Args ab{};
@@ -765,10 +785,10 @@ void enqueue_backward(ScoreModel* h, bool fused_adam = false, bool defer_join = 
     RowGemmArgs dxl[2];
     for (int s = 0; s < 2; ++s) {
         std::string g = std::string(sides[s]) + "/gru_cell/gates", c = std::string(sides[s]) + "/gru_cell/candidate";
-        wl[2 * s] = gemm_bwd_weight_args(h, h->xhg[s], ldx, h->dpx[s], 3 * H, Wo(g), Bo(g), M, ldx, 2 * H);
-        wl[2 * s + 1] = gemm_bwd_weight_args(h, h->xhc[s], ldx, h->dpx[s] + 2 * H, 3 * H, Wo(c), Bo(c), M, ldx, H);
+        wl[2 * s] = gemm_bwd_weight_args(h, h->xhg[s], dm.ldxs[s], h->dpx[s], 3 * H, Wo(g), Bo(g), M, dm.ldxs[s], 2 * H);
+        wl[2 * s + 1] = gemm_bwd_weight_args(h, h->xhc[s], dm.ldxs[s], h->dpx[s] + 2 * H, 3 * H, Wo(c), Bo(c), M, dm.ldxs[s], H);
         // dx = dpx [Wg_x | Wc_x]^T
-        dxl[s] = RowGemmArgs{h->dpx[s], 3 * H, h->Dv + h->dv_WxT[s], Ds, nullptr, h->dx[s], Ds, M, 3 * H, Ds};
+        dxl[s] = RowGemmArgs{h->dpx[s], 3 * H, h->Dv + h->dv_WxT[s], dm.Dx[s], nullptr, h->dx[s], dm.Dx[s], M, 3 * H, dm.Dx[s]};
     }
     gemm_bwd_weight_batch(h, wl, 4);
     launch_rowgemm(h->st, dxl, 2);
@@ -778,6 +798,7 @@ void enqueue_backward(ScoreModel* h, bool fused_adam = false, bool defer_join = 
     cb.emb = h->emb_fwd; cb.es = h->es_fwd; cb.keys = h->keys_fwd; cb.length = h->length;
     if (has_coatt) { cb.w_item = W(nm.co_item); cb.w_user = W(nm.co_user); }
     cb.sum_pool = has_coatt ? 0 : 1;
+    cb.live = dm.T <= 255 ? h->live : nullptr;
     cb.save_r = h->save_r; cb.save_w = h->save_w;
     cb.dxu = h->dx[0]; cb.dxi = h->dx[1];
     cb.dkey = (has_att && has_coatt) ? h->dkey : nullptr;   // RIA never consumes atten_info; RCA has none
@@ -852,13 +873,13 @@ void enqueue_step(ScoreModel* h, int mode) {
     if (h->cfg.adam_mode == SCORE_ADAM_LAZY) {
         probe_begin(h, PR_CATCHUP, h->st);
         ClaimArgs ca{h->last_step, h->hyper_dev, h->claim_list, h->claim_counter, 1};
-        launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag, &ca);
+        launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag, &ca, h->live);
         if (h->sort_deferred) { cudaEventRecord(h->ev_keys, h->st); enqueue_sort_branch(h, h->ev_keys, 1); }
         launch_emb_replay(h->st, h->claim_list, h->claim_counter, dm.N, h->emb, h->emb_m, h->emb_v, dm.d, h->es, h->alpha_hist,
                           h->hyper_dev, 1);
         probe_end(h, PR_CATCHUP, h->st);
     } else {
-        launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag);
+        launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag, nullptr, h->live);
         if (h->sort_deferred) { cudaEventRecord(h->ev_keys, h->st); enqueue_sort_branch(h, h->ev_keys, 1); }
     }
     cudaEventRecord(h->ev_fork, h->st);
@@ -1112,7 +1133,7 @@ int score_create(const ScoreConfig* cfg, int device, ScoreHandle* out) {
     if (cfg->obj_per_time_slice < 1 || cfg->obj_per_time_slice > 32) return bad("obj_per_time_slice must be in [1, 32]");
     if (cfg->hidden_size < 1 || cfg->hidden_size > 128) return bad("hidden_size must be in [1, 128]");
     if (cfg->max_time_len < 1 || cfg->user_fnum < 1 || cfg->item_fnum < 1) return bad("max_time_len / fnum must be positive");
-    if (cfg->model_type < 0 || cfg->model_type > 4) return bad("unknown model_type");
+    if (cfg->model_type < 0 || cfg->model_type > SCORE_MODEL_RRN) return bad("unknown model_type");
     if (cfg->adam_mode < 0 || cfg->adam_mode > 2) return bad("unknown adam_mode");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1187,8 +1208,11 @@ int score_destroy(ScoreHandle h) {
     free_workspace(h);
     for (void* p : {(void*)h->emb_tab, (void*)h->last_step, (void*)h->P, (void*)h->G,
                     (void*)h->M1, (void*)h->V1, (void*)h->PG, (void*)h->flags, (void*)h->Dv, (void*)h->n_heads_dev, (void*)h->claim_counter, (void*)h->claim_ext, (void*)h->alpha_buf, (void*)h->l2sum,
-                    (void*)h->loss_dev, (void*)h->err_flag, (void*)h->step_dev, (void*)h->seg_rows, (void*)h->seg_heads})
+                    (void*)h->loss_dev, (void*)h->err_flag, (void*)h->step_dev, (void*)h->seg_rows, (void*)h->seg_heads,
+                    (void*)h->sh_owner, (void*)h->sh_counts, (void*)h->sh_send_rows, (void*)h->sh_sel, (void*)h->sh_mini,
+                    (void*)h->sh_staged, (void*)h->sh_grad_send})
         if (p) cudaFree(p);
+    if (h->ev_presort) cudaEventDestroy(h->ev_presort);
     if (h->hyper_ring) cudaFreeHost(h->hyper_ring);
     for (int i = 0; i < ScoreModel::kHyperSlots; ++i) if (h->hyper_ev[i]) cudaEventDestroy(h->hyper_ev[i]);
     if (h->loss_host) cudaFreeHost(h->loss_host);
@@ -1634,7 +1658,7 @@ int score_prepare_batch(ScoreHandle h, const ScoreBatch* batch) {
     dm.V = ((int64_t)1 << 31) - 1;   // ids are GLOBAL row numbers here; the owner checks the range
     rc = upload_hyper(h, B, 0.f, 0.f, 1.f, 0, 0);   // carries the batch's pointer table
     if (rc) return rc;
-    launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag);
+    launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag, nullptr, h->live);
     stage_release(h);
     return SCORE_OK;
 }
@@ -1674,6 +1698,67 @@ int score_gather_rows(ScoreHandle h, const int32_t* idx_dev, int64_t n, float* o
                                 h->hyper_dev, h->claim_ext, h->claim_counter);
     }
     launch_gather_rows(h->st, h->emb, h->es, idx_dev, n, h->dm.d, h->dm.V, out_dev, h->err_flag);
+    return SCORE_OK;
+}
+
+int score_shard_plan(ScoreHandle h, int32_t world, ScoreShardPlan* out) {
+    if (!h || !out || world < 1 || world > 64) return SCORE_ERR_ARG;
+    if (h->dm.B <= 0 || h->last_N <= 0) return fail(h, SCORE_ERR_ARG, "score_shard_plan needs score_prepare_batch first");
+    CK(cudaSetDevice(h->device));
+    const int64_t N = h->last_N;
+    const int d = h->dm.d;
+    if (N > h->sh_cap) {
+        CK(cudaStreamSynchronize(h->st));
+        drop_graphs(h);   // a captured half-step holds the old staged / mini_keys addresses
+        cudaFree(h->sh_owner); cudaFree(h->sh_send_rows); cudaFree(h->sh_sel); cudaFree(h->sh_mini);
+        cudaFree(h->sh_staged); cudaFree(h->sh_grad_send);
+        const int64_t cap = N + N / 8;
+        CK(cudaMalloc(&h->sh_owner, sizeof(int32_t) * cap));
+        CK(cudaMalloc(&h->sh_send_rows, sizeof(int32_t) * cap));
+        CK(cudaMalloc(&h->sh_sel, sizeof(int32_t) * cap));
+        CK(cudaMalloc(&h->sh_mini, sizeof(int32_t) * cap));
+        CK(cudaMalloc(&h->sh_staged, sizeof(float) * (cap + 1) * d));
+        CK(cudaMemsetAsync(h->sh_staged, 0, sizeof(float) * d, h->st));
+        CK(cudaMalloc(&h->sh_grad_send, sizeof(float) * cap * d));
+        h->sh_cap = cap;
+    }
+    if (!h->sh_counts) CK(cudaMalloc(&h->sh_counts, sizeof(int32_t) * 65));
+    h->sh_world = world;
+    launch_shard_plan(h->st, h->sb, h->keys, N, world, h->sh_owner, h->sh_counts, h->sh_send_rows, h->sh_sel, h->sh_mini);
+    out->counts = h->sh_counts; out->send_rows = h->sh_send_rows; out->staged = h->sh_staged; out->mini_keys = h->sh_mini;
+    out->grad_send = h->sh_grad_send; out->n_positions = N;
+    CK(cudaGetLastError());
+    return SCORE_OK;
+}
+
+int score_shard_pack_grads(ScoreHandle h) {
+    if (!h || !h->sh_world) return SCORE_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    launch_shard_pack_grads(h->st, h->grad_rows, h->sh_sel, h->sh_counts, h->sh_world, h->last_N, h->dm.d, h->sh_grad_send);
+    CK(cudaGetLastError());
+    return SCORE_OK;
+}
+
+// Owner-side key list of a row-sharded step: known as soon as the ids have been exchanged, so its sort (and the run
+// descriptors) run on the side stream under forward / backward instead of in front of the update.
+int score_shard_presort(ScoreHandle h, const int32_t* ext_keys, int64_t n_ext) {
+    if (!h || n_ext < 0 || (n_ext > 0 && !ext_keys)) return SCORE_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    h->presorted_keys = nullptr; h->presorted_n = 0;
+    if (n_ext == 0) return SCORE_OK;
+    if (n_ext >= ((int64_t)1 << 31)) return fail(h, SCORE_ERR_ARG, "too many gradient rows for int32 positions");
+    if (n_ext > h->sb_ext_cap) CK(cudaStreamSynchronize(h->st));   // the previous step's update may still read the old buffers
+    int rc = ensure_ext_sort(h, n_ext);
+    if (rc) return rc;
+    if (!h->ev_presort) CK(cudaEventCreateWithFlags(&h->ev_presort, cudaEventDisableTiming));
+    cudaEvent_t e = h->ev_pool[h->ev_next++ & 15];
+    CK(cudaEventRecord(e, h->st));                 // the key list is complete (the exchange ran on the main stream)
+    CK(cudaStreamWaitEvent(h->st2, e, 0));
+    const int out = launch_sort_pairs(h->st2, h->sb_ext, ext_keys, n_ext, key_bits(h->dm.V));
+    launch_emb_runs(h->st2, h->sb_ext.keys[out], h->sb_ext.vals[out], n_ext, h->sb_ext.runs, h->sb_ext.runs_long, h->n_heads_dev);
+    CK(cudaEventRecord(h->ev_presort, h->st2));
+    h->presorted_keys = ext_keys; h->presorted_n = n_ext; h->presorted_out = out;
+    CK(cudaGetLastError());
     return SCORE_OK;
 }
 
@@ -1718,7 +1803,7 @@ int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg
         const bool fused_claim = with_keys && !staged_table && lazy;   // claim of the stale rows rides on build_keys
         if (with_keys) {
             ClaimArgs ca{h->last_step, h->hyper_dev, h->claim_list, h->claim_counter, 1};
-            launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag, fused_claim ? &ca : nullptr);
+            launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag, fused_claim ? &ca : nullptr, h->live);
         }
         if (own_sort) {
             cudaEventRecord(h->ev_keys, h->st);
@@ -1740,15 +1825,18 @@ int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg
         if (train && !staged_table) cudaStreamWaitEvent(h->st, h->ev_join, 0);   // joins the sort branch (capture needs it)
     };
     h->local_sorted = train && !staged_table;
-    // the data-parallel training half-step is the same launch sequence every step: replay it as a CUDA graph
+    // the training half-step is the same launch sequence every step: replay it as a CUDA graph (data-parallel: keyed by
+    // B; row-sharded: only with the handle's own staged table / mini keys, whose addresses are stable - score_shard_plan)
     bool launched = false;
-    if (h->cfg.use_graph && train && !staged_table && with_keys) {
-        const int B = dm.B;
+    const bool staged_own = staged_table && !with_keys && staged_table == h->sh_staged && staged_keys == h->sh_mini;
+    if (h->cfg.use_graph && train && ((!staged_table && with_keys) || staged_own)) {
+        const int B = dm.B + (staged_own ? (1 << 28) : 0);
         auto it = h->graphs_begin.find(B);
         if (it != h->graphs_begin.end()) {
             CK(cudaGraphLaunch(it->second, h->st));
             g_launch_count += h->graph_kernels_begin[B];
-            h->emb_fwd = h->emb; h->es_fwd = h->es; h->keys_fwd = h->keys;
+            if (staged_own) { h->emb_fwd = staged_table; h->es_fwd = h->dm.d; h->keys_fwd = staged_keys; }
+            else { h->emb_fwd = h->emb; h->es_fwd = h->es; h->keys_fwd = h->keys; }
             launched = true;
         } else if (h->warm_begin[B] >= 1) {
             cudaGraph_t graph = nullptr;
@@ -1911,11 +1999,18 @@ int score_step_finish(ScoreHandle h, const int32_t* ext_keys, const float* ext_r
         if (n_ext >= ((int64_t)1 << 31)) return fail(h, SCORE_ERR_ARG, "too many gradient rows for int32 positions");
         launch_dense_adam(h->st, h->P, h->M1, h->V1, h->G, h->flags, (int)h->n_dense, h->hyper_dev, h->alpha_hist);
         if (n_ext > 0) {
-            int rc = ensure_ext_sort(h, n_ext);
-            if (rc) return rc;
-            const int out = launch_sort_pairs(h->st, h->sb_ext, ext_keys, n_ext, key_bits(h->dm.V));
+            int out;
+            if (h->presorted_keys == ext_keys && h->presorted_n == n_ext) {   // score_shard_presort did it on the side stream
+                out = h->presorted_out;
+                CK(cudaStreamWaitEvent(h->st, h->ev_presort, 0));
+            } else {
+                int rc = ensure_ext_sort(h, n_ext);
+                if (rc) return rc;
+                out = launch_sort_pairs(h->st, h->sb_ext, ext_keys, n_ext, key_bits(h->dm.V));
+                launch_emb_runs(h->st, h->sb_ext.keys[out], h->sb_ext.vals[out], n_ext, h->sb_ext.runs, h->sb_ext.runs_long, h->n_heads_dev);
+            }
+            h->presorted_keys = nullptr; h->presorted_n = 0;
             EmbUpdateArgs ea{};
-            launch_emb_runs(h->st, h->sb_ext.keys[out], h->sb_ext.vals[out], n_ext, h->sb_ext.runs, h->sb_ext.runs_long, h->n_heads_dev);
             ea.skeys = h->sb_ext.keys[out]; ea.spos = h->sb_ext.vals[out]; ea.n = n_ext;
             ea.runs = h->sb_ext.runs; ea.runs_long = h->sb_ext.runs_long; ea.long_cap = emb_runs_long_cap(n_ext); ea.counters = h->n_heads_dev;
             ea.grad_rows = ext_rows; ea.d = h->dm.d;

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _capi
 
-MODEL_TYPES = {"SCORE": 0, "RIA": 1, "RCA": 2, "SCORE_USER": 3, "SCORE_ITEM": 4}
+MODEL_TYPES = {"SCORE": 0, "RIA": 1, "RCA": 2, "SCORE_USER": 3, "SCORE_ITEM": 4, "RRN": 5}
 ADAM_MODES = {"dense": 0, "lazy": 1, "sparse": 2}
 TRAIN_KEEP_PROB = 0.8   # score.py:113
 
@@ -251,3 +251,8 @@ class SCORE_USER(SCOREBASE):
 
 class SCORE_ITEM(SCOREBASE):
     MODEL_TYPE = "SCORE_ITEM"
+
+
+class RRN(SCOREBASE):
+    """code/slice_models/slice_model.py:155-173 (train_slice.py builds it with the same seven arguments)."""
+    MODEL_TYPE = "RRN"

@@ -233,18 +233,73 @@ class DataParallelTrainer(_Base):
 class ShardedEmbeddingTrainer(_Base):
     """Row-sharded embedding table + data-parallel dense part (BASELINE.json config 5).
 
-    ``model`` must have been built with feature_size = shard_rows(V_global, world)."""
+    ``model`` must have been built with feature_size = shard_rows(V_global, world).
+
+    One step, everything on the handle's stream:
+      score_prepare_batch -> score_shard_plan (CUDA: positions grouped by owner, counts stay on the device) ->
+      ONE all-gather of the [world, world+1] count matrix + its D2H copy (the only host synchronisation of the step) ->
+      all-to-all ids -> owners: score_shard_presort (side stream) + score_gather_rows -> all-to-all rows straight into the
+      staged table -> score_step_begin(staged, mini_keys) (CUDA graph) -> all-reduce dense gradient, score_shard_pack_grads,
+      all-to-all gradient rows -> score_step_finish on the owners (presorted keys).
+    ``ExchangePlan`` above states the same bucketing rule in torch ops (CPU / gloo tests, and the parity test of the
+    CUDA plan)."""
+
+    def __init__(self, model, world, rank, group=None):
+        super().__init__(model, world, rank, group)
+        self._bufs = {}
+        self._counts_host = torch.empty(world * (world + 1), dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
+
+    def _buf(self, name, n, dtype):
+        """persistent device buffer of at least n elements (grown with slack; the stream is drained before a regrow)"""
+        t = self._bufs.get(name)
+        if t is None or t.numel() < n:
+            if t is not None:
+                self.stream.synchronize()
+            t = torch.empty(int(n * 1.25) + 1024, dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t[:n]
+
+    def _view(self, ptr, n, dtype):
+        ts = "<f4" if dtype == torch.float32 else "<i4"
+        return torch.as_tensor(_DevView(ptr, (int(n),), ts), device=self.device)
+
+    def _plan(self, b):
+        """-> (send_counts, recv_counts, n_valid, n_recv, plan struct); one host synchronisation."""
+        W = self.world
+        self.m._check(self.lib.score_prepare_batch(self.h, C.byref(b.struct)))
+        plan = _capi.ScoreShardPlan()
+        self.m._check(self.lib.score_shard_plan(self.h, W, C.byref(plan)))
+        mine = self._view(plan.counts, W + 1, torch.int32)
+        if W > 1:
+            mat = self._buf("count_mat", W * (W + 1), torch.int32)
+            dist.all_gather_into_tensor(mat, mine, group=self.group)
+        else:
+            mat = mine
+        self._counts_host.copy_(mat, non_blocking=True)
+        self.stream.synchronize()
+        cm = self._counts_host.view(W, W + 1)
+        send_counts = cm[self.rank, :W].tolist()
+        recv_counts = cm[:, self.rank].tolist()
+        return send_counts, recv_counts, int(sum(send_counts)), int(sum(recv_counts)), plan
 
     def _fetch(self, b):
-        self.m._check(self.lib.score_prepare_batch(self.h, C.byref(b.struct)))
-        keys = self._dev("keys", torch.int32)
-        plan = ExchangePlan(keys, self.world, self.group)
-        want = plan.exchange_ids()
         d = self.m.cfg["eb_dim"]
-        served = torch.empty(plan.n_recv, d, dtype=torch.float32, device=self.device)
-        self.m._check(self.lib.score_gather_rows(self.h, want.data_ptr(), plan.n_recv, served.data_ptr()))
-        staged = plan.return_rows(served)
-        return plan, want, staged
+        send_counts, recv_counts, n_valid, n_recv, plan = self._plan(b)
+        send_rows = self._view(plan.send_rows, n_valid, torch.int32)
+        want = self._buf("want", n_recv, torch.int32)
+        if self.world > 1:
+            dist.all_to_all_single(want, send_rows, recv_counts, send_counts, group=self.group)
+        else:
+            want.copy_(send_rows)
+        served = self._buf("served", n_recv * d, torch.float32).view(n_recv, d)
+        self.m._check(self.lib.score_gather_rows(self.h, want.data_ptr(), n_recv, served.data_ptr()))
+        staged = self._view(plan.staged, (plan.n_positions + 1) * d, torch.float32).view(-1, d)
+        got = staged[1:1 + n_valid]
+        if self.world > 1:
+            dist.all_to_all_single(got, served, send_counts, recv_counts, group=self.group)
+        else:
+            got.copy_(served)
+        return plan, want, (send_counts, recv_counts, n_valid, n_recv)
 
     def train(self, sess, batch_data, lr, reg_lambda, keep_prob=TRAIN_KEEP_PROB, want_loss=True):
         b = _Batch(batch_data, self.m.cfg)
@@ -252,17 +307,23 @@ class ShardedEmbeddingTrainer(_Base):
         d = self.m.cfg["eb_dim"]
         self.m._check(self.lib.score_set_sample_offset(self.h, self.rank * b.B))   # dropout masks of the global batch
         with torch.cuda.stream(self.stream):
-            plan, want, staged = self._fetch(b)
+            plan, want, (send_counts, recv_counts, n_valid, n_recv) = self._fetch(b)
             self._keep_batch = b
-            self.m._check(self.lib.score_step_begin(self.h, None, lr, reg_lambda, keep_prob, gb, 1,
-                                                    staged.data_ptr(), plan.mini_keys.data_ptr()))
+            # the owner-side key list is complete: its sort runs on the side stream under forward / backward
+            self.m._check(self.lib.score_shard_presort(self.h, want.data_ptr(), n_recv))
+            self.m._check(self.lib.score_step_begin(self.h, None, lr, reg_lambda, keep_prob, gb, 1, plan.staged, plan.mini_keys))
             g = self._dev("dense_grad", torch.float32)
-            dist.all_reduce(g, group=self.group)
-            grad_rows = self._dev("grad_rows", torch.float32).view(-1, d)
-            owned = plan.send_grads(grad_rows)
+            if self.world > 1:
+                dist.all_reduce(g, group=self.group)
+            self.m._check(self.lib.score_shard_pack_grads(self.h))
+            gsend = self._view(plan.grad_send, n_valid * d, torch.float32).view(n_valid, d)
+            owned = self._buf("owned", n_recv * d, torch.float32).view(n_recv, d)
+            if self.world > 1:
+                dist.all_to_all_single(owned, gsend, recv_counts, send_counts, group=self.group)
+            else:
+                owned.copy_(gsend)
             loss2 = (C.c_float * 2)() if want_loss else None
-            self.m._check(self.lib.score_step_finish(self.h, want.data_ptr(), owned.data_ptr(), plan.n_recv, loss2))
-            self._keep = (plan, want, staged, owned)   # alive until the next step's kernels are enqueued behind them
+            self.m._check(self.lib.score_step_finish(self.h, want.data_ptr(), owned.data_ptr(), n_recv, loss2))
             return self._global_loss(loss2) if want_loss else None
 
     def train_async(self, batch_data, lr, reg_lambda, keep_prob=TRAIN_KEEP_PROB):
@@ -271,9 +332,8 @@ class ShardedEmbeddingTrainer(_Base):
     def eval(self, sess, batch_data, reg_lambda):
         b = _Batch(batch_data, self.m.cfg)
         with torch.cuda.stream(self.stream):
-            plan, want, staged = self._fetch(b)
-            self.m._check(self.lib.score_step_begin(self.h, None, 0.0, reg_lambda, 1.0, b.B, 0,
-                                                    staged.data_ptr(), plan.mini_keys.data_ptr()))
+            plan, want, _ = self._fetch(b)
+            self.m._check(self.lib.score_step_begin(self.h, None, 0.0, reg_lambda, 1.0, b.B, 0, plan.staged, plan.mini_keys))
             loss2 = (C.c_float * 2)()
             self.m._check(self.lib.score_step_finish(self.h, None, None, 0, loss2))
             preds = self._dev("y_pred", torch.float32).cpu().numpy().tolist()

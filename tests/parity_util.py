@@ -77,13 +77,16 @@ def make_models(shape: Shape, seed=7, adam_mode="dense", model_type="SCORE", use
 
 
 def forward_backward_report(shape: Shape, batch, seed=7, reg_lambda=1e-4, keep_prob=1.0, model_type="SCORE",
-                            dtype=torch.float32):
-    """Returns {name: relative error} for every compared tensor plus exact-match flags."""
+                            dtype=torch.float32, fp64_twin=False):
+    """Returns {name: relative error} for every compared tensor plus exact-match flags.
+    fp64_twin: also run the oracle's fp64 twin and report, per gradient, 'grad64/<name>' = CUDA vs fp64 and
+    'noise/<name>' = the oracle's OWN fp32 result vs fp64 (normwise): how well-conditioned the quantity is in fp32."""
     cfg, params, m = make_models(shape, seed, model_type=model_type, dtype=dtype)
     loss_c = m.forward_backward(batch, reg_lambda, keep_prob)
     B = batch[0].shape[0]
     T, K, H = cfg.max_time_len, cfg.obj_per_time_slice, cfg.hidden_size
     Ds, Dk = cfg.d_side, cfg.d_key
+    Dxu, Dxi = cfg.d_side_user, cfg.d_side_item   # GRU input widths per side (= Ds except RRN)
     masks = None
     if keep_prob < 1.0:   # inject the masks the CUDA path drew (a zero output is either dropped or relu-dead)
         g1 = m.get_buffer("fc1").reshape(B, 200)
@@ -93,17 +96,16 @@ def forward_backward_report(shape: Shape, batch, seed=7, reg_lambda=1e-4, keep_p
     loss_o, y_o, g_o, inter = ref.loss_and_grads(params, tb, cfg, reg_lambda, keep_prob, masks)
     rep = Report()
     live = (np.arange(T)[None, :] < np.asarray(batch[7])[:, None])   # [B,T]
-    ldx = Ds + H
 
     def live_rows(x, width):
         return x.reshape(B, T, width)[live]
 
     rep["loss"] = rel_err(loss_c, float(loss_o))
     rep.add("y_pred", m.get_buffer("y_pred"), y_o.numpy())
-    xu = m.get_buffer("xhg_user").reshape(B * T, ldx)[:, :Ds]
-    xi = m.get_buffer("xhg_item").reshape(B * T, ldx)[:, :Ds]
-    rep.add("user_side", live_rows(xu, Ds), inter["user_side"].numpy()[live])
-    rep.add("item_side", live_rows(xi, Ds), inter["item_side"].numpy()[live])
+    xu = m.get_buffer("xhg_user").reshape(B * T, Dxu + H)[:, :Dxu]
+    xi = m.get_buffer("xhg_item").reshape(B * T, Dxi + H)[:, :Dxi]
+    rep.add("user_side", live_rows(xu, Dxu), inter["user_side"].numpy()[live])
+    rep.add("item_side", live_rows(xi, Dxi), inter["item_side"].numpy()[live])
     key = m.get_buffer("key").reshape(B * T, Dk)
     rep.add("user_rep_t", key[:, :H].reshape(B, T, H), inter["user_rep_t"].numpy())
     rep.add("item_rep_t", key[:, H:2 * H].reshape(B, T, H), inter["item_rep_t"].numpy())
@@ -126,6 +128,25 @@ def forward_backward_report(shape: Shape, batch, seed=7, reg_lambda=1e-4, keep_p
         rep["elem/grad/" + name] = float((np.abs(a - b) / (REL_TOL * np.abs(b) + grad_abs_frac(B * T) * max(scale, 1e-30))).max())
     rows_c, vals_c = m.embedding_row_grads()
     rows_o, vals_o = ref.embedding_row_grads(g_o["emb_mtx"])
+    if fp64_twin:
+        p64 = type(params)((k, v.double()) for k, v in params.items())
+        m64 = None if masks is None else tuple(x.double() for x in masks)
+        _, _, g_64, _ = ref.loss_and_grads(p64, tb, cfg, reg_lambda, keep_prob, m64)
+        for name, _ in m.tensor_names():
+            if name == "emb_mtx" or name in ref.NON_TRAINABLE:
+                continue
+            t = g_64[name].numpy().reshape(-1)
+            scale = float(np.abs(t).max())
+            if name.endswith("/bias"):
+                scale = max(scale, float(g_64[name[:-5] + "/kernel"].abs().max()))
+            scale = max(scale, 1e-30)
+            rep["grad64/" + name] = float(np.abs(np.asarray(m.get_buffer("grad/" + name), np.float64) - t).max() / scale)
+            rep["noise/" + name] = float(np.abs(g_o[name].numpy().reshape(-1).astype(np.float64) - t).max() / scale)
+        t = g_64["emb_mtx"].numpy()[rows_o.numpy()]
+        scale = max(float(np.abs(t).max()), 1e-30)
+        rep["noise/emb_row_grads"] = float(np.abs(vals_o.numpy().astype(np.float64) - t).max() / scale)
+        if np.array_equal(rows_c, rows_o.numpy()):
+            rep["grad64/emb_row_grads"] = float(np.abs(vals_c.astype(np.float64) - t).max() / scale)
     rep["emb_rows_exact"] = bool(np.array_equal(rows_c, rows_o.numpy()))
     if rep["emb_rows_exact"]:
         rep.add("emb_row_grads", vals_c, vals_o.numpy())
@@ -147,6 +168,8 @@ def expected_keys(batch, cfg):
     B = np.asarray(batch[0]).shape[0]
     live = (np.arange(T)[None, :] < np.asarray(batch[7])[:, None])
     u1, u2, i1, i2 = (np.asarray(x).astype(np.int32).reshape(B, T, -1) for x in batch[:4])
+    if cfg.model_type == "RRN":   # the 2-hop tensors have no consumer (slice_model.py:158-159): their positions carry key 0
+        i2, u2 = np.zeros_like(i2), np.zeros_like(u2)
     hist = np.concatenate([u1, i2, u2, i1], axis=2).copy()
     hist[~live] = 0
     return np.concatenate([hist.reshape(-1), np.asarray(batch[4]).astype(np.int32).reshape(-1),

@@ -17,7 +17,7 @@ from oracle import score_ref as ref
 from score_b200.synth import SHAPES
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CUDA_MODEL_TYPES = ("SCORE", "RIA", "RCA", "SCORE_USER", "SCORE_ITEM")
+CUDA_MODEL_TYPES = ("SCORE", "RIA", "RCA", "SCORE_USER", "SCORE_ITEM", "RRN")
 
 
 def _load(name):
@@ -41,7 +41,7 @@ def _params(g):
 # ------------------------------------------------------------------------------------------ CPU: oracle vs fixtures
 def test_fixture_inventory():
     assert os.path.exists(os.path.join(GOLDEN, "metrics_reference.npz"))
-    assert len(_model_cases()) >= 7
+    assert len(_model_cases()) >= 8
     assert str(_load("metrics_reference.npz")["source"]).startswith("reference:")
 
 
@@ -58,7 +58,7 @@ def test_metrics_oracle_matches_the_references_own_functions():
     assert [metrics_ref.getMRR(rl, t) for t in (10, 12, 14, 15, 29, 99)] == g["helpers/mrr"].tolist()
 
 
-@pytest.mark.parametrize("case", ["tiny_score", "tiny_ragged", "tiny_rca"])
+@pytest.mark.parametrize("case", ["tiny_score", "tiny_ragged", "tiny_rca", "tiny_rrn"])
 def test_model_oracle_reproduces_its_fixture(case):
     """The restatement has not drifted since the fixture was written (same seeds -> same numbers)."""
     g = _load("model_%s.npz" % case)

@@ -76,16 +76,17 @@ def test_forward_backward_runtime_geometry_fallback(geom):
     _check_fb(rep)
 
 
-@pytest.mark.parametrize("model_type", ["RIA", "RCA", "SCORE_USER", "SCORE_ITEM"])
+@pytest.mark.parametrize("model_type", ["RIA", "RCA", "SCORE_USER", "SCORE_ITEM", "RRN"])
 @pytest.mark.parametrize("name", ["tiny", "tiny_tb"])
 def test_forward_backward_ablation_classes(model_type, name):
-    """score.py:226-369: the four ablation classes run through the same kernels (flags), parity like SCORE."""
+    """score.py:226-369: the four ablation classes, and RRN (slice_models/slice_model.py:155-173: 1-hop sum pooling,
+    per-side GRU widths, final states), run through the same kernels (flags), parity like SCORE."""
     shape = SHAPES[name]
     rep = pu.forward_backward_report(shape, make_batch(shape, seed=31), model_type=model_type)
     _check_fb(rep)
 
 
-@pytest.mark.parametrize("model_type", ["RIA", "RCA", "SCORE_USER", "SCORE_ITEM"])
+@pytest.mark.parametrize("model_type", ["RIA", "RCA", "SCORE_USER", "SCORE_ITEM", "RRN"])
 def test_train_steps_ablation_classes(model_type):
     shape = SHAPES["tiny"]
     batches = [make_batch(shape, seed=40 + i) for i in range(3)]
@@ -572,9 +573,28 @@ def test_full_size_taobao_values_match_the_oracle():
     """BASELINE.json config 3 at its real size (V = 5 042 754, B = 1024): loss, predictions, every intermediate, dense
     gradients and the embedding row gradients against the oracle (one oracle step is ~1 s on the box's host cores)."""
     shape = SHAPES["taobao"]
-    rep = pu.forward_backward_report(shape, make_batch(shape, seed=91))
+    rep = pu.forward_backward_report(shape, make_batch(shape, seed=91), fp64_twin=True)
     pu.print_report("taobao full size", rep)
-    _check_fb(rep)
+    # With N(0,1) rows, 1024 samples and the attention over large atten_info values, some gradients are ill-conditioned
+    # in fp32: the oracle's OWN fp32 result is 1e-4 .. 7e-3 away from its fp64 twin ('noise/...', measured: co-attention
+    # kernels 1.6e-3, attention MLP 3e-3 .. 7e-3, GRU 5e-5 .. 1e-4, embedding rows 2.4e-3), and two fp32 evaluations with
+    # different (valid) summation orders differ by as much.  The bar for a gradient is therefore: 1e-5 against the fp32
+    # oracle, OR as close to the fp64 result as the reference's own fp32 arithmetic gets (factor 1.5).
+    noise = {k[len("noise/"):]: v for k, v in rep.items() if k.startswith("noise/")}
+    g64 = {k[len("grad64/"):]: v for k, v in rep.items() if k.startswith("grad64/")}
+    strict = {}
+    for k, v in rep.items():
+        if k.startswith(("noise/", "grad64/")):
+            continue
+        base = k[len("elem/"):] if k.startswith("elem/") else k
+        name = base[len("grad/"):] if base.startswith("grad/") else base
+        if name in g64 and not isinstance(v, bool):
+            ok32 = v <= (1.0 if k.startswith("elem/") else pu.REL_TOL)
+            ok64 = g64[name] <= max(pu.REL_TOL, 1.5 * noise[name])
+            assert ok32 or ok64, "%s: %.3e vs fp32 oracle, %.3e vs fp64 (oracle fp32 noise %.3e)" % (k, v, g64[name], noise[name])
+            continue
+        strict[k] = v
+    _check_fb(strict)
 
 
 # ---------------------------------------------------------------------------------- ADVICE.md round 1
@@ -658,3 +678,39 @@ def test_dp_exchange_buffers_regrow_between_steps():
     assert pu.rel_err(ms[0].get_tensor("emb_mtx"), m1.get_tensor("emb_mtx")) <= 2e-4
     for m in ms + [m1]:
         m.close()
+
+
+@pytest.mark.parametrize("world", [1, 3, 8])
+def test_shard_plan_kernel_groups_positions_by_owner(world):
+    """score_shard_plan (CUDA) against the bucketing rule of parallel.ExchangePlan stated in NumPy: owner = id % world,
+    position order inside a group (stable), owner-local row = id // world + 1, dummy positions last and keyless."""
+    import ctypes as C
+    from score_b200 import _capi
+    shape = SHAPES["tiny_tb"]
+    m = sb.SCORE(*shape.ctor_args(), init_weights=False, use_graph=False)
+    batch = make_batch(shape, seed=77, dummy_frac=0.3)
+    b = sb._Batch(batch, m.cfg)
+    m._check(m._lib.score_prepare_batch(m._h, C.byref(b.struct)))
+    keys = m.get_buffer("keys").astype(np.int64)
+    plan = _capi.ScoreShardPlan()
+    m._check(m._lib.score_shard_plan(m._h, world, C.byref(plan)))
+    n = int(plan.n_positions)
+    assert n == keys.size
+    torch.cuda.synchronize()   # the plan kernels run on the handle's stream
+
+    def dev_i32(ptr, cnt):
+        out = np.empty(cnt, np.int32)
+        m._check(m._lib.score_copy_to_host(out.ctypes.data, ptr, out.nbytes))
+        return out
+
+    counts = dev_i32(plan.counts, world + 1)
+    owner = np.where(keys != 0, keys % world, world)
+    assert np.array_equal(counts, np.bincount(owner, minlength=world + 1))
+    order = np.argsort(owner, kind="stable")
+    n_valid = n - counts[world]
+    assert np.array_equal(dev_i32(plan.send_rows, n_valid), keys[order[:n_valid]] // world + 1)
+    mini = dev_i32(plan.mini_keys, n)
+    want_mini = np.zeros(n, np.int64)
+    want_mini[order[:n_valid]] = np.arange(1, n_valid + 1)
+    assert np.array_equal(mini, want_mini)
+    m.close()

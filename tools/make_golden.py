@@ -266,6 +266,7 @@ MODEL_CASES = [
     ("tiny_rca", "tiny", "RCA", dict(seed=105, batch=12), None),
     ("tiny_score_user", "tiny", "SCORE_USER", dict(seed=106, batch=12), None),
     ("tiny_score_item", "tiny", "SCORE_ITEM", dict(seed=107, batch=12), None),
+    ("tiny_rrn", "tiny", "RRN", dict(seed=108, batch=12), None),
 ]
 PARAM_SEED, REG, LR = 7, 1e-4, 5e-4
 
