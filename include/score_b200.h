@@ -242,6 +242,22 @@ int score_graph_sample(ScoreGraphHandle g, const int32_t* uids, const int32_t* i
                        int32_t group, int32_t start_time, int32_t pred_time, int32_t max_time_len,
                        int32_t obj_per_time_slice, int32_t mode, uint64_t seed, uint32_t draw_id, void* cuda_stream,
                        ScoreBatch* out);
+/* 2-hop graph construction: replaces GraphStore.construct_coll_2hop (code/graph_storage.py:127-246).
+ * Input: the 1-hop lists of every node and slice as a CSR array (hop1_off / hop1_ids as in ScoreGraphDesc, HOST pointers).
+ * Output (HOST pointers): hop1_ids_out - the same lists with the in-place shuffles of the lists longer than max_1hop applied
+ * (graph_storage.py:171-173, 211-213: the new documents store the shuffled lists); hop2_off_out [(n_user+n_item+1)*n_slices+1],
+ * hop2_ids_out / hop2_deg_out [*n2_out] - doc['2hop'] / doc['degrees'].  Call with hop2_ids_out == NULL to learn *n2_out
+ * (hop2_off_out is filled), then again with buffers of that capacity.  Randomness: the k-th random.shuffle / np.random.choice
+ * call of the reference's processing order (items, then users) becomes the stable argsort of Philox4x32-10 uniforms keyed
+ * by (seed, stream 11 / 12, k, element) - csrc/hop2.cu; max_1hop <= 32. */
+typedef struct ScoreHop2Desc {
+    int32_t n_user, n_item, n_slices, start_time, max_1hop, max_2hop;
+    const int64_t* hop1_off; const int32_t* hop1_ids;
+    uint64_t seed;
+} ScoreHop2Desc;
+int score_graph_build_2hop(const ScoreHop2Desc* desc, int device, int32_t* hop1_ids_out, int64_t* hop2_off_out,
+                           int32_t* hop2_ids_out, int32_t* hop2_deg_out, int64_t capacity, int64_t* n2_out);
+const char* score_graph_build_2hop_error(void);
 int score_graph_sync(ScoreGraphHandle g, void* cuda_stream);   /* waits; SCORE_ERR_ID_RANGE if a target was unknown */
 int score_copy_to_host(void* dst_host, const void* src_device, size_t bytes);
 

@@ -31,6 +31,12 @@ class ScoreGraphDesc(C.Structure):
                 ("hop2_ids", C.c_void_p), ("hop2_deg", C.c_void_p), ("user_feat", C.c_void_p), ("item_feat", C.c_void_p)]
 
 
+class ScoreHop2Desc(C.Structure):
+    _fields_ = [("n_user", C.c_int32), ("n_item", C.c_int32), ("n_slices", C.c_int32), ("start_time", C.c_int32),
+                ("max_1hop", C.c_int32), ("max_2hop", C.c_int32), ("hop1_off", C.c_void_p), ("hop1_ids", C.c_void_p),
+                ("seed", C.c_uint64)]
+
+
 class ScoreShardPlan(C.Structure):
     _fields_ = [("counts", C.c_void_p), ("send_rows", C.c_void_p), ("staged", C.c_void_p), ("mini_keys", C.c_void_p),
                 ("grad_send", C.c_void_p), ("n_positions", C.c_int64)]
@@ -83,6 +89,9 @@ SYMBOLS = {
     "score_graph_sample": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(ScoreBatch)]),
     "score_graph_sync": (C.c_int, [_H, C.c_void_p]),
+    "score_graph_build_2hop": (C.c_int, [C.POINTER(ScoreHop2Desc), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int64, C.POINTER(C.c_int64)]),
+    "score_graph_build_2hop_error": (C.c_char_p, []),
     "score_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
 }
 

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # SCORE_B200_LIB: load / build another library file (compile-time variants for A/B runs, tools/build_variants.py)
 LIB = os.environ.get("SCORE_B200_LIB") or os.path.join(HERE, "libscore_b200.so")
-SOURCES = ["gemm.cu", "embed.cu", "coatt.cu", "seq.cu", "chain.cu", "attn.cu", "scatter.cu", "shard.cu", "metrics.cu", "sampler.cu", "model.cu"]
+SOURCES = ["gemm.cu", "embed.cu", "coatt.cu", "seq.cu", "chain.cu", "attn.cu", "scatter.cu", "shard.cu", "metrics.cu", "sampler.cu", "hop2.cu", "model.cu"]
 HEADERS = ["common.cuh", "tile.cuh", "kernels.h", os.path.join("..", "..", "include", "score_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]

@@ -48,6 +48,35 @@ def feat_table(feat_dict, lo, n, width):
     return out
 
 
+def build_2hop(hop1_off, hop1_ids, n_user, n_item, n_slices, start_time=0, max_1hop=10, max_2hop=100, seed=11, device=0):
+    """GraphStore.construct_coll_2hop (code/graph_storage.py:127-246) on the GPU (csrc/hop2.cu).
+    -> (hop1_ids with the reference's in-place shuffles applied, hop2_off, hop2_ids, hop2_deg): the CSR arrays
+    ``GraphStore`` below takes.  No CPU fallback: raises RuntimeError without a device."""
+    lib = _capi.load()
+    off = np.ascontiguousarray(hop1_off, np.int64)
+    ids = np.ascontiguousarray(hop1_ids, np.int32)
+    n_lists = (n_user + n_item + 1) * n_slices
+    if off.size != n_lists + 1:
+        raise ValueError("hop1_off must have (n_user + n_item + 1) * n_slices + 1 entries")
+    d = _capi.ScoreHop2Desc(int(n_user), int(n_item), int(n_slices), int(start_time), int(max_1hop), int(max_2hop),
+                            off.ctypes.data, ids.ctypes.data if ids.size else None, int(seed))
+    ids_out = np.empty_like(ids)
+    off2 = np.empty(n_lists + 1, np.int64)
+    n2 = C.c_int64()
+
+    def check(rc):
+        if rc:
+            msg = lib.score_graph_build_2hop_error().decode()
+            raise (ValueError if rc == _capi.ERR_ARG else RuntimeError)(msg)
+
+    check(lib.score_graph_build_2hop(C.byref(d), int(device), None, off2.ctypes.data, None, None, 0, C.byref(n2)))
+    ids2 = np.empty(max(n2.value, 1), np.int32)
+    deg2 = np.empty(max(n2.value, 1), np.int32)
+    check(lib.score_graph_build_2hop(C.byref(d), int(device), ids_out.ctypes.data if ids.size else None, off2.ctypes.data,
+                                     ids2.ctypes.data, deg2.ctypes.data, ids2.size, C.byref(n2)))
+    return ids_out, off2, ids2[:n2.value], deg2[:n2.value]
+
+
 class GraphStore(object):
     """The interaction graph in device memory."""
 

@@ -247,7 +247,6 @@ class ShardedEmbeddingTrainer(_Base):
     def __init__(self, model, world, rank, group=None):
         super().__init__(model, world, rank, group)
         self._bufs = {}
-        self._counts_host = torch.empty(world * (world + 1), dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
 
     def _buf(self, name, n, dtype):
         """persistent device buffer of at least n elements (grown with slack; the stream is drained before a regrow)"""
@@ -275,9 +274,9 @@ class ShardedEmbeddingTrainer(_Base):
             dist.all_gather_into_tensor(mat, mine, group=self.group)
         else:
             mat = mine
-        self._counts_host.copy_(mat, non_blocking=True)
-        self.stream.synchronize()
-        cm = self._counts_host.view(W, W + 1)
+        # synchronous D2H on the handle's stream (a pageable destination: torch's pinned-host cache would keep a
+        # reference to this external stream beyond the handle's life)
+        cm = mat[:W * (W + 1)].view(W, W + 1).cpu()
         send_counts = cm[self.rank, :W].tolist()
         recv_counts = cm[:, self.rank].tolist()
         return send_counts, recv_counts, int(sum(send_counts)), int(sum(recv_counts)), plan
