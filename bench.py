@@ -393,6 +393,23 @@ def main():
         e2e_ms = float(t.item())
     e2e_value = B * world / (e2e_ms / e2e_steps * 1e-3)
     h2d = int(sum(x.numel() * 4 for x in pin_pool[0]))
+    # the reference's caller feeds NESTED PYTHON LISTS (graph_loader.py:383 -> score.py:102-115, TF converts them inside
+    # sess.run): the same call with lists, so the list -> int32 array conversion the boundary must do is inside the region
+    e2e_lists = None
+    if world == 1:
+        list_pool = [tuple(x.tolist() for x in b) for b in host_pool[:4]]
+        m.train(None, list_pool[0], LR, REG)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_l = 6
+        for i in range(n_l):
+            m.train(None, list_pool[i % 4], LR, REG)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_l
+        e2e_lists = {"value": B / dt, "unit": "samples/s", "ms_per_step": dt * 1e3, "steps": n_l,
+                     "note": "batch_data as nested Python lists, as GraphLoader yields them: the step is the same, the time is "
+                             "NumPy's list -> array conversion of %d ids per batch on one host core" % (h2d // 4)}
+        del list_pool
     if trainer:
         loss = loss_e2e      # the trainer's synchronous step returns the GLOBAL loss (m.wait() is this rank's share only)
     m.close()
@@ -444,7 +461,8 @@ def main():
                         "steps": e2e_steps,
                         "api": "SCORE.train(sess, batch_data, lr, reg_lambda) -> float, pinned host ids; the call returns "
                                "when the step's result packet (loss, error flag) has reached the host, the region ends "
-                               "with a device synchronize"},
+                               "with a device synchronize",
+                        "nested_lists": e2e_lists},
                 "gpu_launches": int(launches),
                 # `roofline` = the dominant HBM-bound kernel of the step (most DRAM traffic, longest of the HBM-side
                 # kernels): the scatter + row Adam; the gather kernel is reported beside it (BASELINE.json's metric

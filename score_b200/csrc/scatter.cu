@@ -191,19 +191,28 @@ __global__ void sort_scan_local_kernel(uint32_t* __restrict__ hist, int total, u
     if (threadIdx.x == 1023) chunk_sums[blockIdx.x] = wsum[31];
 }
 
+// Ranked scatter of one tile.  The (key, value) pairs are first put in digit order INSIDE the tile (shared memory), then
+// written out by consecutive threads: the pairs of one (tile, digit) run are consecutive in the output, so a warp's
+// stores cover a few contiguous runs instead of 32 unrelated 4-byte sectors (the scattered version spent most of the
+// CCMR-size sort - 9.8 M keys - on write sectors).
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
                     int32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out, int64_t n, int shift,
                     const uint32_t* __restrict__ hist, int nblocks, const uint32_t* __restrict__ chunk_sums) {
     constexpr int WARPS = SORT_THREADS / 32;
     __shared__ uint32_t whist[WARPS][256];
-    __shared__ uint32_t gbase[256];
+    __shared__ uint32_t gbase[256];      // global position of the tile's first pair of each digit, minus its local start
+    __shared__ uint32_t lstart[256];     // start of each digit inside the tile
+    __shared__ uint32_t wscan[WARPS];
+    __shared__ int32_t skey[SORT_TILE], sval[SORT_TILE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int tile = blockIdx.x; tile < nblocks; tile += gridDim.x) {
-    __syncthreads();   // the previous tile's readers of whist / gbase are done
+    __syncthreads();   // the previous tile's readers of the shared arrays are done
     for (int i = threadIdx.x; i < WARPS * 256; i += SORT_THREADS) (&whist[0][0])[i] = 0;
     __syncthreads();
-    const int64_t wbase = (int64_t)tile * SORT_TILE + warp * (32 * SORT_ITEMS);
+    const int64_t tbase = (int64_t)tile * SORT_TILE;
+    const int64_t wbase = tbase + warp * (32 * SORT_ITEMS);
+    const int tile_n = (int)min((int64_t)SORT_TILE, n - tbase);
     int32_t k[SORT_ITEMS];
     uint32_t lrank[SORT_ITEMS];
 #pragma unroll
@@ -222,16 +231,29 @@ sort_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restri
         __syncwarp();
     }
     __syncthreads();
-    {   // exclusive prefix over warps for each digit; global base of (digit, this tile)
+    {   // per digit: exclusive prefix over the warps, the tile's count, its start inside the tile (256-wide scan)
         const int dgt = threadIdx.x;
         uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) { uint32_t c = whist[w][dgt]; whist[w][dgt] = run; run += c; }
+        uint32_t incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) wscan[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) before += w < warp ? wscan[w] : 0u;
+        const uint32_t ls = before + incl - run;
+        lstart[dgt] = ls;
         const int64_t hidx = (int64_t)dgt * nblocks + tile;
         uint32_t pre = 0;
         const int chunk = (int)(hidx >> 10);
         for (int c = 0; c < chunk; ++c) pre += chunk_sums[c];   // prefix of the 1024-entry chunk totals
-        gbase[dgt] = hist[hidx] + pre;
+        gbase[dgt] = hist[hidx] + pre - ls;
     }
     __syncthreads();
 #pragma unroll
@@ -239,10 +261,17 @@ sort_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restri
         int64_t i = wbase + r * 32 + lane;
         if (i < n) {
             uint32_t digit = ((uint32_t)k[r] >> shift) & 255u;
-            uint32_t pos = gbase[digit] + whist[warp][digit] + lrank[r];
-            keys_out[pos] = k[r];
-            vals_out[pos] = vals_in ? vals_in[i] : (int32_t)i;
+            const uint32_t lp = lstart[digit] + whist[warp][digit] + lrank[r];
+            skey[lp] = k[r];
+            sval[lp] = vals_in ? vals_in[i] : (int32_t)i;
         }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < tile_n; e += SORT_THREADS) {
+        const int32_t key = skey[e];
+        const uint32_t pos = gbase[((uint32_t)key >> shift) & 255u] + (uint32_t)e;
+        keys_out[pos] = key;
+        vals_out[pos] = sval[e];
     }
     }   // tiles
 }

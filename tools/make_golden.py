@@ -228,17 +228,129 @@ def make_loader(reference_root):
     np.savez_compressed(os.path.join(OUT, "loader_reference.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------ 2-hop construction (graph_storage.py)
+class _MemColl(object):
+    """in-memory stand-in for one Mongo collection: find({}) hands out the stored documents, insert_many keeps them"""
+    def __init__(self):
+        self.docs = []
+
+    def find(self, q):
+        import copy
+        assert q == {}
+        return copy.deepcopy(self.docs)
+
+    def insert_many(self, docs):
+        self.docs.extend(docs)
+
+
+class _MemDB(dict):
+    def __missing__(self, name):
+        self[name] = _MemColl()
+        return self[name]
+
+
+def load_reference_graph_store(reference_root, ns):
+    """exec the module-level constants and class GraphStore of code/graph_storage.py (source untouched; the module
+    itself cannot be imported: it imports pymongo and matplotlib)"""
+    path = os.path.join(reference_root, "code", "graph_storage.py")
+    tree = ast.parse(open(path).read())
+    for node in tree.body:
+        if isinstance(node, ast.Assign) or (isinstance(node, ast.ClassDef) and node.name == "GraphStore"):
+            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    return ns["GraphStore"]
+
+
+HOP2_CASES = [
+    # name, n_user, n_item, slices, start, max_1hop, max_2hop, edges, users / items per collection
+    ("caps_10_100", 40, 30, 5, 0, 10, 100, 2600, 20, 15),     # the reference's constants: the max_2hop cap can never bind
+    ("caps_4_9_start1", 30, 24, 4, 1, 4, 9, 900, 10, 8),      # both caps bind, start_time > 0
+    ("caps_3_5", 24, 20, 3, 0, 3, 5, 500, 24, 20),
+]
+
+
+def make_hop2(reference_root):
+    from oracle import graph_ref as G
+    out = {"source": np.array("reference: GraphStore.construct_coll_2hop of code/graph_storage.py:127-246 executed unmodified "
+                              "(ast-extracted class; MongoDB replaced by in-memory collections; random.shuffle / "
+                              "np.random.choice apply the Philox permutations of csrc/hop2.cu, call k of the reference's "
+                              "own call order)")}
+    names = []
+    for ci, (name, nu, ni, S, start, m1, m2, edges, upc, ipc) in enumerate(HOP2_CASES):
+        rng = np.random.default_rng(900 + ci)
+        u1, i1 = G.random_1hop(rng, nu, ni, S, edges)
+        seed = 4242 + ci
+        calls = {"shuffle": 0, "choice": 0}
+
+        class _Random(object):
+            @staticmethod
+            def shuffle(lst):
+                perm = G.permutation(seed, G.STREAM_SHUFFLE, calls["shuffle"], len(lst))
+                calls["shuffle"] += 1
+                lst[:] = [lst[int(p)] for p in perm]
+
+            @staticmethod
+            def seed(x):
+                pass
+
+        class _NPRandom(object):
+            @staticmethod
+            def choice(a, size=None, replace=True, p=None):
+                assert replace is False and p is None and size == len(a)
+                perm = G.permutation(seed, G.STREAM_CHOICE, calls["choice"], len(a))
+                calls["choice"] += 1
+                return np.asarray(a)[perm]
+
+        class _NP(object):
+            random = _NPRandom()
+
+            def __getattr__(self, k):
+                return getattr(np, k)
+
+        db1, db2 = _MemDB(), _MemDB()
+        for i in range(nu // upc):
+            db1["user_%d" % i].insert_many([{"uid": u, "1hop": [list(x) for x in u1[u]]} for u in range(i * upc + 1, (i + 1) * upc + 1)])
+        for i in range(ni // ipc):
+            db1["item_%d" % i].insert_many([{"iid": it, "1hop": [list(x) for x in i1[it]]}
+                                            for it in range(nu + i * ipc + 1, nu + (i + 1) * ipc + 1)])
+        client = {"h1": db1, "h2": db2}
+        pym = type("PM", (), {"MongoClient": staticmethod(lambda url: client)})
+        ns = {"pymongo": pym, "np": _NP(), "random": _Random(), "print": lambda *a, **k: None}
+        GS = load_reference_graph_store(reference_root, ns)
+        gs = GS(os.devnull, user_per_collection=upc, item_per_collection=ipc, start_time=start, max_1hop=m1, max_2hop=m2,
+                user_num=nu, item_num=ni, db_1hop="h1", db_2hop="h2", time_slice_num=S)
+        gs.construct_coll_2hop()
+        user_docs = {d["uid"]: d for k, c in db2.items() if k.startswith("user_") for d in c.docs}
+        item_docs = {d["iid"]: d for k, c in db2.items() if k.startswith("item_") for d in c.docs}
+        assert len(user_docs) == nu and len(item_docs) == ni
+        from score_b200.graph import docs_to_csr
+        in_u = {u: {"1hop": u1[u], "2hop": [[] for _ in range(S)], "degrees": [[] for _ in range(S)]} for u in u1}
+        in_i = {i: {"1hop": i1[i], "2hop": [[] for _ in range(S)], "degrees": [[] for _ in range(S)]} for i in i1}
+        off1, ids1_in, _, _, _ = docs_to_csr(in_u, in_i, nu, ni, S)
+        off1b, ids1_out, off2, ids2, deg2 = docs_to_csr(user_docs, item_docs, nu, ni, S)
+        assert np.array_equal(off1, off1b)
+        pre = name + "/"
+        out[pre + "params"] = np.array([nu, ni, S, start, m1, m2, seed], np.int64)
+        out[pre + "hop1_off"], out[pre + "hop1_ids"] = off1, ids1_in
+        out[pre + "hop1_ids_out"], out[pre + "hop2_off"], out[pre + "hop2_ids"], out[pre + "hop2_deg"] = ids1_out, off2, ids2, deg2
+        names.append(name)
+        print("hop2 case %s: %d shuffle calls, %d choice calls, %d 2-hop ids, %d of %d 1-hop ids moved" % (
+            name, calls["shuffle"], calls["choice"], len(ids2), int((ids1_in != ids1_out).sum()), len(ids1_in)))
+    out["cases"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "hop2_reference.npz"), **out)
+
+
 def make_tmall(reference_root):
     """BASELINE.json config 1: the reference's bundled Tmall sample as a derived fixture (graph CSR + feature tables +
     target lines); the raw log itself stays in the reference tree"""
-    from score_b200 import tmall_sample as ts
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import tmall_sample as ts
     from score_b200.graph import docs_to_csr, feat_table
     d = ts.build(os.path.join(reference_root, "score-data", "Tmall", "raw_data", "user_log_format1.csv"))
     off1, ids1, off2, ids2, deg2 = docs_to_csr(d["user_docs"], d["item_docs"], d["n_user"], d["n_item"], d["n_slices"])
     np.savez_compressed(
         os.path.join(OUT, "tmall_sample.npz"),
         source=np.array("derived from the reference's score-data/Tmall/raw_data/user_log_format1.csv by "
-                        "score_b200/tmall_sample.py (restated feateng_tmall.py / graph_storage.py / gen_target.py; "
+                        "tools/tmall_sample.py (restated feateng_tmall.py / graph_storage.py / gen_target.py; "
                         "age and gender synthesised: user_info_format1.csv is not shipped)"),
         dims=np.array([d["n_user"], d["n_item"], d["feature_size"], d["n_slices"]], np.int64),
         hop1_off=off1, hop1_ids=ids1, hop2_off=off2, hop2_ids=ids2, hop2_deg=deg2,
@@ -331,6 +443,8 @@ def main():
         make_loader(args.reference)
     if not args.only or args.only == "tmall":
         make_tmall(args.reference)
+    if not args.only or args.only == "hop2":
+        make_hop2(args.reference)
     for c in MODEL_CASES:
         if not args.only or args.only == c[0]:
             make_model_case(*c)
