@@ -197,15 +197,17 @@ def large_vocab_leg(args, world, rank, local, steps=30, warmup=5):
 
         for i in range(warmup):
             step(i)
-        m.wait()
+        (trainer or m).wait()
         dist.barrier(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             e0.record(stream)
             for i in range(steps):
                 step(i)
+            if trainer:
+                trainer._flush_finish()       # the last step's deferred optimizer half belongs to the timed region
             e1.record(stream)
-        m.wait()
+        (trainer or m).wait()
         dist.barrier(); torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -317,9 +319,12 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    def wait_all():
+        return trainer.wait() if trainer else m.wait()
+
     for i in range(args.warmup):
         step_dev(i)
-    m.wait()
+    wait_all()
     m.enable_probes(False)
 
     def timed_region(steps):
@@ -330,8 +335,10 @@ def main():
             e0.record(stream)
             for i in range(steps):
                 step_dev(i)
+            if trainer and hasattr(trainer, "_flush_finish"):
+                trainer._flush_finish()       # row-sharded: the last step's deferred optimizer half is part of the region
             e1.record(stream)
-        last = m.wait()
+        last = wait_all()
         barrier()
         t_ms = e0.elapsed_time(e1)
         if world > 1:
@@ -353,7 +360,7 @@ def main():
         m.enable_probes(True)
         for i in range(3):
             step_dev(i)
-            m.wait()
+            wait_all()
         m.enable_probes(True)       # same state: resets the accumulators only, graphs are kept
         ms_p, _ = timed_region(args.steps)
         ms_probed = ms_p / args.steps
@@ -363,7 +370,7 @@ def main():
         while len(sampler.rows) < 3 and time.perf_counter() < t_end:
             for i in range(20):
                 step_dev(i)
-            m.wait()
+            wait_all()
     clocks = sampler.stop() if rank == 0 else None
     stats = m.last_step_stats()
 

@@ -188,6 +188,11 @@ typedef struct ScoreShardPlan {
 } ScoreShardPlan;
 int score_shard_plan(ScoreHandle h, int32_t world, ScoreShardPlan* out);
 int score_shard_pack_grads(ScoreHandle h);
+/* read-back of the all-gathered [world, world+1] count matrix (device pointer, n ints) into pinned memory of the handle:
+ * fetch enqueues the copy + an event, wait blocks on that event only and copies the n ints to `out` - work enqueued in
+ * between (the previous step's score_step_finish) keeps the device busy while the host learns the exchange sizes. */
+int score_shard_counts_fetch(ScoreHandle h, const int32_t* counts_dev, int32_t n);
+int score_shard_counts_wait(ScoreHandle h, int32_t* out, int32_t n);
 int score_shard_presort(ScoreHandle h, const int32_t* ext_keys, int64_t n_ext);
 
 /* Global index of the first sample of the batches this handle steps on (a data-parallel rank: rank * per-rank batch;

@@ -76,6 +76,8 @@ SYMBOLS = {
     "score_step_finish": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "score_shard_plan": (C.c_int, [_H, C.c_int32, C.POINTER(ScoreShardPlan)]),
     "score_shard_pack_grads": (C.c_int, [_H]),
+    "score_shard_counts_fetch": (C.c_int, [_H, C.c_void_p, C.c_int32]),
+    "score_shard_counts_wait": (C.c_int, [_H, C.c_void_p, C.c_int32]),
     "score_shard_presort": (C.c_int, [_H, C.c_void_p, C.c_int64]),
     "score_set_sample_offset": (C.c_int, [_H, C.c_int32]),
     "score_stream": (C.c_int, [_H, C.POINTER(C.c_void_p)]),

@@ -149,6 +149,7 @@ struct ScoreModel {
     int32_t *sh_owner = nullptr, *sh_counts = nullptr, *sh_send_rows = nullptr, *sh_sel = nullptr, *sh_mini = nullptr;
     float *sh_staged = nullptr, *sh_grad_send = nullptr;
     const int32_t* presorted_keys = nullptr; int64_t presorted_n = 0; int presorted_out = 0; cudaEvent_t ev_presort = nullptr;
+    int32_t* sh_counts_host = nullptr; cudaEvent_t ev_sh_counts = nullptr;   // count matrix read-back (pinned, own event)
 
     // graphs
     std::map<int, cudaGraphExec_t> graphs_train;
@@ -953,6 +954,21 @@ int upload_hyper(ScoreModel* h, int B, float lr, float reg_lambda, float keep_pr
     return SCORE_OK;
 }
 
+// new batch pointer table, SAME hyper-parameters: a begun step whose optimizer half is still to be enqueued keeps
+// reading its own alpha / step / reg_lambda (row-sharded pipelining: the next batch is planned before the finish)
+int upload_bp_keep_hyper(ScoreModel* h) {
+    const Hyper keep = *h->hyper_host;
+    const int slot = h->hyper_next++ % ScoreModel::kHyperSlots;
+    if (h->hyper_used[slot]) CK(cudaEventSynchronize(h->hyper_ev[slot]));
+    h->hyper_ring[slot].hp = keep;
+    h->hyper_host = &h->hyper_ring[slot].hp;
+    h->hyper_ring[slot].bp = h->bp_cur;
+    CK(cudaMemcpyAsync(h->step_dev, h->hyper_ring + slot, sizeof(ScoreModel::StepParams), cudaMemcpyHostToDevice, h->st));
+    CK(cudaEventRecord(h->hyper_ev[slot], h->st));
+    h->hyper_used[slot] = true;
+    return SCORE_OK;
+}
+
 int flush_lazy(ScoreModel* h) {
     if (h->cfg.adam_mode == SCORE_ADAM_LAZY && h->step > 0) {
         launch_emb_catchup_all(h->st, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.V, h->dm.d, h->es, h->alpha_hist, h->step);
@@ -1213,6 +1229,8 @@ int score_destroy(ScoreHandle h) {
                     (void*)h->sh_staged, (void*)h->sh_grad_send})
         if (p) cudaFree(p);
     if (h->ev_presort) cudaEventDestroy(h->ev_presort);
+    if (h->ev_sh_counts) cudaEventDestroy(h->ev_sh_counts);
+    if (h->sh_counts_host) cudaFreeHost(h->sh_counts_host);
     if (h->hyper_ring) cudaFreeHost(h->hyper_ring);
     for (int i = 0; i < ScoreModel::kHyperSlots; ++i) if (h->hyper_ev[i]) cudaEventDestroy(h->hyper_ev[i]);
     if (h->loss_host) cudaFreeHost(h->loss_host);
@@ -1656,7 +1674,8 @@ int score_prepare_batch(ScoreHandle h, const ScoreBatch* batch) {
     h->last_N = h->dm.N;
     Dims dm = h->dm;
     dm.V = ((int64_t)1 << 31) - 1;   // ids are GLOBAL row numbers here; the owner checks the range
-    rc = upload_hyper(h, B, 0.f, 0.f, 1.f, 0, 0);   // carries the batch's pointer table
+    // carries the batch's pointer table; a begun step that still waits for score_step_finish keeps its hyper-parameters
+    rc = h->begun ? upload_bp_keep_hyper(h) : upload_hyper(h, B, 0.f, 0.f, 1.f, 0, 0);
     if (rc) return rc;
     launch_build_keys(h->st, dm, h->bp_dev, h->keys, h->label, h->length, h->err_flag, nullptr, h->live);
     stage_release(h);
@@ -1728,6 +1747,26 @@ int score_shard_plan(ScoreHandle h, int32_t world, ScoreShardPlan* out) {
     out->counts = h->sh_counts; out->send_rows = h->sh_send_rows; out->staged = h->sh_staged; out->mini_keys = h->sh_mini;
     out->grad_send = h->sh_grad_send; out->n_positions = N;
     CK(cudaGetLastError());
+    return SCORE_OK;
+}
+
+// Read-back of the all-gathered count matrix without draining the stream: the copy and its event are enqueued, the caller
+// enqueues more work (the previous step's score_step_finish) and then waits for the event alone.
+int score_shard_counts_fetch(ScoreHandle h, const int32_t* counts_dev, int32_t n) {
+    if (!h || !counts_dev || n < 1 || n > 65 * 64) return SCORE_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (!h->sh_counts_host) {
+        CK(cudaMallocHost(&h->sh_counts_host, sizeof(int32_t) * 65 * 64));
+        CK(cudaEventCreateWithFlags(&h->ev_sh_counts, cudaEventDisableTiming));
+    }
+    CK(cudaMemcpyAsync(h->sh_counts_host, counts_dev, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaEventRecord(h->ev_sh_counts, h->st));
+    return SCORE_OK;
+}
+int score_shard_counts_wait(ScoreHandle h, int32_t* out, int32_t n) {
+    if (!h || !out || !h->sh_counts_host || n < 1 || n > 65 * 64) return SCORE_ERR_ARG;
+    CK(cudaEventSynchronize(h->ev_sh_counts));
+    memcpy(out, h->sh_counts_host, sizeof(int32_t) * n);
     return SCORE_OK;
 }
 

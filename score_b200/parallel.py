@@ -226,6 +226,9 @@ class DataParallelTrainer(_Base):
     def train_async(self, batch_data, lr, reg_lambda, keep_prob=TRAIN_KEEP_PROB):
         self.train(None, batch_data, lr, reg_lambda, keep_prob, want_loss=False)
 
+    def wait(self):
+        return self.m.wait()
+
     def eval(self, sess, batch_data, reg_lambda):
         return self.m.eval(sess, batch_data, reg_lambda)   # replicas are identical
 
@@ -237,16 +240,20 @@ class ShardedEmbeddingTrainer(_Base):
 
     One step, everything on the handle's stream:
       score_prepare_batch -> score_shard_plan (CUDA: positions grouped by owner, counts stay on the device) ->
-      ONE all-gather of the [world, world+1] count matrix + its D2H copy (the only host synchronisation of the step) ->
-      all-to-all ids -> owners: score_shard_presort (side stream) + score_gather_rows -> all-to-all rows straight into the
-      staged table -> score_step_begin(staged, mini_keys) (CUDA graph) -> all-reduce dense gradient, score_shard_pack_grads,
-      all-to-all gradient rows -> score_step_finish on the owners (presorted keys).
+      ONE all-gather of the [world, world+1] count matrix + its D2H copy (the only host wait of the step, on the copy's
+      own event) -> all-to-all ids -> owners: score_shard_presort (side stream) + score_gather_rows -> all-to-all rows
+      straight into the staged table -> score_step_begin(staged, mini_keys) (CUDA graph) -> all-reduce dense gradient,
+      score_shard_pack_grads, all-to-all gradient rows -> score_step_finish on the owners (presorted keys).
+    Asynchronous stepping (train_async) defers a step's score_step_finish into the NEXT call, behind that call's plan
+    and count read-back: the device runs the owner-side update while the host waits for the exchange sizes.
     ``ExchangePlan`` above states the same bucketing rule in torch ops (CPU / gloo tests, and the parity test of the
     CUDA plan)."""
 
     def __init__(self, model, world, rank, group=None):
         super().__init__(model, world, rank, group)
         self._bufs = {}
+        self._pending = None      # (want, owned, n_recv) of a begun step whose score_step_finish is still to be enqueued
+        self._cm = (C.c_int32 * (self.world * (self.world + 1)))()
 
     def _buf(self, name, n, dtype):
         """persistent device buffer of at least n elements (grown with slack; the stream is drained before a regrow)"""
@@ -274,12 +281,32 @@ class ShardedEmbeddingTrainer(_Base):
             dist.all_gather_into_tensor(mat, mine, group=self.group)
         else:
             mat = mine
-        # synchronous D2H on the handle's stream (a pageable destination: torch's pinned-host cache would keep a
-        # reference to this external stream beyond the handle's life)
-        cm = mat[:W * (W + 1)].view(W, W + 1).cpu()
-        send_counts = cm[self.rank, :W].tolist()
-        recv_counts = cm[:, self.rank].tolist()
+        # read-back into pinned memory of the handle + its own event; the previous step's deferred optimizer half goes in
+        # between, so the device is busy while the host waits for the sizes
+        nn = W * (W + 1)
+        self.m._check(self.lib.score_shard_counts_fetch(self.h, mat.data_ptr(), nn))
+        self._flush_finish()
+        self.m._check(self.lib.score_shard_counts_wait(self.h, self._cm, nn))
+        cm = list(self._cm)
+        send_counts = cm[self.rank * (W + 1):self.rank * (W + 1) + W]
+        recv_counts = [cm[r * (W + 1) + self.rank] for r in range(W)]
         return send_counts, recv_counts, int(sum(send_counts)), int(sum(recv_counts)), plan
+
+    def _flush_finish(self, want_loss=False):
+        """enqueue the optimizer half (score_step_finish) of the step begun last, if it is still pending"""
+        if self._pending is None:
+            return None
+        want, owned, n_recv = self._pending
+        self._pending = None
+        loss2 = (C.c_float * 2)() if want_loss else None
+        self.m._check(self.lib.score_step_finish(self.h, want.data_ptr(), owned.data_ptr(), n_recv, loss2))
+        return loss2
+
+    def wait(self):
+        """all enqueued steps are complete (asynchronous stepping); returns this rank's last loss share"""
+        with torch.cuda.stream(self.stream):
+            self._flush_finish()
+        return self.m.wait()
 
     def _fetch(self, b):
         d = self.m.cfg["eb_dim"]
@@ -321,9 +348,10 @@ class ShardedEmbeddingTrainer(_Base):
                 dist.all_to_all_single(owned, gsend, recv_counts, send_counts, group=self.group)
             else:
                 owned.copy_(gsend)
-            loss2 = (C.c_float * 2)() if want_loss else None
-            self.m._check(self.lib.score_step_finish(self.h, want.data_ptr(), owned.data_ptr(), n_recv, loss2))
-            return self._global_loss(loss2) if want_loss else None
+            self._pending = (want, owned, n_recv)
+            if not want_loss:
+                return None        # the optimizer half rides behind the next call's plan (or wait())
+            return self._global_loss(self._flush_finish(True))
 
     def train_async(self, batch_data, lr, reg_lambda, keep_prob=TRAIN_KEEP_PROB):
         self.train(None, batch_data, lr, reg_lambda, keep_prob, want_loss=False)
@@ -331,6 +359,7 @@ class ShardedEmbeddingTrainer(_Base):
     def eval(self, sess, batch_data, reg_lambda):
         b = _Batch(batch_data, self.m.cfg)
         with torch.cuda.stream(self.stream):
+            self._flush_finish()
             plan, want, _ = self._fetch(b)
             self.m._check(self.lib.score_step_begin(self.h, None, 0.0, reg_lambda, 1.0, b.B, 0, plan.staged, plan.mini_keys))
             loss2 = (C.c_float * 2)()
