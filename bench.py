@@ -283,21 +283,52 @@ def main():
     from score_b200 import parallel
 
     B = shape.batch
-    par = args.parallel if args.parallel != "auto" else ("sharded" if shape.feature_size > 50_000_000 else "dp")
-    args.par = par if world > 1 else "single"
-    ctor = list(shape.ctor_args())
-    if world > 1 and par == "sharded":
-        ctor[0] = parallel.shard_rows(shape.feature_size, world)
-    # every rank draws the same dense initial values (the dense part is data-parallel: replicas must start equal); a
-    # row-sharded table is drawn per rank from the same stream, which only makes the shards look alike - harmless here
-    m = sb.SCORE(*ctor, device=local, adam_mode=args.adam_mode, use_graph=not args.no_graph, seed=1111, max_batch=B)
-    trainer = None
-    if world > 1:
-        trainer = (parallel.ShardedEmbeddingTrainer if par == "sharded" else parallel.DataParallelTrainer)(m, world, rank)
-    stream = torch.cuda.ExternalStream(m.stream(), device=torch.device("cuda", local))
-
     host_pool = [make_batch(shape, batch=B, seed=1000 * (rank + 1) + i, zipf=args.zipf) for i in range(POOL)]
     dev_pool = [tuple(torch.from_numpy(x).cuda() for x in b) for b in host_pool]
+
+    def build(par_):
+        ctor = list(shape.ctor_args())
+        if world > 1 and par_ == "sharded":
+            ctor[0] = parallel.shard_rows(shape.feature_size, world)
+        # every rank draws the same dense initial values (the dense part is data-parallel: replicas must start equal); a
+        # row-sharded table is drawn per rank from the same stream, which only makes the shards look alike - harmless here
+        m_ = sb.SCORE(*ctor, device=local, adam_mode=args.adam_mode, use_graph=not args.no_graph, seed=1111, max_batch=B)
+        t_ = None
+        if world > 1:
+            t_ = (parallel.ShardedEmbeddingTrainer if par_ == "sharded" else parallel.DataParallelTrainer)(m_, world, rank)
+        return m_, t_
+
+    # Multi-GPU on a table that fits one GPU: both schemes apply - replicated table + packed all-gather, or row-sharded
+    # table + all-to-all - and which one wins depends on N (the replicated update grows with the world size, the sharded
+    # exchange has a fixed latency): a short probe of both picks the faster one for this N (recorded in config)
+    par_probe = None
+    par = args.parallel
+    if par == "auto":
+        par = "sharded" if shape.feature_size > 50_000_000 else "dp"
+        if world > 1 and par == "dp":
+            par_probe = {}
+            for cand in ("dp", "sharded"):
+                m_, t_ = build(cand)
+                for i in range(8):
+                    t_.train_async(dev_pool[i % POOL], LR, REG)
+                t_.wait()
+                dist.barrier(); torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for i in range(30):
+                    t_.train_async(dev_pool[i % POOL], LR, REG)
+                t_.wait()
+                torch.cuda.synchronize()
+                tt = torch.tensor([(time.perf_counter() - t0) / 30 * 1e3], device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                par_probe[cand] = float(tt.item())
+                m_.close()
+                del m_, t_
+                torch.cuda.empty_cache()
+            par = min(par_probe, key=par_probe.get)
+    args.par = par if world > 1 else "single"
+    m, trainer = build(par)
+    stream = torch.cuda.ExternalStream(m.stream(), device=torch.device("cuda", local))
+
     pin_pool = [tuple(torch.from_numpy(x).pin_memory() for x in b) for b in host_pool]
     torch.cuda.synchronize()
 
@@ -461,7 +492,8 @@ def main():
         line = {"metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(shape, args, B * world),
+                "config": dict(workload_config(shape, args, B * world),
+                               **({"parallelism_probe_ms_per_step": par_probe} if par_probe else {})),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 16 if world == 1 else 20,

@@ -121,7 +121,9 @@ __global__ void build_keys_kernel(Dims dm, const BatchPtrs* __restrict__ bpp, in
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         old[u] = upto;
-        if (seen[u] < upto) old[u] = atomicExch(&ca.last_step[id[u]], upto);
+        // unsigned compare: last_step == -1 marks a row no optimizer step has touched (m = v = 0: every skipped
+        // zero-gradient step is exactly a no-op) - it is current by construction and never claimed
+        if ((uint32_t)seen[u] < (uint32_t)upto) old[u] = atomicExch(&ca.last_step[id[u]], upto);
         nwin += old[u] < upto ? 1 : 0;
     }
     // warp-aggregated append

@@ -301,8 +301,10 @@ int alloc_params(ScoreModel* h) {
     CK(cudaMemsetAsync(h->emb_tab, 0, sizeof(float) * V * h->es, h->st));
     h->emb = h->emb_tab; h->emb_m = h->emb_tab + d; h->emb_v = h->emb_tab + 2 * d;
     if (h->cfg.adam_mode != SCORE_ADAM_SPARSE) {
+        // -1 = no optimizer step has touched the row (its slots are zero, so the dense-gradient semantics leave it where it
+        // is): such rows are current by construction; anything that writes a row's slots stamps it with a real step
         CK(cudaMalloc(&h->last_step, sizeof(int32_t) * V));
-        CK(cudaMemsetAsync(h->last_step, 0, sizeof(int32_t) * V, h->st));
+        CK(cudaMemsetAsync(h->last_step, 0xff, sizeof(int32_t) * V, h->st));
     }
     const int64_t n = h->n_dense;
     CK(cudaMalloc(&h->P, sizeof(float) * n));
@@ -1438,7 +1440,13 @@ int score_set_tensor(ScoreHandle h, const char* name, const float* data, size_t 
     if (is_emb) {
         rc = flush_lazy(h);
         if (rc) return rc;
-        return emb_copy(h, p, 0, h->dm.V, const_cast<float*>(data), false);
+        rc = emb_copy(h, p, 0, h->dm.V, const_cast<float*>(data), false);
+        if (rc) return rc;
+        if (h->last_step) {   // externally written state: the rows count as touched (current at the present step)
+            launch_fill_i32(h->st, h->last_step, h->dm.V, h->step);
+            CK(cudaStreamSynchronize(h->st));
+        }
+        return SCORE_OK;
     }
     CK(cudaMemcpyAsync(p, data, cnt * sizeof(float), cudaMemcpyHostToDevice, h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -1468,7 +1476,13 @@ int score_set_rows(ScoreHandle h, const char* name, int64_t row0, int64_t nrows,
     if (row0 < 0 || nrows < 0 || row0 + nrows > h->dm.V) return fail(h, SCORE_ERR_ARG, "row range out of bounds");
     rc = flush_lazy(h);
     if (rc) return rc;
-    return emb_copy(h, p, row0, nrows, const_cast<float*>(data), false);
+    rc = emb_copy(h, p, row0, nrows, const_cast<float*>(data), false);
+    if (rc) return rc;
+    if (h->last_step && nrows > 0) {   // externally written rows count as touched (see alloc_params: last_step)
+        launch_fill_i32(h->st, h->last_step + row0, nrows, h->step);
+        CK(cudaStreamSynchronize(h->st));
+    }
+    return SCORE_OK;
 }
 
 // Checkpoint: "SCB2CKPT" | version | n tensors | per tensor {name, rows, cols, var, [Adam, Adam_1]} | beta powers.

@@ -966,7 +966,7 @@ __global__ void emb_claim_kernel(const int32_t* __restrict__ keys, int64_t n, in
     int old = upto;
     if (key > 0 && (int64_t)key < V) {
         const int seen = last_step[key];
-        if (seen < upto) {
+        if ((uint32_t)seen < (uint32_t)upto) {   // -1: never touched by an optimizer step, nothing to replay (build_keys_kernel)
             old = atomicExch(&last_step[key], upto);
             win = old < upto;
         }
@@ -1050,7 +1050,7 @@ __global__ void emb_catchup_all_kernel(float* __restrict__ emb, float* __restric
 }
 __global__ void set_last_step_kernel(int32_t* last_step, int64_t V, int upto) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < V && last_step[i] < upto) last_step[i] = upto;
+    if (i < V && (uint32_t)last_step[i] < (uint32_t)upto) last_step[i] = upto;   // the never-touched mark (-1) stays
 }
 void launch_emb_catchup_all(cudaStream_t st, float* emb, float* m, float* v, int32_t* last_step, int64_t V, int d, int es,
                             const float* alpha_hist, int upto) {

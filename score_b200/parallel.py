@@ -253,6 +253,7 @@ class ShardedEmbeddingTrainer(_Base):
         super().__init__(model, world, rank, group)
         self._bufs = {}
         self._pending = None      # (want, owned, n_recv) of a begun step whose score_step_finish is still to be enqueued
+        self.timeline = None      # tools/shard_timeline.py: {phase: [CUDA events]} recorded at the phase boundaries
         self._cm = (C.c_int32 * (self.world * (self.world + 1)))()
 
     def _buf(self, name, n, dtype):
@@ -269,9 +270,16 @@ class ShardedEmbeddingTrainer(_Base):
         ts = "<f4" if dtype == torch.float32 else "<i4"
         return torch.as_tensor(_DevView(ptr, (int(n),), ts), device=self.device)
 
+    def _mark(self, name):
+        if self.timeline is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(self.stream)
+            self.timeline.setdefault(name, []).append(e)
+
     def _plan(self, b):
         """-> (send_counts, recv_counts, n_valid, n_recv, plan struct); one host synchronisation."""
         W = self.world
+        self._mark("start")
         self.m._check(self.lib.score_prepare_batch(self.h, C.byref(b.struct)))
         plan = _capi.ScoreShardPlan()
         self.m._check(self.lib.score_shard_plan(self.h, W, C.byref(plan)))
@@ -285,7 +293,9 @@ class ShardedEmbeddingTrainer(_Base):
         # between, so the device is busy while the host waits for the sizes
         nn = W * (W + 1)
         self.m._check(self.lib.score_shard_counts_fetch(self.h, mat.data_ptr(), nn))
+        self._mark("plan+counts")
         self._flush_finish()
+        self._mark("finish(prev)")
         self.m._check(self.lib.score_shard_counts_wait(self.h, self._cm, nn))
         cm = list(self._cm)
         send_counts = cm[self.rank * (W + 1):self.rank * (W + 1) + W]
@@ -317,14 +327,17 @@ class ShardedEmbeddingTrainer(_Base):
             dist.all_to_all_single(want, send_rows, recv_counts, send_counts, group=self.group)
         else:
             want.copy_(send_rows)
+        self._mark("a2a ids")
         served = self._buf("served", n_recv * d, torch.float32).view(n_recv, d)
         self.m._check(self.lib.score_gather_rows(self.h, want.data_ptr(), n_recv, served.data_ptr()))
+        self._mark("gather")
         staged = self._view(plan.staged, (plan.n_positions + 1) * d, torch.float32).view(-1, d)
         got = staged[1:1 + n_valid]
         if self.world > 1:
             dist.all_to_all_single(got, served, send_counts, recv_counts, group=self.group)
         else:
             got.copy_(served)
+        self._mark("a2a rows")
         return plan, want, (send_counts, recv_counts, n_valid, n_recv)
 
     def train(self, sess, batch_data, lr, reg_lambda, keep_prob=TRAIN_KEEP_PROB, want_loss=True):
@@ -338,16 +351,20 @@ class ShardedEmbeddingTrainer(_Base):
             # the owner-side key list is complete: its sort runs on the side stream under forward / backward
             self.m._check(self.lib.score_shard_presort(self.h, want.data_ptr(), n_recv))
             self.m._check(self.lib.score_step_begin(self.h, None, lr, reg_lambda, keep_prob, gb, 1, plan.staged, plan.mini_keys))
+            self._mark("fwd+bwd")
             g = self._dev("dense_grad", torch.float32)
             if self.world > 1:
                 dist.all_reduce(g, group=self.group)
+            self._mark("allreduce")
             self.m._check(self.lib.score_shard_pack_grads(self.h))
+            self._mark("pack")
             gsend = self._view(plan.grad_send, n_valid * d, torch.float32).view(n_valid, d)
             owned = self._buf("owned", n_recv * d, torch.float32).view(n_recv, d)
             if self.world > 1:
                 dist.all_to_all_single(owned, gsend, recv_counts, send_counts, group=self.group)
             else:
                 owned.copy_(gsend)
+            self._mark("a2a grads")
             self._pending = (want, owned, n_recv)
             if not want_loss:
                 return None        # the optimizer half rides behind the next call's plan (or wait())

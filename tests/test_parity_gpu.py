@@ -714,3 +714,24 @@ def test_shard_plan_kernel_groups_positions_by_owner(world):
     want_mini[order[:n_valid]] = np.arange(1, n_valid + 1)
     assert np.array_equal(mini, want_mini)
     m.close()
+
+
+def test_lazy_never_touched_mark_equals_dense():
+    """device-initialised tables keep last_step = -1 for rows no optimizer step has touched (nothing to replay: their
+    slots are zero); LAZY with that mark must stay bit-identical to DENSE, rows re-touched after gaps included, and a
+    row written from outside (set_rows) loses the mark."""
+    shape = SHAPES["tiny_tb"]
+    batches = [make_batch(shape, seed=60 + (i % 3)) for i in range(7)]
+    out = {}
+    for mode in ("dense", "lazy"):
+        m = sb.SCORE(*shape.ctor_args(), adam_mode=mode, init_weights=True, seed=77, use_graph=(mode == "lazy"))
+        losses = [m.train(None, b, 1e-3, 1e-4, keep_prob=1.0) for b in batches[:4]]
+        # rewrite the slots of a few rows from outside in the middle of the run (same values in both modes)
+        rows = np.full((5, shape.eb_dim), 0.01, np.float32)
+        m._check(m._lib.score_set_rows(m._h, b"emb_mtx/Adam", 10, 5, rows.ctypes.data))
+        losses += [m.train(None, b, 1e-3, 1e-4, keep_prob=1.0) for b in batches[4:]]
+        out[mode] = (losses, m.get_tensor("emb_mtx"), m.get_tensor("emb_mtx/Adam"), m.get_tensor("emb_mtx/Adam_1"))
+        m.close()
+    assert out["dense"][0] == out["lazy"][0]
+    for a, b in zip(out["dense"][1:], out["lazy"][1:]):
+        assert np.array_equal(a, b)
