@@ -190,10 +190,13 @@ def large_vocab_leg(args, world, rank, local, steps=30, warmup=5):
         m = sb.SCORE(*ctor, device=local, adam_mode=args.adam_mode, use_graph=not args.no_graph, seed=1111, max_batch=shape.batch)
         trainer = parallel.ShardedEmbeddingTrainer(m, world, rank) if sharded else None
         stream = torch.cuda.ExternalStream(m.stream(), device=dev)
-        pool = [tuple(torch.from_numpy(x).cuda() for x in make_batch(shape, seed=7000 * (rank + 1) + i)) for i in range(8)]
+        # one distinct batch per step: with uniform ids over 10^8 rows a row practically never comes back, a short
+        # rotating pool would make EVERY row of a batch stale by pool-size steps and bill that replay to the step
+        npool = steps + warmup + 1
+        pool = [tuple(torch.from_numpy(x).cuda() for x in make_batch(shape, seed=7000 * (rank + 1) + i)) for i in range(npool)]
 
         def step(i):
-            (trainer or m).train_async(pool[i % 8], LR, REG)
+            (trainer or m).train_async(pool[i % npool], LR, REG)
 
         for i in range(warmup):
             step(i)
@@ -203,7 +206,7 @@ def large_vocab_leg(args, world, rank, local, steps=30, warmup=5):
         with torch.cuda.stream(stream):
             e0.record(stream)
             for i in range(steps):
-                step(i)
+                step(warmup + i)
             if trainer:
                 trainer._flush_finish()       # the last step's deferred optimizer half belongs to the timed region
             e1.record(stream)
@@ -211,7 +214,7 @@ def large_vocab_leg(args, world, rank, local, steps=30, warmup=5):
         dist.barrier(); torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        loss = (trainer.train(None, pool[0], LR, REG) if trainer else m.train(None, pool[0], LR, REG))
+        loss = (trainer.train(None, pool[-1], LR, REG) if trainer else m.train(None, pool[-1], LR, REG))
         m.close()
         del pool, m, trainer
         torch.cuda.empty_cache()

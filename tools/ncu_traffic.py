@@ -7,7 +7,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KERNELS = {"coatt_fwd": "coatt_fwd_kernel", "coatt_bwd": "coatt_bwd_kernel", "emb_update": "emb_update_kernel",
+# substring match; the lean instances (coatt.cu) are coatt_fwd_lean_kernel / coatt_bwd_lean_kernel
+KERNELS = {"coatt_fwd": "coatt_fwd_", "coatt_bwd": "coatt_bwd_", "emb_update": "emb_update_kernel",
            "emb_replay": "emb_replay_kernel", "build_keys": "build_keys_kernel"}
 
 
