@@ -6,6 +6,8 @@
 //           time loop into one SGEMM over all B*T rows (px); this kernel runs the recurrence with
 //           the state-side weights resident in shared memory.
 //   (attention() + pooling live in attn.cu, build_fc_net + log-loss in chain.cu)
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace score {
@@ -92,9 +94,21 @@ __global__ void gru_fwd_kernel(Dims dm, GruArgs a, int RB) {
     if (a.last && row_ok && j < H) a.last[(int64_t)b * a.ldlast + side * H + j] = hs[r * H + j];
 }
 
+// Rows per CTA.  A CTA keeps the state-side kernels in shared memory ((2H+1) H + (H+1) H floats: 12 KB at H = 32, 198 KB at
+// H = 128) and a thread owns one (row, column) pair, so the rows of a CTA share one copy of the weights: with 256 threads
+// H = 128 left ONE row per CTA - 2 048 CTAs each pulling 198 KB through L2 for six recurrence steps (ncu: 430 + 487 us per
+// step of the large-vocab shape).  Wide cells therefore take 1 024-thread CTAs (4 rows at H = 128); SCORE_GRU_THREADS overrides.
+static int gru_threads(int H) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("SCORE_GRU_THREADS"); forced = e ? atoi(e) : 0; }
+    int t = forced > 0 ? forced : (2 * H >= 256 ? 1024 : 256);
+    if (t > 1024) t = 1024;
+    if (t < 2 * H) t = 2 * H;
+    return t;
+}
 static void gru_geometry(const Dims& dm, int* RB, size_t* smem, bool bwd) {
     int h2 = 2 * dm.H;
-    int rb = 256 / h2;
+    int rb = gru_threads(dm.H) / h2;
     if (rb < 1) rb = 1;
     *RB = rb;
     size_t fl = (size_t)dm.H * (h2 + 1) + (size_t)dm.H * (dm.H + 1) + (size_t)rb * dm.H * (bwd ? 5 : 3);
