@@ -491,6 +491,10 @@ def main():
                   "timing": "CUDA events around the kernel on its own stream inside every step of a second timed region "
                             "of the same K steps (ms_per_step_probed; the event nodes add ~3 us to each bracketed kernel)",
                   "bytes_per_launch": scatter_bytes, "ms_per_launch": t_s, "unique_rows": uniq,
+                  "random_access_ceiling": {"frac": 0.41, "what": "a kernel that ONLY reads and rewrites the same number of "
+                                                                   "random 192-byte records (var | m | v)",
+                                            "source": "tools/randrow_bench.cu, profiles/r2d_randrow_bench.txt (d = 16 tables)"}
+                  if d == 16 else None,
                   "bytes_rule": "live ids x (4 + 4d) + unique rows x 6 x 4d"}
         line = {"metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
