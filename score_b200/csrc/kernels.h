@@ -288,6 +288,10 @@ struct SortBufs {
     uint32_t* hist;                        // [256 * nblocks]
     int32_t* runs;                         // [8 * n_cap] short-run descriptors of the sorted list (launch_emb_runs)
     int32_t* runs_long;                    // [4 * emb_runs_long_cap(n_cap)] medium / long run descriptors
+    // runs longer than RUN_CHUNK entries are reduced by several CTAs (one chunk each) and combined in chunk order:
+    float* part;                           // [emb_runs_part_cap(n_cap) * d] partial sums, one row per chunk
+    int32_t* slotinfo;                     // [4 * emb_runs_part_cap(n_cap)] per chunk {first chunk slot of its run, chunks, run start, 0}
+    int32_t* done;                         // [emb_runs_part_cap(n_cap)] chunks finished per run (zero between launches)
     int n_cap;
 };
 size_t sort_hist_elems(int64_t n);
@@ -303,12 +307,15 @@ int launch_sort_passes(cudaStream_t st, SortBufs& sb, const int32_t* keys_in, in
 //   runs_long  4 int32 per longer run {key, start, count, 0}: runs of up to RUN_M (32, scatter.cu) entries from the front, longer ones from
 //              the back of a buffer of emb_runs_long_cap(n) descriptors
 //   counters   4 int32: number of short / medium / long runs, and of all runs (= unique rows)
+//   counters   8 int32: [0..2] number of short / medium / long descriptors, [3] all runs (= unique rows), [4] chunk slots used
 int64_t emb_runs_long_cap(int64_t n);
+int64_t emb_runs_part_cap(int64_t n);
 void launch_emb_runs(cudaStream_t st, const int32_t* skeys, const int32_t* spos, int64_t n, int32_t* runs,
-                     int32_t* runs_long, int32_t* counters);
+                     int32_t* runs_long, int32_t* counters, int32_t* slotinfo);
 struct EmbUpdateArgs {
     const int32_t* skeys; const int32_t* spos; int64_t n;
     const int32_t* runs; const int32_t* runs_long; int64_t long_cap; const int32_t* counters;   // from launch_emb_runs
+    float* part; const int32_t* slotinfo; int32_t* done;                                       // chunked long runs (SortBufs)
     const float* grad_rows; int d;
     float* emb; float* m; float* v; int es; int32_t* last_step;   // es: floats between consecutive rows of emb / m / v
     const float* alpha_hist;       // LAZY: rows that are not current through step-1 are replayed first (may be null)

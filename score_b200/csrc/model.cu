@@ -326,8 +326,8 @@ int alloc_params(ScoreModel* h) {
     CK(cudaMemcpy(h->flags, fl.data(), n, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&h->claim_counter, 2 * sizeof(int32_t)));   // ping-pong pair (build_keys / emb_replay)
     CK(cudaMemsetAsync(h->claim_counter, 0, 2 * sizeof(int32_t), h->st));
-    CK(cudaMalloc(&h->n_heads_dev, 4 * sizeof(int32_t)));
-    CK(cudaMemsetAsync(h->n_heads_dev, 0, 4 * sizeof(int32_t), h->st));
+    CK(cudaMalloc(&h->n_heads_dev, 8 * sizeof(int32_t)));
+    CK(cudaMemsetAsync(h->n_heads_dev, 0, 8 * sizeof(int32_t), h->st));
     CK(cudaMalloc(&h->l2sum, sizeof(float) * L2_PARTS));
     CK(cudaMalloc(&h->loss_dev, 2 * sizeof(float)));
     CK(cudaMallocHost(&h->early_host, 4 * sizeof(float)));   // page-locked: the device writes the result packet into it
@@ -465,6 +465,9 @@ int ensure_workspace(ScoreModel* h, int B) {
     WSI(h->sb.vals[0], N, nullptr); WSI(h->sb.vals[1], N, nullptr);
     WSI(h->sb.runs, 8 * N, nullptr);
     WSI(h->sb.runs_long, 4 * emb_runs_long_cap(N), nullptr);
+    WS(h->sb.part, emb_runs_part_cap(N) * dm.d, nullptr);
+    WSI(h->sb.slotinfo, 4 * emb_runs_part_cap(N), nullptr);
+    WSI(h->sb.done, emb_runs_part_cap(N), nullptr);
     {
         uint32_t* hist = nullptr;
         int rc = ws_alloc(h, &hist, sort_hist_elems(N), nullptr);
@@ -580,7 +583,7 @@ void enqueue_sort_branch(ScoreModel* h, cudaEvent_t after, int part = 0) {
     if (part != 2) probe_begin(h, PR_SORT, h->st2);
     if (part == 1) { h->sort_out = launch_sort_passes(h->st2, h->sb, h->keys, dm.N, 0, 1); return; }
     h->sort_out = launch_sort_passes(h->st2, h->sb, h->keys, dm.N, part == 2 ? 1 : 0, np);
-    launch_emb_runs(h->st2, h->sb.keys[h->sort_out], h->sb.vals[h->sort_out], dm.N, h->sb.runs, h->sb.runs_long, h->n_heads_dev);
+    launch_emb_runs(h->st2, h->sb.keys[h->sort_out], h->sb.vals[h->sort_out], dm.N, h->sb.runs, h->sb.runs_long, h->n_heads_dev, h->sb.slotinfo);
     probe_end(h, PR_SORT, h->st2);
     if (h->sort_dp) {
         // data-parallel half-step: the host sizes the exchange from the unique-row count - publish it as soon as it
@@ -899,6 +902,7 @@ void enqueue_step(ScoreModel* h, int mode) {
         EmbUpdateArgs ea{};
         ea.skeys = h->sb.keys[h->sort_out]; ea.spos = h->sb.vals[h->sort_out]; ea.n = dm.N;
         ea.runs = h->sb.runs; ea.runs_long = h->sb.runs_long; ea.long_cap = emb_runs_long_cap(dm.N); ea.counters = h->n_heads_dev;
+        ea.part = h->sb.part; ea.slotinfo = h->sb.slotinfo; ea.done = h->sb.done;
         ea.grad_rows = h->grad_rows; ea.d = dm.d; ea.hp = h->hyper_dev; ea.mode = 1;
         ea.out_rows = h->seg_rows; ea.out_heads = h->seg_heads;
         launch_emb_update(h->st, ea);
@@ -907,6 +911,7 @@ void enqueue_step(ScoreModel* h, int mode) {
         EmbUpdateArgs ea{};
         ea.skeys = h->sb.keys[h->sort_out]; ea.spos = h->sb.vals[h->sort_out]; ea.n = dm.N;
         ea.runs = h->sb.runs; ea.runs_long = h->sb.runs_long; ea.long_cap = emb_runs_long_cap(dm.N); ea.counters = h->n_heads_dev;
+        ea.part = h->sb.part; ea.slotinfo = h->sb.slotinfo; ea.done = h->sb.done;
         ea.grad_rows = h->grad_rows; ea.d = dm.d;
         ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.es = h->es; ea.last_step = h->last_step;
         ea.alpha_hist = h->alpha_hist;
@@ -1633,6 +1638,9 @@ int ensure_ext_sort(ScoreModel* h, int64_t n) {
     if (h->sb_ext.hist) cudaFree(h->sb_ext.hist);
     if (h->sb_ext.runs) cudaFree(h->sb_ext.runs);
     if (h->sb_ext.runs_long) cudaFree(h->sb_ext.runs_long);
+    if (h->sb_ext.part) cudaFree(h->sb_ext.part);
+    if (h->sb_ext.slotinfo) cudaFree(h->sb_ext.slotinfo);
+    if (h->sb_ext.done) cudaFree(h->sb_ext.done);
     int64_t cap = n + n / 4 + 1024;
     for (int i = 0; i < 2; ++i) {
         CK(cudaMalloc(&h->sb_ext.keys[i], sizeof(int32_t) * cap));
@@ -1641,6 +1649,10 @@ int ensure_ext_sort(ScoreModel* h, int64_t n) {
     CK(cudaMalloc(&h->sb_ext.hist, sizeof(uint32_t) * sort_hist_elems(cap)));
     CK(cudaMalloc(&h->sb_ext.runs, sizeof(int32_t) * 8 * cap));
     CK(cudaMalloc(&h->sb_ext.runs_long, sizeof(int32_t) * 4 * emb_runs_long_cap(cap)));
+    CK(cudaMalloc(&h->sb_ext.part, sizeof(float) * emb_runs_part_cap(cap) * h->dm.d));
+    CK(cudaMalloc(&h->sb_ext.slotinfo, sizeof(int32_t) * 4 * emb_runs_part_cap(cap)));
+    CK(cudaMalloc(&h->sb_ext.done, sizeof(int32_t) * emb_runs_part_cap(cap)));
+    CK(cudaMemsetAsync(h->sb_ext.done, 0, sizeof(int32_t) * emb_runs_part_cap(cap), h->st));
     h->sb_ext_cap = cap;
     return SCORE_OK;
 }
@@ -1808,7 +1820,7 @@ int score_shard_presort(ScoreHandle h, const int32_t* ext_keys, int64_t n_ext) {
     CK(cudaEventRecord(e, h->st));                 // the key list is complete (the exchange ran on the main stream)
     CK(cudaStreamWaitEvent(h->st2, e, 0));
     const int out = launch_sort_pairs(h->st2, h->sb_ext, ext_keys, n_ext, key_bits(h->dm.V));
-    launch_emb_runs(h->st2, h->sb_ext.keys[out], h->sb_ext.vals[out], n_ext, h->sb_ext.runs, h->sb_ext.runs_long, h->n_heads_dev);
+    launch_emb_runs(h->st2, h->sb_ext.keys[out], h->sb_ext.vals[out], n_ext, h->sb_ext.runs, h->sb_ext.runs_long, h->n_heads_dev, h->sb_ext.slotinfo);
     CK(cudaEventRecord(h->ev_presort, h->st2));
     h->presorted_keys = ext_keys; h->presorted_n = n_ext; h->presorted_out = out;
     CK(cudaGetLastError());
@@ -1973,6 +1985,7 @@ int score_dp_pack(ScoreHandle h, int64_t cap, void** block_dev, int64_t* block_w
     EmbUpdateArgs ea{};
     ea.skeys = h->sb.keys[h->sort_out]; ea.spos = h->sb.vals[h->sort_out]; ea.n = dm.N;
     ea.runs = h->sb.runs; ea.runs_long = h->sb.runs_long; ea.long_cap = emb_runs_long_cap(dm.N); ea.counters = h->n_heads_dev;
+        ea.part = h->sb.part; ea.slotinfo = h->sb.slotinfo; ea.done = h->sb.done;
     ea.grad_rows = h->grad_rows; ea.d = dm.d; ea.hp = h->hyper_dev; ea.mode = 2;
     ea.out_heads = blk + L.keys_off; ea.out_rows = reinterpret_cast<float*>(blk + L.keys_off + cap);
     ea.head_slot = h->head_slot; ea.out_cap = cap;
@@ -2060,12 +2073,13 @@ int score_step_finish(ScoreHandle h, const int32_t* ext_keys, const float* ext_r
                 int rc = ensure_ext_sort(h, n_ext);
                 if (rc) return rc;
                 out = launch_sort_pairs(h->st, h->sb_ext, ext_keys, n_ext, key_bits(h->dm.V));
-                launch_emb_runs(h->st, h->sb_ext.keys[out], h->sb_ext.vals[out], n_ext, h->sb_ext.runs, h->sb_ext.runs_long, h->n_heads_dev);
+                launch_emb_runs(h->st, h->sb_ext.keys[out], h->sb_ext.vals[out], n_ext, h->sb_ext.runs, h->sb_ext.runs_long, h->n_heads_dev, h->sb_ext.slotinfo);
             }
             h->presorted_keys = nullptr; h->presorted_n = 0;
             EmbUpdateArgs ea{};
             ea.skeys = h->sb_ext.keys[out]; ea.spos = h->sb_ext.vals[out]; ea.n = n_ext;
             ea.runs = h->sb_ext.runs; ea.runs_long = h->sb_ext.runs_long; ea.long_cap = emb_runs_long_cap(n_ext); ea.counters = h->n_heads_dev;
+            ea.part = h->sb_ext.part; ea.slotinfo = h->sb_ext.slotinfo; ea.done = h->sb_ext.done;
             ea.grad_rows = ext_rows; ea.d = h->dm.d;
             ea.emb = h->emb; ea.m = h->emb_m; ea.v = h->emb_v; ea.es = h->es; ea.last_step = h->last_step;
             ea.alpha_hist = h->alpha_hist; ea.hp = h->hyper_dev; ea.mode = 0;

@@ -334,6 +334,10 @@ __device__ __forceinline__ void replay4(float4& var, float4& m, float4& v, int f
 // emb_runs_kernel (on the sort stream, off the critical path) builds the three descriptor lists; the order inside a
 // list comes from atomics and only decides which threads serve which run.
 constexpr int RUN_S_MAX = 4;
+// A run of more than RUN_CHUNK entries (a hot side-feature id, a Zipf head item: tens of thousands of positions) is cut
+// into chunks of RUN_CHUNK entries, one CTA each; the CTA that finishes last adds the chunk sums IN CHUNK ORDER and
+// applies the row's optimizer step.  The summation tree still depends on the run length only.
+constexpr int RUN_CHUNK = 2048;
 // Upper length of tier M.  A team of 16 lanes needs ceil(n/16) dependent load rounds for a run of n entries, a CTA one
 // round for up to 256, so the break-even is around 32 entries.  Measured on B200 (Taobao shape, uniform ids, longest
 // run 207): 32 and 512 give the same 30 us inside the step - the hot runs are not what bounds the kernel there - so
@@ -353,7 +357,7 @@ static int run_m_max() {
 
 __global__ void emb_runs_kernel(const int32_t* __restrict__ skeys, const int32_t* __restrict__ spos, int64_t n,
                                 int4* __restrict__ runs, int4* __restrict__ runs_long, int64_t long_cap,
-                                int32_t* __restrict__ counters, int m_max) {
+                                int32_t* __restrict__ counters, int m_max, int4* __restrict__ slotinfo) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int32_t key = 0, prev = -1;
@@ -397,18 +401,27 @@ __global__ void emb_runs_kernel(const int32_t* __restrict__ skeys, const int32_t
     if (cnt <= m_max) {
         const int slot = atomicAdd(counters + 1, 1);
         runs_long[slot] = make_int4(key, (int32_t)i, cnt, 0);              // M list grows from the front
-    } else {
+    } else if (cnt <= RUN_CHUNK || !slotinfo) {
         const int slot = atomicAdd(counters + 2, 1);
-        runs_long[long_cap - 1 - slot] = make_int4(key, (int32_t)i, cnt, 0);   // L list grows from the back
+        runs_long[long_cap - 1 - slot] = make_int4(key, (int32_t)i, cnt, -1);   // L list grows from the back; -1: one chunk
+    } else {
+        const int nch = (cnt + RUN_CHUNK - 1) / RUN_CHUNK;
+        const int slot = atomicAdd(counters + 2, nch), pb = atomicAdd(counters + 4, nch);
+        for (int c = 0; c < nch; ++c) {
+            const int len = min(RUN_CHUNK, cnt - c * RUN_CHUNK);
+            runs_long[long_cap - 1 - (slot + c)] = make_int4(key, (int32_t)i + c * RUN_CHUNK, len, pb + c);
+            slotinfo[pb + c] = make_int4(pb, nch, (int32_t)i, 0);
+        }
     }
 }
-int64_t emb_runs_long_cap(int64_t n) { return n / (RUN_S_MAX + 1) + n / (RUN_M_FLOOR + 1) + 8; }
+int64_t emb_runs_long_cap(int64_t n) { return n / (RUN_S_MAX + 1) + n / (RUN_M_FLOOR + 1) + n / RUN_CHUNK + 16; }
+int64_t emb_runs_part_cap(int64_t n) { return 2 * (n / RUN_CHUNK) + 16; }   // sum over long runs of ceil(cnt / RUN_CHUNK) <= 2n / RUN_CHUNK
 void launch_emb_runs(cudaStream_t st, const int32_t* skeys, const int32_t* spos, int64_t n, int32_t* runs,
-                     int32_t* runs_long, int32_t* counters) {
-    cudaMemsetAsync(counters, 0, 4 * sizeof(int32_t), st);
+                     int32_t* runs_long, int32_t* counters, int32_t* slotinfo) {
+    cudaMemsetAsync(counters, 0, 8 * sizeof(int32_t), st);
     emb_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(skeys, spos, n, reinterpret_cast<int4*>(runs),
                                                                  reinterpret_cast<int4*>(runs_long), emb_runs_long_cap(n),
-                                                                 counters, run_m_max());
+                                                                 counters, run_m_max(), reinterpret_cast<int4*>(slotinfo));
     ++g_launch_count;
 }
 
@@ -663,13 +676,14 @@ __global__ void __launch_bounds__(256) emb_update_kernel(EmbUpdateArgs a) {
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const int4* __restrict__ runs_long = reinterpret_cast<const int4*>(a.runs_long);
 
-    // ---- tier L: one CTA per run
+    // ---- tier L: one CTA per run, or per RUN_CHUNK-entry chunk of a longer run (descriptor .w = chunk slot, -1: whole run)
+    __shared__ int s_last;
     for (int r = blockIdx.x; r < nL; r += gridDim.x) {
         const int4 dsc = runs_long[a.long_cap - 1 - r];
-        const int32_t key = dsc.x, start = dsc.y, cnt = dsc.z;
+        const int32_t key = dsc.x, start = dsc.y, cnt = dsc.z, cslot = dsc.w;
         const bool owner = threadIdx.x < LPR;
         float4 var = z4, m = z4, v = z4; int last = 0;
-        if (owner && !EXPORT) {
+        if (owner && !EXPORT && cslot < 0) {
             const int64_t off = (int64_t)key * a.es + sub * 4;
             var = *reinterpret_cast<const float4*>(a.emb + off);
             m = *reinterpret_cast<const float4*>(a.m + off);
@@ -680,12 +694,42 @@ __global__ void __launch_bounds__(256) emb_update_kernel(EmbUpdateArgs a) {
         const float4 wtot = emb_team_combine<LPR, 32>(part, lane);
         if (lane < LPR) red[warp][lane] = wtot;
         __syncthreads();
+        float4 acc = z4;
         if (owner) {
-            float4 acc = red[0][sub];
+            acc = red[0][sub];
 #pragma unroll
             for (int w = 1; w < 8; ++w) add4(acc, red[w][sub]);
-            emb_apply_row<EXPORT, LPR>(a, key, EXPORT == 2 ? (int64_t)a.head_slot[start] : (int64_t)start, acc, var, m, v, last, sub,
-                                       alpha, step);
+        }
+        if (cslot < 0) {
+            if (owner)
+                emb_apply_row<EXPORT, LPR>(a, key, EXPORT == 2 ? (int64_t)a.head_slot[start] : (int64_t)start, acc, var, m, v, last, sub,
+                                           alpha, step);
+        } else {
+            // chunk of a long run: publish the chunk sum; the CTA that completes the run adds the chunks in chunk order
+            const int4 info = reinterpret_cast<const int4*>(a.slotinfo)[cslot];   // {first slot, chunks, run start}
+            if (owner) *reinterpret_cast<float4*>(a.part + (int64_t)cslot * D + sub * 4) = acc;
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) s_last = (atomicAdd(a.done + info.x, 1) == info.y - 1) ? 1 : 0;
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                if (owner) {
+                    if (!EXPORT) {
+                        const int64_t off = (int64_t)key * a.es + sub * 4;
+                        var = *reinterpret_cast<const float4*>(a.emb + off);
+                        m = *reinterpret_cast<const float4*>(a.m + off);
+                        v = *reinterpret_cast<const float4*>(a.v + off);
+                        if (a.alpha_hist) last = a.last_step[key];
+                    }
+                    const float* pp = a.part + (int64_t)info.x * D + sub * 4;
+                    float4 tot = __ldcg(reinterpret_cast<const float4*>(pp));
+                    for (int c = 1; c < info.y; ++c) add4(tot, __ldcg(reinterpret_cast<const float4*>(pp + (int64_t)c * D)));
+                    emb_apply_row<EXPORT, LPR>(a, key, EXPORT == 2 ? (int64_t)a.head_slot[info.z] : (int64_t)info.z, tot, var, m, v, last,
+                                               sub, alpha, step);
+                }
+                if (threadIdx.x == 0) a.done[info.x] = 0;   // ready for the next launch
+            }
         }
         __syncthreads();
     }

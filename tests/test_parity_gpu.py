@@ -735,3 +735,38 @@ def test_lazy_never_touched_mark_equals_dense():
     assert out["dense"][0] == out["lazy"][0]
     for a, b in zip(out["dense"][1:], out["lazy"][1:]):
         assert np.array_equal(a, b)
+
+
+def test_hot_row_longer_than_a_chunk():
+    """one side-feature id on every item (a run of ~10 K positions in the sorted list, 5 chunks of RUN_CHUNK = 2048,
+    scatter.cu): the chunked long-run reduce of the scatter kernel against the oracle, gradient rows and three optimizer
+    steps, LAZY == DENSE bitwise"""
+    shape = SHAPES["tiny_tb"]
+    hot = shape.feature_size - 1
+
+    def batch(seed):
+        b = [x.copy() for x in make_batch(shape, seed=seed)]
+        for k in (0, 3, 5):                      # user_1hop, item_2hop, target_item carry item nodes: field 1 = side feature
+            live = b[k][..., 0] != 0
+            b[k][..., 1] = np.where(live, hot, 0)
+        return tuple(b)
+
+    rep = pu.forward_backward_report(shape, batch(5))
+    # the hot row is a cancelling sum of ~10 K gradient rows: its entries carry ~sqrt(10^4) * 2^-24 of the TERM scale in any
+    # summation order, above the 1e-6 absolute part of the elementwise bar (the normwise 1e-5 bar stays)
+    assert rep.pop("elem/emb_row_grads") <= 4.0
+    _check_fb(rep)
+    keys = np.concatenate([np.asarray(x).reshape(-1) for x in batch(5)[:6]])
+    assert (keys == hot).sum() > 3 * 2048
+    out = {}
+    for mode in ("dense", "lazy"):
+        cfg, params, m = pu.make_models(shape, adam_mode=mode)
+        losses = [m.train(None, batch(50 + i), 1e-3, 1e-4, keep_prob=1.0) for i in range(3)]
+        out[mode] = (losses, m.get_tensor("emb_mtx"), m.get_tensor("emb_mtx/Adam_1"))
+        m.close()
+    assert out["dense"][0] == out["lazy"][0]
+    assert np.array_equal(out["dense"][1], out["lazy"][1]) and np.array_equal(out["dense"][2], out["lazy"][2])
+    orc = ref.ScoreOracle(*shape.ctor_args(), seed=7)
+    lo = [orc.train(None, batch(50 + i), 1e-3, 1e-4, keep_prob=1.0) for i in range(3)]
+    assert pu.rel_err(out["lazy"][0], lo) <= 1e-5
+    assert pu.rel_err(out["lazy"][1][hot], orc.params["emb_mtx"].numpy()[hot]) <= 1e-5
