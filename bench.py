@@ -253,8 +253,14 @@ def main():
                     help="N>1: dp = replicated table + gradient all-gather, sharded = row-sharded table + all-to-all")
     ap.add_argument("--no-large-vocab", action="store_true",
                     help="N>1: skip the extra large_vocab leg (row-sharded 200 M-row table + the 1-GPU 25 M-row shard)")
+    ap.add_argument("--watchdog", type=int, default=env_int("SCORE_BENCH_WATCHDOG", 480),
+                    help="seconds after which every thread's stack is dumped to stderr and the process exits (a stuck "
+                         "collective must not hang the caller); 0 disables")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.watchdog > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
     # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner) go to stderr instead
     json_fd = os.dup(1)
     os.dup2(2, 1)
@@ -399,12 +405,19 @@ def main():
         ms_p, _ = timed_region(args.steps)
         ms_probed = ms_p / args.steps
         probes = m.probe_times()
-    if rank == 0 and len(sampler.rows) < 3:      # very short runs: keep the load up until a few samples exist
-        t_end = time.perf_counter() + 1.0
-        while len(sampler.rows) < 3 and time.perf_counter() < t_end:
-            for i in range(20):
-                step_dev(i)
-            wait_all()
+    # very short runs: keep the load up until a few clock samples exist.  The steps are collective at N > 1, so rank 0
+    # (which owns the sampler) decides and every rank follows the broadcast decision
+    for _ in range(10):
+        need = 1 if (rank == 0 and len(sampler.rows) < 3) else 0
+        if world > 1:
+            flag = torch.tensor([need], device="cuda")
+            dist.broadcast(flag, 0)
+            need = int(flag.item())
+        if not need:
+            break
+        for i in range(40):
+            step_dev(i)
+        wait_all()
     clocks = sampler.stop() if rank == 0 else None
     stats = m.last_step_stats()
 

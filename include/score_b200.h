@@ -194,6 +194,18 @@ int score_shard_pack_grads(ScoreHandle h);
 int score_shard_counts_fetch(ScoreHandle h, const int32_t* counts_dev, int32_t n);
 int score_shard_counts_wait(ScoreHandle h, int32_t* out, int32_t n);
 int score_shard_presort(ScoreHandle h, const int32_t* ext_keys, int64_t n_ext);
+/* Peer-memory exchange (NVLink / NVSwitch): gather and pack FUSED with the all-to-all.  count_matrix_dev = the all-gathered
+ * [world][world+1] counts on the device; peers[r] = rank r's destination buffer as mapped into this process (device
+ * addresses, e.g. torch symmetric memory).  score_shard_serve_push: LAZY catch-up of the served rows, then every served row is
+ * stored straight into its requester's staged table (row slot+1, the layout of score_shard_plan).  score_shard_grad_push: every
+ * gradient row is stored straight into its owner's gradient buffer, grouped by requester - the order score_step_finish
+ * expects next to the served key list.  The caller runs a cross-rank barrier on score_stream() after each.
+ * score_shard_register_staged: staged tables owned by the caller (two, alternating steps) whose addresses are stable, so the
+ * half-step on them is replayed as a CUDA graph. */
+int score_shard_serve_push(ScoreHandle h, const int32_t* want_dev, int64_t n_recv, const int32_t* count_matrix_dev,
+                           int32_t world, int32_t rank, const uint64_t* peers);
+int score_shard_grad_push(ScoreHandle h, const int32_t* count_matrix_dev, int32_t world, int32_t rank, const uint64_t* peers);
+int score_shard_register_staged(ScoreHandle h, const float* a, const float* b);
 
 /* Global index of the first sample of the batches this handle steps on (a data-parallel rank: rank * per-rank batch;
  * default 0).  It keys the dropout stream of tf.nn.dropout's stand-in (score.py:71-73), so N ranks draw the masks one

@@ -79,6 +79,9 @@ SYMBOLS = {
     "score_shard_counts_fetch": (C.c_int, [_H, C.c_void_p, C.c_int32]),
     "score_shard_counts_wait": (C.c_int, [_H, C.c_void_p, C.c_int32]),
     "score_shard_presort": (C.c_int, [_H, C.c_void_p, C.c_int64]),
+    "score_shard_serve_push": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
+    "score_shard_grad_push": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
+    "score_shard_register_staged": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "score_set_sample_offset": (C.c_int, [_H, C.c_int32]),
     "score_stream": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "score_launch_count": (C.c_int64, [_H]),

@@ -59,13 +59,14 @@ __global__ void __launch_bounds__(TL_CT) fc_fwd_kernel(FcArgs a) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int gm = row0 + 4 * rg + i;
+            // the four columns of a micro-tile row share one Philox block (F1 is a multiple of 4)
+            float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (drop) u4 = philox_uniform4(s_lo, s_hi, 1u, step, ((sbase + (uint64_t)gm) * F1 + 4 * cg) >> 2);
+            const float uj[4] = {u4.x, u4.y, u4.z, u4.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float v = fmaxf(acc[i][j] + bj[j], 0.f);
-                if (drop) {
-                    const float u = philox_uniform(s_lo, s_hi, 1u, step, (sbase + (uint64_t)gm) * F1 + 4 * cg + j);
-                    v = (u < keep) ? v / keep : 0.f;
-                }
+                if (drop) v = (uj[j] < keep) ? v / keep : 0.f;
                 acc[i][j] = v;
             }
             if (gm < a.B) st4(a.g1 + (int64_t)gm * F1 + 4 * cg, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
@@ -82,13 +83,14 @@ __global__ void __launch_bounds__(TL_CT) fc_fwd_kernel(FcArgs a) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int gm = row0 + 4 * rg + i;
+            // the four columns of a micro-tile row share one Philox block (F2 is a multiple of 4)
+            float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (drop) u4 = philox_uniform4(s_lo, s_hi, 2u, step, ((sbase + (uint64_t)gm) * F2 + 4 * cg) >> 2);
+            const float uj[4] = {u4.x, u4.y, u4.z, u4.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float v = fmaxf(acc[i][j] + bj[j], 0.f);
-                if (drop) {
-                    const float u = philox_uniform(s_lo, s_hi, 2u, step, (sbase + (uint64_t)gm) * F2 + 4 * cg + j);
-                    v = (u < keep) ? v / keep : 0.f;
-                }
+                if (drop) v = (uj[j] < keep) ? v / keep : 0.f;
                 acc[i][j] = v;
             }
             if (gm < a.B) st4(a.g2 + (int64_t)gm * F2 + 4 * cg, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));

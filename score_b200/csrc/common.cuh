@@ -79,4 +79,13 @@ __device__ __forceinline__ float philox_uniform(uint32_t seed_lo, uint32_t seed_
     return (float)(w >> 8) * (1.0f / 16777216.0f);
 }
 
+// the four uniforms of elements 4*idx4 .. 4*idx4+3 of a stream: ONE Philox block (same values as philox_uniform)
+__device__ __forceinline__ float4 philox_uniform4(uint32_t seed_lo, uint32_t seed_hi, uint32_t stream_id, uint32_t step,
+                                                  uint64_t idx4) {
+    uint4 c = make_uint4((uint32_t)idx4, (uint32_t)(idx4 >> 32), stream_id, step);
+    uint4 r = philox4x32(c, make_uint2(seed_lo, seed_hi));
+    const float s = 1.0f / 16777216.0f;
+    return make_float4((float)(r.x >> 8) * s, (float)(r.y >> 8) * s, (float)(r.z >> 8) * s, (float)(r.w >> 8) * s);
+}
+
 }  // namespace score

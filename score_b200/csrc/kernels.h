@@ -375,6 +375,15 @@ void launch_shard_plan(cudaStream_t st, SortBufs& sb, const int32_t* keys, int64
 void launch_shard_pack_grads(cudaStream_t st, const float* grad_rows, const int32_t* sel, const int32_t* counts, int world,
                              int64_t n, int d, float* out);
 
+// peer-memory variant of the row-sharded exchange (shard.cu): rows / gradient rows are stored straight into the peer's
+// staged table / gradient buffer; p[r] = that buffer of rank r as mapped into this process
+constexpr int SHARD_MAX_PEERS = 64;
+struct ShardPeers { float* p[SHARD_MAX_PEERS]; };
+void launch_shard_serve_push(cudaStream_t st, const float* table, int es, int d, int64_t V, const int32_t* want, int64_t n_recv,
+                             const int32_t* cm, int world, int me, const ShardPeers& peers, int32_t* err_flag);
+void launch_shard_grad_push(cudaStream_t st, const float* grad_rows, const int32_t* sel, int64_t n, int d, const int32_t* cm,
+                            int world, int me, const ShardPeers& peers);
+
 // out[i] = table[idx[i]] (idx 0 -> zeros; out-of-range -> zeros + error flag): owner side of a sharded gather
 void launch_gather_rows(cudaStream_t st, const float* table, int es, const int32_t* idx, int64_t n, int d, int64_t V, float* out,
                         int32_t* err_flag);

@@ -150,6 +150,7 @@ struct ScoreModel {
     float *sh_staged = nullptr, *sh_grad_send = nullptr;
     const int32_t* presorted_keys = nullptr; int64_t presorted_n = 0; int presorted_out = 0; cudaEvent_t ev_presort = nullptr;
     int32_t* sh_counts_host = nullptr; cudaEvent_t ev_sh_counts = nullptr;   // count matrix read-back (pinned, own event)
+    const float* sh_ext_staged[2] = {nullptr, nullptr};   // caller-owned staged tables with stable addresses (graph capture)
 
     // graphs
     std::map<int, cudaGraphExec_t> graphs_train;
@@ -1723,26 +1724,70 @@ int score_device_buffer(ScoreHandle h, const char* name, void** dev_ptr, size_t*
 
 // Owner side of a row-sharded gather: out[i] = current value of local row idx[i] (idx 0 -> zeros).  In LAZY mode the
 // requested rows are first brought up to date.  All pointers are device pointers; ordered on score_stream().
+namespace {
+// LAZY: bring the rows idx_dev[0..n) (owner-local row numbers) up to date before they are served
+int serve_catchup(ScoreModel* h, const int32_t* idx_dev, int64_t n) {
+    int rc = upload_hyper(h, 1, 0.f, 0.f, 1.f, 0, 1);
+    if (rc) return rc;
+    if (h->cfg.adam_mode != SCORE_ADAM_LAZY) return SCORE_OK;
+    if (n > h->claim_ext_cap) {
+        CK(cudaStreamSynchronize(h->st));
+        if (h->claim_ext) cudaFree(h->claim_ext);
+        h->claim_ext = nullptr; h->claim_ext_cap = 0;
+        CK(cudaMalloc(&h->claim_ext, sizeof(int32_t) * 2 * (n + n / 4)));
+        h->claim_ext_cap = n + n / 4;
+    }
+    launch_emb_catchup_rows(h->st, idx_dev, n, h->dm.V, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.d, h->es, h->alpha_hist,
+                            h->hyper_dev, h->claim_ext, h->claim_counter);
+    return SCORE_OK;
+}
+}  // namespace
+
 int score_gather_rows(ScoreHandle h, const int32_t* idx_dev, int64_t n, float* out_dev) {
     if (!h || (n > 0 && (!idx_dev || !out_dev))) return SCORE_ERR_ARG;
     CK(cudaSetDevice(h->device));
     if (n == 0) return SCORE_OK;
-    {
-        int rc = upload_hyper(h, 1, 0.f, 0.f, 1.f, 0, 1);
+    int rc = serve_catchup(h, idx_dev, n);
+    if (rc) return rc;
+    launch_gather_rows(h->st, h->emb, h->es, idx_dev, n, h->dm.d, h->dm.V, out_dev, h->err_flag);
+    return SCORE_OK;
+}
+
+// Peer-memory variants (NVLink): the owner stores the rows it serves straight into the requesters' staged tables, the
+// requester stores its gradient rows straight into the owners' gradient buffers - gather / pack fused with the
+// all-to-all.  count_matrix_dev: the all-gathered [world][world+1] counts; peers[r]: rank r's staged table (gradient
+// buffer) as mapped into this process.  The caller runs a barrier across the ranks on score_stream() afterwards.
+int score_shard_serve_push(ScoreHandle h, const int32_t* want_dev, int64_t n_recv, const int32_t* count_matrix_dev,
+                           int32_t world, int32_t rank, const uint64_t* peers) {
+    if (!h || !count_matrix_dev || !peers || world < 1 || world > SHARD_MAX_PEERS || rank < 0 || rank >= world || n_recv < 0 ||
+        (n_recv > 0 && !want_dev))
+        return SCORE_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (n_recv > 0) {
+        int rc = serve_catchup(h, want_dev, n_recv);
         if (rc) return rc;
     }
-    if (h->cfg.adam_mode == SCORE_ADAM_LAZY) {
-        if (n > h->claim_ext_cap) {
-            CK(cudaStreamSynchronize(h->st));
-            if (h->claim_ext) cudaFree(h->claim_ext);
-            h->claim_ext = nullptr; h->claim_ext_cap = 0;
-            CK(cudaMalloc(&h->claim_ext, sizeof(int32_t) * 2 * (n + n / 4)));
-            h->claim_ext_cap = n + n / 4;
-        }
-        launch_emb_catchup_rows(h->st, idx_dev, n, h->dm.V, h->emb, h->emb_m, h->emb_v, h->last_step, h->dm.d, h->es, h->alpha_hist,
-                                h->hyper_dev, h->claim_ext, h->claim_counter);
-    }
-    launch_gather_rows(h->st, h->emb, h->es, idx_dev, n, h->dm.d, h->dm.V, out_dev, h->err_flag);
+    ShardPeers sp{};
+    for (int r = 0; r < world; ++r) sp.p[r] = reinterpret_cast<float*>(peers[r]);
+    launch_shard_serve_push(h->st, h->emb, h->es, h->dm.d, h->dm.V, want_dev, n_recv, count_matrix_dev, world, rank, sp, h->err_flag);
+    CK(cudaGetLastError());
+    return SCORE_OK;
+}
+int score_shard_grad_push(ScoreHandle h, const int32_t* count_matrix_dev, int32_t world, int32_t rank, const uint64_t* peers) {
+    if (!h || !count_matrix_dev || !peers || world < 1 || world > SHARD_MAX_PEERS || rank < 0 || rank >= world || !h->sh_world)
+        return SCORE_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    ShardPeers sp{};
+    for (int r = 0; r < world; ++r) sp.p[r] = reinterpret_cast<float*>(peers[r]);
+    launch_shard_grad_push(h->st, h->grad_rows, h->sh_sel, h->last_N, h->dm.d, count_matrix_dev, world, rank, sp);
+    CK(cudaGetLastError());
+    return SCORE_OK;
+}
+// staged tables that live outside the handle (symmetric memory of the peer-memory exchange): their addresses are stable,
+// so the half-step on them may be captured as a CUDA graph like the handle's own staged table
+int score_shard_register_staged(ScoreHandle h, const float* a, const float* b) {
+    if (!h) return SCORE_ERR_ARG;
+    h->sh_ext_staged[0] = a; h->sh_ext_staged[1] = b;
     return SCORE_OK;
 }
 
@@ -1893,9 +1938,11 @@ int score_step_begin(ScoreHandle h, const ScoreBatch* batch, float lr, float reg
     // the training half-step is the same launch sequence every step: replay it as a CUDA graph (data-parallel: keyed by
     // B; row-sharded: only with the handle's own staged table / mini keys, whose addresses are stable - score_shard_plan)
     bool launched = false;
-    const bool staged_own = staged_table && !with_keys && staged_table == h->sh_staged && staged_keys == h->sh_mini;
+    const int staged_which = !staged_table ? -1 : staged_table == h->sh_staged ? 0 : staged_table == h->sh_ext_staged[0] ? 1
+                             : staged_table == h->sh_ext_staged[1] ? 2 : -1;
+    const bool staged_own = staged_which >= 0 && !with_keys && staged_keys == h->sh_mini;
     if (h->cfg.use_graph && train && ((!staged_table && with_keys) || staged_own)) {
-        const int B = dm.B + (staged_own ? (1 << 28) : 0);
+        const int B = dm.B + (staged_own ? ((staged_which + 1) << 28) : 0);
         auto it = h->graphs_begin.find(B);
         if (it != h->graphs_begin.end()) {
             CK(cudaGraphLaunch(it->second, h->st));

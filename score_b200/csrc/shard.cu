@@ -79,4 +79,87 @@ void launch_shard_pack_grads(cudaStream_t st, const float* grad_rows, const int3
     ++g_launch_count;
 }
 
+// ---- fused exchange over peer memory (NVLink): instead of gathering into a send buffer and calling an all-to-all, the
+// kernels below store every row straight into its destination on the peer GPU.  cm = the all-gathered count matrix
+// [world][world + 1] (cm[r][o] = positions of rank r owned by rank o), resident on every device; all offsets derive from it:
+//   send_off(r, o) = sum_{o' < o} cm[r][o']   first slot of owner o in rank r's send order (= its staged-table rows - 1)
+//   recv_off(o, r) = sum_{r' < r} cm[r'][o]   first element of requester r in owner o's served list / gradient buffer
+__device__ __forceinline__ void shard_offsets(const int32_t* __restrict__ cm, int world, int me, int* send_off_me, int* recv_off_me,
+                                              int* send_off_peer_me) {
+    // shared arrays of world + 1 ints each, filled by the first warps; send_off_peer_me[r] = send_off(r, me)
+    for (int i = threadIdx.x; i <= world; i += blockDim.x) {
+        int s = 0, rcv = 0;
+        for (int j = 0; j < i; ++j) { s += cm[me * (world + 1) + j]; rcv += cm[j * (world + 1) + me]; }
+        send_off_me[i] = s; recv_off_me[i] = rcv;
+        if (i < world) {
+            int sp = 0;
+            for (int j = 0; j < me; ++j) sp += cm[i * (world + 1) + j];
+            send_off_peer_me[i] = sp;
+        }
+    }
+    __syncthreads();
+}
+
+// owner side: served element e (local row want[e], requested by rank r) -> row send_off(r, me) + k + 1 of r's staged table
+__global__ void __launch_bounds__(256) shard_serve_push_kernel(const float* __restrict__ table, int es, int d, int64_t V,
+                                                               const int32_t* __restrict__ want, const int32_t* __restrict__ cm,
+                                                               int world, int me, ShardPeers peers, int32_t* __restrict__ err_flag) {
+    __shared__ int send_off_me[SHARD_MAX_WORLD + 1], recv_off_me[SHARD_MAX_WORLD + 1], send_off_peer_me[SHARD_MAX_WORLD];
+    shard_offsets(cm, world, me, send_off_me, recv_off_me, send_off_peer_me);
+    const int lpr = d >> 2;
+    const int64_t total = (int64_t)recv_off_me[world] * lpr;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)(t / lpr), c = (int)(t - (int64_t)e * lpr);
+        int r = 0;
+        while (r + 1 < world && recv_off_me[r + 1] <= e) ++r;      // world <= 64: a short scan over shared memory
+        int32_t id = want[e];
+        if (id < 0 || id >= V) { atomicExch(err_flag, 1); id = 0; }
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (id != 0) v = *reinterpret_cast<const float4*>(table + (int64_t)id * es + c * 4);
+        const int64_t slot = (int64_t)send_off_peer_me[r] + (e - recv_off_me[r]) + 1;
+        *reinterpret_cast<float4*>(peers.p[r] + slot * d + c * 4) = v;
+    }
+}
+
+// requester side: send slot s (position sel[s], owner o) -> element recv_off(o, me) + k of o's gradient buffer
+__global__ void __launch_bounds__(256) shard_grad_push_kernel(const float* __restrict__ grad_rows, const int32_t* __restrict__ sel,
+                                                              int d, const int32_t* __restrict__ cm, int world, int me, ShardPeers peers) {
+    __shared__ int send_off_me[SHARD_MAX_WORLD + 1], recv_off_me[SHARD_MAX_WORLD + 1], send_off_peer_me[SHARD_MAX_WORLD];
+    __shared__ int recv_off_at[SHARD_MAX_WORLD];      // recv_off(o, me) for every owner o
+    shard_offsets(cm, world, me, send_off_me, recv_off_me, send_off_peer_me);
+    for (int o = threadIdx.x; o < world; o += blockDim.x) {
+        int rcv = 0;
+        for (int j = 0; j < me; ++j) rcv += cm[j * (world + 1) + o];
+        recv_off_at[o] = rcv;
+    }
+    __syncthreads();
+    const int lpr = d >> 2;
+    const int64_t total = (int64_t)send_off_me[world] * lpr;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int s = (int)(t / lpr), c = (int)(t - (int64_t)s * lpr);
+        int o = 0;
+        while (o + 1 < world && send_off_me[o + 1] <= s) ++o;
+        const float4 v = *reinterpret_cast<const float4*>(grad_rows + (int64_t)sel[s] * d + c * 4);
+        const int64_t dst = (int64_t)recv_off_at[o] + (s - send_off_me[o]);
+        *reinterpret_cast<float4*>(peers.p[o] + dst * d + c * 4) = v;
+    }
+}
+
+void launch_shard_serve_push(cudaStream_t st, const float* table, int es, int d, int64_t V, const int32_t* want, int64_t n_recv,
+                             const int32_t* cm, int world, int me, const ShardPeers& peers, int32_t* err_flag) {
+    int64_t want_ctas = (n_recv * (d >> 2) + 255) / 256;
+    if (want_ctas > 148 * 16) want_ctas = 148 * 16;
+    if (want_ctas < 1) want_ctas = 1;
+    shard_serve_push_kernel<<<(unsigned)want_ctas, 256, 0, st>>>(table, es, d, V, want, cm, world, me, peers, err_flag);
+    ++g_launch_count;
+}
+void launch_shard_grad_push(cudaStream_t st, const float* grad_rows, const int32_t* sel, int64_t n, int d, const int32_t* cm,
+                            int world, int me, const ShardPeers& peers) {
+    int64_t want_ctas = (n * (d >> 2) + 255) / 256;
+    if (want_ctas > 148 * 16) want_ctas = 148 * 16;
+    if (want_ctas < 1) want_ctas = 1;
+    shard_grad_push_kernel<<<(unsigned)want_ctas, 256, 0, st>>>(grad_rows, sel, d, cm, world, me, peers);
+    ++g_launch_count;
+}
+
 }  // namespace score

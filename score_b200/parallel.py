@@ -249,9 +249,16 @@ class ShardedEmbeddingTrainer(_Base):
     ``ExchangePlan`` above states the same bucketing rule in torch ops (CPU / gloo tests, and the parity test of the
     CUDA plan)."""
 
-    def __init__(self, model, world, rank, group=None):
+    def __init__(self, model, world, rank, group=None, p2p=None):
         super().__init__(model, world, rank, group)
         self._bufs = {}
+        # peer-memory exchange (SCORE_SHARD_P2P=1): the owners store the served rows straight into the requesters' staged
+        # tables and the requesters store their gradient rows straight into the owners' buffers over NVLink (kernels of
+        # shard.cu, torch symmetric memory for the mappings and the cross-rank barrier) - gather / pack fused with the
+        # all-to-all, no NCCL call for the two large exchanges
+        self.p2p = ((os.environ.get("SCORE_SHARD_P2P") == "1") if p2p is None else bool(p2p)) and self.world > 1
+        self._symm = None
+        self._fetch_no = 0
         self._pending = None      # (want, owned, n_recv) of a begun step whose score_step_finish is still to be enqueued
         self.timeline = None      # tools/shard_timeline.py: {phase: [CUDA events]} recorded at the phase boundaries
         self._cm = (C.c_int32 * (self.world * (self.world + 1)))()
@@ -300,7 +307,30 @@ class ShardedEmbeddingTrainer(_Base):
         cm = list(self._cm)
         send_counts = cm[self.rank * (W + 1):self.rank * (W + 1) + W]
         recv_counts = [cm[r * (W + 1) + self.rank] for r in range(W)]
+        self._mat = mat
+        self._max_recv = max(sum(cm[r * (W + 1) + o] for r in range(W)) for o in range(W))
         return send_counts, recv_counts, int(sum(send_counts)), int(sum(recv_counts)), plan
+
+    def _p2p_setup(self, n_positions, d):
+        """symmetric buffer [staged table 0 | staged table 1 | gradient rows], the same size on every rank"""
+        import torch.distributed._symmetric_memory as symm_mem
+        t = torch.tensor([n_positions], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        self._n_cap = int(t.item()) + int(t.item()) // 8
+        self._owned_cap = 2 * self._n_cap
+        self._staged_elems = (self._n_cap + 1) * d
+        total = 2 * self._staged_elems + self._owned_cap * d
+        self._symm = symm_mem.empty(total, dtype=torch.float32, device=self.device)
+        self._symm[:2 * self._staged_elems].zero_()
+        grp = self.group if self.group is not None else dist.group.WORLD
+        self._symm_hdl = symm_mem.rendezvous(self._symm, grp)
+        bases = [int(p) for p in self._symm_hdl.buffer_ptrs]
+        self._peer_staged = [(C.c_uint64 * self.world)(*[b + 4 * k * self._staged_elems for b in bases]) for k in (0, 1)]
+        self._peer_owned = (C.c_uint64 * self.world)(*[b + 4 * 2 * self._staged_elems for b in bases])
+        mine = bases[self.rank]
+        self._my_staged = [mine, mine + 4 * self._staged_elems]
+        self.m._check(self.lib.score_shard_register_staged(self.h, self._my_staged[0], self._my_staged[1]))
+        self.stream.synchronize()
 
     def _flush_finish(self, want_loss=False):
         """enqueue the optimizer half (score_step_finish) of the step begun last, if it is still pending"""
@@ -328,6 +358,20 @@ class ShardedEmbeddingTrainer(_Base):
         else:
             want.copy_(send_rows)
         self._mark("a2a ids")
+        self._fetch_no += 1
+        if self.p2p:
+            if self._symm is None:
+                self._p2p_setup(int(plan.n_positions), d)
+            if plan.n_positions > self._n_cap or self._max_recv > self._owned_cap:
+                raise RuntimeError("batch larger than the symmetric exchange buffers")
+            par = self._fetch_no & 1      # alternate the staged tables: a peer may still read the other one in its backward pass
+            self.m._check(self.lib.score_shard_serve_push(self.h, want.data_ptr(), n_recv, self._mat.data_ptr(), self.world,
+                                                          self.rank, self._peer_staged[par]))
+            self._symm_hdl.barrier(channel=0)     # every owner's rows have landed in every staged table
+            self._mark("gather")
+            self._mark("a2a rows")
+            plan.staged = self._my_staged[par]
+            return plan, want, (send_counts, recv_counts, n_valid, n_recv)
         served = self._buf("served", n_recv * d, torch.float32).view(n_recv, d)
         self.m._check(self.lib.score_gather_rows(self.h, want.data_ptr(), n_recv, served.data_ptr()))
         self._mark("gather")
@@ -356,14 +400,20 @@ class ShardedEmbeddingTrainer(_Base):
             if self.world > 1:
                 dist.all_reduce(g, group=self.group)
             self._mark("allreduce")
-            self.m._check(self.lib.score_shard_pack_grads(self.h))
-            self._mark("pack")
-            gsend = self._view(plan.grad_send, n_valid * d, torch.float32).view(n_valid, d)
-            owned = self._buf("owned", n_recv * d, torch.float32).view(n_recv, d)
-            if self.world > 1:
-                dist.all_to_all_single(owned, gsend, recv_counts, send_counts, group=self.group)
+            if self.p2p:
+                self.m._check(self.lib.score_shard_grad_push(self.h, self._mat.data_ptr(), self.world, self.rank, self._peer_owned))
+                self._symm_hdl.barrier(channel=1)     # every requester's gradient rows have landed
+                self._mark("pack")
+                owned = self._symm[2 * self._staged_elems:2 * self._staged_elems + n_recv * d].view(n_recv, d)
             else:
-                owned.copy_(gsend)
+                self.m._check(self.lib.score_shard_pack_grads(self.h))
+                self._mark("pack")
+                gsend = self._view(plan.grad_send, n_valid * d, torch.float32).view(n_valid, d)
+                owned = self._buf("owned", n_recv * d, torch.float32).view(n_recv, d)
+                if self.world > 1:
+                    dist.all_to_all_single(owned, gsend, recv_counts, send_counts, group=self.group)
+                else:
+                    owned.copy_(gsend)
             self._mark("a2a grads")
             self._pending = (want, owned, n_recv)
             if not want_loss:
