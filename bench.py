@@ -258,7 +258,7 @@ def main():
                          "collective must not hang the caller); 0 disables")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.watchdog > 0:
+    if args.watchdog > 0 and args.impl == "ours":
         import faulthandler
         faulthandler.dump_traceback_later(args.watchdog, exit=True)
     # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner) go to stderr instead

@@ -770,3 +770,98 @@ def test_hot_row_longer_than_a_chunk():
     lo = [orc.train(None, batch(50 + i), 1e-3, 1e-4, keep_prob=1.0) for i in range(3)]
     assert pu.rel_err(out["lazy"][0], lo) <= 1e-5
     assert pu.rel_err(out["lazy"][1][hot], orc.params["emb_mtx"].numpy()[hot]) <= 1e-5
+
+
+@pytest.mark.parametrize("world,mode", [(3, "lazy"), (8, "lazy"), (2, "dense")])
+def test_sharded_peer_push_emulated_ranks(world, mode):
+    """`world` handles on ONE GPU driven through the phases of the row-sharded step with the PEER-MEMORY kernels
+    (score_shard_serve_push / score_shard_grad_push: every "peer" buffer is a tensor of this process, the barrier is a
+    device synchronize, the id exchange a host-side regrouping): losses and owned table rows must equal one model
+    stepping on the concatenated batch - this pins the offset arithmetic of shard.cu for world sizes a small box cannot run."""
+    import ctypes as C
+    from score_b200 import _capi, parallel
+    shape = SHAPES["tiny_tb"]
+    d = shape.eb_dim
+    steps, lr, lam = 3, 1e-3, 1e-4
+    per = [[make_batch(shape, seed=800 + 10 * s + r, batch=16) for r in range(world)] for s in range(steps)]
+    glob = [tuple(np.concatenate([b[i] for b in bs], 0) for i in range(8)) for bs in per]
+    cfg, params, m1 = pu.make_models(shape, adam_mode=mode)
+    l1 = [m1.train(None, g, lr, lam, keep_prob=1.0) for g in glob]
+    ms = []
+    for r in range(world):
+        a = list(shape.ctor_args())
+        a[0] = parallel.shard_rows(shape.feature_size, world)
+        m = sb.SCORE(*a, adam_mode=mode, init_weights=False, use_graph=False)
+        for name, _ in m.tensor_names():
+            v = params[name]
+            if name == "emb_mtx":
+                v = parallel.global_to_local_table(v, world, r)
+            m.set_tensor(name, v.numpy())
+        ms.append(m)
+    lib = ms[0]._lib
+    dev = torch.device("cuda", 0)
+    W = world
+
+    def view(ptr, n, dt):
+        return torch.as_tensor(parallel._DevView(ptr, (int(n),), "<f4" if dt == torch.float32 else "<i4"), device=dev)
+
+    l2 = []
+    for bs in per:
+        gb = sum(b[0].shape[0] for b in bs)
+        plans, keep = [], []
+        for r, (m, b) in enumerate(zip(ms, bs)):
+            bb = sb._Batch(b, m.cfg); keep.append(bb)
+            m._check(lib.score_set_sample_offset(m._h, sum(x[0].shape[0] for x in bs[:r])))
+            m._check(lib.score_prepare_batch(m._h, C.byref(bb.struct)))
+            p = _capi.ScoreShardPlan()
+            m._check(lib.score_shard_plan(m._h, W, C.byref(p)))
+            plans.append(p)
+        torch.cuda.synchronize()
+        cm = torch.stack([view(p.counts, W + 1, torch.int32).clone() for p in plans]).contiguous()      # [W, W+1] on the device
+        cmh = cm.cpu().numpy()
+        n_valid = [int(cmh[r, :W].sum()) for r in range(W)]
+        n_recv = [int(cmh[:, o].sum()) for o in range(W)]
+        sends = [view(plans[r].send_rows, max(n_valid[r], 1), torch.int32)[:n_valid[r]].cpu().numpy() for r in range(W)]
+        so = np.concatenate([np.zeros((W, 1), np.int64), np.cumsum(cmh[:, :W], axis=1)], axis=1)        # send_off(r, o)
+        wants = [torch.from_numpy(np.concatenate([sends[r][so[r, o]:so[r, o + 1]] for r in range(W)]).astype(np.int32)).to(dev)
+                 for o in range(W)]                                                                     # the id all-to-all
+        n_pos = int(plans[0].n_positions)
+        staged = [torch.zeros((n_pos + 1) * d, dtype=torch.float32, device=dev) for _ in range(W)]
+        owned = [torch.zeros(max(n_recv[o], 1) * d, dtype=torch.float32, device=dev) for o in range(W)]
+        peers_staged = (C.c_uint64 * W)(*[t.data_ptr() for t in staged])
+        peers_owned = (C.c_uint64 * W)(*[t.data_ptr() for t in owned])
+        for o, m in enumerate(ms):
+            m._check(lib.score_shard_serve_push(m._h, wants[o].data_ptr(), n_recv[o], cm.data_ptr(), W, o, peers_staged))
+        torch.cuda.synchronize()
+        for r, m in enumerate(ms):
+            m._check(lib.score_step_begin(m._h, None, lr, lam, 1.0, gb, 1, staged[r].data_ptr(), plans[r].mini_keys))
+        torch.cuda.synchronize()
+        g = [view(*_devbuf(m, "dense_grad"), torch.float32) for m in ms]
+        tot = torch.stack(g).sum(0)
+        for x in g:
+            x.copy_(tot)
+        for r, m in enumerate(ms):
+            m._check(lib.score_shard_grad_push(m._h, cm.data_ptr(), W, r, peers_owned))
+        torch.cuda.synchronize()
+        data = 0.0
+        for o, m in enumerate(ms):
+            loss2 = (C.c_float * 2)()
+            m._check(lib.score_step_finish(m._h, wants[o].data_ptr(), owned[o].data_ptr(), n_recv[o], loss2))
+            data += loss2[0] - loss2[1]
+            l2_term = loss2[1]
+        l2.append(data + l2_term)
+    assert pu.rel_err(l2, l1) <= 2e-6
+    emb1 = m1.get_tensor("emb_mtx")
+    for r, m in enumerate(ms):
+        loc = parallel.global_to_local_table(torch.from_numpy(emb1), world, r).numpy()
+        assert pu.rel_err(m.get_tensor("emb_mtx")[1:], loc[1:]) <= 2e-6, r
+        assert pu.rel_err(m.get_tensor("fc1/kernel"), m1.get_tensor("fc1/kernel")) <= 2e-6
+    for m in ms + [m1]:
+        m.close()
+
+
+def _devbuf(m, name):
+    import ctypes as C
+    ptr, cnt = C.c_void_p(), C.c_size_t()
+    m._check(m._lib.score_device_buffer(m._h, name.encode(), C.byref(ptr), C.byref(cnt)))
+    return ptr.value, cnt.value
