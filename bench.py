@@ -170,6 +170,51 @@ def workload_config(shape, args, global_batch):
                          "batches; no explicit flush" % (3 * shape.feature_size * shape.eb_dim * 4 / 1e9, POOL)}
 
 
+def rooflines(shape, stats, probes):
+    """(roofline_gather, roofline_scatter) of the bench line from the step statistics and the per-kernel event times
+    (kept apart from main() so the CPU tests can run it)"""
+    peak, peak_src = peaks()
+    d = shape.eb_dim
+    live, uniq = stats["live"], stats["unique_rows"]
+    gather_bytes = live * (4 + 4 * d)
+    scatter_bytes = live * (4 + 4 * d) + uniq * 6 * 4 * d
+
+    def per_launch(name):
+        tot, n = probes.get(name, (0.0, 0))
+        return tot / n if n else None
+
+    t_g, t_s = per_launch("coatt_fwd"), per_launch("emb_update")
+    tr_g, src_g = ncu_traffic(shape.name, "coatt_fwd")
+    tr_s, src_s = ncu_traffic(shape.name, "emb_update")
+    roof = {"bound": "hbm", "kernel": "coatt_fwd_kernel (fused embedding gather + co-attention + pooling)",
+            "achieved": gather_bytes / (t_g * 1e-3) / 1e9 if t_g else None, "peak": peak, "unit": "GB/s",
+            "frac": gather_bytes / (t_g * 1e-3) / 1e9 / peak if t_g else None, "traffic": tr_g,
+            "traffic_source": src_g,
+            "peak_source": peak_src, "bytes_per_launch": gather_bytes, "ms_per_launch": t_g,
+            "bytes_rule": "live non-zero ids x (4 + 4d); every index counted, no credit for the duplicates the "
+                          "loader's cyclic padding and the 1+neg user-side replication create (those hit L2, "
+                          "which is why traffic < bytes_per_launch)",
+            "timing": "CUDA events around the kernel on its own stream inside every step of a second timed region of "
+                      "the same K steps (ms_per_step_probed); the sort / weight-gradient streams run concurrently"}
+    roof["random_access_ceiling"] = {
+        "frac_at_this_launch_size": 0.28, "frac_asymptotic": 0.45,
+        "what": "a kernel that ONLY gathers the same number of random 64-byte rows (129.5 B of DRAM reads per row on this part)",
+        "source": "tools/randrow_bench.cu, profiles/r2d_randrow_bench.txt (d = 16 tables)"} if d == 16 else None
+    roof_s = {"bound": "hbm", "kernel": "emb_update_kernel (segment-reduce + fused row Adam)",
+              "achieved": scatter_bytes / (t_s * 1e-3) / 1e9 if t_s else None, "peak": peak, "unit": "GB/s",
+              "frac": scatter_bytes / (t_s * 1e-3) / 1e9 / peak if t_s else None, "traffic": tr_s,
+              "traffic_source": src_s, "peak_source": peak_src,
+              "timing": "CUDA events around the kernel on its own stream inside every step of a second timed region "
+                        "of the same K steps (ms_per_step_probed; the event nodes add ~3 us to each bracketed kernel)",
+              "bytes_per_launch": scatter_bytes, "ms_per_launch": t_s, "unique_rows": uniq,
+              "random_access_ceiling": {"frac": 0.41, "what": "a kernel that ONLY reads and rewrites the same number of "
+                                                               "random 192-byte records (var | m | v)",
+                                        "source": "tools/randrow_bench.cu, profiles/r2d_randrow_bench.txt (d = 16 tables)"}
+              if d == 16 else None,
+              "bytes_rule": "live ids x (4 + 4d) + unique rows x 6 x 4d"}
+    return roof, roof_s
+
+
 def large_vocab_leg(args, world, rank, local, steps=30, warmup=5):
     """N > 1 only: BASELINE.json config 5 (200 M-row table, d=64, row-sharded over the N GPUs, batch 1024 per GPU) and,
     beside it, ONE GPU stepping on a 25 M-row shard of the same table (the per-GPU share at 8 GPUs) - the denominator of
@@ -474,41 +519,7 @@ def main():
         lv_leg = large_vocab_leg(args, world, rank, local)
 
     if rank == 0:
-        peak, peak_src = peaks()
-        d = shape.eb_dim
-        live, uniq = stats["live"], stats["unique_rows"]
-        gather_bytes = live * (4 + 4 * d)
-        scatter_bytes = live * (4 + 4 * d) + uniq * 6 * 4 * d
-
-        def per_launch(name):
-            tot, n = probes.get(name, (0.0, 0))
-            return tot / n if n else None
-
-        t_g, t_s = per_launch("coatt_fwd"), per_launch("emb_update")
-        tr_g, src_g = ncu_traffic(shape.name, "coatt_fwd")
-        tr_s, src_s = ncu_traffic(shape.name, "emb_update")
-        roof = {"bound": "hbm", "kernel": "coatt_fwd_kernel (fused embedding gather + co-attention + pooling)",
-                "achieved": gather_bytes / (t_g * 1e-3) / 1e9 if t_g else None, "peak": peak, "unit": "GB/s",
-                "frac": gather_bytes / (t_g * 1e-3) / 1e9 / peak if t_g else None, "traffic": tr_g,
-                "traffic_source": src_g,
-                "peak_source": peak_src, "bytes_per_launch": gather_bytes, "ms_per_launch": t_g,
-                "bytes_rule": "live non-zero ids x (4 + 4d); every index counted, no credit for the duplicates the "
-                              "loader's cyclic padding and the 1+neg user-side replication create (those hit L2, "
-                              "which is why traffic < bytes_per_launch)",
-                "timing": "CUDA events around the kernel on its own stream inside every step of a second timed region of "
-                          "the same K steps (ms_per_step_probed); the sort / weight-gradient streams run concurrently"}
-        roof_s = {"bound": "hbm", "kernel": "emb_update_kernel (segment-reduce + fused row Adam)",
-                  "achieved": scatter_bytes / (t_s * 1e-3) / 1e9 if t_s else None, "peak": peak, "unit": "GB/s",
-                  "frac": scatter_bytes / (t_s * 1e-3) / 1e9 / peak if t_s else None, "traffic": tr_s,
-                  "traffic_source": src_s, "peak_source": peak_src,
-                  "timing": "CUDA events around the kernel on its own stream inside every step of a second timed region "
-                            "of the same K steps (ms_per_step_probed; the event nodes add ~3 us to each bracketed kernel)",
-                  "bytes_per_launch": scatter_bytes, "ms_per_launch": t_s, "unique_rows": uniq,
-                  "random_access_ceiling": {"frac": 0.41, "what": "a kernel that ONLY reads and rewrites the same number of "
-                                                                   "random 192-byte records (var | m | v)",
-                                            "source": "tools/randrow_bench.cu, profiles/r2d_randrow_bench.txt (d = 16 tables)"}
-                  if d == 16 else None,
-                  "bytes_rule": "live ids x (4 + 4d) + unique rows x 6 x 4d"}
+        roof, roof_s = rooflines(shape, stats, probes)
         line = {"metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -34,3 +34,22 @@ def test_product_arm_fails_loudly_without_cuda():
     r = _run("--workload", "tiny_tb", "--steps", "1", "--warmup", "1", "--no-cpu-baseline", timeout=120)
     assert r.returncode != 0
     assert "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_rooflines_assembly_runs_on_cpu():
+    """the roofline objects of the bench line (algorithmic bytes, fractions, ceilings) from stand-in step statistics"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from score_b200.synth import SHAPES
+    stats = {"positions": 494592, "live": 334232, "unique_rows": 128337}
+    probes = {"coatt_fwd": (1.4, 100), "emb_update": (2.8, 100), "sort": (0.0, 0)}
+    g, s = bench.rooflines(SHAPES["taobao"], stats, probes)
+    assert g["bytes_per_launch"] == 334232 * 68 and s["bytes_per_launch"] == 334232 * 68 + 128337 * 384
+    assert abs(g["frac"] - g["achieved"] / g["peak"]) < 1e-12 and 0 < g["frac"] < 1 and 0 < s["frac"] < 1
+    assert g["random_access_ceiling"]["frac_at_this_launch_size"] == 0.28 and s["random_access_ceiling"]["frac"] == 0.41
+    g2, s2 = bench.rooflines(SHAPES["large_vocab_shard"], stats, {})
+    assert g2["frac"] is None and g2["random_access_ceiling"] is None
+    import json
+    json.dumps([g, s, g2, s2])
