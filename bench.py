@@ -164,8 +164,9 @@ def workload_config(shape, args, global_batch):
             "parallelism": {"single": "single GPU",
                             "dp": "dp%d: replicated table, ONE all-gather per step of packed blocks (dense gradient + one embedding-"
                                   "gradient row per unique id), rank-ordered deterministic reduce on every replica" % args.gpus,
-                            "sharded": "dp%d dense + embedding rows sharded by id %% %d, all-to-all of ids / rows / gradient rows"
-                                       % (args.gpus, args.gpus)}[getattr(args, "par", "single")],
+                            "sharded": "dp%d dense + embedding rows sharded by id %% %d: ids through one NCCL all-to-all, rows and "
+                                       "gradient rows stored straight into the peers' buffers over NVLink (peer memory; "
+                                       "SCORE_SHARD_P2P=0: NCCL all-to-alls)" % (args.gpus, args.gpus)}[getattr(args, "par", "single")],
             "l2_policy": "inputs larger than L2: %.2f GB of embedding state (var+m+v), uniform-random rows, %d rotating "
                          "batches; no explicit flush" % (3 * shape.feature_size * shape.eb_dim * 4 / 1e9, POOL)}
 
