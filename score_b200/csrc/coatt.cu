@@ -7,14 +7,16 @@
 // trees and per-chunk index math - against a random-row DRAM ceiling of 12.4 us per launch (tools/randrow_bench.cu).
 // Here
 //   * the warps walk the list of LIVE slices (t < length, built by build_keys): a dead slice costs nothing and the
-//     Taobao batch fits one resident wave (10 CTAs x 4 warps per SM);
+//     Taobao batch fits one resident wave (8 CTAs x 4 warps per SM: 64 registers);
 //   * every shared-memory access is lane base + immediate (the chunk -> (segment, neighbor, field) maps are compile
 //     time), the co-attention kernel chunk of a lane sits in registers whenever 32 is a multiple of the chunks per
 //     neighbor;
 //   * the dot products stay per-chunk partials in shared memory and are summed by the lane that owns the neighbor
 //     (no shuffle tree per row);
 //   * backward keeps the warp's share of the co-attention kernel gradient in registers across its slices.
-// Any other configuration (run-time geometry, RCA / RRN sum pooling, RIA) takes the general kernels of embed.cu.
+// Any other configuration (run-time geometry, K > 16, RCA / RRN sum pooling) takes the general kernels of embed.cu.
+// Measured on B200 (profiles/r2n_*): 5.19 M -> 3.33 M warp instructions per launch, K-A alone 15.3-16.5 -> 12.4-13.7 us
+// (a kernel that only gathers the same rows: 12.4 us), K-D 17.7 -> 14.3-15.7 us; SCORE_COATT_LEAN=0 selects the general kernels.
 #include "kernels.h"
 
 namespace score {

@@ -12,9 +12,10 @@ The reference is single-device; both schemes keep SCOREB
   bit-identical without ever broadcasting the table.
 
 * ``ShardedEmbeddingTrainer`` - row-sharded table (large-vocab config): owner(id) = id % world, local row
-  = id // world + 1 (local row 0 is the dummy).  Forward: bucket ids by owner -> all-to-all ids -> owners gather
-  (lazy-Adam catch-up first) -> all-to-all rows back -> a per-batch staged mini-table feeds the unchanged
-  kernels.  Backward: all-to-all (local row, gradient row) to the owners -> owner-side sort / reduce / Adam.
+  = id // world + 1 (local row 0 is the dummy).  Forward: positions grouped by owner on the device (score_shard_plan)
+  -> all-to-all ids -> the owners bring the rows up to date (lazy Adam) and store them straight into the requesters'
+  staged tables over NVLink (peer memory) -> the unchanged kernels run on the staged table.  Backward: the gradient rows
+  are stored straight into the owners' buffers -> owner-side sort (done earlier, on a side stream) / reduce / Adam.
 
 The pure-torch exchange helpers below run on CPU tensors with the gloo backend too (tests/test_parallel_cpu.py).
 """
