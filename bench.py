@@ -513,7 +513,10 @@ def main():
     if trainer:
         loss = loss_e2e      # the trainer's synchronous step returns the GLOBAL loss (m.wait() is this rank's share only)
     m.close()
+    trainer = None       # releases the trainer's exchange buffers (symmetric memory) while the process group is alive
     del dev_pool
+    import gc
+    gc.collect()
     torch.cuda.empty_cache()
     lv_leg = None
     if world > 1 and not args.no_large_vocab and args.workload == "taobao":
