@@ -520,7 +520,10 @@ def main():
     torch.cuda.empty_cache()
     lv_leg = None
     if world > 1 and not args.no_large_vocab and args.workload == "taobao":
-        lv_leg = large_vocab_leg(args, world, rank, local)
+        try:
+            lv_leg = large_vocab_leg(args, world, rank, local)
+        except Exception as e:      # the main line must survive a failure of the extra leg
+            lv_leg = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
     if rank == 0:
         roof, roof_s = rooflines(shape, stats, probes)
