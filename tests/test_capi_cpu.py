@@ -31,22 +31,25 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header(tmp_path):
-    """Compile the real header with gcc and compare sizeof/offsetof with the ctypes mirror."""
+    """Compile the real header with gcc and compare sizeof/offsetof of every struct with its ctypes mirror."""
     import ctypes as C
     import subprocess
+    structs = ["ScoreConfig", "ScoreBatch", "ScoreGraphDesc", "ScoreHop2Desc", "ScoreShardPlan"]
     src = tmp_path / "layout.c"
-    fields_c = [f for f, _ in _capi.ScoreConfig._fields_]
-    fields_b = [f for f, _ in _capi.ScoreBatch._fields_]
-    body = "".join('printf("%%zu\\n", offsetof(ScoreConfig, %s));' % f for f in fields_c)
-    body += "".join('printf("%%zu\\n", offsetof(ScoreBatch, %s));' % f for f in fields_b)
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "score_b200.h"\nint main(){'
-                   'printf("%zu\\n%zu\\n", sizeof(ScoreConfig), sizeof(ScoreBatch));' + body + 'return 0;}')
+    body = ""
+    for name in structs:
+        body += 'printf("%%zu\\n", sizeof(%s));' % name
+        for f, _ in getattr(_capi, name)._fields_:
+            body += 'printf("%%zu\\n", offsetof(%s, %s));' % (name, f)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "score_b200.h"\nint main(){' + body + 'return 0;}')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     out = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
-    assert out[0] == C.sizeof(_capi.ScoreConfig) and out[1] == C.sizeof(_capi.ScoreBatch)
-    got = [getattr(_capi.ScoreConfig, f).offset for f in fields_c] + [getattr(_capi.ScoreBatch, f).offset for f in fields_b]
-    assert out[2:] == got
+    want = []
+    for name in structs:
+        cls = getattr(_capi, name)
+        want += [C.sizeof(cls)] + [getattr(cls, f).offset for f, _ in cls._fields_]
+    assert out == want
 
 
 def test_argument_validation_without_gpu():
