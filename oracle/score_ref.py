@@ -11,11 +11,18 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline leg
 this module, and only as the checker / the timed CPU baseline.  The product
 (``score_b200``) never imports it and has no CPU fallback.
 
-PARITY UNPINNED: the reference ships no tests, no golden vectors and no fixtures for this
-path, and TensorFlow 1.x cannot be installed in this image (no wheel
-for Python 3.12, no network), so this restatement could not be diffed against TF itself.
-It is pinned instead by hand-derivable known-answer tests (tests/test_oracle.py, KA-1..KA-7
-of SURVEY.md section 4), by an fp64 twin and by finite-difference gradient checks.
+PARITY STATUS.  The reference ships no tests, no golden vectors and no fixtures for this path, and
+TensorFlow 1.x cannot be installed in this image (no wheel for Python 3.12, no network), so no TensorFlow-produced vector
+of the graph exists.  What pins this restatement instead:
+  * the WIRING - which ids are looked up, what is tiled / concatenated / fed to which layer, variable names, shapes and
+    creation order, what train() and eval() feed and fetch - against the reference's OWN classes: score.py's SCORE / RIA /
+    RCA / SCORE_USER / SCORE_ITEM and slice_model.py's RRN executed unmodified over a stand-in for the TF ops they call
+    (tools/tf_shim.py -> tests/golden/refwiring_*.npz -> tests/test_reference_wiring.py: eval, gradients, optimizer steps);
+  * the OP SEMANTICS (GRUCell, ApplyAdam, log_loss, batch_normalization, l2_loss) against TensorFlow's published unit-test
+    constants (tests/test_tf_known_answers.py);
+  * hand-derivable known answers KA-1..KA-7 (tests/test_oracle.py), an fp64 twin and finite-difference gradient checks.
+What stays unpinned: TensorFlow's own numerics of the remaining ops (softmax, dense matmul order, sigmoid) at the last bit -
+nothing TF-executed can be produced offline.
 
 TF-1.x semantics encoded here (each differs from a PyTorch default):
   * embedding init truncated_normal(0,1) re-drawn beyond 2 sigma (score.py:44);

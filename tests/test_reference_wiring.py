@@ -1,0 +1,95 @@
+"""The oracle against the reference's OWN model classes.
+
+tests/golden/refwiring_*.npz were produced by executing class SCORE / RIA / RCA / SCORE_USER / SCORE_ITEM of
+code/score/score.py and class RRN of code/slice_models/slice_model.py UNMODIFIED (source lifted out with ast) over a
+stand-in for the TensorFlow-1.x ops they call (tools/tf_shim.py; tools/make_golden.py: make_wiring).  The reference's
+source decides the wiring - which ids are looked up, what is tiled / concatenated / fed to which layer, the variable
+names, shapes and creation order, what eval() and train() feed and fetch; the stand-in supplies the op semantics, which
+are pinned separately to TensorFlow's published unit-test constants (tests/test_tf_known_answers.py).  The oracle
+(oracle/score_ref.py), given the same weights and batches, must reproduce those outputs; the CUDA path is compared with
+the oracle on the GPU (tests/test_parity_gpu.py), so the chain reference source -> oracle -> CUDA is closed."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import score_ref as ref
+from score_b200.synth import SHAPES
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[len("refwiring_"):-len(".npz")] for p in glob.glob(os.path.join(GOLDEN, "refwiring_*.npz")))
+
+
+def _load(case):
+    g = np.load(os.path.join(GOLDEN, "refwiring_%s.npz" % case), allow_pickle=False)
+    shape = SHAPES[str(g["shape"])]
+    cfg = ref.ScoreConfig(*shape.ctor_args(), model_type=str(g["model_type"]))
+    return g, shape, cfg
+
+
+def _batch(g, prefix="batch"):
+    return tuple(g["%s/%d" % (prefix, i)] for i in range(8))
+
+
+def test_every_model_class_of_the_path_has_a_reference_wiring_fixture():
+    types = set()
+    for c in CASES:
+        g, _, _ = _load(c)
+        assert str(g["source"]).startswith("reference:")
+        types.add(str(g["model_type"]))
+    assert types == set(ref.MODEL_TYPES)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_variable_names_and_creation_order_are_the_references(case):
+    """tf.layers.dense auto-numbering ('dense', 'dense_1', ...), GRU scopes, bn1 / fc names: the list the reference's
+    constructor actually creates, in its order"""
+    g, shape, cfg = _load(case)
+    assert [str(n) for n in g["var_names"]] == [n for n, _ in ref.param_specs(cfg)]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_reproduces_the_references_eval_and_gradients(case):
+    g, shape, cfg = _load(case)
+    params = ref.init_params(cfg, int(g["param_seed"]), torch.float32)
+    reg = float(g["reg_lambda"])
+    orc = ref.ScoreOracle(*shape.ctor_args(), model_type=cfg.model_type, seed=int(g["param_seed"]))
+    preds, labels, eloss = orc.eval(None, _batch(g), reg)                  # vs the reference's own eval()
+    np.testing.assert_allclose(preds, g["eval_preds"], rtol=2e-6, atol=1e-7)
+    assert labels == g["eval_labels"].tolist()
+    assert eloss == pytest.approx(float(g["eval_loss"]), rel=2e-6)
+    loss, y, grads, _ = ref.loss_and_grads(params, ref.to_batch(_batch(g)), cfg, reg, 1.0)
+    assert float(loss) == pytest.approx(float(g["loss"]), rel=2e-6)
+    rows, vals = ref.embedding_row_grads(grads["emb_mtx"])
+    assert np.array_equal(rows.numpy(), g["emb_rows"])                    # gradient row set
+    assert np.abs(vals.numpy() - g["emb_row_grads"]).max() <= 2e-6 * np.abs(g["emb_row_grads"]).max()
+    for k, gr in grads.items():
+        if k == "emb_mtx":
+            continue
+        want = g["grad/" + k]
+        scale = np.abs(want).max()
+        if k.endswith("/bias"):
+            scale = max(scale, np.abs(g["grad/" + k[:-5] + "/kernel"]).max())
+        assert np.abs(gr.numpy() - want).max() <= 5e-6 * max(scale, 1e-30), k
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_reproduces_the_references_train_steps(case):
+    """two optimizer steps through the reference's [loss, train_step] fetch (keep_prob fed as 1), then one call of the
+    reference's own train() - keep_prob 0.8, score.py:113 - with the dropout masks injected on both sides"""
+    g, shape, cfg = _load(case)
+    lr, reg = float(g["lr"]), float(g["reg_lambda"])
+    orc = ref.ScoreOracle(*shape.ctor_args(), model_type=cfg.model_type, seed=int(g["param_seed"]))
+    l0 = orc.train(None, _batch(g), lr, reg, keep_prob=1.0)
+    l1 = orc.train(None, _batch(g, "batch2"), lr, reg, keep_prob=1.0)
+    np.testing.assert_allclose([l0, l1], g["train_losses"], rtol=3e-6)
+    for k in ("fc1/kernel", "fc3/bias", "bn1/gamma", "gru_user_side/gru_cell/gates/kernel"):
+        assert np.abs(orc.params[k].numpy() - g["after2/" + k]).max() <= 1e-2 * lr, k     # two Adam steps move a weight by ~2 lr
+    rows = g["after2/rows"]
+    assert np.abs(orc.params["emb_mtx"].numpy()[rows] - g["after2/emb"]).max() <= 1e-2 * lr
+    masks = (torch.from_numpy(g["dropout_mask1"].astype(np.float32)), torch.from_numpy(g["dropout_mask2"].astype(np.float32)))
+    l2 = orc.train(None, _batch(g), lr, reg, keep_prob=0.8, dropout_masks=masks)
+    assert l2 == pytest.approx(float(g["train_dropout_loss"]), rel=5e-6)
+    assert np.abs(orc.params["fc1/kernel"].numpy() - g["after3/fc1/kernel"]).max() <= 1e-2 * lr

@@ -339,6 +339,100 @@ def make_hop2(reference_root):
     np.savez_compressed(os.path.join(OUT, "hop2_reference.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------ the reference's own graph code
+WIRING_CASES = [
+    # fixture name, source file, class, shape key, batch kwargs
+    ("score", "code/score/score.py", "SCORE", "tiny", dict(seed=201, batch=10)),
+    ("score_tb", "code/score/score.py", "SCORE", "tiny_tb", dict(seed=202, batch=12)),
+    ("ria", "code/score/score.py", "RIA", "tiny", dict(seed=203, batch=8)),
+    ("rca", "code/score/score.py", "RCA", "tiny", dict(seed=204, batch=8)),
+    ("score_user", "code/score/score.py", "SCORE_USER", "tiny", dict(seed=205, batch=8)),
+    ("score_item", "code/score/score.py", "SCORE_ITEM", "tiny", dict(seed=206, batch=8)),
+    ("rrn", "code/slice_models/slice_model.py", "RRN", "tiny", dict(seed=207, batch=8)),
+]
+
+
+def load_reference_model_classes(reference_root, rel_path, shim):
+    """exec the module-level constants and the model classes of the reference file (source untouched) with the TF stand-in
+    bound to the names the file imports (`tf`, `GRUCell`, `np`)"""
+    path = os.path.join(reference_root, rel_path)
+    tree = ast.parse(open(path).read())
+    ns = {"tf": shim, "GRUCell": shim.GRUCell, "np": np}
+    for node in tree.body:
+        if isinstance(node, (ast.Assign, ast.ClassDef)):
+            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    return ns
+
+
+def make_wiring(reference_root):
+    """the reference's OWN model classes (score.py SCORE / RIA / RCA / SCORE_USER / SCORE_ITEM, slice_model.py RRN), executed
+    unmodified over tools/tf_shim.py: variable names / shapes / creation order, eval() through the reference's own eval(), the
+    gradient of the loss node the reference built, two optimizer steps through its [loss, train_step] fetch, and one call of
+    its own train() (keep_prob 0.8) with the dropout masks injected"""
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import tf_shim as shim
+    from oracle import score_ref as ref
+    from score_b200.synth import SHAPES, make_batch
+    for name, rel, cls, shape_key, bkw in WIRING_CASES:
+        shape = SHAPES[shape_key]
+        cfg = ref.ScoreConfig(*shape.ctor_args(), model_type=cls)
+        params = ref.init_params(cfg, PARAM_SEED, torch.float32)
+        ns = load_reference_model_classes(reference_root, rel, shim)
+        model = ns[cls](*shape.ctor_args())
+        spec = shim.set_variables(params)
+        assert spec == [(n, tuple(s)) for n, s in ref.param_specs(cfg)], "variable names / shapes / creation order differ"
+        sess = shim.Session()
+        batch = [x.tolist() for x in make_batch(shape, **bkw)]
+        batch2 = [x.tolist() for x in make_batch(shape, **dict(bkw, seed=bkw["seed"] + 1000))]
+        preds, labels, eloss = model.eval(sess, batch, REG)                      # the reference's own eval()
+
+        def feed(b, lr, keep):
+            return {model.user_1hop_ph: b[0], model.user_2hop_ph: b[1], model.item_1hop_ph: b[2], model.item_2hop_ph: b[3],
+                    model.target_user_ph: b[4], model.target_item_ph: b[5], model.label_ph: b[6], model.length_ph: b[7],
+                    model.lr: lr, model.reg_lambda: REG, model.keep_prob: keep}
+        loss, grads = shim.gradients(sess, model.loss, feed(batch, LR, 1.0))
+        out = {"source": np.array("reference: class %s of %s executed unmodified (ast-extracted) over the TensorFlow stand-in "
+                                  "tools/tf_shim.py; weights = oracle init_params(seed %d) assigned by TF variable name" % (cls, rel, PARAM_SEED)),
+               "shape": np.array(shape_key), "model_type": np.array(cls), "param_seed": np.array(PARAM_SEED),
+               "reg_lambda": np.array(REG), "lr": np.array(LR),
+               "var_names": np.array([n for n, _ in spec]),
+               "eval_preds": np.asarray(preds, np.float32), "eval_labels": np.asarray(labels, np.int32), "eval_loss": np.array(eloss, np.float32),
+               "loss": np.array(float(loss), np.float32)}
+        for i in range(8):
+            out["batch/%d" % i] = np.asarray(batch[i]).astype(np.int32)
+            out["batch2/%d" % i] = np.asarray(batch2[i]).astype(np.int32)
+        rows, vals = ref.embedding_row_grads(grads["emb_mtx"])
+        out["emb_rows"], out["emb_row_grads"] = rows.numpy().astype(np.int64), vals.numpy().astype(np.float32)
+        for k, g in grads.items():
+            if k != "emb_mtx":
+                out["grad/" + k] = g.numpy().astype(np.float32)
+        # two optimizer steps through the reference's fetch list [loss, train_step] (keep_prob fed as 1 so that the result
+        # does not depend on a random mask)
+        l0, _ = sess.run([model.loss, model.train_step], feed_dict=feed(batch, LR, 1.0))
+        l1, _ = sess.run([model.loss, model.train_step], feed_dict=feed(batch2, LR, 1.0))
+        out["train_losses"] = np.array([l0, l1], np.float32)
+        for k in ("fc1/kernel", "fc3/bias", "bn1/gamma", "gru_user_side/gru_cell/gates/kernel"):
+            out["after2/" + k] = shim.G.by_name[k].value.numpy().copy()
+        touched = np.unique(np.concatenate([np.asarray(x).reshape(-1) for x in batch[:6]] + [np.asarray(x).reshape(-1) for x in batch2[:6]]))
+        touched = touched[touched > 0][:256].astype(np.int64)
+        out["after2/rows"] = touched
+        out["after2/emb"] = shim.G.by_name["emb_mtx"].value.numpy()[touched].copy()
+        # the reference's own train(): keep_prob 0.8 (score.py:113), masks injected so that the oracle can follow
+        gen = torch.Generator().manual_seed(4000 + bkw["seed"])
+        B = len(batch[6])
+        masks = [(torch.rand(B, 200, generator=gen) < 0.8).float(), (torch.rand(B, 80, generator=gen) < 0.8).float()]
+        shim.G.dropout_masks = iter([m.clone() for m in masks])
+        l2 = model.train(sess, batch, LR, REG)
+        shim.G.dropout_masks = None
+        out["train_dropout_loss"] = np.array(l2, np.float32)
+        out["dropout_mask1"], out["dropout_mask2"] = masks[0].numpy().astype(np.uint8), masks[1].numpy().astype(np.uint8)
+        out["after3/fc1/kernel"] = shim.G.by_name["fc1/kernel"].value.numpy().copy()
+        np.savez_compressed(os.path.join(OUT, "refwiring_%s.npz" % name), **out)
+        print("refwiring_%s.npz: %d variables, eval loss %.6f, train losses %.6f %.6f, dropout step %.6f" % (
+            name, len(spec), float(eloss), float(l0), float(l1), float(l2)))
+
+
 def make_tmall(reference_root):
     """BASELINE.json config 1: the reference's bundled Tmall sample as a derived fixture (graph CSR + feature tables +
     target lines); the raw log itself stays in the reference tree"""
@@ -445,6 +539,8 @@ def main():
         make_tmall(args.reference)
     if not args.only or args.only == "hop2":
         make_hop2(args.reference)
+    if not args.only or args.only == "wiring":
+        make_wiring(args.reference)
     for c in MODEL_CASES:
         if not args.only or args.only == c[0]:
             make_model_case(*c)
