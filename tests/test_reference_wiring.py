@@ -93,3 +93,40 @@ def test_oracle_reproduces_the_references_train_steps(case):
     l2 = orc.train(None, _batch(g), lr, reg, keep_prob=0.8, dropout_masks=masks)
     assert l2 == pytest.approx(float(g["train_dropout_loss"]), rel=5e-6)
     assert np.abs(orc.params["fc1/kernel"].numpy() - g["after3/fc1/kernel"]).max() <= 1e-2 * lr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_cuda_path_matches_the_references_own_classes(case):
+    """the CUDA path directly against the outputs of the reference's classes.  This is the WIRING check - an error there is
+    O(1) - so the bar is 1e-4; the 1e-5 bar itself is held against the oracle (tests/test_parity_gpu.py), and the oracle
+    equals these fixtures to 1e-7 (tests above)"""
+    from score_b200 import model as sb
+    g, shape, cfg = _load(case)
+    params = ref.init_params(cfg, int(g["param_seed"]), torch.float32)
+    reg = float(g["reg_lambda"])
+    m = getattr(sb, cfg.model_type)(*shape.ctor_args(), adam_mode="dense", init_weights=False, use_graph=False, seed=7)
+    assert [n for n, _ in m.tensor_names()] == [str(n) for n in g["var_names"]]       # same variables, same order
+    m.load_params(params)
+    preds, labels, eloss = m.eval(None, _batch(g), reg)
+    np.testing.assert_allclose(preds, g["eval_preds"], rtol=1e-4, atol=1e-6)
+    assert labels == g["eval_labels"].tolist()
+    assert eloss == pytest.approx(float(g["eval_loss"]), rel=1e-4)
+    loss = m.forward_backward(_batch(g), reg, 1.0)
+    assert loss == pytest.approx(float(g["loss"]), rel=1e-4)
+    rows, vals = m.embedding_row_grads()
+    assert np.array_equal(rows, g["emb_rows"])
+    assert np.abs(vals - g["emb_row_grads"]).max() <= 1e-4 * np.abs(g["emb_row_grads"]).max()
+    for name, _ in m.tensor_names():
+        if name == "emb_mtx" or name in ref.NON_TRAINABLE:
+            continue
+        want = g["grad/" + name].reshape(-1)
+        scale = np.abs(want).max()
+        if name.endswith("/bias"):
+            scale = max(scale, np.abs(g["grad/" + name[:-5] + "/kernel"]).max())
+        assert np.abs(m.get_buffer("grad/" + name) - want).max() <= 1e-4 * max(scale, 1e-30), name
+    lr = float(g["lr"])
+    l0 = m.train(None, _batch(g), lr, reg, keep_prob=1.0)
+    l1 = m.train(None, _batch(g, "batch2"), lr, reg, keep_prob=1.0)
+    np.testing.assert_allclose([l0, l1], g["train_losses"], rtol=1e-4)
+    m.close()
