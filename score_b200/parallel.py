@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 
 import torch
 import torch.distributed as dist
@@ -361,12 +362,17 @@ class ShardedEmbeddingTrainer(_Base):
             want.copy_(send_rows)
         self._mark("a2a ids")
         self._fetch_no += 1
-        if self.p2p:
-            if self._symm is None or self._max_pos > self._n_cap or self._max_recv > self._owned_cap:
-                # decided from the count matrix alone, which every rank holds: all ranks (re)allocate together
-                self.stream.synchronize()
-                self._symm = None
+        if self.p2p and (self._symm is None or self._max_pos > self._n_cap or self._max_recv > self._owned_cap):
+            # decided from the count matrix alone, which every rank holds: all ranks (re)allocate together
+            self.stream.synchronize()
+            self._symm = None
+            try:
                 self._p2p_setup(max(self._max_pos, (self._max_recv + 1) // 2), d)
+            except Exception as e:      # no symmetric memory on this system: the NCCL all-to-alls below do the same job
+                sys.stderr.write("score_b200: peer-memory exchange unavailable (%s: %s), using NCCL all-to-all\n" % (type(e).__name__, e))
+                self.p2p = False
+                self._symm = None
+        if self.p2p:
             par = self._fetch_no & 1      # alternate the staged tables: a peer may still read the other one in its backward pass
             self.m._check(self.lib.score_shard_serve_push(self.h, want.data_ptr(), n_recv, self._mat.data_ptr(), self.world,
                                                           self.rank, self._peer_staged[par]))
