@@ -130,3 +130,26 @@ def test_cuda_path_matches_the_references_own_classes(case):
     l1 = m.train(None, _batch(g, "batch2"), lr, reg, keep_prob=1.0)
     np.testing.assert_allclose([l0, l1], g["train_losses"], rtol=1e-4)
     m.close()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/code/score"), reason="needs the reference checkout (build container only)")
+def test_fixtures_regenerate_from_the_reference_source(tmp_path, monkeypatch):
+    """run the generator again - the reference's classes are lifted out of /root/reference and executed over the stand-in
+    right now - and compare with the committed fixtures (the GPU box has no reference checkout: it uses the files)"""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_golden_mod", os.path.join(root, "tools", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    monkeypatch.setattr(mg, "OUT", str(tmp_path))
+    monkeypatch.setattr(mg, "WIRING_CASES", [c for c in mg.WIRING_CASES if c[0] in ("score", "rrn")])
+    mg.make_wiring("/root/reference")
+    for name in ("score", "rrn"):
+        new = np.load(os.path.join(str(tmp_path), "refwiring_%s.npz" % name), allow_pickle=False)
+        old = np.load(os.path.join(GOLDEN, "refwiring_%s.npz" % name), allow_pickle=False)
+        assert sorted(new.files) == sorted(old.files)
+        for k in old.files:
+            if old[k].dtype.kind in "fc":
+                np.testing.assert_allclose(new[k], old[k], rtol=1e-6, atol=1e-9, err_msg=k)
+            else:
+                assert np.array_equal(new[k], old[k]), k
