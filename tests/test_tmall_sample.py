@@ -34,3 +34,20 @@ def test_tmall_sample_end_to_end_auc_parity():
         assert abs(c[8] - o[8]) <= 1e-5 * abs(o[8])                          # mean batch loss incl. L2
         assert log[split]["max_pred_diff"] <= 1e-5
         assert 0.0 <= c[1] <= 1.0 and all(0.0 <= x <= 1.0 for x in c[2:8])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/code/score"), reason="needs the reference checkout (build container only)")
+def test_config1_through_the_references_own_class_matches_the_cuda_run():
+    """BASELINE.json config 1 with the reference's OWN code on the CPU - class SCORE of score.py over the TF stand-in, its
+    own eval(), its own get_ranking_quality, sklearn - against the numbers the CUDA path produced on B200 for the same
+    flow (profiles/r01_tmall_sample_config1.json): AUC within 1e-4 (BASELINE.json), losses / metrics within 1e-5."""
+    import json
+    import run_tmall_sample_reference as rr
+    log = rr.run(epochs=5, verbose=False)
+    cuda = json.load(open(os.path.join(ROOT, "profiles", "r01_tmall_sample_config1.json")))
+    a, b = np.asarray(log["train_loss_reference"]), np.asarray(cuda["train_loss_cuda"])
+    assert a.shape == b.shape and np.abs(a - b).max() <= 1e-5 * np.abs(b).max()
+    for split in ("validation", "test"):
+        r, c = np.asarray(log[split]["reference"]), np.asarray(cuda[split]["cuda"])
+        assert abs(r[1] - c[1]) <= 1e-4, (split, "auc", r[1], c[1])
+        assert np.abs(r - c).max() <= 1e-5, (split, r, c)
