@@ -6,7 +6,8 @@ What this pins and what it does not.  The reference's source decides the WIRING 
 concatenated, tiled, fed to which layer, in which order the variables are created and how they are named, what train() and
 eval() feed and fetch.  The stand-in decides what each op computes; those op semantics are the TF-1.x ones the oracle
 documents (oracle/score_ref.py header) and are themselves anchored to TensorFlow's published unit-test constants
-(tests/test_tf_known_answers.py: GRUCell, Adam, log_loss, batch_normalization, l2_loss).  A tensor here is a lazy graph
+(tests/test_tf_known_answers.py on the oracle; tests/test_tf_shim.py on this file's own graph API: GRUCell through
+dynamic_rnn, AdamOptimizer.minimize, log_loss, batch_normalization, l2_loss, sequence_mask, layer auto-numbering).  A tensor here is a lazy graph
 node (like tf.Tensor): ops build nodes, Session.run evaluates the fetches for a feed_dict.  Static shapes
 (get_shape().as_list()) come from evaluating every node once on zero inputs with batch size 2 while the graph is built.
 
