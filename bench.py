@@ -311,8 +311,14 @@ def main():
     json_fd = os.dup(1)
     os.dup2(2, 1)
 
+    emit_lock = threading.Lock()
+    pending = {"line": None, "done": False}
+
     def emit(line):
-        os.write(json_fd, (json.dumps(line) + "\n").encode())
+        with emit_lock:
+            if not pending["done"]:
+                pending["done"] = True
+                os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     from score_b200.synth import SHAPES, make_batch
     shape = SHAPES[args.workload]
@@ -320,6 +326,19 @@ def main():
         import dataclasses
         shape = dataclasses.replace(shape, batch=args.batch)
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+
+    def rescue():
+        # 30 s before the hard watchdog: if the main measurement is complete and only the extra large-vocab leg is still
+        # running (or stuck), the measured line goes out without it and every rank leaves with status 0
+        if pending["line"] is None or pending["done"]:
+            return
+        if rank == 0:
+            emit(dict(pending["line"], large_vocab={"error": "not finished within the bench's time limit (%d s)" % args.watchdog}))
+        os._exit(0)
+    if args.watchdog > 60 and args.impl == "ours":
+        timer = threading.Timer(args.watchdog - 30, rescue)
+        timer.daemon = True
+        timer.start()
 
     if args.impl == "reference":
         run_reference(args, shape, rank, world, emit)
@@ -518,13 +537,7 @@ def main():
     import gc
     gc.collect()
     torch.cuda.empty_cache()
-    lv_leg = None
-    if world > 1 and not args.no_large_vocab and args.workload == "taobao":
-        try:
-            lv_leg = large_vocab_leg(args, world, rank, local)
-        except Exception as e:      # the main line must survive a failure of the extra leg
-            lv_leg = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
-
+    line = None
     if rank == 0:
         roof, roof_s = rooflines(shape, stats, probes)
         line = {"metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
@@ -548,8 +561,16 @@ def main():
                 "kernel_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in probes.items()},
                 "ms_per_step_probed": ms_probed,
                 "final_loss": loss}
-        if lv_leg:
+    if world > 1 and not args.no_large_vocab and args.workload == "taobao":
+        pending["line"] = line if rank == 0 else {}      # from here on the rescue timer may close the run
+        try:
+            lv_leg = large_vocab_leg(args, world, rank, local)
+        except Exception as e:      # the main line must survive a failure of the extra leg
+            lv_leg = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        pending["line"] = None
+        if rank == 0:
             line["large_vocab"] = lv_leg
+    if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_baseline(shape, B)
             line["cpu_baseline"] = cb
