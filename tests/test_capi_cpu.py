@@ -30,6 +30,16 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_capi.SYMBOLS) == declared
 
 
+def test_every_entry_point_is_documented_and_cites_the_reference():
+    """INTEGRATION.md names every exported entry point (the table of what each one replaces in the reference), and the
+    header cites reference file:line for the interface it stands in for."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in _declared_symbols() if n not in doc]
+    assert not missing, missing
+    header = open(os.path.join(ROOT, "include", "score_b200.h")).read()
+    assert len(re.findall(r"[a-z_]+\.py:\d+", header)) >= 10
+
+
 def test_struct_layout_matches_header(tmp_path):
     """Compile the real header with gcc and compare sizeof/offsetof of every struct with its ctypes mirror."""
     import ctypes as C
