@@ -61,5 +61,25 @@ def build_library(force: bool = False, verbose: bool = False, defines=(), varian
     return target
 
 
+def listfeed_path() -> str:
+    import sysconfig
+    return os.path.join(HERE, "_listfeed" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_listfeed(force: bool = False) -> str:
+    """Host-side helper of the Python mirror (csrc/listfeed.c: nested lists -> int32 array), a CPython extension built
+    with gcc next to the library.  No CUDA in it."""
+    import sysconfig
+    target, src = listfeed_path(), os.path.join(CSRC, "listfeed.c")
+    if not force and os.path.exists(target) and os.path.getmtime(target) >= os.path.getmtime(src):
+        return target
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        raise RuntimeError("gcc not found: cannot build the list feed helper")
+    subprocess.run([cc, "-O2", "-fPIC", "-shared", "-Wall", "-I", sysconfig.get_paths()["include"], src, "-o", target], check=True)
+    return target
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_listfeed(force="--force" in sys.argv))
