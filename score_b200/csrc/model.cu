@@ -1787,6 +1787,13 @@ int score_shard_grad_push(ScoreHandle h, const int32_t* count_matrix_dev, int32_
 // so the half-step on them may be captured as a CUDA graph like the handle's own staged table
 int score_shard_register_staged(ScoreHandle h, const float* a, const float* b) {
     if (!h) return SCORE_ERR_ARG;
+    if (a != h->sh_ext_staged[0] || b != h->sh_ext_staged[1]) {
+        // the caller re-allocated its exchange buffers (they grow with the count matrix, which may happen while this
+        // rank's own position count - and with it sh_cap - stays put): a half-step captured on the old tables must go
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->st));
+        drop_graphs(h);
+    }
     h->sh_ext_staged[0] = a; h->sh_ext_staged[1] = b;
     return SCORE_OK;
 }
