@@ -284,6 +284,20 @@ int score_graph_build_2hop(const ScoreHop2Desc* d, int device, int32_t* hop1_ids
     g.seed_lo = (uint32_t)d->seed; g.seed_hi = (uint32_t)(d->seed >> 32);
     const int64_t L = g.n_lists, n1 = d->hop1_off[L];
     if (n1 > 0 && !d->hop1_ids) { g_hop2_error = "score_graph_build_2hop: hop1_ids is NULL"; return SCORE_ERR_ARG; }
+    // the kernels index the offset array with the neighbor ids: validate the CSR arrays here, on the host, where they live
+    // (the reference fails with an IndexError on a neighbor that has no document, graph_storage.py:160,208)
+    if (d->hop1_off[0] != 0) { g_hop2_error = "score_graph_build_2hop: hop1_off[0] must be 0"; return SCORE_ERR_ARG; }
+    for (int64_t i = 0; i < L; ++i)
+        if (d->hop1_off[i + 1] < d->hop1_off[i]) { g_hop2_error = "score_graph_build_2hop: hop1_off is not ascending"; return SCORE_ERR_ARG; }
+    {
+        const int32_t hi = (int32_t)(d->n_user + d->n_item);
+        for (int64_t i = 0; i < n1; ++i)
+            if (d->hop1_ids[i] < 0 || d->hop1_ids[i] > hi) {
+                g_hop2_error = "score_graph_build_2hop: neighbor id " + std::to_string(d->hop1_ids[i]) + " at position " + std::to_string(i) +
+                               " is outside 0.." + std::to_string(hi);
+                return SCORE_ERR_ID_RANGE;
+            }
+    }
     const int64_t nb = (L + 1023) / 1024 + 1;
     int64_t *off1 = nullptr, *off2 = nullptr, *sums64 = nullptr, *long_lists = nullptr;
     int32_t *ids_old = nullptr, *ids_new = nullptr, *flag = nullptr, *excl = nullptr, *sums32 = nullptr, *len2 = nullptr, *flag2 = nullptr,

@@ -67,7 +67,7 @@ def build_2hop(hop1_off, hop1_ids, n_user, n_item, n_slices, start_time=0, max_1
     def check(rc):
         if rc:
             msg = lib.score_graph_build_2hop_error().decode()
-            raise (ValueError if rc == _capi.ERR_ARG else RuntimeError)(msg)
+            raise (ValueError if rc in (_capi.ERR_ARG, _capi.ERR_ID_RANGE) else RuntimeError)(msg)
 
     check(lib.score_graph_build_2hop(C.byref(d), int(device), None, off2.ctypes.data, None, None, 0, C.byref(n2)))
     ids2 = np.empty(max(n2.value, 1), np.int32)

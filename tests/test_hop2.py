@@ -87,3 +87,29 @@ def test_cuda_builder_rejects_bad_arguments():
         build_2hop(np.zeros(3, np.int64), np.zeros(0, np.int32), 1, 1, 2)                  # hop1_off has the wrong size
     with pytest.raises(ValueError):
         build_2hop(np.zeros(5, np.int64), np.zeros(0, np.int32), 1, 1, 2, max_1hop=64)     # max_1hop > 32
+
+
+def test_builder_validates_the_csr_arrays_on_the_host():
+    """argument and CSR validation happens before any CUDA call (no GPU needed): sizes, caps, ascending offsets, neighbor
+    ids inside 0..n_user+n_item (the kernels index the offset array with them; the reference raises IndexError on a
+    neighbor without a document, graph_storage.py:160,208)"""
+    from score_b200.graph import build_2hop
+    nu, ni, S = 2, 2, 2
+    off = np.array([0, 0, 0, 1, 2, 2, 3, 4, 4, 5, 5], np.int64)          # (nu + ni + 1) * S + 1 entries
+    ids = np.array([3, 4, 3, 1, 2], np.int32)
+    with pytest.raises(ValueError):
+        build_2hop(off[:-1], ids, nu, ni, S)                                # wrong number of offsets
+    with pytest.raises(ValueError):
+        build_2hop(off, ids, nu, ni, S, max_1hop=64)                        # max_1hop > 32
+    bad = ids.copy(); bad[1] = nu + ni + 1
+    with pytest.raises(ValueError, match="outside"):
+        build_2hop(off, bad, nu, ni, S)
+    bad = ids.copy(); bad[0] = -1
+    with pytest.raises(ValueError, match="outside"):
+        build_2hop(off, bad, nu, ni, S)
+    dec = off.copy(); dec[4] = 0
+    with pytest.raises(ValueError, match="ascending"):
+        build_2hop(dec, ids, nu, ni, S)
+    shifted = off.copy(); shifted[0] = 1
+    with pytest.raises(ValueError, match="must be 0"):
+        build_2hop(shifted, ids, nu, ni, S)
