@@ -171,10 +171,39 @@ extern "C" {
 
 const char* score_graph_last_error(ScoreGraphHandle h) { return h ? h->err.c_str() : g_graph_error.c_str(); }
 
+// The sampler indexes the side-feature tables with the neighbor ids it picks ([id] + feat[id], graph_loader.py:186-191,
+// where an id without a feature entry is a KeyError): the graph is bipartite by construction (graph_storage.py:127-246),
+// so a user's 1-hop entries and an item's 2-hop entries are item ids, a user's 2-hop entries and an item's 1-hop entries
+// are user ids; 0 is the dummy.  Checked once here, on the host arrays, before anything is uploaded.
+static bool validate_csr(const ScoreGraphDesc* d, const int64_t* off, const int32_t* ids, bool hop1, std::string* msg) {
+    const int64_t S = d->n_slices, n_lists = ((int64_t)d->n_user + d->n_item + 1) * S;
+    const char* what = hop1 ? "hop1" : "hop2";
+    if (off[0] != 0) { *msg = std::string(what) + "_off[0] must be 0"; return false; }
+    for (int64_t i = 0; i < n_lists; ++i)
+        if (off[i + 1] < off[i]) { *msg = std::string(what) + "_off is not ascending"; return false; }
+    if (off[n_lists] > 0 && !ids) { *msg = std::string(what) + "_ids is NULL"; return false; }
+    for (int64_t node = 1; node <= (int64_t)d->n_user + d->n_item; ++node) {
+        const bool node_is_user = node <= d->n_user;
+        const bool want_user = node_is_user != hop1;      // 1-hop neighbors are of the other type, 2-hop of the own type
+        const int32_t lo = want_user ? 1 : d->n_user + 1, hi = want_user ? d->n_user : d->n_user + d->n_item;
+        for (int64_t i = off[node * S]; i < off[(node + 1) * S]; ++i) {
+            const int32_t v = ids[i];
+            if (v != 0 && (v < lo || v > hi)) {
+                *msg = std::string(what) + " list of node " + std::to_string(node) + " holds id " + std::to_string(v) + ", expected 0 or " +
+                       std::to_string(lo) + ".." + std::to_string(hi) + (want_user ? " (a user id)" : " (an item id)");
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
 int score_graph_create(const ScoreGraphDesc* d, int device, ScoreGraphHandle* out) {
     if (!d || !out) { g_graph_error = "null argument"; return SCORE_ERR_ARG; }
     if (d->n_user <= 0 || d->n_item <= 0 || d->n_slices <= 0 || d->user_fnum < 1 || d->item_fnum < 1 || !d->hop1_off ||
         !d->hop2_off) { g_graph_error = "bad graph description"; return SCORE_ERR_ARG; }
+    if (!validate_csr(d, d->hop1_off, d->hop1_ids, true, &g_graph_error) || !validate_csr(d, d->hop2_off, d->hop2_ids, false, &g_graph_error))
+        return SCORE_ERR_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
         g_graph_error = "no CUDA device: the graph store has no CPU fallback";

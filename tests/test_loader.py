@@ -86,6 +86,46 @@ def test_graph_store_needs_a_gpu_and_validates_arguments():
             GraphStore(1, 1, 2, off, [], off, [])                       # no CPU fallback
 
 
+def test_graph_store_checks_the_neighbor_types_on_the_host():
+    """score_graph_create validates the CSR arrays before it touches the device: the sampler indexes the side-feature
+    tables with the neighbor ids (graph_loader.py:186-191 raises KeyError for an id without an entry).  Every graph the
+    GPU tests use passes the check (on a CPU box construction then stops at 'no CUDA device'); a mistyped id does not."""
+    import torch
+    from score_b200.graph import GraphStore, docs_to_csr, feat_table
+    if torch.cuda.is_available():
+        pytest.skip("CPU-side check of the validation order")
+    g = np.load(GOLDEN)
+    for name in _cases():
+        with pytest.raises(RuntimeError, match="no CUDA device"):
+            _store(g, name, _case(g, name))
+    for seed, (nu, ni, tsn, uf, fi, kw) in {9: (400, 600, 12, 3, 4, {}), 12: (300, 500, 9, 1, 2, {"n_feat": 40})}.items():
+        user_docs, item_docs, ufd, ifd = L.random_graph(np.random.default_rng(seed), nu, ni, tsn, user_fnum=uf, item_fnum=fi, **kw)
+        off1, ids1, off2, ids2, deg2 = docs_to_csr(user_docs, item_docs, nu, ni, tsn)
+        args = (nu, ni, tsn, off1, ids1, off2, ids2, deg2, feat_table(ufd, 1, nu, uf - 1) if uf > 1 else None,
+                feat_table(ifd, nu + 1, ni, fi - 1) if fi > 1 else None, uf, fi)
+        with pytest.raises(RuntimeError, match="no CUDA device"):
+            GraphStore(*args)
+        u_first = int(off1[1 * tsn])                       # first 1-hop entry of user 1: must be an item id
+        if int(off1[(nu + 1) * tsn]) > u_first:
+            bad = ids1.copy(); bad[u_first] = 1            # a user id in a user's 1-hop list
+            with pytest.raises(ValueError, match="hop1 list of node"):
+                GraphStore(*(args[:4] + (bad,) + args[5:]))
+        if ids2.size:
+            bad2 = ids2.copy(); bad2[0] = nu + ni + 1      # outside the node range
+            with pytest.raises(ValueError, match="hop2 list of node"):
+                GraphStore(*(args[:6] + (bad2,) + args[7:]))
+        dec = off1.copy(); dec[5] = dec[-1] + 1
+        with pytest.raises(ValueError, match="ascending"):
+            GraphStore(*(args[:3] + (dec,) + args[4:]))
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import run_tmall_sample as rt
+    gt, nu, ni, V, S = rt.load_fixture()
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        GraphStore(nu, ni, S, gt["hop1_off"], gt["hop1_ids"], gt["hop2_off"], gt["hop2_ids"], gt["hop2_deg"], gt["user_feat"],
+                   gt["item_feat"], rt.UF, rt.IF)
+
+
 # ------------------------------------------------------------------------------------------ GPU
 def _store(g, name, c):
     from score_b200.graph import GraphStore
