@@ -246,6 +246,10 @@ typedef struct ScoreGraphDesc {
     const int32_t* user_feat;      /* [(n_user+1) * (user_fnum-1)]  user_feat_dict[str(uid)]; NULL if user_fnum == 1 */
     const int32_t* item_feat;      /* [(n_item+1) * (item_fnum-1)]  row iid - n_user; NULL if item_fnum == 1   */
 } ScoreGraphDesc;
+/* SCORE_ERR_ARG (before any device work) when an offset array is not ascending from 0 or a list holds an id of the wrong
+   type: 1-hop neighbors of a user / 2-hop neighbors of an item are item ids (n_user+1 .. n_user+n_item), 1-hop neighbors
+   of an item / 2-hop neighbors of a user are user ids (1 .. n_user), 0 is the dummy - graph_storage.py:127-246 builds the
+   lists that way, and graph_loader.py:186-191 raises KeyError for an id without a feature entry */
 int score_graph_create(const ScoreGraphDesc* desc, int device, ScoreGraphHandle* out);
 int score_graph_destroy(ScoreGraphHandle g);
 const char* score_graph_last_error(ScoreGraphHandle g);
