@@ -128,7 +128,7 @@ class SCOREBASE(object):
         preds = np.empty(b.B, np.float32)
         loss = C.c_float()
         self._check(self._lib.score_eval(self._h, C.byref(b.struct), reg_lambda, preds.ctypes.data, C.byref(loss)))
-        lab = batch_data[6]
+        lab = b.keep[6]          # the int32 labels the call consumed (already converted once at the boundary)
         if hasattr(lab, "is_cuda"):
             lab = lab.cpu().numpy()
         return preds.reshape([-1, ]).tolist(), np.asarray(lab).astype(np.int32).reshape([-1, ]).tolist(), loss.value
