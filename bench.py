@@ -187,7 +187,7 @@ def rooflines(shape, stats, probes):
     t_g, t_s = per_launch("coatt_fwd"), per_launch("emb_update")
     tr_g, src_g = ncu_traffic(shape.name, "coatt_fwd")
     tr_s, src_s = ncu_traffic(shape.name, "emb_update")
-    roof = {"bound": "hbm", "kernel": "coatt_fwd_kernel (fused embedding gather + co-attention + pooling)",
+    roof = {"bound": "hbm", "kernel": "coatt_fwd_lean_kernel / coatt_fwd_kernel (fused embedding gather + co-attention + pooling; the lean instance serves the compiled-in geometries, Taobao among them)",
             "achieved": gather_bytes / (t_g * 1e-3) / 1e9 if t_g else None, "peak": peak, "unit": "GB/s",
             "frac": gather_bytes / (t_g * 1e-3) / 1e9 / peak if t_g else None, "traffic": tr_g,
             "traffic_source": src_g,
