@@ -147,7 +147,9 @@ def run_reference(args, shape, rank, world, emit):
     line = {"impl": "reference", "metric": "train_samples_per_sec", "value": cb["value"], "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(shape, args, shape.batch),
+            # the arm's config at this N (global batch = per-GPU batch x N); a step of THIS arm is a bounded sample of it:
+            # one batch of `per_gpu_batch` samples on the host cores (cpu_baseline.sample) - samples/s does not depend on it
+            "config": workload_config(shape, args, shape.batch * max(1, args.gpus)),
             "cpu_baseline": dict(cb),
             "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -161,14 +163,25 @@ def workload_config(shape, args, global_batch):
             "global_batch": global_batch, "per_gpu_batch": shape.batch, "length": shape.length,
             "ids": "uniform" if not args.zipf else "zipf %.2f" % args.zipf,
             "adam": args.adam_mode, "cuda_graph": not args.no_graph,
-            "parallelism": {"single": "single GPU",
-                            "dp": "dp%d: replicated table, ONE all-gather per step of packed blocks (dense gradient + one embedding-"
-                                  "gradient row per unique id), rank-ordered deterministic reduce on every replica" % args.gpus,
-                            "sharded": "dp%d dense + embedding rows sharded by id %% %d: ids through one NCCL all-to-all, rows and "
-                                       "gradient rows stored straight into the peers' buffers over NVLink (peer memory; "
-                                       "SCORE_SHARD_P2P=0: NCCL all-to-alls)" % (args.gpus, args.gpus)}[getattr(args, "par", "single")],
+            # the same text in both arms of a run at this N (the reference arm cannot know which scheme the probe picks):
+            # the scheme that ran is the line's top-level `parallelism_scheme`
+            "parallelism": "single GPU" if args.gpus <= 1 else
+                           "dp%d: batch split over %d GPUs (%d samples each); embedding table replicated (one packed all-gather per "
+                           "step) or row-sharded by id %% %d (peer-memory exchange over NVLink), as selected for this N - see "
+                           "parallelism_scheme" % (args.gpus, args.gpus, shape.batch, args.gpus),
             "l2_policy": "inputs larger than L2: %.2f GB of embedding state (var+m+v), uniform-random rows, %d rotating "
                          "batches; no explicit flush" % (3 * shape.feature_size * shape.eb_dim * 4 / 1e9, POOL)}
+
+
+def scheme_info(args, par_probe):
+    """which multi-GPU scheme the timed region ran (and the probe that chose it)"""
+    text = {"single": "single GPU",
+            "dp": "dp%d: replicated table, ONE all-gather per step of packed blocks (dense gradient + one embedding-"
+                  "gradient row per unique id), rank-ordered deterministic reduce on every replica" % args.gpus,
+            "sharded": "dp%d dense + embedding rows sharded by id %% %d: ids through one NCCL all-to-all, rows and "
+                       "gradient rows stored straight into the peers' buffers over NVLink (peer memory; "
+                       "SCORE_SHARD_P2P=0: NCCL all-to-alls)" % (args.gpus, args.gpus)}[getattr(args, "par", "single")]
+    return {"chosen": getattr(args, "par", "single"), "description": text, "probe_ms_per_step": par_probe}
 
 
 def rooflines(shape, stats, probes):
@@ -544,8 +557,8 @@ def main():
         line = {"metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(workload_config(shape, args, B * world),
-                               **({"parallelism_probe_ms_per_step": par_probe} if par_probe else {})),
+                "config": workload_config(shape, args, B * world),
+                "parallelism_scheme": scheme_info(args, par_probe),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 16 if world == 1 else 20,
