@@ -17,7 +17,7 @@ python - <<'PY'
 import json
 try:
     d=json.loads(open('gpurun_out/r2r_bench8.json').read().strip().splitlines()[-1])
-    print("value %.0f ms %.3f e2e %.0f loss %s"%(d['value'],d['ms_per_step'],d['e2e']['value'],d['final_loss']), d['config'].get('parallelism_probe_ms_per_step'))
+    print("value %.0f ms %.3f e2e %.0f loss %s"%(d['value'],d['ms_per_step'],d['e2e']['value'],d['final_loss']), (d.get('parallelism_scheme') or {}).get('probe_ms_per_step'))
     lv=d.get('large_vocab'); print("large_vocab: %.0f samples/s %.3f ms, x %.2f (1 GPU %.3f ms)"%(lv['value'],lv['ms_per_step'],lv['x_vs_1gpu_shard'],lv['one_gpu_shard']['ms_per_step']))
 except Exception as e: print("no json",e)
 PY
