@@ -53,3 +53,26 @@ def test_rooflines_assembly_runs_on_cpu():
     assert g2["frac"] is None and g2["random_access_ceiling"] is None
     import json
     json.dumps([g, s, g2, s2])
+
+
+def test_both_arms_describe_the_same_config_at_every_n():
+    """the reference arm's config is the product arm's config at that N (global batch = per-GPU batch x N, same texts): the
+    driver compares the two lines of a run; the scheme the product arm ran is reported outside `config`"""
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from score_b200.synth import SHAPES
+    shape = SHAPES["taobao"]
+    for n in (1, 2, 8):
+        ours = argparse.Namespace(gpus=n, zipf=0.0, adam_mode="lazy", no_graph=False, par="single" if n == 1 else "sharded")
+        ref = argparse.Namespace(gpus=n, zipf=0.0, adam_mode="lazy", no_graph=False)
+        a = bench.workload_config(shape, ours, shape.batch * n)
+        b = bench.workload_config(shape, ref, shape.batch * max(1, ref.gpus))
+        assert a == b and a["global_batch"] == 1024 * n and a["per_gpu_batch"] == 1024
+        info = bench.scheme_info(ours, {"dp": 0.5, "sharded": 0.4} if n > 1 else None)
+        assert info["chosen"] == ours.par and info["description"]
+    r = _run("--impl", "reference", "--gpus", "2", "--workload", "tiny_tb", "--steps", "1", "--warmup", "1")
+    j = json.loads(r.stdout.strip().splitlines()[-1])
+    assert j["n_gpus"] == 2 and j["config"]["global_batch"] == 2 * j["config"]["per_gpu_batch"]
