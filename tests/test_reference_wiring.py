@@ -153,3 +153,74 @@ def test_fixtures_regenerate_from_the_reference_source(tmp_path, monkeypatch):
                 np.testing.assert_allclose(new[k], old[k], rtol=1e-6, atol=1e-9, err_msg=k)
             else:
                 assert np.array_equal(new[k], old[k]), k
+
+
+GEOMETRIES = [
+    # name, model class, overrides of the tiny shape, ragged lengths
+    ("ccmr_widths", "SCORE", dict(user_fnum=1, item_fnum=5, max_time_len=7, length=5), False),       # train_score.py:24-32
+    ("k20", "SCORE", dict(user_fnum=1, item_fnum=5, obj_per_time_slice=20, max_time_len=4, length=3), False),
+    ("wide_d64_h128", "SCORE", dict(eb_dim=64, hidden_size=128, user_fnum=1, item_fnum=1, max_time_len=5, length=4), False),
+    ("tmall_t11_ragged", "SCORE", dict(max_time_len=11, length=9), True),                             # train_score.py:46-54
+    ("ria_ragged", "RIA", dict(user_fnum=1, item_fnum=2, max_time_len=8, length=6), True),
+    ("rca_k5", "RCA", dict(obj_per_time_slice=5), False),
+    ("rrn_ccmr_widths", "RRN", dict(user_fnum=1, item_fnum=5, max_time_len=7, length=5), True),
+]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/code/score"), reason="needs the reference checkout (build container only)")
+@pytest.mark.parametrize("name,cls,over,ragged", GEOMETRIES, ids=[g[0] for g in GEOMETRIES])
+def test_oracle_matches_the_references_classes_on_other_geometries(name, cls, over, ragged):
+    """beyond the committed fixtures: the reference's class is built for another geometry right here (CCMR field counts,
+    K = 20, d = 64 / H = 128, Tmall's T = 11, ragged lengths incl. 0 and T) over the stand-in and compared with the oracle -
+    variable list, eval() through the reference's own eval(), loss and every gradient, one optimizer step"""
+    import dataclasses
+    import importlib.util
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import tf_shim as shim
+    spec = importlib.util.spec_from_file_location("make_golden_mod2", os.path.join(root, "tools", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    from score_b200.synth import make_batch
+    shape = dataclasses.replace(SHAPES["tiny"], **over)
+    cfg = ref.ScoreConfig(*shape.ctor_args(), model_type=cls)
+    params = ref.init_params(cfg, 77, torch.float32)
+    rel = "code/slice_models/slice_model.py" if cls == "RRN" else "code/score/score.py"
+    ns = mg.load_reference_model_classes("/root/reference", rel, shim)
+    model = ns[cls](*shape.ctor_args())
+    assert shim.set_variables(params) == [(n, tuple(s)) for n, s in ref.param_specs(cfg)]
+    batch = list(make_batch(shape, seed=900 + len(name), batch=9))
+    if ragged:
+        batch[7] = np.array([0, shape.max_time_len, 1, 3, 2, shape.max_time_len, 4, 1, 2], np.int32)
+    lists = [x.tolist() for x in batch]
+    sess = shim.Session()
+    reg, lr = 1e-4, 5e-4
+    preds, labels, eloss = model.eval(sess, lists, reg)
+    orc = ref.ScoreOracle(*shape.ctor_args(), model_type=cls, seed=77)
+    o_preds, o_labels, o_loss = orc.eval(None, tuple(batch), reg)
+    np.testing.assert_allclose(o_preds, preds, rtol=3e-6, atol=1e-7)
+    assert o_labels == labels and o_loss == pytest.approx(eloss, rel=3e-6)
+    feed = {model.user_1hop_ph: lists[0], model.user_2hop_ph: lists[1], model.item_1hop_ph: lists[2], model.item_2hop_ph: lists[3],
+            model.target_user_ph: lists[4], model.target_item_ph: lists[5], model.label_ph: lists[6], model.length_ph: lists[7],
+            model.lr: lr, model.reg_lambda: reg, model.keep_prob: 1.0}
+    loss, grads = shim.gradients(sess, model.loss, feed)
+    o_loss2, _, o_grads, _ = ref.loss_and_grads(params, ref.to_batch(tuple(batch)), cfg, reg, 1.0)
+    assert float(o_loss2) == pytest.approx(float(loss), rel=3e-6)
+    r_rows, r_vals = ref.embedding_row_grads(grads["emb_mtx"])
+    o_rows, o_vals = ref.embedding_row_grads(o_grads["emb_mtx"])
+    assert np.array_equal(o_rows.numpy(), r_rows.numpy())
+    assert np.abs(o_vals.numpy() - r_vals.numpy()).max() <= 5e-6 * np.abs(r_vals.numpy()).max()
+    for k, want in grads.items():
+        if k == "emb_mtx":
+            continue
+        want = want.numpy()
+        scale = np.abs(want).max()
+        if k.endswith("/bias"):
+            scale = max(scale, np.abs(grads[k[:-5] + "/kernel"].numpy()).max())
+        assert np.abs(o_grads[k].numpy() - want).max() <= 1e-5 * max(scale, 1e-30), k
+    l_ref, _ = sess.run([model.loss, model.train_step], feed_dict=feed)
+    l_orc = orc.train(None, tuple(batch), lr, reg, keep_prob=1.0)
+    assert l_orc == pytest.approx(float(l_ref), rel=3e-6)
+    for k in ("fc1/kernel", "bn1/beta"):
+        assert np.abs(orc.params[k].numpy() - shim.G.by_name[k].value.numpy()).max() <= 1e-2 * lr, k
