@@ -433,7 +433,7 @@ int ensure_workspace(ScoreModel* h, int B) {
     int cap = B;
     const Dims& dm = h->dm;
     const int64_t M = (int64_t)cap * dm.T, N = (int64_t)cap * ids_per_sample(dm);
-    const int H = dm.H, K = dm.K, Ds = dm.Ds, Dk = dm.Dk, Dfc = dm.Dfc, ldx = dm.ldx;
+    const int H = dm.H, K = dm.K, Ds = dm.Ds, Dk = dm.Dk, Dfc = dm.Dfc;
     WSI(h->ids, N, "ids"); WSI(h->label, cap, "label"); WSI(h->length, cap, "length"); WSI(h->keys, N, "keys");
     WSI(h->live, M + 1, "live_slices");
     WS(h->q0, (int64_t)cap * Ds, "q0"); WS(h->c_item, cap, "c_item"); WS(h->c_user, cap, "c_user");
@@ -599,7 +599,7 @@ void enqueue_sort_branch(ScoreModel* h, cudaEvent_t after, int part = 0) {
 // forward graph of class SCORE (score.py:188-224); everything enqueued on h->st
 void enqueue_forward(ScoreModel* h, bool will_bwd) {
     const Dims& dm = h->dm;
-    const int B = dm.B, T = dm.T, H = dm.H, Ds = dm.Ds, Dk = dm.Dk, Dfc = dm.Dfc, ldx = dm.ldx;
+    const int B = dm.B, T = dm.T, H = dm.H, Ds = dm.Ds, Dk = dm.Dk, Dfc = dm.Dfc;
     const int M = B * T;
     Names nm = role_names(dm.model_type);
     auto W = [&](const std::string& n) { return pp(h, (n + "/kernel").c_str()); };
@@ -715,7 +715,7 @@ void enqueue_backward(ScoreModel* h, bool fused_adam = false, bool defer_join = 
     DenseAdamArgs adam_args{h->P, h->M1, h->V1, h->flags, h->hyper_dev, h->alpha_hist};
     const DenseAdamArgs* adam = fused_adam ? &adam_args : nullptr;
     const Dims& dm = h->dm;
-    const int B = dm.B, T = dm.T, H = dm.H, Ds = dm.Ds, Dk = dm.Dk, Dfc = dm.Dfc, ldx = dm.ldx;
+    const int B = dm.B, T = dm.T, H = dm.H, Ds = dm.Ds, Dk = dm.Dk, Dfc = dm.Dfc;
     const int M = B * T;
     Names nm = role_names(dm.model_type);
     auto W = [&](const std::string& n) { return pp(h, (n + "/kernel").c_str()); };

@@ -665,7 +665,6 @@ template <int EXPORT, int LPR>
 __global__ void __launch_bounds__(256) emb_update_kernel(EmbUpdateArgs a) {
     pdl_enter();
     constexpr int D = LPR * 4;
-    constexpr int G = 32 / LPR;          // groups per warp
     constexpr int NGC = 256 / LPR;       // groups per CTA
     __shared__ float4 red[8][LPR];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
