@@ -113,6 +113,46 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class LineGuard(object):
+    """stdout carries exactly ONE JSON line, whatever happens to the optional tail of the run: emit() writes once; between
+    arm(line) and disarm() the rescue timer may close the run - rank 0 prints the measured line with the unfinished leg
+    marked, every rank leaves with status 0 (a stuck collective in the extra leg must not cost the main measurement)"""
+
+    def __init__(self, fd, rank, limit_s, exit_fn=os._exit):
+        self.fd, self.rank, self.limit_s, self.exit_fn = fd, rank, limit_s, exit_fn
+        self.lock = threading.Lock()
+        self.done = False
+        self.armed = None
+
+    def emit(self, line):
+        with self.lock:
+            if not self.done:
+                self.done = True
+                os.write(self.fd, (json.dumps(line) + "\n").encode())
+
+    def arm(self, line):
+        self.armed = line if self.rank == 0 else {}
+
+    def disarm(self):
+        self.armed = None
+
+    def rescue(self):
+        line = self.armed
+        if line is None or self.done:
+            return
+        if self.rank == 0:
+            self.emit(dict(line, large_vocab={"error": "not finished within the bench's time limit (%d s)" % self.limit_s}))
+        with self.lock:
+            self.done = True
+        self.exit_fn(0)
+
+    def start_timer(self, seconds):
+        t = threading.Timer(seconds, self.rescue)
+        t.daemon = True
+        t.start()
+        return t
+
+
 def cpu_baseline(shape, batch_size, budget_s=20.0, max_steps=8):
     """Literal CPU restatement of score.py timed on the host cores (bounded sample of the workload)."""
     import torch
@@ -324,35 +364,17 @@ def main():
     json_fd = os.dup(1)
     os.dup2(2, 1)
 
-    emit_lock = threading.Lock()
-    pending = {"line": None, "done": False}
-
-    def emit(line):
-        with emit_lock:
-            if not pending["done"]:
-                pending["done"] = True
-                os.write(json_fd, (json.dumps(line) + "\n").encode())
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    guard = LineGuard(json_fd, rank, args.watchdog)
+    emit = guard.emit
+    if args.watchdog > 60 and args.impl == "ours":
+        guard.start_timer(args.watchdog - 30)     # 30 s before the hard watchdog
 
     from score_b200.synth import SHAPES, make_batch
     shape = SHAPES[args.workload]
     if args.batch > 0:
         import dataclasses
         shape = dataclasses.replace(shape, batch=args.batch)
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-
-    def rescue():
-        # 30 s before the hard watchdog: if the main measurement is complete and only the extra large-vocab leg is still
-        # running (or stuck), the measured line goes out without it and every rank leaves with status 0
-        if pending["line"] is None or pending["done"]:
-            return
-        if rank == 0:
-            emit(dict(pending["line"], large_vocab={"error": "not finished within the bench's time limit (%d s)" % args.watchdog}))
-        os._exit(0)
-    if args.watchdog > 60 and args.impl == "ours":
-        timer = threading.Timer(args.watchdog - 30, rescue)
-        timer.daemon = True
-        timer.start()
-
     if args.impl == "reference":
         run_reference(args, shape, rank, world, emit)
         return
@@ -576,12 +598,12 @@ def main():
                 "ms_per_step_probed": ms_probed,
                 "final_loss": loss}
     if world > 1 and not args.no_large_vocab and args.workload == "taobao":
-        pending["line"] = line if rank == 0 else {}      # from here on the rescue timer may close the run
+        guard.arm(line)      # from here on the rescue timer may close the run
         try:
             lv_leg = large_vocab_leg(args, world, rank, local)
         except Exception as e:      # the main line must survive a failure of the extra leg
             lv_leg = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
-        pending["line"] = None
+        guard.disarm()
         if rank == 0:
             line["large_vocab"] = lv_leg
     if rank == 0:

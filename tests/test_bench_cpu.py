@@ -76,3 +76,43 @@ def test_both_arms_describe_the_same_config_at_every_n():
     r = _run("--impl", "reference", "--gpus", "2", "--workload", "tiny_tb", "--steps", "1", "--warmup", "1")
     j = json.loads(r.stdout.strip().splitlines()[-1])
     assert j["n_gpus"] == 2 and j["config"]["global_batch"] == 2 * j["config"]["per_gpu_batch"]
+
+
+def test_line_guard_emits_once_and_rescues_the_measured_line():
+    """bench.LineGuard: one JSON line whatever happens - a rescue while the extra large-vocab leg is still running prints
+    the measured line with the leg marked unfinished (rank 0) and leaves with status 0 (every rank); afterwards nothing
+    else is written"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod3", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for rank in (0, 1):
+        r, w = os.pipe()
+        codes = []
+        g = bench.LineGuard(w, rank, 480, exit_fn=codes.append)
+        g.rescue()                                   # not armed: nothing happens
+        assert codes == [] and not g.done
+        g.arm({"metric": "train_samples_per_sec", "value": 1.0})
+        g.rescue()
+        assert codes == [0]
+        g.emit({"metric": "second line"})            # the late main thread must not add a line
+        os.close(w)
+        out = os.read(r, 1 << 16).decode()
+        os.close(r)
+        if rank == 0:
+            lines = out.splitlines()
+            assert len(lines) == 1
+            j = json.loads(lines[0])
+            assert j["value"] == 1.0 and "not finished" in j["large_vocab"]["error"]
+        else:
+            assert out == ""
+    # normal end: armed, leg finishes, disarmed, line emitted once; a late timer does nothing
+    r, w = os.pipe()
+    codes = []
+    g = bench.LineGuard(w, 0, 480, exit_fn=codes.append)
+    g.arm({"value": 2.0}); g.disarm()
+    g.emit({"value": 2.0, "large_vocab": {"value": 3.0}})
+    g.rescue()
+    os.close(w)
+    assert codes == [] and json.loads(os.read(r, 1 << 16).decode())["large_vocab"]["value"] == 3.0
+    os.close(r)
