@@ -562,8 +562,7 @@ def main():
         dt = (time.perf_counter() - t0) / n_l
         e2e_lists = {"value": B / dt, "unit": "samples/s", "ms_per_step": dt * 1e3, "steps": n_l,
                      "note": "batch_data as nested Python lists, as GraphLoader yields them: the step is the same, the time is "
-                             "the walk over %d Python objects per batch on one host core (csrc/listfeed.c; NumPy's generic "
-                             "converter took 50 ms for it)" % (h2d // 4)}
+                             "the walk over %d Python ints (+ their lists) per batch on one host core (csrc/listfeed.c)" % (h2d // 4)}
         del list_pool
     if trainer:
         loss = loss_e2e      # the trainer's synchronous step returns the GLOBAL loss (m.wait() is this rank's share only)
