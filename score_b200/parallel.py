@@ -119,6 +119,19 @@ class _Base:
         return float(t.item()) + float(loss2[1])
 
 
+def split_count_matrix(cm, world: int, rank: int):
+    """cm: the all-gathered count matrix, flat [world][world + 1]: cm[r][o] = positions of rank r owned by rank o, column
+    `world` = rank r's dummy positions (id 0).  -> (send_counts, recv_counts) of `rank` for the all-to-alls, and two numbers
+    that are identical on every rank (all of them hold the whole matrix) and size the symmetric exchange buffers: the
+    largest number of rows any owner serves, the largest position count of any rank."""
+    W = world
+    send_counts = cm[rank * (W + 1):rank * (W + 1) + W]
+    recv_counts = [cm[r * (W + 1) + rank] for r in range(W)]
+    max_recv = max(sum(cm[r * (W + 1) + o] for r in range(W)) for o in range(W))
+    max_pos = max(sum(cm[r * (W + 1):(r + 1) * (W + 1)]) for r in range(W))
+    return send_counts, recv_counts, max_recv, max_pos
+
+
 def exchange_capacity(counts) -> int:
     """list capacity of the packed exchange: the largest rank count rounded up to a multiple of 1024 (same on all ranks)."""
     return max(1024, (int(max(counts)) + 1023) // 1024 * 1024)
@@ -309,13 +322,8 @@ class ShardedEmbeddingTrainer(_Base):
         self._flush_finish()
         self._mark("finish(prev)")
         self.m._check(self.lib.score_shard_counts_wait(self.h, self._cm, nn))
-        cm = list(self._cm)
-        send_counts = cm[self.rank * (W + 1):self.rank * (W + 1) + W]
-        recv_counts = [cm[r * (W + 1) + self.rank] for r in range(W)]
+        send_counts, recv_counts, self._max_recv, self._max_pos = split_count_matrix(list(self._cm), W, self.rank)
         self._mat = mat
-        # identical on every rank (all of them hold the whole matrix): what sizes the symmetric exchange buffers
-        self._max_recv = max(sum(cm[r * (W + 1) + o] for r in range(W)) for o in range(W))
-        self._max_pos = max(sum(cm[r * (W + 1):(r + 1) * (W + 1)]) for r in range(W))
         return send_counts, recv_counts, int(sum(send_counts)), int(sum(recv_counts)), plan
 
     def _p2p_setup(self, n_positions, d):

@@ -59,6 +59,17 @@ def _worker(rank, world, port, out_dir):
         # deterministic order: grouped by source rank, ascending position inside
         src_sizes = plan.recv_counts
         assert sum(src_sizes) == want.numel()
+        # the count matrix of the CUDA plan (one all-gather of [world + 1] counts per rank) gives the same split sizes as
+        # the count all-to-all above, and buffer sizes every rank agrees on
+        mine = torch.bincount(torch.where(keys != 0, keys.long() % world, torch.full_like(keys.long(), world)), minlength=world + 1)
+        rows = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(rows, mine)
+        cm = torch.stack(rows).reshape(-1).tolist()
+        send_c, recv_c, max_recv, max_pos = parallel.split_count_matrix(cm, world, rank)
+        assert send_c == plan.send_counts and recv_c == plan.recv_counts
+        t = torch.tensor([plan.n_recv, n])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert [max_recv, max_pos] == t.tolist()
         # dense all-reduce + global loss composition
         g = torch.full((5,), float(rank + 1))
         dist.all_reduce(g)
