@@ -107,3 +107,63 @@ def test_exchange_capacity_is_a_common_multiple_of_1024():
     for counts in ([5], [1023, 1024, 1025], [10 ** 6]):
         cap = parallel.exchange_capacity(counts)
         assert cap % 1024 == 0 and cap >= max(counts) and cap - max(counts) < 1024 + (max(counts) == 0) * 1024
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_peer_push_offsets_land_rows_where_the_all_to_all_would(world):
+    """The index arithmetic of the peer-memory exchange (csrc/shard.cu: send_off / recv_off from the count matrix), restated
+    in NumPy for `world` in-process ranks, against the all-to-all semantics of ExchangePlan: a served row lands in the
+    requester's staged table at the row its mini key points to, a gradient row lands in the owner's buffer at the element
+    aligned with the owner's served list.  (The kernels themselves are checked on the GPU with `world` handles on one
+    device, tests/test_parity_gpu.py::test_sharded_peer_push_emulated_ranks.)"""
+    rng = np.random.default_rng(40 + world)
+    V, d, n = 997, 4, 300
+    table = rng.standard_normal((V, d)).astype(np.float32); table[0] = 0
+    keys = [rng.integers(0, V, n + 7 * r).astype(np.int64) for r in range(world)]          # ragged position counts
+    for k in keys:
+        k[::5] = 0
+    # per-rank plan (score_shard_plan): positions grouped by owner, stable; dummies last
+    owner = [np.where(k != 0, k % world, world) for k in keys]
+    order = [np.argsort(o, kind="stable") for o in owner]
+    cm = np.stack([np.bincount(o, minlength=world + 1) for o in owner])                      # [world][world + 1]
+    sel = [order[r][:cm[r, :world].sum()] for r in range(world)]
+    send_rows = [keys[r][sel[r]] // world + 1 for r in range(world)]
+    mini = []
+    for r in range(world):
+        m = np.zeros(len(keys[r]), np.int64)
+        m[sel[r]] = np.arange(1, len(sel[r]) + 1)
+        mini.append(m)
+    send_off = np.concatenate([np.zeros((world, 1), np.int64), np.cumsum(cm[:, :world], 1)], 1)   # send_off(r, o)
+    recv_off = np.concatenate([np.zeros((1, world), np.int64), np.cumsum(cm[:, :world], 0)], 0)   # recv_off(o, r) = [r][o]
+    # ids all-to-all: owner o's `want` list = the ranks' chunks for o, in rank order
+    want = [np.concatenate([send_rows[r][send_off[r, o]:send_off[r, o + 1]] for r in range(world)]) for o in range(world)]
+    local = [np.zeros(((V + world - 1) // world + 1, d), np.float32) for _ in range(world)]
+    for o in range(world):
+        rows = np.arange(o, V, world)
+        local[o][rows // world + 1] = table[rows]
+        local[o][0] = 0
+    staged = [np.zeros((len(keys[r]) + 1, d), np.float32) for r in range(world)]
+    for me in range(world):                                   # shard_serve_push_kernel, element e of owner `me`
+        for e in range(len(want[me])):
+            r = int(np.searchsorted(recv_off[1:, me], e, side="right"))
+            slot = send_off[r, me] + (e - recv_off[r, me]) + 1
+            staged[r][slot] = local[me][want[me][e]]
+    for r in range(world):
+        assert np.array_equal(staged[r][mini[r]], table[keys[r]])
+    grads = [rng.standard_normal((len(keys[r]), d)).astype(np.float32) for r in range(world)]
+    owned = [np.full((len(want[o]), d), np.nan, np.float32) for o in range(world)]
+    for me in range(world):                                   # shard_grad_push_kernel, send slot s of requester `me`
+        for s in range(len(sel[me])):
+            o = int(np.searchsorted(send_off[me, 1:], s, side="right"))
+            dst = recv_off[me, o] + (s - send_off[me, o])
+            owned[o][dst] = grads[me][sel[me][s]]
+    acc = np.zeros((V, d), np.float64)
+    for o in range(world):
+        assert not np.isnan(owned[o]).any()
+        glob = (want[o] - 1) * world + o                      # owner-local row -> global id
+        np.add.at(acc, glob, owned[o].astype(np.float64))
+    exp = np.zeros((V, d), np.float64)
+    for r in range(world):
+        nz = keys[r] != 0
+        np.add.at(exp, keys[r][nz], grads[r][nz].astype(np.float64))
+    assert np.allclose(acc, exp, atol=1e-12)
