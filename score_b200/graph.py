@@ -200,3 +200,72 @@ class DeviceGraphLoader(object):
                                   seed=self.seed, draw_id=self._next, stream=self.stream)
         self._next += 1
         return batch
+
+
+# ------------------------------------------------------------------------------------------ reference-signature loader
+_GRAPHS = {}
+
+
+def register_graph(db_name, store):
+    """The reference addresses its graph by MongoDB database name (graph_handler_params[1], train_score.py:292-297:
+    'tmall_2hop', 'taobao_2hop', 'ccmr_2hop'); here that name maps to a GraphStore in device memory."""
+    _GRAPHS[str(db_name)] = store
+
+
+class _HostReadable(object):
+    """A device-resident id tensor that NumPy can read as well: train_score.py:157 takes the target item ids of a batch
+    with np.array(batch_data[5])[:, 0].  Everything else (is_cuda, data_ptr, shape, ...) is the tensor's own."""
+
+    def __init__(self, tensor):
+        self._t = tensor
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._t.cpu().numpy() if hasattr(self._t, "cpu") else np.asarray(self._t)
+        return a.astype(dtype) if dtype is not None else a
+
+    def __getattr__(self, name):
+        return getattr(self._t, name)
+
+    def __len__(self):
+        return len(self._t)
+
+
+class GraphLoader(DeviceGraphLoader):
+    """GraphLoader of the reference by its own constructor signature (graph_loader.py:279-281):
+
+        GraphLoader(graph_handler_params, batch_size, target_file, start_time, pred_time, worker_n, neg_sample_num)
+
+    with graph_handler_params the list train_score.py builds (:292-297: time_slice_num, db_name, obj_per_time_slice,
+    user_num, item_num, start_time, user_per_collection, item_per_collection, mode, user / item feature files, user_fnum,
+    item_fnum).  db_name selects a GraphStore registered with register_graph(); the Mongo sharding parameters, the
+    feature files (the store holds the tables) and worker_n (one kernel, no worker processes) are accepted and unused.
+    Iterating yields the reference's 8-element batches with the id tensors in device memory."""
+
+    _instances = 0      # every loader the caller builds (one per epoch / evaluation, train_score.py:151,214) draws anew
+
+    def __init__(self, graph_handler_params, batch_size, target_file, start_time, pred_time, worker_n, neg_sample_num,
+                 max_q_size=10, wait_time=0.01, seed=1111):
+        p = list(graph_handler_params)
+        if len(p) < 9:
+            raise ValueError("graph_handler_params must be the list of train_score.py:292-297")
+        time_slice_num, db_name, obj_per_time_slice, mode = int(p[0]), str(p[1]), int(p[2]), p[8]
+        if db_name not in _GRAPHS:
+            raise KeyError("no graph registered under %r: call score_b200.graph.register_graph(%r, store) first" % (db_name, db_name))
+        if batch_size % (1 + neg_sample_num) != 0:
+            print('batch size should be time of {}'.format(1 + neg_sample_num))        # graph_loader.py:289-291
+            raise SystemExit(1)
+        with open(target_file, 'r') as f:
+            lines = f.readlines()
+        DeviceGraphLoader.__init__(self, _GRAPHS[db_name], batch_size, lines, start_time, pred_time, neg_sample_num,
+                                   time_slice_num - start_time - 1, obj_per_time_slice, mode=mode,
+                                   seed=seed + GraphLoader._instances)
+        GraphLoader._instances += 1
+        self.batch_size, self.worker_n = batch_size, worker_n
+
+    def __next__(self):
+        batch = list(DeviceGraphLoader.__next__(self))
+        batch[5] = _HostReadable(batch[5])
+        return batch
+
+    def stop(self):
+        pass

@@ -37,7 +37,7 @@ class StubModel(object):
         n = len(batch_data[6])
         preds = rng.random(n) * 0.5
         preds[::100] += 0.3 * min(1.0, self.n_train / 6.0)       # the positives climb as training proceeds
-        return preds.tolist(), list(batch_data[6]), 0.69 - 0.01 * self.n_train
+        return preds.tolist(), [int(x) for x in np.asarray(batch_data[6]).reshape(-1)], 0.69 - 0.01 * self.n_train
 
     def save(self, sess, path):
         StubModel.saved.append(path)
@@ -158,3 +158,68 @@ def test_references_eval_equals_the_metric_oracle_on_the_same_predictions(monkey
     want = metrics_ref.eval_metrics(np.asarray(preds), np.asarray(labels), np.asarray(iids), group=100)
     np.testing.assert_allclose(got[:8], want[:8], rtol=1e-12, atol=1e-15)
     assert got[8] == pytest.approx(sum(losses) / len(losses), rel=1e-15)
+
+
+class FakeStore(object):
+    """stands in for GraphStore.sample on a CPU box: same signature, host tensors, ids derived from the arguments"""
+    user_fnum, item_fnum = 1, 2
+    calls = []
+
+    def sample(self, uids, iids, group, start_time, pred_time, max_time_len, obj_per_time_slice, mode="rs", seed=0,
+               draw_id=0, stream=None, as_numpy=False):
+        import torch
+        B, T, K = len(iids), max_time_len, obj_per_time_slice
+        FakeStore.calls.append((B, group, start_time, pred_time, T, K, mode, seed, draw_id))
+        z = lambda f: torch.zeros(B, T, K, f, dtype=torch.int32)
+        tu = torch.as_tensor(np.repeat(np.asarray(uids, np.int32), group)[:B].reshape(B, 1))
+        ti = torch.as_tensor(np.stack([np.asarray(iids, np.int32), np.full(B, 7, np.int32)], 1))
+        label = torch.as_tensor((np.arange(B) % group == 0).astype(np.int32))
+        return (z(2), z(1), z(1), z(2), tu, ti, label, torch.full((B,), pred_time - start_time, dtype=torch.int32))
+
+
+def test_reference_signature_graph_loader_serves_the_references_own_eval_and_train(tmp_path, monkeypatch, capsys):
+    """score_b200.graph.GraphLoader takes the reference's constructor arguments (graph_loader.py:279-281, the
+    graph_handler_params list of train_score.py:292-297) and feeds train_score.py's OWN eval() / train() unchanged:
+    batch count incl. the short last batch, one uid per 1 + neg items, labels, lengths, and np.array(batch_data[5])[:, 0]
+    (train_score.py:157) on a tensor that otherwise lives in device memory.  The sampling itself is the CUDA sampler's
+    (GPU tests); a host stand-in for GraphStore.sample lets this run without a device."""
+    from score_b200 import graph
+    ns = reference_functions()
+    ns["GraphLoader"] = graph.GraphLoader
+    graph.register_graph("tmall_2hop", FakeStore())
+    params = [12, "tmall_2hop", 10, 50, 80, 0, 200, 500, "rs", None, None, 1, 2]
+    target = tmp_path / "target_10_sample.txt"
+    rng = np.random.default_rng(3)
+    n_users = 5                                     # 5 lines x 100 items: EVAL_BATCH_SIZE 100 -> 5 batches of one line
+    target.write_text("".join("%d,%s\n" % (u + 1, ",".join(str(51 + int(x)) for x in rng.integers(0, 80, 100))) for u in range(n_users)))
+    FakeStore.calls = []
+    m = StubModel()
+    monkeypatch.chdir(tmp_path)
+    out = ns["eval"](m, None, params, str(target), 0, 10, 1e-4)
+    assert len(out) == 9 and m.n_eval == n_users
+    assert all(c[:7] == (100, 100, 0, 10, 11, 10, "rs") for c in FakeStore.calls)          # T = 12 - 0 - 1, group 1 + 99
+    # training: batch 4 with 1 negative -> 2 lines per batch, 5 lines -> 3 batches per epoch, the last one short
+    train_file = tmp_path / "target_9.txt"
+    train_file.write_text(target.read_text())
+    FakeStore.calls = []
+    StubModel.saved, StubModel.restored, StubModel.created = [], [], []
+    ns["train"]("tmall", str(train_file), str(target), params, 0, 9, 10, "SCORE", 4, 5000, 16, 32, 11, 10, 5e-4, 1e-4, 12,
+                None, None, 1, 2)
+    train_calls = [c for c in FakeStore.calls if c[1] == 2]
+    assert train_calls and {c[0] for c in train_calls} == {4, 2} and all(c[3] == 9 and c[4] == 11 for c in train_calls)
+    assert len({c[7] for c in train_calls}) > 1                                             # a new loader (epoch) draws anew
+    # the reference's own error behaviour for a batch size that is not a multiple of 1 + neg (graph_loader.py:289-291)
+    with pytest.raises(SystemExit):
+        graph.GraphLoader(params, 5, str(train_file), 0, 9, 8, 1)
+    assert "batch size should be time of 2" in capsys.readouterr().out
+    with pytest.raises(KeyError):
+        graph.GraphLoader([12, "unknown_db"] + params[2:], 4, str(train_file), 0, 9, 8, 1)
+    # the target-item tensor reads like the reference's nested list AND like a device tensor
+    b = next(iter(graph.GraphLoader(params, 4, str(train_file), 0, 9, 8, 1)))
+    assert np.array(b[5])[:, 0].tolist() == [int(x) for x in train_file.read_text().splitlines()[0].split(",")[1:3]] + \
+        [int(x) for x in train_file.read_text().splitlines()[1].split(",")[1:3]]
+    assert hasattr(b[5], "data_ptr") and b[5].is_cuda is False and tuple(b[5].shape) == (4, 2)
+    # and the model boundary takes the batch as it is (pointer path of _Batch: no NumPy round trip)
+    from score_b200 import model as sb
+    bb = sb._Batch(b, dict(max_time_len=11, obj_per_time_slice=10, user_fnum=1, item_fnum=2))
+    assert bb.B == 4 and bb.struct.target_item == b[5].data_ptr()
